@@ -1,0 +1,537 @@
+/*
+ * qn_oracle.c — CPU oracle for the BFGS hot path.  TEST INFRASTRUCTURE ONLY
+ * (see qn_oracle.h for who may load it and for the parity-pinning status).
+ *
+ * Every function cites the reference lines it restates.  "QN.jl" abbreviates
+ * /root/reference/src/QuasiNewtonMethods.jl.
+ *
+ * Build with -ffp-contract=off: the compiler must never fuse or reassociate.
+ * Every fused multiply-add below is an explicit fma() and is part of the
+ * canonical order.
+ *
+ * CANONICAL ORDER (what LoopVectorization's @turbo decides in the reference
+ * and what is therefore fixed here; the CUDA kernels do exactly the same):
+ *
+ *  C1  csum(v, n): 32 lane accumulators.  p[l] = v[l] (+0.0 when l >= n);
+ *      then p[i mod 32] += v[i] for i = 32, 33, ... in ascending i; then a
+ *      butterfly  p[l] = p[l] + p[l xor off]  for off = 16, 8, 4, 2, 1; the
+ *      result is p[0].  Dot products are csum over individually rounded
+ *      products a[i]*b[i].  (The SIMD analogue: vector accumulators, then a
+ *      horizontal reduce.)
+ *  C2  Row sums over r (the GEMV at QN.jl:44-52 and the fused update+GEMV at
+ *      QN.jl:56-67): for a fixed row c one sequential FMA chain over ascending
+ *      r, started from +0.0, in blocks of `rblock` (=256) columns; block
+ *      partials are added in ascending block order.  n <= 256 is one chain.
+ *      (@turbo vectorises over the unit-stride index c and carries the r-sum
+ *      in each lane.)
+ *  C3  t += a*b, muladd(a,b,c), x + alpha*s under @turbo, and x +- a*b under
+ *      @fastmath with exactly one product operand are one fma.  Expressions
+ *      with two product operands (a*b - c*d) round both products.
+ *  C4  The rank-2 update is ((H + (c1*s[r])*s[c]) - u[r]*s[c]) - u[c]*s[r]
+ *      as three chained fma, in the source's left-to-right order (QN.jl:61);
+ *      c1*s[r] is rounded once per r.
+ *  C5  Objective code that the reference writes without @turbo/@fastmath
+ *      (Rosenbrock, test/runtests.jl:4-33) uses no fma except its explicit
+ *      muladd; its @simd sum is a csum.
+ */
+#define _GNU_SOURCE
+#include "qn_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <sched.h>
+#include <stdatomic.h>
+#include <stdlib.h>
+#include <string.h>
+
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(QO_NO_CLONES)
+#define QO_HOT __attribute__((target_clones("arch=x86-64-v4", "arch=x86-64-v3", "default")))
+#else
+#define QO_HOT
+#endif
+
+#define QO_W 32
+#define QO_EPS 2.220446049250313e-16 /* eps(Float64) */
+
+/* ------------------------------------------------------------------ C1 */
+static double qo_csum(const double* v, int n) {
+  double p[QO_W], q[QO_W];
+  for (int l = 0; l < QO_W; ++l) p[l] = (l < n) ? v[l] : 0.0;
+  for (int i = QO_W; i < n; ++i) p[i & (QO_W - 1)] = p[i & (QO_W - 1)] + v[i];
+  for (int off = QO_W / 2; off >= 1; off >>= 1) {
+    for (int l = 0; l < QO_W; ++l) q[l] = p[l] + p[l ^ off];
+    memcpy(p, q, sizeof p);
+  }
+  return p[0];
+}
+
+int qo_state_ld(int n, int native_w) {
+  /* pick_vector_width(Val(P), Float64) = min(native width, nextpow2(P));
+   * align(P, W) rounds P up to a multiple of W.  QN.jl:96-99 */
+  int w = 1;
+  while (w < n && w < native_w) w <<= 1;
+  return ((n + w - 1) / w) * w;
+}
+
+int64_t qo_state_len(int n, int L) { return 7 * (int64_t)L + (int64_t)n * L; }
+
+/* ---------------------------------------------- objectives (QN.jl:8-9) */
+
+/* Rosenbrock value: test/runtests.jl:5-17 */
+static double rosen_value(int n, const double* th, double* scratch) {
+  const int N = n >> 1;
+  for (int i = 0; i < N; ++i) {
+    const double t1 = th[i], t2 = th[i + N];
+    const double a = t2 - t1 * t1;
+    const double b = 1.0 - t1;
+    scratch[i] = 100.0 * (a * a) + b * b; /* 100(θ[i+N]-θ[i]^2)^2 + (1-θ[i])^2 */
+  }
+  double s = 0.0 - qo_csum(scratch, N); /* s -= term, lane-reassociated (@simd) */
+  if (n & 1) {
+    const double d = 1.0 - th[n - 1];
+    s = -fma(d, d, -s); /* -muladd(δ, δ, -s), runtests.jl:13 */
+  }
+  return s;
+}
+
+/* Rosenbrock value + gradient: test/runtests.jl:19-33 */
+static double rosen_grad(double* g, int n, const double* th, double* scratch) {
+  const int N = n >> 1;
+  for (int i = 0; i < N; ++i) {
+    const double t1 = th[i], t2 = th[i + N];
+    const double a = t2 - t1 * t1;
+    const double b = 1.0 - t1;
+    scratch[i] = 100.0 * (a * a) + b * b;
+    g[i] = (400.0 * a) * t1 + 2.0 * b;    /* 400(θ[i+N]-θ[i]^2)*θ[i] + 2(1-θ[i]) */
+    g[i + N] = 200.0 * (t1 * t1 - t2);    /* 200(θ[i]^2 - θ[i+N]) */
+  }
+  double s = 0.0 - qo_csum(scratch, N);
+  if (n & 1) {
+    const double d = 1.0 - th[n - 1];
+    s = -fma(d, d, -s);
+    g[n - 1] = 2.0 * d;
+  }
+  return s;
+}
+
+/* Dense Gaussian (build-defined): z = Λ(θ-μ) by C2
+ * row chains, ∇ = -z, ell = -1/2 csum((θ-μ)[c] z[c]).  scratch: 3n doubles. */
+QO_HOT static double gauss_eval(double* g, int n, const qo_gaussian* p, const double* th,
+                                int rblock, double* scratch) {
+  double* d = scratch;
+  double* z = scratch + n;
+  double* t = scratch + 2 * n;
+  for (int r = 0; r < n; ++r) d[r] = th[r] - p->mu[r];
+  for (int r0 = 0; r0 < n; r0 += rblock) {
+    const int r1 = (r0 + rblock < n) ? r0 + rblock : n;
+    for (int c = 0; c < n; ++c) t[c] = 0.0;
+    for (int r = r0; r < r1; ++r) {
+      const double dr = d[r];
+      const double* col = p->lambda + (size_t)n * r;
+      for (int c = 0; c < n; ++c) t[c] = fma(col[c], dr, t[c]);
+    }
+    if (r0 == 0) for (int c = 0; c < n; ++c) z[c] = t[c];
+    else for (int c = 0; c < n; ++c) z[c] = z[c] + t[c];
+  }
+  for (int c = 0; c < n; ++c) t[c] = d[c] * z[c];
+  const double q = qo_csum(t, n);
+  if (g) for (int c = 0; c < n; ++c) g[c] = -z[c];
+  return -0.5 * q;
+}
+
+static double qo_softplus(double z) { return z > 0.0 ? z + log1p(exp(-z)) : log1p(exp(z)); }
+static double qo_sigmoid(double z) {
+  if (z >= 0.0) return 1.0 / (1.0 + exp(-z));
+  const double e = exp(z);
+  return e / (1.0 + e);
+}
+
+/* Logistic regression (build-defined).
+ * scratch: 2m + 2n doubles. */
+QO_HOT static double logit_eval(double* g, int n, const qo_logistic* p, const double* th,
+                                int rblock, double* scratch) {
+  const int m = p->m;
+  double* z = scratch;
+  double* v = scratch + m;
+  double* w = scratch + 2 * m;
+  for (int i = 0; i < m; ++i) z[i] = 0.0;
+  for (int j = 0; j < n; ++j) {
+    const double tj = th[j];
+    const double* col = p->X + (size_t)m * j;
+    for (int i = 0; i < m; ++i) z[i] = fma(col[i], tj, z[i]);
+  }
+  for (int i = 0; i < m; ++i) v[i] = p->y[i] * z[i] - qo_softplus(z[i]);
+  const double S = qo_csum(v, m);
+  for (int j = 0; j < n; ++j) w[j] = th[j] * th[j];
+  const double pen = qo_csum(w, n);
+  const double ell = fma(-(0.5 * p->lam), pen, S);
+  if (g) {
+    for (int i = 0; i < m; ++i) v[i] = p->y[i] - qo_sigmoid(z[i]);
+    /* rule C2: chains of `rblock` rows, block partials added in ascending order */
+    double* T = scratch + 2 * m + n;
+    for (int i0 = 0; i0 < m; i0 += rblock) {
+      const int i1 = (i0 + rblock < m) ? i0 + rblock : m;
+      for (int j = 0; j < n; ++j) w[j] = 0.0;
+      for (int i = i0; i < i1; ++i) {
+        const double ri = v[i];
+        const double* col = p->Xt + (size_t)n * i;
+        for (int j = 0; j < n; ++j) w[j] = fma(col[j], ri, w[j]);
+      }
+      if (i0 == 0) for (int j = 0; j < n; ++j) T[j] = w[j];
+      else for (int j = 0; j < n; ++j) T[j] = T[j] + w[j];
+    }
+    for (int j = 0; j < n; ++j) g[j] = fma(-p->lam, th[j], T[j]);
+  }
+  return ell;
+}
+
+static size_t qo_scratch_len(const qo_model* model, int n) {
+  size_t len = 4 * (size_t)n + 64;
+  if (model->kind == QO_LOGISTIC) {
+    const qo_logistic* p = (const qo_logistic*)model->params;
+    len += 2 * (size_t)p->m;
+  }
+  return len;
+}
+
+static double qo_eval(double* g, const qo_model* model, int n, const double* th, int rblock,
+                      double* scratch) {
+  switch (model->kind) {
+    case QO_ROSENBROCK:
+      return g ? rosen_grad(g, n, th, scratch) : rosen_value(n, th, scratch);
+    case QO_DENSE_GAUSSIAN:
+      return gauss_eval(g, n, (const qo_gaussian*)model->params, th, rblock, scratch);
+    case QO_LOGISTIC:
+      return logit_eval(g, n, (const qo_logistic*)model->params, th, rblock, scratch);
+    default:
+      return NAN;
+  }
+}
+
+double qo_logdensity(const qo_model* model, int n, const double* theta) {
+  double* scratch = (double*)malloc(sizeof(double) * qo_scratch_len(model, n));
+  const double v = qo_eval(NULL, model, n, theta, 256, scratch);
+  free(scratch);
+  return v;
+}
+
+double qo_dlogdensity(double* grad, const qo_model* model, int n, const double* theta) {
+  double* scratch = (double*)malloc(sizeof(double) * qo_scratch_len(model, n));
+  const double v = qo_eval(grad, model, n, theta, 256, scratch);
+  free(scratch);
+  return v;
+}
+
+/* ------------------------------------------- BFGS_update! (QN.jl:34-69) */
+QO_HOT double qo_bfgs_update(int n, int L, double* H, double* u, double* y, const double* s,
+                             const double* g_new, const double* g_old, int rblock,
+                             double* scratch) {
+  double* t = scratch;         /* chain accumulators, one per row c */
+  double* T = scratch + n;     /* block-combined row sums */
+  double* w = scratch + 2 * n; /* c1*s[r] */
+  double* v = scratch + 3 * n; /* products for csum */
+
+  /* QN.jl:36-41  y = ∇_old - ∇_new ; sᵀy */
+  for (int i = 0; i < n; ++i) {
+    const double yi = g_old[i] - g_new[i];
+    y[i] = yi;
+    v[i] = s[i] * yi;
+  }
+  const double sy = qo_csum(v, n);
+  const double rho = 1.0 / sy; /* QN.jl:42, no guard */
+
+  /* QN.jl:44-52  t[c] = Σ_r y[r] H[c,r] ; u = t ρ ; yᵀHy */
+  for (int r0 = 0; r0 < n; r0 += rblock) {
+    const int r1 = (r0 + rblock < n) ? r0 + rblock : n;
+    for (int c = 0; c < n; ++c) t[c] = 0.0;
+    for (int r = r0; r < r1; ++r) {
+      const double yr = y[r];
+      const double* col = H + (size_t)L * r;
+      for (int c = 0; c < n; ++c) t[c] = fma(yr, col[c], t[c]);
+    }
+    if (r0 == 0) for (int c = 0; c < n; ++c) T[c] = t[c];
+    else for (int c = 0; c < n; ++c) T[c] = T[c] + t[c];
+  }
+  for (int c = 0; c < n; ++c) {
+    u[c] = T[c] * rho;
+    v[c] = T[c] * y[c];
+  }
+  const double yHy = qo_csum(v, n);
+
+  /* QN.jl:54 */
+  const double c1 = fma(yHy, rho, 1.0) * rho;
+
+  /* QN.jl:56-67  rank-2 update fused with d = H⁺ ∇_new */
+  for (int r = 0; r < n; ++r) w[r] = c1 * s[r];
+  for (int r0 = 0; r0 < n; r0 += rblock) {
+    const int r1 = (r0 + rblock < n) ? r0 + rblock : n;
+    for (int c = 0; c < n; ++c) t[c] = 0.0;
+    for (int r = r0; r < r1; ++r) {
+      const double wr = w[r], nur = -u[r], sr = s[r], gr = g_new[r];
+      double* col = H + (size_t)L * r;
+      for (int c = 0; c < n; ++c) {
+        double h = col[c];
+        h = fma(wr, s[c], h);    /*  + (c1 s[r]) s[c] */
+        h = fma(nur, s[c], h);   /*  - u[r] s[c]      */
+        h = fma(-u[c], sr, h);   /*  - u[c] s[r]      */
+        col[c] = h;
+        t[c] = fma(h, gr, t[c]);
+      }
+    }
+    if (r0 == 0) for (int c = 0; c < n; ++c) T[c] = t[c];
+    else for (int c = 0; c < n; ++c) T[c] = T[c] + t[c];
+  }
+  for (int c = 0; c < n; ++c) {
+    y[c] = T[c]; /* new direction overwrites y, QN.jl:65 */
+    v[c] = T[c] * g_new[c];
+  }
+  return qo_csum(v, n); /* m, QN.jl:66-68 */
+}
+
+/* nanmin / nanmax: QN.jl:152-153 */
+static double qo_nanmin(double a, double b) { return a < b ? a : (isnan(b) ? a : b); }
+static double qo_nanmax(double a, double b) { return a < b ? b : (isnan(a) ? b : a); }
+
+/* step!: QN.jl:157-162 */
+static double qo_step(int n, double* x_new, const double* x_old, const double* s,
+                      const qo_model* model, double alpha, int rblock, double* scratch) {
+  for (int i = 0; i < n; ++i) x_new[i] = fma(alpha, s[i], x_old[i]);
+  return qo_eval(NULL, model, n, x_new, rblock, scratch);
+}
+
+/* linesearch!: QN.jl:165-232 */
+static double qo_linesearch_impl(int n, double* x_new, const double* x_old, const double* s,
+                                 const qo_model* model, double l0, double m,
+                                 const qo_backtracking* ls, int64_t* fevals, int rblock,
+                                 double* scratch) {
+  const double c1 = ls->c1, rho_hi = ls->rho_hi, rho_lo = ls->rho_lo;
+  const int64_t iterations = ls->iterations;
+  const double sqrttol = 1.0 / (double)(1 << 26); /* sqrttolerance(Float64), QN.jl:155 */
+
+  double lx0 = l0, lx1 = l0;
+  double a1 = 1.0, a2 = 1.0;
+  lx1 = qo_step(n, x_new, x_old, s, model, a1, rblock, scratch); /* QN.jl:174 */
+  ++*fevals;
+
+  /* QN.jl:178-184: halve until finite, at most significand_bits(Float64)=52 times */
+  int iterfinite = 0;
+  while (!isfinite(lx1) && iterfinite < 52) {
+    ++iterfinite;
+    a1 = a2;
+    a2 = 0.5 * a2;
+    lx1 = qo_step(n, x_new, x_old, s, model, a2, rblock, scratch);
+    ++*fevals;
+  }
+
+  int64_t iteration = 0;
+  /* QN.jl:187: while !(ℓx₁ ≥ ℓ₀ + α₂ c₁ m) */
+  while (!(lx1 >= fma(a2 * c1, m, l0))) {
+    ++iteration;
+    if (iteration > iterations) return 0.0; /* QN.jl:193 */
+    double at;
+    if (ls->order == 2 || iteration == 1) {
+      /* QN.jl:205: -(m α₂ α₂) / (2 (ℓx₁ - ℓ₀ - m α₂)) */
+      at = -((m * a2) * a2) / (2.0 * fma(-m, a2, lx1 - l0));
+    } else {
+      /* QN.jl:207-209 */
+      const double denom = 1.0 / ((((a1 * a1) * a2) * a2) * (a2 - a1));
+      const double r1 = fma(-m, a2, lx1 - l0);
+      const double r0 = fma(-m, a1, lx0 - l0);
+      const double a = ((a1 * a1) * r1 - (a2 * a2) * r0) * denom;
+      const double b = ((((-a1) * a1) * a1) * r1 + ((a2 * a2) * a2) * r0) * denom;
+      if (fabs(a) <= QO_EPS + sqrttol * fabs(a)) { /* QN.jl:211 */
+        at = m / (2.0 * b);                        /* QN.jl:212 */
+      } else {
+        const double d = qo_nanmax(b * b - (3.0 * a) * m, 0.0); /* QN.jl:215 */
+        at = (sqrt(d) + b) / (-3.0 * a);                         /* QN.jl:218 */
+      }
+    }
+    a1 = a2;                                   /* QN.jl:222 */
+    at = qo_nanmin(at, a2 * rho_hi);           /* QN.jl:224 */
+    a2 = qo_nanmax(at, a2 * rho_lo);           /* QN.jl:225 */
+    lx0 = lx1;                                 /* QN.jl:228 */
+    lx1 = qo_step(n, x_new, x_old, s, model, a2, rblock, scratch);
+    ++*fevals;
+  }
+  return a2;
+}
+
+double qo_linesearch(int n, double* x_new, const double* x_old, const double* s,
+                     const qo_model* model, double l0, double m, const qo_backtracking* ls,
+                     int64_t* fevals) {
+  double* scratch = (double*)malloc(sizeof(double) * qo_scratch_len(model, n));
+  const double a = qo_linesearch_impl(n, x_new, x_old, s, model, l0, m, ls, fevals, 256, scratch);
+  free(scratch);
+  return a;
+}
+
+/* optimize!: QN.jl:237-292 */
+static double qo_optimize_impl(int n, int L, double* state, const qo_model* model,
+                               const double* x0, const qo_backtracking* ls, double tol,
+                               int64_t max_iter, int rblock, int ntrace, double* trace,
+                               double* trace_scalars, qo_info* info, double* scratch) {
+  /* field order of BFGSState, QN.jl:84-92; views QN.jl:135-142 */
+  double* x_old = state;
+  double* g_new = state + (size_t)L;
+  double* x_new = state + 2 * (size_t)L;
+  double* g_old = state + 3 * (size_t)L;
+  double* y = state + 4 * (size_t)L;
+  double* s = state + 5 * (size_t)L;
+  double* u = state + 6 * (size_t)L;
+  double* H = state + 7 * (size_t)L;
+  double* const g_canon = g_new;
+
+  int64_t fevals = 0, gevals = 0, iters = 0;
+  int status = QO_MAX_ITER;
+  double result = NAN;
+
+  memcpy(x_old, x0, sizeof(double) * (size_t)n); /* QN.jl:248 */
+  for (int64_t it = 1; it <= max_iter; ++it) {   /* QN.jl:250,253 */
+    const double l0 = qo_eval(g_new, model, n, x_old, rblock, scratch); /* QN.jl:254 */
+    ++fevals;
+    ++gevals;
+    if (!isfinite(l0)) { status = QO_NONFINITE; break; } /* QN.jl:255 */
+    /* QN.jl:257: maximum(abs, ∇) < tol  (a NaN entry makes it false) */
+    int conv = 1;
+    for (int i = 0; i < n; ++i) conv &= (fabs(g_new[i]) < tol);
+    if (conv) {
+      if (g_new != g_canon) memcpy(g_canon, g_new, sizeof(double) * (size_t)n); /* QN.jl:258-259 */
+      status = QO_CONVERGED;
+      result = l0;
+      break;
+    }
+    double m;
+    if (it == 1) {
+      m = -1.0; /* QN.jl:263-264 */
+    } else {
+      m = qo_bfgs_update(n, L, H, u, y, s, g_new, g_old, rblock, scratch); /* QN.jl:267 */
+      double* tmp = s; s = y; y = tmp;                                          /* QN.jl:268 */
+    }
+    if (m <= 0.0) { /* QN.jl:272-280 */
+      for (int r = 0; r < n; ++r)
+        for (int c = 0; c < n; ++c) H[c + (size_t)L * r] = (r == c) ? 1.0 : 0.0; /* QN.jl:144-148 */
+      double* v = scratch;
+      for (int i = 0; i < n; ++i) {
+        const double si = g_new[i];
+        s[i] = si;
+        v[i] = si * si;
+      }
+      m = qo_csum(v, n);
+    }
+    int64_t fe = 0;
+    const double alpha = qo_linesearch_impl(n, x_new, x_old, s, model, l0, m, ls, &fe, rblock,
+                                            scratch); /* QN.jl:283 */
+    fevals += fe;
+    if (alpha == 0.0) { status = QO_LINESEARCH_FAILED; break; } /* QN.jl:284 */
+    /* update_state!: QN.jl:21-27 */
+    for (int i = 0; i < n; ++i) {
+      const double si = alpha * s[i];
+      s[i] = si;
+      x_old[i] = x_old[i] + si;
+    }
+    ++iters;
+    if (trace && it <= ntrace) {
+      memcpy(trace + (size_t)(it - 1) * n, x_old, sizeof(double) * (size_t)n);
+      if (trace_scalars) {
+        double* ts = trace_scalars + (size_t)(it - 1) * 4;
+        ts[0] = l0; ts[1] = m; ts[2] = alpha; ts[3] = (double)fe;
+      }
+    }
+    double* tmp = g_old; g_old = g_new; g_new = tmp; /* QN.jl:286 */
+  }
+  if (info) {
+    info->iters = iters;
+    info->fevals = fevals;
+    info->gevals = gevals;
+    info->status = status;
+  }
+  return result; /* NaN unless converged, QN.jl:291 */
+}
+
+double qo_optimize(int n, int L, double* state, const qo_model* model, const double* x0,
+                   const qo_backtracking* ls, double tol, int64_t max_iter, int rblock,
+                   int ntrace, double* trace, double* trace_scalars, qo_info* info) {
+  double* scratch = (double*)malloc(sizeof(double) * qo_scratch_len(model, n));
+  const double r = qo_optimize_impl(n, L, state, model, x0, ls, tol, max_iter, rblock, ntrace,
+                                    trace, trace_scalars, info, scratch);
+  free(scratch);
+  return r;
+}
+
+/* ------------------------------------------------------- batch driver */
+int qo_num_cores(void) {
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof set, &set) == 0) return CPU_COUNT(&set);
+  return 1;
+}
+
+typedef struct {
+  int n;
+  int64_t batch;
+  const double* theta0;
+  const qo_model* model;
+  const qo_backtracking* ls;
+  double tol;
+  int64_t max_iter;
+  int rblock;
+  double *x_out, *g_out, *ell_out;
+  int64_t *iters_out, *fevals_out;
+  int32_t* status_out;
+  int ntrace;
+  double* trace;
+  atomic_long next;
+  atomic_long converged;
+} qo_batch_job;
+
+static void* qo_batch_worker(void* arg) {
+  qo_batch_job* job = (qo_batch_job*)arg;
+  const int n = job->n;
+  const int L = (n + 7) & ~7;
+  double* state = (double*)aligned_alloc(64, sizeof(double) * (size_t)qo_state_len(n, L));
+  double* scratch = (double*)malloc(sizeof(double) * qo_scratch_len(job->model, n));
+  for (;;) {
+    /* grab a small block of problems at a time (dynamic schedule) */
+    const long j0 = atomic_fetch_add(&job->next, 16);
+    if (j0 >= job->batch) break;
+    const long j1 = (j0 + 16 < job->batch) ? j0 + 16 : job->batch;
+    for (long j = j0; j < j1; ++j) {
+      qo_info info;
+      double* tr = job->trace ? job->trace + (size_t)j * job->ntrace * n : NULL;
+      const double ell = qo_optimize_impl(n, L, state, job->model, job->theta0 + (size_t)j * n,
+                                          job->ls, job->tol, job->max_iter, job->rblock,
+                                          job->ntrace, tr, NULL, &info, scratch);
+      if (job->x_out) memcpy(job->x_out + (size_t)j * n, state, sizeof(double) * (size_t)n);
+      if (job->g_out) memcpy(job->g_out + (size_t)j * n, state + L, sizeof(double) * (size_t)n);
+      if (job->ell_out) job->ell_out[j] = ell;
+      if (job->iters_out) job->iters_out[j] = info.iters;
+      if (job->fevals_out) job->fevals_out[j] = info.fevals;
+      if (job->status_out) job->status_out[j] = info.status;
+      if (info.status == QO_CONVERGED) atomic_fetch_add(&job->converged, 1);
+    }
+  }
+  free(scratch);
+  free(state);
+  return NULL;
+}
+
+int64_t qo_optimize_batch(int n, int64_t batch, const double* theta0, const qo_model* model,
+                          const qo_backtracking* ls, double tol, int64_t max_iter, int rblock,
+                          double* x_out, double* g_out, double* ell_out, int64_t* iters_out,
+                          int64_t* fevals_out, int32_t* status_out, int ntrace, double* trace,
+                          int nthreads) {
+  qo_batch_job job;
+  job.n = n; job.batch = batch; job.theta0 = theta0; job.model = model; job.ls = ls;
+  job.tol = tol; job.max_iter = max_iter; job.rblock = rblock;
+  job.x_out = x_out; job.g_out = g_out; job.ell_out = ell_out;
+  job.iters_out = iters_out; job.fevals_out = fevals_out; job.status_out = status_out;
+  job.ntrace = ntrace; job.trace = trace;
+  atomic_init(&job.next, 0);
+  atomic_init(&job.converged, 0);
+  if (nthreads <= 0) nthreads = qo_num_cores();
+  if (nthreads > 256) nthreads = 256;
+  pthread_t th[256];
+  for (int t = 1; t < nthreads; ++t) pthread_create(&th[t], NULL, qo_batch_worker, &job);
+  qo_batch_worker(&job);
+  for (int t = 1; t < nthreads; ++t) pthread_join(th[t], NULL);
+  return atomic_load(&job.converged);
+}

@@ -1,0 +1,511 @@
+// qn_capi.cu — the C ABI of libqn_cuda.so (include/qn_cuda.h) and the host-side
+// dispatch onto the sm_100a kernels.  No CPU fallback exists anywhere in this
+// file: every entry either runs a CUDA kernel or returns an error.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/qn_cuda.h"
+#include "qn_device.cuh"
+#include "qn_objectives.cuh"
+#include "qn_resident.cuh"
+#include "qn_internal.h"
+
+namespace {
+thread_local char g_err[512] = "";
+}  // namespace
+
+int qn_fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define fail qn_fail
+
+int qn_ensure_stage(qn_context* ctx, size_t bytes) {
+  if (bytes <= ctx->stage_bytes) return QN_OK;
+  if (ctx->stage) cudaFree(ctx->stage);
+  ctx->stage = nullptr;
+  ctx->stage_bytes = 0;
+  QN_CUDA_TRY(cudaMalloc(&ctx->stage, bytes));
+  ctx->stage_bytes = bytes;
+  return QN_OK;
+}
+
+unsigned long long* qn_next_counter(qn_context* ctx, cudaStream_t st) {
+  unsigned long long* c = ctx->counter + ctx->counter_slot;
+  ctx->counter_slot = (ctx->counter_slot + 1) % qn_context::kCounterSlots;
+  cudaMemsetAsync(c, 0, sizeof(unsigned long long), st);
+  return c;
+}
+
+namespace {
+
+// ---- kernel launchers ------------------------------------------------------
+template <class Obj, int NREG, int BLOCK, int MINB>
+int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Params& op,
+                    cudaStream_t st) {
+  const int n = p.n;
+  const qn::ResidentSmem L = qn::resident_smem_layout<Obj>(n, NREG == 0, op);
+  const size_t smem = sizeof(double) * (size_t)L.total;
+  if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin)
+    return fail(QN_ERR_UNSUPPORTED_SIZE,
+                "n=%d needs %zu bytes of shared memory per problem; the device allows %zu "
+                "(use the streaming path)",
+                n, smem, (size_t)ctx->prop.sharedMemPerBlockOptin);
+  auto kern = qn::qn_resident_kernel<Obj, NREG, BLOCK, MINB>;
+  QN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int block = (NREG > 0) ? BLOCK : qn::resident_block_threads(n);
+  int occ = 0;
+  QN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
+  if (occ < 1) return fail(QN_ERR_UNSUPPORTED_SIZE, "resident kernel does not fit on an SM (n=%d)", n);
+  long long grid = (long long)occ * ctx->prop.multiProcessorCount;
+  if (grid > p.batch) grid = p.batch;
+  if (grid < 1) grid = 1;
+  p.counter = qn_next_counter(ctx, st);
+  kern<<<(unsigned)grid, block, smem, st>>>(p, op);
+  QN_CUDA_TRY(cudaGetLastError());
+  ctx->last_path = (NREG > 0) ? 0 : 1;
+  ctx->last_grid = (int)grid;
+  ctx->last_block = block;
+  ctx->last_smem = (int)smem;
+  ctx->last_launches = 1;
+  return QN_OK;
+}
+
+template <class Obj>
+int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Params& op,
+                  uint32_t flags, cudaStream_t st) {
+  const int n = p.n;
+  if (!(flags & QN_FLAG_FORCE_SMEM)) {
+    switch (n) {
+#define QN_REG_CASE(N, BLOCK, MINB) \
+  case N: return launch_resident<Obj, N, BLOCK, MINB>(ctx, p, op, st);
+#include "qn_reg_sizes.inc"
+#undef QN_REG_CASE
+      default: break;
+    }
+  }
+  if (n <= 256) return launch_resident<Obj, 0, 256, 1>(ctx, p, op, st);
+  return fail(QN_ERR_UNSUPPORTED_SIZE, "n=%d: resident path supports n <= 160", n);
+}
+
+int dispatch_model(qn_context* ctx, const qn_model* model, qn::BatchParams& p, uint32_t flags,
+                   cudaStream_t st) {
+  switch (model->kind) {
+    case QN_OBJ_ROSENBROCK:
+      return dispatch_size<qn::Rosenbrock>(ctx, p, qn::Rosenbrock::Params{}, flags, st);
+    case QN_OBJ_DENSE_GAUSSIAN: {
+      if (model->n != p.n)
+        return fail(QN_ERR_INVALID_ARGUMENT, "dense Gaussian model has n=%d, call has n=%d",
+                    model->n, p.n);
+      qn::DenseGaussian::Params op{model->d_a, model->d_b};
+      return dispatch_size<qn::DenseGaussian>(ctx, p, op, flags | QN_FLAG_FORCE_SMEM, st);
+    }
+    case QN_OBJ_LOGISTIC: {
+      if (model->n != p.n)
+        return fail(QN_ERR_INVALID_ARGUMENT, "logistic model has n=%d, call has n=%d", model->n,
+                    p.n);
+      qn::Logistic::Params op{model->m, model->d_a, model->d_b, model->d_c, model->lam};
+      return dispatch_size<qn::Logistic>(ctx, p, op, flags | QN_FLAG_FORCE_SMEM, st);
+    }
+    default:
+      return fail(QN_ERR_UNREGISTERED_OBJECTIVE,
+                  "objective kind %d has no registered device implementation", model->kind);
+  }
+}
+
+int check_common(qn_context* ctx, const qn_model* model, int32_t n, int64_t batch,
+                 const double* theta0, const qn_backtracking* ls, int32_t max_iter) {
+  if (!ctx) return fail(QN_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (!model) return fail(QN_ERR_UNREGISTERED_OBJECTIVE, "model is NULL (unregistered objective)");
+  if (model->ctx != ctx) return fail(QN_ERR_INVALID_ARGUMENT, "model belongs to another context");
+  if (n < 1) return fail(QN_ERR_INVALID_ARGUMENT, "n must be >= 1 (got %d)", n);
+  if (batch < 0) return fail(QN_ERR_INVALID_ARGUMENT, "batch must be >= 0");
+  if (batch > 0 && !theta0) return fail(QN_ERR_INVALID_ARGUMENT, "theta0 is NULL");
+  if (!ls) return fail(QN_ERR_INVALID_ARGUMENT, "ls is NULL");
+  if (ls->order != 2 && ls->order != 3)
+    return fail(QN_ERR_INVALID_ARGUMENT, "BackTracking order must be 2 or 3 (got %d)", ls->order);
+  if (max_iter < 0) return fail(QN_ERR_INVALID_ARGUMENT, "max_iter must be >= 0");
+  return QN_OK;
+}
+
+}  // namespace
+
+// --------------------------------------------------------------- public API
+extern "C" {
+
+int32_t qn_version(void) { return QN_VERSION; }
+const char* qn_last_error(void) { return g_err; }
+
+void qn_backtracking_default(qn_backtracking* ls, int32_t order) {
+  if (!ls) return;
+  ls->c1 = 1e-4;
+  ls->rho_hi = 0.5;
+  ls->rho_lo = 0.1;
+  ls->iterations = 1000;
+  ls->order = order;
+  ls->_pad = 0;
+}
+
+int32_t qn_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int32_t qn_create(qn_context** out, int32_t device) {
+  if (!out) return fail(QN_ERR_INVALID_ARGUMENT, "ctx out-pointer is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(QN_ERR_NO_DEVICE,
+                "no usable CUDA device (%s); libqn_cuda has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= ndev)
+    return fail(QN_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", device, ndev);
+  QN_CUDA_TRY(cudaSetDevice(device));
+  qn_context* ctx = new (std::nothrow) qn_context;
+  if (!ctx) return fail(QN_ERR_CUDA, "out of host memory");
+  ctx->device = device;
+  cudaError_t err = cudaGetDeviceProperties(&ctx->prop, device);
+  if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (err == cudaSuccess)
+    err = cudaMalloc(&ctx->counter, sizeof(unsigned long long) * qn_context::kCounterSlots);
+  if (err != cudaSuccess) {
+    delete ctx;
+    return fail(QN_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(err));
+  }
+  if (ctx->prop.major < 10) {
+    // The kernels are compiled for sm_100a only; refuse early with a clear message.
+    int major = ctx->prop.major, minor = ctx->prop.minor;
+    cudaFree(ctx->counter);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return fail(QN_ERR_NO_DEVICE, "device is sm_%d%d; libqn_cuda is built for sm_100a only", major,
+                minor);
+  }
+  *out = ctx;
+  return QN_OK;
+}
+
+int32_t qn_destroy(qn_context* ctx) {
+  if (!ctx) return QN_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stage) cudaFree(ctx->stage);
+  cudaFree(ctx->counter);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return QN_OK;
+}
+
+int32_t qn_device_info(qn_context* ctx, char* name, size_t name_len, int32_t* sm_count,
+                       int32_t* smem_per_block, int32_t* clock_khz) {
+  if (!ctx) return fail(QN_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (name && name_len) {
+    strncpy(name, ctx->prop.name, name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+  if (smem_per_block) *smem_per_block = (int32_t)ctx->prop.sharedMemPerBlockOptin;
+  if (clock_khz) {
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+    *clock_khz = khz;
+  }
+  return QN_OK;
+}
+
+int32_t qn_host_alloc(void** ptr, size_t bytes) {
+  if (!ptr) return fail(QN_ERR_INVALID_ARGUMENT, "ptr is NULL");
+  QN_CUDA_TRY(cudaMallocHost(ptr, bytes ? bytes : 1));
+  return QN_OK;
+}
+int32_t qn_host_free(void* ptr) {
+  if (ptr) QN_CUDA_TRY(cudaFreeHost(ptr));
+  return QN_OK;
+}
+
+int32_t qn_state_ld(int32_t n, int32_t native_w) { return qn_host_state_ld(n, native_w); }
+int64_t qn_state_len(int32_t n, int32_t ld) { return 7 * (int64_t)ld + (int64_t)n * ld; }
+
+// ---- models
+int32_t qn_model_create(qn_context* ctx, int32_t kind, qn_model** out) {
+  if (!ctx || !out) return fail(QN_ERR_INVALID_ARGUMENT, "NULL argument");
+  *out = nullptr;
+  if (kind != QN_OBJ_ROSENBROCK)
+    return fail(QN_ERR_UNREGISTERED_OBJECTIVE,
+                "objective kind %d has no registered parameter-free device implementation "
+                "(no CPU fallback; see INTEGRATION.md)", kind);
+  qn_model* m = new qn_model;
+  m->ctx = ctx;
+  m->kind = kind;
+  *out = m;
+  return QN_OK;
+}
+
+int32_t qn_model_dense_gaussian(qn_context* ctx, int32_t n, const double* mu, const double* lambda,
+                                qn_model** out) {
+  if (!ctx || !out || !mu || !lambda || n < 1) return fail(QN_ERR_INVALID_ARGUMENT, "bad argument");
+  *out = nullptr;
+  QN_CUDA_TRY(cudaSetDevice(ctx->device));
+  qn_model* m = new qn_model;
+  m->ctx = ctx;
+  m->kind = QN_OBJ_DENSE_GAUSSIAN;
+  m->n = n;
+  cudaError_t e = cudaMalloc(&m->d_a, sizeof(double) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_b, sizeof(double) * (size_t)n * n);
+  if (e == cudaSuccess) e = cudaMemcpy(m->d_a, mu, sizeof(double) * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(m->d_b, lambda, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    qn_model_free(m);
+    return fail(QN_ERR_CUDA, "uploading Gaussian model failed: %s", cudaGetErrorString(e));
+  }
+  *out = m;
+  return QN_OK;
+}
+
+int32_t qn_model_logistic(qn_context* ctx, int32_t mrows, int32_t n, const double* X,
+                          const double* y, double lam, qn_model** out) {
+  if (!ctx || !out || !X || !y || n < 1 || mrows < 1)
+    return fail(QN_ERR_INVALID_ARGUMENT, "bad argument");
+  *out = nullptr;
+  QN_CUDA_TRY(cudaSetDevice(ctx->device));
+  qn_model* m = new qn_model;
+  m->ctx = ctx;
+  m->kind = QN_OBJ_LOGISTIC;
+  m->n = n;
+  m->m = mrows;
+  m->lam = lam;
+  const size_t nx = (size_t)mrows * n;
+  std::vector<double> xt(nx);
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < mrows; ++i) xt[(size_t)n * i + j] = X[(size_t)mrows * j + i];
+  cudaError_t e = cudaMalloc(&m->d_a, sizeof(double) * nx);
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_b, sizeof(double) * nx);
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_c, sizeof(double) * mrows);
+  if (e == cudaSuccess) e = cudaMemcpy(m->d_a, X, sizeof(double) * nx, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(m->d_b, xt.data(), sizeof(double) * nx, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(m->d_c, y, sizeof(double) * mrows, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    qn_model_free(m);
+    return fail(QN_ERR_CUDA, "uploading logistic model failed: %s", cudaGetErrorString(e));
+  }
+  *out = m;
+  return QN_OK;
+}
+
+int32_t qn_model_free(qn_model* m) {
+  if (!m) return QN_OK;
+  if (m->ctx) cudaSetDevice(m->ctx->device);
+  if (m->d_a) cudaFree(m->d_a);
+  if (m->d_b) cudaFree(m->d_b);
+  if (m->d_c) cudaFree(m->d_c);
+  delete m;
+  return QN_OK;
+}
+
+// ---- optimize!, device pointers
+int32_t qn_bfgs_optimize_batched_device_f64(qn_context* ctx, const qn_model* model, int32_t n,
+                                            int64_t batch, const double* theta0,
+                                            int64_t theta_stride, const qn_backtracking* ls,
+                                            double tol, int32_t max_iter, double* states,
+                                            int64_t state_stride, int32_t ld, double* x_out,
+                                            double* g_out, double* ell_out, int32_t* iters_out,
+                                            int32_t* fevals_out, int32_t* status_out,
+                                            int32_t ntrace, double* trace_out, uint32_t flags,
+                                            void* stream) {
+  int rc = check_common(ctx, model, n, batch, theta0, ls, max_iter);
+  if (rc) return rc;
+  if (theta_stride < n) return fail(QN_ERR_INVALID_ARGUMENT, "theta_stride < n");
+  if (states && (ld < n || state_stride < qn_state_len(n, ld)))
+    return fail(QN_ERR_INVALID_ARGUMENT, "state block too small: ld=%d stride=%lld for n=%d", ld,
+                (long long)state_stride, n);
+  if (states && (x_out || g_out))
+    return fail(QN_ERR_INVALID_ARGUMENT,
+                "device entry: pass either states or compact x_out/g_out, not both");
+  if (ntrace < 0 || (ntrace > 0 && !trace_out))
+    return fail(QN_ERR_INVALID_ARGUMENT, "ntrace > 0 needs trace_out");
+  if (batch == 0) return QN_OK;
+  QN_CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+
+  qn::BatchParams p{};
+  p.n = n;
+  p.max_iter = max_iter;
+  p.batch = batch;
+  p.theta0 = theta0;
+  p.theta_stride = theta_stride;
+  p.tol = tol;
+  p.ls = qn::LsParams{ls->c1, ls->rho_hi, ls->rho_lo, (long long)ls->iterations, ls->order};
+  if (states) {
+    p.x_out = states;
+    p.x_stride = state_stride;
+    p.g_out = states + ld;
+    p.g_stride = state_stride;
+    if (flags & QN_FLAG_WRITE_H) {
+      p.h_out = states + 7 * (int64_t)ld;
+      p.h_stride = state_stride;
+      p.ldh = ld;
+    }
+  } else {
+    p.x_out = x_out;
+    p.x_stride = n;
+    p.g_out = g_out;
+    p.g_stride = n;
+  }
+  p.ell_out = ell_out;
+  p.iters_out = iters_out;
+  p.fevals_out = fevals_out;
+  p.status_out = status_out;
+  p.ntrace = ntrace;
+  p.trace = trace_out;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  return dispatch_model(ctx, model, p, flags, st);
+}
+
+// ---- optimize!, host pointers (the call a Julia / Python user makes)
+int32_t qn_bfgs_optimize_batched_f64(qn_context* ctx, const qn_model* model, int32_t n,
+                                     int64_t batch, const double* theta0,
+                                     const qn_backtracking* ls, double tol, int32_t max_iter,
+                                     double* states, int64_t state_stride, int32_t ld,
+                                     double* x_out, double* g_out, double* ell_out,
+                                     int32_t* iters_out, int32_t* fevals_out,
+                                     int32_t* status_out, int32_t ntrace, double* trace_out,
+                                     uint32_t flags) {
+  int rc = check_common(ctx, model, n, batch, theta0, ls, max_iter);
+  if (rc) return rc;
+  if (states && (ld < n || state_stride < qn_state_len(n, ld)))
+    return fail(QN_ERR_INVALID_ARGUMENT, "state block too small: ld=%d stride=%lld for n=%d", ld,
+                (long long)state_stride, n);
+  if (ntrace < 0 || (ntrace > 0 && !trace_out))
+    return fail(QN_ERR_INVALID_ARGUMENT, "ntrace > 0 needs trace_out");
+  if (batch == 0) return QN_OK;
+  QN_CUDA_TRY(cudaSetDevice(ctx->device));
+
+  const bool want_h = states && (flags & QN_FLAG_WRITE_H);
+  const size_t nb = (size_t)n * batch;
+  // device staging: theta | x | g | ell | iters | fevals | status | trace | H
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_theta = carve(sizeof(double) * nb);
+  const size_t o_x = carve(sizeof(double) * nb);
+  const size_t o_g = carve(sizeof(double) * nb);
+  const size_t o_ell = carve(sizeof(double) * batch);
+  const size_t o_it = carve(sizeof(int32_t) * batch);
+  const size_t o_fe = carve(sizeof(int32_t) * batch);
+  const size_t o_st = carve(sizeof(int32_t) * batch);
+  const size_t o_tr = carve(sizeof(double) * nb * (size_t)ntrace);
+  const size_t o_h = carve(want_h ? sizeof(double) * (size_t)n * n * batch : 0);
+  {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    rc = qn_ensure_stage(ctx, off);
+  }
+  if (rc) return rc;
+  char* base = (char*)ctx->stage;
+  cudaStream_t st = ctx->stream;
+  QN_CUDA_TRY(cudaMemcpyAsync(base + o_theta, theta0, sizeof(double) * nb, cudaMemcpyHostToDevice, st));
+  if (ntrace > 0) {
+    // rows past a problem's last iteration stay as the caller initialised them
+    QN_CUDA_TRY(cudaMemcpyAsync(base + o_tr, trace_out, sizeof(double) * nb * ntrace,
+                                cudaMemcpyHostToDevice, st));
+  }
+
+  qn::BatchParams p{};
+  p.n = n;
+  p.max_iter = max_iter;
+  p.batch = batch;
+  p.theta0 = (const double*)(base + o_theta);
+  p.theta_stride = n;
+  p.tol = tol;
+  p.ls = qn::LsParams{ls->c1, ls->rho_hi, ls->rho_lo, (long long)ls->iterations, ls->order};
+  p.x_out = (double*)(base + o_x);
+  p.x_stride = n;
+  p.g_out = (double*)(base + o_g);
+  p.g_stride = n;
+  if (want_h) {
+    p.h_out = (double*)(base + o_h);
+    p.h_stride = (long long)n * n;
+    p.ldh = n;
+  }
+  p.ell_out = (double*)(base + o_ell);
+  p.iters_out = (int*)(base + o_it);
+  p.fevals_out = (int*)(base + o_fe);
+  p.status_out = (int*)(base + o_st);
+  p.ntrace = ntrace;
+  p.trace = ntrace ? (double*)(base + o_tr) : nullptr;
+  {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    rc = dispatch_model(ctx, model, p, flags, st);
+  }
+  if (rc) return rc;
+
+  // results back to the caller's buffers
+  if (states) {
+    // θ* -> offset 0, ∇ -> offset ld of each block (QN.jl:135,138): strided 2-D copies
+    QN_CUDA_TRY(cudaMemcpy2DAsync(states, sizeof(double) * state_stride, base + o_x,
+                                  sizeof(double) * n, sizeof(double) * n, batch,
+                                  cudaMemcpyDeviceToHost, st));
+    QN_CUDA_TRY(cudaMemcpy2DAsync(states + ld, sizeof(double) * state_stride, base + o_g,
+                                  sizeof(double) * n, sizeof(double) * n, batch,
+                                  cudaMemcpyDeviceToHost, st));
+    if (want_h) {
+      for (int64_t j = 0; j < batch; ++j)
+        QN_CUDA_TRY(cudaMemcpy2DAsync(states + j * state_stride + 7 * (int64_t)ld,
+                                      sizeof(double) * ld,
+                                      base + o_h + sizeof(double) * (size_t)n * n * j,
+                                      sizeof(double) * n, sizeof(double) * n, n,
+                                      cudaMemcpyDeviceToHost, st));
+    }
+  }
+  if (x_out) QN_CUDA_TRY(cudaMemcpyAsync(x_out, base + o_x, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+  if (g_out) QN_CUDA_TRY(cudaMemcpyAsync(g_out, base + o_g, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+  if (ell_out) QN_CUDA_TRY(cudaMemcpyAsync(ell_out, base + o_ell, sizeof(double) * batch, cudaMemcpyDeviceToHost, st));
+  if (iters_out) QN_CUDA_TRY(cudaMemcpyAsync(iters_out, base + o_it, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, st));
+  if (fevals_out) QN_CUDA_TRY(cudaMemcpyAsync(fevals_out, base + o_fe, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, st));
+  if (status_out) QN_CUDA_TRY(cudaMemcpyAsync(status_out, base + o_st, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, st));
+  if (ntrace > 0)
+    QN_CUDA_TRY(cudaMemcpyAsync(trace_out, base + o_tr, sizeof(double) * nb * ntrace, cudaMemcpyDeviceToHost, st));
+  QN_CUDA_TRY(cudaStreamSynchronize(st));
+  return QN_OK;
+}
+
+int32_t qn_bfgs_optimize_f64(qn_context* ctx, const qn_model* model, int32_t n, const double* x,
+                             const qn_backtracking* ls, double tol, double* state, int32_t ld,
+                             double* ell, int32_t* iters, int32_t* fevals, int32_t* status,
+                             uint32_t flags) {
+  if (!state) return fail(QN_ERR_INVALID_ARGUMENT, "state is NULL");
+  return qn_bfgs_optimize_batched_f64(ctx, model, n, 1, x, ls, tol, 10000, state,
+                                      qn_state_len(n, ld), ld, nullptr, nullptr, ell, iters, fevals,
+                                      status, 0, nullptr, flags);
+}
+
+int32_t qn_last_launch_info(qn_context* ctx, int32_t* path, int32_t* grid, int32_t* block,
+                            int32_t* smem_bytes, int32_t* kernel_launches) {
+  if (!ctx) return fail(QN_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (path) *path = ctx->last_path;
+  if (grid) *grid = ctx->last_grid;
+  if (block) *block = ctx->last_block;
+  if (smem_bytes) *smem_bytes = ctx->last_smem;
+  if (kernel_launches) *kernel_launches = ctx->last_launches;
+  return QN_OK;
+}
+
+}  // extern "C"

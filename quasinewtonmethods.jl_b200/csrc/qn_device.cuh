@@ -1,0 +1,95 @@
+// qn_device.cuh — device-side building blocks shared by the resident kernels.
+//
+// Compile this translation unit with -fmad=false: the canonical arithmetic
+// order fixes where a fused multiply-add happens, so nvcc must
+// never contract a*b+c on its own.  Every fma() below is deliberate.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/qn_cuda.h"
+
+namespace qn {
+
+constexpr double kEps = 2.220446049250313e-16;     // eps(Float64)
+constexpr double kSqrtTol = 1.0 / (double)(1 << 26); // sqrttolerance(Float64), QN.jl:155
+
+// BackTracking fields, QN.jl:72-77
+struct LsParams {
+  double c1, rho_hi, rho_lo;
+  long long iterations;
+  int order;
+};
+
+// Arguments of one batched solve (all pointers are device pointers).
+struct BatchParams {
+  int n;
+  int max_iter;
+  long long batch;
+  const double* theta0;
+  long long theta_stride;
+  double tol;
+  LsParams ls;
+  double* x_out;   // θ* of problem j at x_out + j*x_stride
+  long long x_stride;
+  double* g_out;   // ∇  of problem j at g_out + j*g_stride
+  long long g_stride;
+  double* h_out;   // B⁻¹ of problem j at h_out + j*h_stride, column stride ldh (or null)
+  long long h_stride;
+  int ldh;
+  double* ell_out;
+  int* iters_out;
+  int* fevals_out;
+  int* status_out;
+  int ntrace;
+  double* trace;   // [batch][ntrace][n]
+  unsigned long long* counter; // persistent-grid work queue
+};
+
+// nanmin / nanmax, QN.jl:152-153
+__device__ __forceinline__ double nanmin(double a, double b) { return a < b ? a : (isnan(b) ? a : b); }
+__device__ __forceinline__ double nanmax(double a, double b) { return a < b ? b : (isnan(a) ? b : a); }
+
+// Butterfly of the canonical reduction (rule C1): off = 16,8,4,2,1.
+// IEEE addition is commutative, so every lane ends with the same bits.
+__device__ __forceinline__ double warp_butterfly(double p) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) p = p + __shfl_xor_sync(0xffffffffu, p, off);
+  return p;
+}
+
+// A "team" is the set of threads that owns one problem: thread c owns element c
+// of every vector and row c of B⁻¹.  Here a team is one CTA.
+struct Team {
+  int n;        // problem dimension
+  int c;        // this thread's element / row
+  int lane;     // c & 31
+  double* red;  // two staging buffers of `stride` doubles each
+  int stride;
+  int phase;
+  double* xs;      // the point the objective is evaluated at (n doubles, shared)
+  double* scratch; // objective scratch (shared)
+
+  // canonical csum (rule C1) split around a barrier the caller provides
+  __device__ __forceinline__ void stage(double v) {
+    red[phase * stride + c] = v;
+  }
+  __device__ __forceinline__ double finish(int count) {
+    const double* r = red + phase * stride;
+    phase ^= 1;
+    double p = (lane < count) ? r[lane] : 0.0;
+    for (int i = lane + 32; i < count; i += 32) p = p + r[i];
+    return warp_butterfly(p);
+  }
+  // Thread c contributes v when c < count.  Result is identical in every thread.
+  // Two staging buffers alternate, so the barrier inside the NEXT csum is what
+  // protects this one's buffer from being overwritten while a slow warp reads.
+  __device__ __forceinline__ double csum(double v, int count) {
+    stage(v);
+    __syncthreads();
+    return finish(count);
+  }
+};
+
+}  // namespace qn

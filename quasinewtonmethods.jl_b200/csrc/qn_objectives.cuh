@@ -1,0 +1,168 @@
+// qn_objectives.cuh — registered device objectives.
+//
+// The reference's objective protocol is two generic functions,
+// `logdensity(obj, θ)` and `∂logdensity!(∇, obj, θ)` (QN.jl:8-9), called at
+// QN.jl:161 and QN.jl:254.  Here an objective is a type with
+//
+//   template <bool GRAD> static double eval(Team&, const Params&, double& g)
+//
+// called by every thread of the team after the point θ has been published in
+// team.xs (and a barrier).  It returns ℓ(θ) in every thread and, when GRAD,
+// leaves ∇[c] in g for the thread that owns element c.  eval must end with a
+// barrier-containing reduction before which all of its reads of team.xs are
+// done (the caller overwrites xs right after).
+#pragma once
+
+#include "qn_device.cuh"
+
+namespace qn {
+
+// ---------------------------------------------------------------- Rosenbrock
+// test/runtests.jl:4-33 (= README.md:19-48).  Pairs (θ[i], θ[i+N]), N = n>>1,
+// plus a tail term for odd n.  No fma except the explicit muladd (rule C5).
+struct Rosenbrock {
+  struct Params {};
+  static constexpr int kKind = QN_OBJ_ROSENBROCK;
+  __host__ __device__ static int scratch_doubles(int, const Params&) { return 0; }
+
+  template <bool GRAD>
+  __device__ __forceinline__ static double eval(Team& t, const Params&, double& g) {
+    const int n = t.n, N = n >> 1, c = t.c;
+    const double* xs = t.xs;
+    double term = 0.0;
+    if (c < N) {
+      const double t1 = xs[c], t2 = xs[c + N];
+      const double a = t2 - t1 * t1;
+      const double b = 1.0 - t1;
+      term = 100.0 * (a * a) + b * b;               // runtests.jl:9,23
+      if (GRAD) g = (400.0 * a) * t1 + 2.0 * b;     // runtests.jl:24
+    } else if (c < 2 * N) {
+      if (GRAD) {
+        const double t1 = xs[c - N], t2 = xs[c];
+        g = 200.0 * (t1 * t1 - t2);                 // runtests.jl:25
+      }
+    } else if (c < n) {
+      if (GRAD) g = 2.0 * (1.0 - xs[c]);            // runtests.jl:30
+    }
+    double s = 0.0 - t.csum(term, N);               // s -= term, @simd-reassociated
+    if (n & 1) {
+      const double d = 1.0 - xs[n - 1];
+      s = -fma(d, d, -s);                           // -muladd(δ, δ, -s), runtests.jl:13,29
+    }
+    return s;
+  }
+};
+
+// ------------------------------------------------------------ dense Gaussian
+// Build-defined (the reference ships no such objective):
+// ℓ(θ) = -½ (θ-μ)ᵀ Λ (θ-μ), ∇ = -Λ(θ-μ).  z = Λ(θ-μ) is a row-chain GEMV
+// (rule C2) with Λ read from global memory / L2, shared by the whole batch.
+struct DenseGaussian {
+  struct Params {
+    const double* mu;     // n
+    const double* lambda; // n×n column-major, ld = n
+  };
+  static constexpr int kKind = QN_OBJ_DENSE_GAUSSIAN;
+  __host__ __device__ static int scratch_doubles(int n, const Params&) { return (n + 31) & ~31; }
+
+  template <bool GRAD>
+  __device__ __forceinline__ static double eval(Team& t, const Params& p, double& g) {
+    const int n = t.n, c = t.c;
+    double* ds = t.scratch;
+    double d = 0.0;
+    if (c < n) {
+      d = t.xs[c] - __ldg(p.mu + c);
+      ds[c] = d;
+    }
+    __syncthreads();
+    double z = 0.0;
+    if (c < n) {
+      const double* row = p.lambda + c;
+      int r = 0;
+      for (; r + 4 <= n; r += 4) {
+        const double l0 = __ldg(row + (size_t)n * r), l1 = __ldg(row + (size_t)n * (r + 1));
+        const double l2 = __ldg(row + (size_t)n * (r + 2)), l3 = __ldg(row + (size_t)n * (r + 3));
+        z = fma(l0, ds[r], z);
+        z = fma(l1, ds[r + 1], z);
+        z = fma(l2, ds[r + 2], z);
+        z = fma(l3, ds[r + 3], z);
+      }
+      for (; r < n; ++r) z = fma(__ldg(row + (size_t)n * r), ds[r], z);
+    }
+    const double q = t.csum(d * z, n);
+    if (GRAD) g = -z;
+    return -0.5 * q;
+  }
+};
+
+// ------------------------------------------------------- logistic regression
+// Build-defined: ℓ(θ) = Σᵢ [yᵢ zᵢ - log(1+e^{zᵢ})] - ½λ‖θ‖²,
+// z = Xθ, X m×n.  exp/log1p come from the CUDA math library, which is not
+// bit-identical to glibc's: parity for this objective is to a tolerance.
+struct Logistic {
+  struct Params {
+    int m;
+    const double* X;  // m×n column-major (ld = m)
+    const double* Xt; // n×m column-major (ld = n)
+    const double* y;  // m
+    double lam;
+  };
+  static constexpr int kKind = QN_OBJ_LOGISTIC;
+  __host__ __device__ static int scratch_doubles(int, const Params& p) { return 2 * ((p.m + 31) & ~31); }
+
+  __device__ __forceinline__ static double softplus(double z) {
+    return z > 0.0 ? z + log1p(exp(-z)) : log1p(exp(z));
+  }
+  __device__ __forceinline__ static double sigmoid(double z) {
+    if (z >= 0.0) return 1.0 / (1.0 + exp(-z));
+    const double e = exp(z);
+    return e / (1.0 + e);
+  }
+
+  template <bool GRAD>
+  __device__ __forceinline__ static double eval(Team& t, const Params& p, double& g) {
+    const int n = t.n, c = t.c, m = p.m;
+    const int nthr = blockDim.x;
+    double* vs = t.scratch;                     // yᵢzᵢ - softplus(zᵢ)
+    double* rs = t.scratch + ((m + 31) & ~31);  // yᵢ - σ(zᵢ)
+    for (int i = c; i < m; i += nthr) {
+      double z = 0.0;
+      const double* col = p.X + i;
+#pragma unroll 4
+      for (int j = 0; j < n; ++j) z = fma(__ldg(col + (size_t)m * j), t.xs[j], z);
+      const double yi = __ldg(p.y + i);
+      vs[i] = yi * z - softplus(z);
+      if (GRAD) rs[i] = yi - sigmoid(z);
+    }
+    const double th = (c < n) ? t.xs[c] : 0.0;
+    t.stage(th * th);
+    __syncthreads();
+    const double pen = t.finish(n);
+    // csum over the m staged values (rule C1), every warp redundantly
+    double pp = (t.lane < m) ? vs[t.lane] : 0.0;
+    for (int i = t.lane + 32; i < m; i += 32) pp = pp + vs[i];
+    const double S = warp_butterfly(pp);
+    const double ell = fma(-(0.5 * p.lam), pen, S);
+    if (GRAD) {
+      double T = 0.0;
+      if (c < n) {
+        // rule C2: chains of 256 rows, block partials added in ascending order
+        for (int i0 = 0; i0 < m; i0 += 256) {
+          const int i1 = (i0 + 256 < m) ? i0 + 256 : m;
+          double w = 0.0;
+          const double* col = p.Xt + c;
+#pragma unroll 4
+          for (int i = i0; i < i1; ++i) w = fma(__ldg(col + (size_t)n * i), rs[i], w);
+          T = (i0 == 0) ? w : T + w;
+        }
+        g = fma(-p.lam, th, T);
+      }
+    }
+    // every read of xs / vs / rs above happens before the caller's next barrier
+    // only if we close with one: the next eval overwrites vs/rs straight away.
+    __syncthreads();
+    return ell;
+  }
+};
+
+}  // namespace qn

@@ -1,0 +1,288 @@
+// qn_resident.cuh — the resident BFGS kernel: one CTA owns one problem for its
+// whole run (QN.jl:237-292 entirely on the device), B⁻¹ never leaves the SM.
+//
+// Thread c owns element c of every vector and ROW c of B⁻¹ (the reference's
+// unit-stride index, QN.jl:48,61-62).  Two storage policies for the row:
+//
+//   NREG > 0  register-resident: n = NREG is a compile-time constant and the
+//             row lives in NREG fp64 registers (n = 60: 120 of the thread's
+//             registers).  B⁻¹ costs no shared-memory or HBM traffic at all; the
+//             only shared-memory reads of the two O(n²) passes are warp-wide
+//             BROADCASTS of the vectors.  Bound: the FP64 pipe.
+//   NREG == 0 shared-memory-resident: runtime n, B⁻¹ in shared memory in the
+//             reference's own column-major layout H[c + n r]; a warp's access
+//             to one column is 32 consecutive doubles (conflict-free).
+//             Bound: shared-memory bandwidth (24 n² bytes per iteration).
+//
+// The grid is persistent: gridDim = (#SMs × resident CTAs per SM) and CTAs pull
+// problem indices from an atomic counter, so the spread of iteration counts
+// across starts (≈300-680 at n = 60) does not idle SMs.
+#pragma once
+
+#include "qn_device.cuh"
+#include "qn_objectives.cuh"
+
+namespace qn {
+
+// packed per-column operands of the fused update+GEMV pass (QN.jl:56-67):
+// w = c₁ s[r], nu = -u[r], s = s[r], g = ∇_new[r]; 32 bytes = two LDS.128.
+struct __align__(16) Pass2Col {
+  double w, nu, s, g;
+};
+
+__host__ __device__ inline int resident_block_threads(int n) { return (n + 31) & ~31; }
+
+// shared memory carve-up (in doubles)
+struct ResidentSmem {
+  int red, xs, ys, cols, scratch, h, total;
+};
+template <class Obj>
+__host__ __device__ inline ResidentSmem resident_smem_layout(int n, bool h_in_smem,
+                                                             const typename Obj::Params& op) {
+  const int B = resident_block_threads(n);
+  ResidentSmem L;
+  int o = 0;
+  L.cols = o; o += 4 * B;   // Pass2Col[B], 16-byte aligned at offset 0
+  L.ys = o;   o += B;
+  L.xs = o;   o += B;
+  L.red = o;  o += 2 * B;
+  L.scratch = o; o += Obj::scratch_doubles(n, op);
+  L.h = o;    o += h_in_smem ? n * n : 0;
+  L.total = o + 2; // + problem index broadcast slot
+  return L;
+}
+
+template <class Obj, int NREG>
+__device__ __forceinline__ void resident_solve_one(const BatchParams& p,
+                                                   const typename Obj::Params& op,
+                                                   const long long j, Team& tm, double* ys,
+                                                   Pass2Col* cols, double* hs) {
+  const int n = (NREG > 0) ? NREG : p.n;
+  const int c = tm.c;
+  const bool active = c < n;
+  constexpr int HR = (NREG > 0) ? NREG : 1;
+  double h[HR]; // row c of B⁻¹ (register policy)
+  (void)h; (void)hs;
+
+  double x = active ? p.theta0[j * p.theta_stride + c] : 0.0; // copyto!(x_old, x), QN.jl:248
+  double g = 0.0, g_prev = 0.0, s = 0.0;
+  double result = __longlong_as_double(0x7ff8000000000000LL); // NaN, QN.jl:291
+  int iters = 0, fevals = 0, status = QN_MAX_ITER;
+
+  for (int it = 1; it <= p.max_iter; ++it) { // QN.jl:250,253
+    // ---- ℓ₀ = ∂logdensity!(∇_new, obj, x_old)   QN.jl:254
+    tm.xs[c] = x;
+    __syncthreads();
+    const double l0 = Obj::template eval<true>(tm, op, g);
+    ++fevals;
+    if (!isfinite(l0)) { status = QN_NONFINITE; break; } // QN.jl:255
+
+    // publish what the update needs, and test convergence, on one barrier.
+    // y = ∇_old - ∇_new, QN.jl:38
+    const double y = g_prev - g;
+    ys[c] = y;
+    cols[c].s = s;
+    cols[c].g = g;
+    tm.stage(s * y);
+    // maximum(abs, ∇_new) < tol, QN.jl:257 (a NaN entry makes it false)
+    const int conv = __syncthreads_and(!active || fabs(g) < p.tol);
+    if (conv) { status = QN_CONVERGED; result = l0; break; } // QN.jl:258-261
+
+    double m;
+    if (it == 1) {
+      tm.phase ^= 1; // staged value unused
+      m = -1.0;      // QN.jl:263-264
+    } else {
+      // ---- BFGS_update!  QN.jl:34-69
+      const double sy = tm.finish(n);  // sᵀy, QN.jl:39
+      const double rho = 1.0 / sy;     // QN.jl:42 (no guard)
+      // pass 1: t = Σ_r y[r] H[c,r]   QN.jl:44-49, one chain per row (rule C2)
+      double t = 0.0;
+      if (NREG > 0) {
+#pragma unroll
+        for (int r = 0; r + 1 < HR; r += 2) {
+          const double2 yy = *reinterpret_cast<const double2*>(ys + r);
+          t = fma(yy.x, h[r], t);
+          t = fma(yy.y, h[r + 1], t);
+        }
+        if (HR & 1) t = fma(ys[HR - 1], h[HR - 1], t);
+      } else if (active) {
+        const double* hrow = hs + c;
+        int r = 0;
+        for (; r + 4 <= n; r += 4) {
+          const double h0 = hrow[n * r], h1 = hrow[n * (r + 1)];
+          const double h2 = hrow[n * (r + 2)], h3 = hrow[n * (r + 3)];
+          t = fma(ys[r], h0, t);
+          t = fma(ys[r + 1], h1, t);
+          t = fma(ys[r + 2], h2, t);
+          t = fma(ys[r + 3], h3, t);
+        }
+        for (; r < n; ++r) t = fma(ys[r], hrow[n * r], t);
+      }
+      const double u = t * rho;       // B⁻¹y[c] = t ρ, QN.jl:50
+      cols[c].nu = -u;
+      const double yHy = tm.csum(t * y, n);          // QN.jl:51
+      const double c1 = fma(yHy, rho, 1.0) * rho;    // QN.jl:54
+      cols[c].w = c1 * s;                            // (c₁ s[r]), rounded once per r (rule C4)
+      __syncthreads();
+      // pass 2: H ← H + c₁ssᵀ - usᵀ - suᵀ fused with d = H⁺∇_new   QN.jl:56-67
+      const double nu_c = -u;
+      double acc = 0.0;
+      if (NREG > 0) {
+#pragma unroll
+        for (int r = 0; r < HR; ++r) {
+          const double2 wn = *reinterpret_cast<const double2*>(&cols[r].w);
+          const double2 sg = *reinterpret_cast<const double2*>(&cols[r].s);
+          double hh = h[r];
+          hh = fma(wn.x, s, hh);   // + (c₁ s[r]) s[c]
+          hh = fma(wn.y, s, hh);   // - u[r] s[c]
+          hh = fma(nu_c, sg.x, hh);// - u[c] s[r]
+          h[r] = hh;
+          acc = fma(hh, sg.y, acc);
+        }
+      } else if (active) {
+        double* hrow = hs + c;
+#pragma unroll 4
+        for (int r = 0; r < n; ++r) {
+          const double2 wn = *reinterpret_cast<const double2*>(&cols[r].w);
+          const double2 sg = *reinterpret_cast<const double2*>(&cols[r].s);
+          double hh = hrow[n * r];
+          hh = fma(wn.x, s, hh);
+          hh = fma(wn.y, s, hh);
+          hh = fma(nu_c, sg.x, hh);
+          hrow[n * r] = hh;
+          acc = fma(hh, sg.y, acc);
+        }
+      }
+      m = tm.csum(acc * g, n); // m = dᵀ∇_new, QN.jl:66-68
+      s = acc;                 // the new direction; `s, y = y, s`, QN.jl:65,268
+    }
+    if (m <= 0.0) { // QN.jl:272-280: H ← I, s ← ∇_new, m ← ∇ᵀ∇
+      if (NREG > 0) {
+#pragma unroll
+        for (int r = 0; r < HR; ++r) h[r] = (r == c) ? 1.0 : 0.0;
+      } else if (active) {
+        for (int r = 0; r < n; ++r) hs[c + n * r] = (r == c) ? 1.0 : 0.0;
+      }
+      s = g;
+      m = tm.csum(g * g, n);
+    }
+
+    // ---- linesearch!  QN.jl:165-232 (every thread runs the same scalar code)
+    double alpha;
+    {
+      const LsParams& ls = p.ls;
+      double lx0 = l0, lx1 = l0;
+      double a1 = 1.0, a2 = 1.0;
+      double dummy;
+      // step!: x_new = x_old + α s (one fma, rule C3), then logdensity. QN.jl:157-162
+      tm.xs[c] = fma(a1, s, x);
+      __syncthreads();
+      lx1 = Obj::template eval<false>(tm, op, dummy);
+      ++fevals;
+      int iterfinite = 0;
+      while (!isfinite(lx1) && iterfinite < 52) { // QN.jl:178-184
+        ++iterfinite;
+        a1 = a2;
+        a2 = 0.5 * a2;
+        tm.xs[c] = fma(a2, s, x);
+        __syncthreads();
+        lx1 = Obj::template eval<false>(tm, op, dummy);
+        ++fevals;
+      }
+      long long iteration = 0;
+      bool failed = false;
+      while (!(lx1 >= fma(a2 * ls.c1, m, l0))) { // QN.jl:187
+        ++iteration;
+        if (iteration > ls.iterations) { failed = true; break; } // QN.jl:193
+        double at;
+        if (ls.order == 2 || iteration == 1) {
+          at = -((m * a2) * a2) / (2.0 * fma(-m, a2, lx1 - l0)); // QN.jl:205
+        } else {
+          const double denom = 1.0 / ((((a1 * a1) * a2) * a2) * (a2 - a1)); // QN.jl:207
+          const double r1 = fma(-m, a2, lx1 - l0);
+          const double r0 = fma(-m, a1, lx0 - l0);
+          const double a = ((a1 * a1) * r1 - (a2 * a2) * r0) * denom;                    // QN.jl:208
+          const double b = ((((-a1) * a1) * a1) * r1 + ((a2 * a2) * a2) * r0) * denom;   // QN.jl:209
+          if (fabs(a) <= kEps + kSqrtTol * fabs(a)) {  // QN.jl:211
+            at = m / (2.0 * b);                        // QN.jl:212
+          } else {
+            const double d = nanmax(b * b - (3.0 * a) * m, 0.0); // QN.jl:215
+            at = (sqrt(d) + b) / (-3.0 * a);                     // QN.jl:218
+          }
+        }
+        a1 = a2;                           // QN.jl:222
+        at = nanmin(at, a2 * ls.rho_hi);   // QN.jl:224
+        a2 = nanmax(at, a2 * ls.rho_lo);   // QN.jl:225
+        lx0 = lx1;                         // QN.jl:228
+        tm.xs[c] = fma(a2, s, x);
+        __syncthreads();
+        lx1 = Obj::template eval<false>(tm, op, dummy);
+        ++fevals;
+      }
+      alpha = failed ? 0.0 : a2;
+    }
+    if (alpha == 0.0) { status = QN_LINESEARCH_FAILED; break; } // QN.jl:284
+    // update_state!: s ← αs ; x_old += s   QN.jl:21-27
+    s = alpha * s;
+    x = x + s;
+    g_prev = g; // ∇_old, ∇_new = ∇_new, ∇_old, QN.jl:286
+    ++iters;
+    if (p.trace != nullptr && it <= p.ntrace && active)
+      p.trace[(j * p.ntrace + (it - 1)) * (long long)n + c] = x;
+  }
+
+  // ---- results: θ* at offset 0 and ∇ at offset L of the state block (QN.jl:135,138)
+  if (active) {
+    if (p.x_out) p.x_out[j * p.x_stride + c] = x;
+    if (p.g_out) p.g_out[j * p.g_stride + c] = g;
+    if (p.h_out) {
+      double* ho = p.h_out + j * p.h_stride + c;
+      if (NREG > 0) {
+#pragma unroll
+        for (int r = 0; r < HR; ++r) ho[(long long)p.ldh * r] = h[r];
+      } else {
+        for (int r = 0; r < n; ++r) ho[(long long)p.ldh * r] = hs[c + n * r];
+      }
+    }
+  }
+  if (c == 0) {
+    if (p.ell_out) p.ell_out[j] = result;
+    if (p.iters_out) p.iters_out[j] = iters;
+    if (p.fevals_out) p.fevals_out[j] = fevals;
+    if (p.status_out) p.status_out[j] = status;
+  }
+}
+
+template <class Obj, int NREG, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+qn_resident_kernel(const BatchParams p, const typename Obj::Params op) {
+  extern __shared__ __align__(16) double smem[];
+  const int n = (NREG > 0) ? NREG : p.n;
+  const ResidentSmem L = resident_smem_layout<Obj>(n, NREG == 0, op);
+
+  Team tm;
+  tm.n = n;
+  tm.c = threadIdx.x;
+  tm.lane = threadIdx.x & 31;
+  tm.red = smem + L.red;
+  tm.stride = resident_block_threads(n);
+  tm.phase = 0;
+  tm.xs = smem + L.xs;
+  tm.scratch = smem + L.scratch;
+  double* ys = smem + L.ys;
+  Pass2Col* cols = reinterpret_cast<Pass2Col*>(smem + L.cols);
+  double* hs = smem + L.h;
+  volatile long long* next = reinterpret_cast<volatile long long*>(smem + L.total - 2);
+
+  for (;;) {
+    __syncthreads(); // previous problem's last reads of shared memory are done
+    if (threadIdx.x == 0) *next = (long long)atomicAdd(p.counter, 1ULL);
+    __syncthreads();
+    const long long j = *next;
+    if (j >= p.batch) break;
+    resident_solve_one<Obj, NREG>(p, op, j, tm, ys, cols, hs);
+  }
+}
+
+}  // namespace qn
