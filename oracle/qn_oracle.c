@@ -51,18 +51,21 @@
 #endif
 
 #define QO_W 32
+#define QO_CB 32 /* rows per register block in the row-chain loops */
 #define QO_EPS 2.220446049250313e-16 /* eps(Float64) */
 
 /* ------------------------------------------------------------------ C1 */
 static double qo_csum(const double* v, int n) {
-  double p[QO_W], q[QO_W];
+  double p[QO_W];
   for (int l = 0; l < QO_W; ++l) p[l] = (l < n) ? v[l] : 0.0;
   for (int i = QO_W; i < n; ++i) p[i & (QO_W - 1)] = p[i & (QO_W - 1)] + v[i];
-  for (int off = QO_W / 2; off >= 1; off >>= 1) {
-    for (int l = 0; l < QO_W; ++l) q[l] = p[l] + p[l ^ off];
-    memcpy(p, q, sizeof p);
-  }
-  return p[0];
+  /* butterfly p[l] + p[l ^ off]: after each level lanes l and l^off hold the same
+   * value (IEEE addition commutes), so only the low half needs computing. */
+  for (int l = 0; l < 16; ++l) p[l] = p[l] + p[l + 16];
+  for (int l = 0; l < 8; ++l) p[l] = p[l] + p[l + 8];
+  for (int l = 0; l < 4; ++l) p[l] = p[l] + p[l + 4];
+  for (int l = 0; l < 2; ++l) p[l] = p[l] + p[l + 2];
+  return p[0] + p[1];
 }
 
 int qo_state_ld(int n, int native_w) {
@@ -226,10 +229,12 @@ double qo_dlogdensity(double* grad, const qo_model* model, int n, const double* 
 QO_HOT double qo_bfgs_update(int n, int L, double* H, double* u, double* y, const double* s,
                              const double* g_new, const double* g_old, int rblock,
                              double* scratch) {
-  double* t = scratch;         /* chain accumulators, one per row c */
-  double* T = scratch + n;     /* block-combined row sums */
-  double* w = scratch + 2 * n; /* c1*s[r] */
-  double* v = scratch + 3 * n; /* products for csum */
+  double* restrict t = scratch;         /* chain accumulators, one per row c */
+  double* restrict T = scratch + n;     /* block-combined row sums */
+  double* restrict w = scratch + 2 * n; /* c1*s[r] */
+  double* restrict v = scratch + 3 * n; /* products for csum */
+  const double* restrict sv = s;        /* s, u, H and the scratch rows never overlap */
+  double* restrict uv = u;
 
   /* QN.jl:36-41  y = ∇_old - ∇_new ; sᵀy */
   for (int i = 0; i < n; ++i) {
@@ -240,14 +245,31 @@ QO_HOT double qo_bfgs_update(int n, int L, double* H, double* u, double* y, cons
   const double sy = qo_csum(v, n);
   const double rho = 1.0 / sy; /* QN.jl:42, no guard */
 
-  /* QN.jl:44-52  t[c] = Σ_r y[r] H[c,r] ; u = t ρ ; yᵀHy */
+  /* QN.jl:44-52  t[c] = Σ_r y[r] H[c,r] ; u = t ρ ; yᵀHy.
+   * Loop nest: blocks of QO_CB rows keep their chain accumulators in registers
+   * while r runs; each row's chain is still sequential in ascending r (rule C2). */
   for (int r0 = 0; r0 < n; r0 += rblock) {
     const int r1 = (r0 + rblock < n) ? r0 + rblock : n;
-    for (int c = 0; c < n; ++c) t[c] = 0.0;
-    for (int r = r0; r < r1; ++r) {
-      const double yr = y[r];
-      const double* col = H + (size_t)L * r;
-      for (int c = 0; c < n; ++c) t[c] = fma(yr, col[c], t[c]);
+    for (int c0 = 0; c0 < n; c0 += QO_CB) {
+      double acc[QO_CB];
+      if (c0 + QO_CB <= n) {
+        for (int k = 0; k < QO_CB; ++k) acc[k] = 0.0;
+        for (int r = r0; r < r1; ++r) {
+          const double yr = y[r];
+          const double* restrict col = H + (size_t)L * r + c0;
+          for (int k = 0; k < QO_CB; ++k) acc[k] = fma(yr, col[k], acc[k]);
+        }
+        for (int k = 0; k < QO_CB; ++k) t[c0 + k] = acc[k];
+      } else {
+        const int cb = n - c0;
+        for (int k = 0; k < cb; ++k) acc[k] = 0.0;
+        for (int r = r0; r < r1; ++r) {
+          const double yr = y[r];
+          const double* restrict col = H + (size_t)L * r + c0;
+          for (int k = 0; k < cb; ++k) acc[k] = fma(yr, col[k], acc[k]);
+        }
+        for (int k = 0; k < cb; ++k) t[c0 + k] = acc[k];
+      }
     }
     if (r0 == 0) for (int c = 0; c < n; ++c) T[c] = t[c];
     else for (int c = 0; c < n; ++c) T[c] = T[c] + t[c];
@@ -265,18 +287,38 @@ QO_HOT double qo_bfgs_update(int n, int L, double* H, double* u, double* y, cons
   for (int r = 0; r < n; ++r) w[r] = c1 * s[r];
   for (int r0 = 0; r0 < n; r0 += rblock) {
     const int r1 = (r0 + rblock < n) ? r0 + rblock : n;
-    for (int c = 0; c < n; ++c) t[c] = 0.0;
-    for (int r = r0; r < r1; ++r) {
-      const double wr = w[r], nur = -u[r], sr = s[r], gr = g_new[r];
-      double* col = H + (size_t)L * r;
-      for (int c = 0; c < n; ++c) {
-        double h = col[c];
-        h = fma(wr, s[c], h);    /*  + (c1 s[r]) s[c] */
-        h = fma(nur, s[c], h);   /*  - u[r] s[c]      */
-        h = fma(-u[c], sr, h);   /*  - u[c] s[r]      */
-        col[c] = h;
-        t[c] = fma(h, gr, t[c]);
+    for (int c0 = 0; c0 < n; c0 += QO_CB) {
+      double acc[QO_CB], sc[QO_CB], nuc[QO_CB];
+      const int cb = (c0 + QO_CB <= n) ? QO_CB : n - c0;
+      for (int k = 0; k < cb; ++k) { acc[k] = 0.0; sc[k] = sv[c0 + k]; nuc[k] = -uv[c0 + k]; }
+      if (cb == QO_CB) {
+        for (int r = r0; r < r1; ++r) {
+          const double wr = w[r], nur = -uv[r], sr = sv[r], gr = g_new[r];
+          double* restrict col = H + (size_t)L * r + c0;
+          for (int k = 0; k < QO_CB; ++k) {
+            double h = col[k];
+            h = fma(wr, sc[k], h);   /*  + (c1 s[r]) s[c] */
+            h = fma(nur, sc[k], h);  /*  - u[r] s[c]      */
+            h = fma(nuc[k], sr, h);  /*  - u[c] s[r]      */
+            col[k] = h;
+            acc[k] = fma(h, gr, acc[k]);
+          }
+        }
+      } else {
+        for (int r = r0; r < r1; ++r) {
+          const double wr = w[r], nur = -uv[r], sr = sv[r], gr = g_new[r];
+          double* restrict col = H + (size_t)L * r + c0;
+          for (int k = 0; k < cb; ++k) {
+            double h = col[k];
+            h = fma(wr, sc[k], h);
+            h = fma(nur, sc[k], h);
+            h = fma(nuc[k], sr, h);
+            col[k] = h;
+            acc[k] = fma(h, gr, acc[k]);
+          }
+        }
       }
+      for (int k = 0; k < cb; ++k) t[c0 + k] = acc[k];
     }
     if (r0 == 0) for (int c = 0; c < n; ++c) T[c] = t[c];
     else for (int c = 0; c < n; ++c) T[c] = T[c] + t[c];

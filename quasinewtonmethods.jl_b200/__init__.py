@@ -8,7 +8,7 @@ include/qn_cuda.h); this package is the Python host mirror of the reference's
 interface.  The directory name contains a dot, so import it through the alias
 module at the repo root:  `import qn_b200`.
 """
-from . import _lib
+from . import _lib, sharding
 from .api import *  # noqa: F401,F403
 from .api import __all__  # noqa: F401
 

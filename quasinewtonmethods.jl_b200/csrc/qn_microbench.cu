@@ -22,24 +22,26 @@ __global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, doubl
   if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-// conflict-free LDS.128: each lane reads 16 B at lane*16 + k*512 of a 32 KB window.
+// conflict-free LDS.128: lane l of a warp reads the 16 bytes at (base + l)*16, so
+// a warp request is 512 consecutive bytes = 4 wavefronts of 128 B.  The window
+// base moves every load so nothing can be hoisted out of the loop.
 __global__ void __launch_bounds__(256) lds_kernel(double* out, int iters) {
   __shared__ __align__(16) double buf[4096];
   for (int i = threadIdx.x; i < 4096; i += blockDim.x) buf[i] = (double)i;
   __syncthreads();
-  const double2* p = reinterpret_cast<const double2*>(buf) + threadIdx.x;
-  double2 acc0 = {0, 0}, acc1 = {0, 0};
+  const double2* p = reinterpret_cast<const double2*>(buf);
   long long bits = 0;
+  int base = threadIdx.x;
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const double2 v = p[k * 256];
+      const double2 v = p[base & 2047];
+      base += 256 + 32 * (k & 1);
       // integer xor keeps the loads alive without touching the FP64 pipe
-      bits ^= __double_as_longlong(v.x) ^ (__double_as_longlong(v.y) + i);
+      bits ^= __double_as_longlong(v.x) ^ __double_as_longlong(v.y);
     }
   }
-  acc0.x = __longlong_as_double(bits);
-  if (acc0.x == 123.456 && acc1.x == 1.0) out[blockIdx.x * blockDim.x + threadIdx.x] = acc0.x;
+  if (bits == 0x123456789LL) out[blockIdx.x * blockDim.x + threadIdx.x] = (double)bits;
 }
 
 __global__ void __launch_bounds__(256) copy_kernel(const double2* __restrict__ src,

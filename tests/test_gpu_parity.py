@@ -1,0 +1,228 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  -m gpu.
+
+The north-star gates (BASELINE.json): converged optimum ‖Δθ‖∞ <= 1e-8, max|∇| < 1e-8,
+first 5 iterates to 1e-12 relative, iteration counts side by side.  Because the kernels
+follow the oracle's canonical arithmetic order the comparison here is
+stricter: BIT-FOR-BIT equality of θ*, ∇, ℓ, the traces and the iteration/evaluation
+counts.  The tolerance gates are asserted as well, so a future kernel that gives up
+bit-exactness still has to meet them.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, starts
+
+pytestmark = pytest.mark.gpu
+
+TOL_X = 1e-8       # ‖Δθ‖∞ at the optimum
+TOL_G = 1e-8       # max|∇|
+TOL_TRACE = 1e-12  # first five iterates, relative
+
+
+def _check(got, ref, bitwise=True):
+    assert np.array_equal(got["status"], ref["status"])
+    conv = ref["status"] == 0
+    # the gates north_star names
+    assert np.nanmax(np.abs(got["x"][:, conv] - ref["x"][:, conv]), initial=0) <= TOL_X
+    assert np.abs(got["g"][:, conv]).max(initial=0) < TOL_G
+    if ref.get("trace") is not None:
+        scale = np.maximum(np.nanmax(np.abs(ref["trace"]), axis=2, keepdims=True), 1e-300)
+        rel = np.abs(got["trace"] - ref["trace"]) / scale
+        assert np.nanmax(rel, initial=0) <= TOL_TRACE
+        assert np.array_equal(np.isnan(got["trace"]), np.isnan(ref["trace"]))
+    if bitwise:
+        for k in ("x", "g", "ell"):
+            assert np.array_equal(got[k], ref[k], equal_nan=True), k
+        if ref.get("trace") is not None:
+            assert np.array_equal(got["trace"], ref["trace"], equal_nan=True)
+        assert np.array_equal(got["iters"], ref["iters"])
+        assert np.array_equal(got["fevals"], ref["fevals"])
+
+
+@pytest.mark.parametrize("n", list(range(2, 25)))
+@pytest.mark.parametrize("order", [2, 3])
+def test_reference_test_range(eng, qn, ob, n, order):
+    """The sizes of the reference's own testset (test/runtests.jl:37): n = 2..24, both orders."""
+    Theta = starts(n, 48, key=100 * order + n)
+    got = eng.optimize_batched(qn.Rosenbrock(), Theta, ls=qn.BackTracking(order=order), ntrace=5)
+    ref = ob.optimize_batch(ob.rosenbrock(), Theta, ls=ob.backtracking(order=order), ntrace=5)
+    _check(got, ref)
+    assert (got["status"] == qn.CONVERGED).all()
+    assert np.abs(got["x"] - 1).max() < 1e-7
+
+
+@pytest.mark.parametrize("order", [2, 3])
+@pytest.mark.parametrize("path", ["register", "smem"])
+def test_n60_both_resident_paths(eng, qn, ob, order, path):
+    """README.md:52-75 size, batched; the register- and smem-resident kernels give the same bits."""
+    Theta = starts(60, 1024, key=60 + order)
+    flags = qn._lib.FLAG_FORCE_SMEM if path == "smem" else 0
+    got = eng.optimize_batched(qn.Rosenbrock(), Theta, ls=qn.BackTracking(order=order), ntrace=5, flags=flags)
+    assert eng.last_launch()["path"] == (qn._lib.PATH_SMEM if path == "smem" else qn._lib.PATH_REGISTER)
+    ref = ob.optimize_batch(ob.rosenbrock(), Theta, ls=ob.backtracking(order=order), ntrace=5)
+    _check(got, ref)
+    assert (got["status"] == qn.CONVERGED).all()
+    print("n=60 order=%d %s: iterations GPU mean %.2f / oracle mean %.2f, max %d / %d" % (
+        order, path, got["iters"].mean(), ref["iters"].mean(), got["iters"].max(), ref["iters"].max()))
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 59, 61, 63, 64, 65, 96, 100, 127, 128, 129, 160])
+def test_ragged_sizes_smem_path(eng, qn, ob, n):
+    """Odd n (tail term), warp-boundary sizes, and the largest resident size (n=160, 205 KB of B⁻¹)."""
+    batch = 12 if n > 100 else 24
+    Theta = starts(n, batch, key=n)
+    got = eng.optimize_batched(qn.Rosenbrock(), Theta, ntrace=5)
+    ref = ob.optimize_batch(ob.rosenbrock(), Theta, ntrace=5)
+    _check(got, ref)
+
+
+def test_committed_oracle_vectors(eng, qn):
+    """Against the committed fixtures (no oracle call): tests/golden/oracle_vectors.npz."""
+    v = np.load(os.path.join(GOLDEN, "oracle_vectors.npz"))
+    keys = sorted({k.rsplit("_", 1)[0] for k in v.files})
+    for k in keys:
+        order = int(k.split("_")[1][1:])
+        got = eng.optimize_batched(qn.Rosenbrock(), v[k + "_theta0"], ls=qn.BackTracking(order=order), ntrace=5)
+        ref = {f: v[k + "_" + f] for f in ("x", "g", "ell", "iters", "fevals", "status", "trace")}
+        _check(got, ref)
+
+
+def test_first_five_iterates_match_mpmath_fixture(eng, qn):
+    """The GPU's first five iterates against the independent 60-digit restatement."""
+    import json
+    d = json.load(open(os.path.join(GOLDEN, "rosenbrock_mp_trace.json")))
+    for case in d["cases"]:
+        x0 = np.array([float.fromhex(h) for h in case["x0"]]).reshape(-1, 1)
+        got = eng.optimize_batched(qn.Rosenbrock(), x0, ls=qn.BackTracking(order=case["order"]), ntrace=5)
+        ref = np.array(case["trace"])
+        scale = np.abs(ref).max(axis=1, keepdims=True)
+        assert (np.abs(got["trace"][0] - ref) / scale).max() <= TOL_TRACE
+
+
+def test_full_size_batch(eng, qn, ob):
+    """BASELINE.json configs[1]: 2^16 starts, n = 60.  Every problem converges; a 2048-problem
+    sample is compared with the oracle bit for bit; results do not depend on batch composition."""
+    n, batch = 60, 1 << 16
+    Theta = starts(n, batch)
+    got = eng.optimize_batched(qn.Rosenbrock(), Theta)
+    assert (got["status"] == qn.CONVERGED).all()
+    assert np.abs(got["g"]).max() < TOL_G
+    assert np.abs(got["x"] - 1).max() < 2e-7
+    assert np.abs(got["ell"]).max() < 1e-14
+    idx = np.arange(0, batch, 32)
+    ref = ob.optimize_batch(ob.rosenbrock(), Theta[:, idx])
+    sub = {k: (got[k][..., idx] if got[k] is not None else None) for k in got}
+    _check(sub, ref)
+    # size-independent property: a problem's result is the same alone, in a small batch, reversed
+    alone = eng.optimize_batched(qn.Rosenbrock(), Theta[:, 4097:4098])
+    assert np.array_equal(alone["x"][:, 0], got["x"][:, 4097])
+    rev = eng.optimize_batched(qn.Rosenbrock(), Theta[:, 1023::-1])
+    assert np.array_equal(rev["x"][:, ::-1], got["x"][:, :1024])
+    assert np.array_equal(rev["iters"][::-1], got["iters"][:1024])
+    print("2^16 batch: iterations mean %.1f median %d max %d; fevals/iter %.3f" % (
+        got["iters"].mean(), np.median(got["iters"]), got["iters"].max(),
+        got["fevals"].sum() / got["iters"].sum()))
+
+
+def test_edge_cases(eng, qn, ob):
+    R = qn.Rosenbrock()
+    # empty batch
+    r = eng.optimize_batched(R, np.empty((7, 0), order="F"))
+    assert r["ell"].shape == (0,)
+    # non-finite start -> NaN + status (QN.jl:255,291); finite neighbours unaffected
+    Theta = starts(10, 6)
+    Theta[3, 2] = np.inf
+    Theta[0, 4] = np.nan
+    got = eng.optimize_batched(R, Theta, ntrace=2)
+    ref = ob.optimize_batch(ob.rosenbrock(), Theta, ntrace=2)
+    _check(got, ref)
+    assert got["status"][2] == qn.NONFINITE and np.isnan(got["ell"][2])
+    assert got["status"][4] == qn.NONFINITE and got["status"][0] == qn.CONVERGED
+    # iteration cap -> NaN (QN.jl:291)
+    got = eng.optimize_batched(R, starts(10, 4), max_iter=3)
+    assert (got["status"] == qn.MAX_ITER).all() and np.isnan(got["ell"]).all() and (got["iters"] == 3).all()
+    # already at the optimum: no step taken
+    got = eng.optimize_batched(R, np.ones((9, 3), order="F"))
+    assert (got["iters"] == 0).all() and (got["ell"] == 0).all() and (got["status"] == 0).all()
+    # huge starts: the non-finite halving loop (QN.jl:178-184) and resets are exercised
+    big = starts(8, 64, key=5) * 1e80
+    got = eng.optimize_batched(R, big)
+    ref = ob.optimize_batch(ob.rosenbrock(), big)
+    _check(got, ref)
+    # tiny c1 / aggressive clamps, user BackTracking parameters pass through
+    ls = qn.BackTracking(c1=0.3, rho_hi=0.9, rho_lo=0.5, iterations=3, order=3)
+    lo = ob.backtracking(c1=0.3, rho_hi=0.9, rho_lo=0.5, iterations=3, order=3)
+    got = eng.optimize_batched(R, starts(12, 64, key=9), ls=ls)
+    ref = ob.optimize_batch(ob.rosenbrock(), starts(12, 64, key=9), ls=lo)
+    _check(got, ref)
+    assert (ref["status"] == ob.LINESEARCH_FAILED).any()  # the α = 0 exit (QN.jl:193,284)
+
+
+def test_state_blocks_and_h_writeback(eng, qn, ob):
+    """Results land in BFGSState layout (QN.jl:135,138): θ* at 0, ∇ at L; with QN_FLAG_WRITE_H the
+    final B⁻¹ at 7L equals the oracle's bit for bit."""
+    for n, flags in ((60, 0), (60, qn._lib.FLAG_FORCE_SMEM), (24, 0)):
+        batch = 16
+        Theta = starts(n, batch, key=n + 1)
+        sb = qn.BFGSStateBatch(n, batch)
+        sb.data[:] = np.nan
+        r = eng.optimize_batched(qn.Rosenbrock(), Theta, states=sb, flags=flags | qn._lib.FLAG_WRITE_H)
+        assert np.array_equal(qn.optimum(sb).T, r["x"]) and np.array_equal(qn.gradient(sb).T, r["g"])
+        for j in range(batch):
+            o = ob.optimize(ob.rosenbrock(), Theta[:, j], L=sb.L)
+            L = sb.L
+            Ho = o["state"][7 * L:].reshape(n, L)[:, :n]
+            Hg = sb.data[j, 7 * L:].reshape(n, L)[:, :n]
+            assert np.array_equal(Hg, Ho)
+            assert np.array_equal(sb.data[j, :n], o["x"]) and np.array_equal(sb.data[j, L:L + n], o["g"])
+
+
+def test_reference_api_single_problem(qn, ob):
+    """optimize!(state, obj, x) exactly as the reference's test uses it (runtests.jl:39-50)."""
+    eps = np.finfo(float).eps
+    for n in (2, 9, 24):
+        state = qn.BFGSState(n)
+        x = starts(n, 1, key=1000 + n)[:, 0]
+        x_before = x.copy()
+        ell = qn.optimize_(state, qn.Rosenbrock(), x)
+        assert abs(ell) < 2 * eps
+        assert np.all(np.isclose(qn.optimum(state), 1, rtol=np.sqrt(eps), atol=0))
+        assert np.max(np.abs(qn.gradient(state))) < 1e-8
+        assert np.array_equal(x, x_before)  # x is read-only (QN.jl:248)
+        ell3 = qn.optimize_(state, qn.Rosenbrock(), x, qn.BackTracking[3]())
+        assert abs(ell3) < eps
+        assert np.max(np.abs(qn.gradient(state))) < 1e-8
+        o = ob.optimize(ob.rosenbrock(), x, ls=ob.backtracking(order=3))
+        assert ell3 == o["ell"] and np.array_equal(qn.optimum(state), o["x"]) and state.iters == o["iters"]
+    # batched optimize!(states, obj, Θ)
+    sb = qn.BFGSStateBatch(12, 32)
+    ell = qn.optimize_(sb, qn.Rosenbrock(), starts(12, 32))
+    assert ell.shape == (32,) and (np.abs(ell) < 2 * eps).all() and (sb.status == 0).all()
+
+
+def test_unregistered_objective_is_an_error(eng, qn):
+    class NotOnTheDevice:
+        pass
+    with pytest.raises(qn.UnregisteredObjectiveError):
+        eng.optimize_batched(NotOnTheDevice(), starts(4, 2))
+    import ctypes as C
+    h = C.c_void_p()
+    rc = eng._lib.qn_model_create(eng._ctx, 77, C.byref(h))
+    assert rc == qn._lib.ERR_UNREGISTERED_OBJECTIVE and not h.value
+
+
+def test_device_objectives_match_oracle(eng, qn, ob):
+    """logdensity / ∂logdensity! (QN.jl:8-9) of the registered device objectives."""
+    for n in (2, 7, 60, 61):
+        Th = starts(n, 33, key=n) * 1.5
+        ell, g = eng.logdensity_batched(qn.Rosenbrock(), Th, grad=True)
+        for j in range(Th.shape[1]):
+            v, gr = ob.dlogdensity(ob.rosenbrock(), Th[:, j])
+            assert v == ell[j] and np.array_equal(gr, g[:, j])
+            assert ob.logdensity(ob.rosenbrock(), Th[:, j]) == ell[j]
+    x = starts(9, 1)[:, 0]
+    gbuf = np.empty(9)
+    assert qn.dlogdensity_(gbuf, qn.Rosenbrock(), x) == qn.logdensity(qn.Rosenbrock(), x)
+    assert np.array_equal(gbuf, ob.dlogdensity(ob.rosenbrock(), x)[1])
