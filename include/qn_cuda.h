@@ -149,8 +149,8 @@ int32_t qn_bfgs_optimize_batched_f64(qn_context* ctx, const qn_model* model, int
                                      uint32_t flags);
 
 /* Same, with every pointer a DEVICE pointer on the context's GPU and the work
- * enqueued on `stream` (a cudaStream_t; NULL = the context's own stream)
- * without synchronising — the PtrBFGSState analogue (QN.jl:117-121): the
+ * enqueued on `stream` (a cudaStream_t, used literally: NULL is the CUDA default
+ * stream) without synchronising — the PtrBFGSState analogue (QN.jl:117-121): the
  * caller owns the memory.  theta_stride = column stride of theta0 (>= n). */
 int32_t qn_bfgs_optimize_batched_device_f64(qn_context* ctx, const qn_model* model, int32_t n,
                                             int64_t batch, const double* theta0,

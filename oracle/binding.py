@@ -15,7 +15,7 @@ _SO = os.path.join(_HERE, "libqn_oracle.so")
 
 ROSENBROCK, DENSE_GAUSSIAN, LOGISTIC = 0, 1, 2
 CONVERGED, NONFINITE, LINESEARCH_FAILED, MAX_ITER = 0, 1, 2, 3
-RBLOCK = 256
+RBLOCK = 0  # canonical rule C2 blocks (qo_chain_block)
 
 
 class Backtracking(C.Structure):
@@ -139,7 +139,7 @@ def bfgs_update(H, s, g_new, g_old, rblock=RBLOCK):
     Hf = np.asfortranarray(H, dtype=np.float64).copy(order="F")
     u = np.zeros(n)
     y = np.zeros(n)
-    scratch = np.zeros(4 * n + 64)
+    scratch = np.zeros(5 * n + 64)
     m = lib().qo_bfgs_update(n, n, _dp(Hf), _dp(u), _dp(y), _dp(np.ascontiguousarray(s)),
                              _dp(np.ascontiguousarray(g_new)), _dp(np.ascontiguousarray(g_old)),
                              rblock, _dp(scratch))

@@ -18,12 +18,18 @@
  *      result is p[0].  Dot products are csum over individually rounded
  *      products a[i]*b[i].  (The SIMD analogue: vector accumulators, then a
  *      horizontal reduce.)
- *  C2  Row sums over r (the GEMV at QN.jl:44-52 and the fused update+GEMV at
- *      QN.jl:56-67): for a fixed row c one sequential FMA chain over ascending
- *      r, started from +0.0, in blocks of `rblock` (=256) columns; block
- *      partials are added in ascending block order.  n <= 256 is one chain.
- *      (@turbo vectorises over the unit-stride index c and carries the r-sum
- *      in each lane.)
+ *  C2  Row sums over K terms (the GEMV at QN.jl:44-52, the fused update+GEMV
+ *      at QN.jl:56-67, and the GEMVs inside the build-defined objectives):
+ *      the terms are cut into balanced blocks of rb = ceil(K / ceil(K/16))
+ *      (<= 16) consecutive columns.  Inside a block: one sequential FMA chain
+ *      in ascending order started from +0.0.  Blocks are grouped 16 at a time
+ *      into super-blocks; inside a super-block the block partials are added
+ *      in ascending order (S = b0; S = S + b1; ...), and the super-block sums
+ *      are added in ascending order the same way.  K <= 256 has one
+ *      super-block.  (@turbo vectorises over the unit-stride index c and
+ *      carries the r-sum in each lane with several accumulators; this is the
+ *      same shape with the accumulator count fixed.  On the GPU a block is the
+ *      16-or-fewer columns one thread's register tile covers.)
  *  C3  t += a*b, muladd(a,b,c), x + alpha*s under @turbo, and x +- a*b under
  *      @fastmath with exactly one product operand are one fma.  Expressions
  *      with two product operands (a*b - c*d) round both products.
@@ -66,6 +72,26 @@ static double qo_csum(const double* v, int n) {
   for (int l = 0; l < 4; ++l) p[l] = p[l] + p[l + 4];
   for (int l = 0; l < 2; ++l) p[l] = p[l] + p[l + 2];
   return p[0] + p[1];
+}
+
+/* rule C2 block length for a chain of K terms */
+int qo_chain_block(int K) {
+  if (K <= 0) return 1;
+  const int nb = (K + 15) / 16;
+  return (K + nb - 1) / nb;
+}
+
+/* rule C2 combine step: fold the chain partial t of block `blk` into the super-block
+ * sums S and the row sums T.  `last` marks the final block of the row. */
+static inline void qo_combine(int n, int blk, int last, const double* restrict t,
+                              double* restrict S, double* restrict T) {
+  const int in_sb = blk & 15;
+  if (in_sb == 0) for (int c = 0; c < n; ++c) S[c] = t[c];
+  else for (int c = 0; c < n; ++c) S[c] = S[c] + t[c];
+  if (in_sb == 15 || last) {
+    if (blk < 16) for (int c = 0; c < n; ++c) T[c] = S[c];
+    else for (int c = 0; c < n; ++c) T[c] = T[c] + S[c];
+  }
 }
 
 int qo_state_ld(int n, int native_w) {
@@ -117,24 +143,26 @@ static double rosen_grad(double* g, int n, const double* th, double* scratch) {
   return s;
 }
 
-/* Dense Gaussian (build-defined): z = Λ(θ-μ) by C2
- * row chains, ∇ = -z, ell = -1/2 csum((θ-μ)[c] z[c]).  scratch: 3n doubles. */
+/* Dense Gaussian (build-defined): z = Λ(θ-μ) by rule C2
+ * row chains, ∇ = -z, ell = -1/2 csum((θ-μ)[c] z[c]).  scratch: 4n doubles. */
 QO_HOT static double gauss_eval(double* g, int n, const qo_gaussian* p, const double* th,
                                 int rblock, double* scratch) {
-  double* d = scratch;
-  double* z = scratch + n;
-  double* t = scratch + 2 * n;
+  double* restrict d = scratch;
+  double* restrict z = scratch + n;
+  double* restrict t = scratch + 2 * n;
+  double* restrict S = scratch + 3 * n;
+  const int rb = rblock > 0 ? rblock : qo_chain_block(n);
   for (int r = 0; r < n; ++r) d[r] = th[r] - p->mu[r];
-  for (int r0 = 0; r0 < n; r0 += rblock) {
-    const int r1 = (r0 + rblock < n) ? r0 + rblock : n;
+  int blk = 0;
+  for (int r0 = 0; r0 < n; r0 += rb, ++blk) {
+    const int r1 = (r0 + rb < n) ? r0 + rb : n;
     for (int c = 0; c < n; ++c) t[c] = 0.0;
     for (int r = r0; r < r1; ++r) {
       const double dr = d[r];
-      const double* col = p->lambda + (size_t)n * r;
+      const double* restrict col = p->lambda + (size_t)n * r;
       for (int c = 0; c < n; ++c) t[c] = fma(col[c], dr, t[c]);
     }
-    if (r0 == 0) for (int c = 0; c < n; ++c) z[c] = t[c];
-    else for (int c = 0; c < n; ++c) z[c] = z[c] + t[c];
+    qo_combine(n, blk, r1 == n, t, S, z);
   }
   for (int c = 0; c < n; ++c) t[c] = d[c] * z[c];
   const double q = qo_csum(t, n);
@@ -149,19 +177,32 @@ static double qo_sigmoid(double z) {
   return e / (1.0 + e);
 }
 
-/* Logistic regression (build-defined).
- * scratch: 2m + 2n doubles. */
+/* Logistic regression (build-defined).  Both GEMVs (z = Xθ over
+ * n terms, Xᵀr over m terms) are rule C2 row chains.  scratch: 4m + 4n doubles. */
 QO_HOT static double logit_eval(double* g, int n, const qo_logistic* p, const double* th,
                                 int rblock, double* scratch) {
   const int m = p->m;
-  double* z = scratch;
-  double* v = scratch + m;
-  double* w = scratch + 2 * m;
-  for (int i = 0; i < m; ++i) z[i] = 0.0;
-  for (int j = 0; j < n; ++j) {
-    const double tj = th[j];
-    const double* col = p->X + (size_t)m * j;
-    for (int i = 0; i < m; ++i) z[i] = fma(col[i], tj, z[i]);
+  double* restrict z = scratch;
+  double* restrict v = scratch + m;
+  double* restrict tm = scratch + 2 * m;
+  double* restrict Sm = scratch + 3 * m;
+  double* restrict w = scratch + 4 * m;
+  double* restrict tn = scratch + 4 * m + n;
+  double* restrict Sn = scratch + 4 * m + 2 * n;
+  double* restrict Tn = scratch + 4 * m + 3 * n;
+  {
+    const int rb = rblock > 0 ? rblock : qo_chain_block(n);
+    int blk = 0;
+    for (int j0 = 0; j0 < n; j0 += rb, ++blk) {
+      const int j1 = (j0 + rb < n) ? j0 + rb : n;
+      for (int i = 0; i < m; ++i) tm[i] = 0.0;
+      for (int j = j0; j < j1; ++j) {
+        const double tj = th[j];
+        const double* restrict col = p->X + (size_t)m * j;
+        for (int i = 0; i < m; ++i) tm[i] = fma(col[i], tj, tm[i]);
+      }
+      qo_combine(m, blk, j1 == n, tm, Sm, z);
+    }
   }
   for (int i = 0; i < m; ++i) v[i] = p->y[i] * z[i] - qo_softplus(z[i]);
   const double S = qo_csum(v, m);
@@ -170,29 +211,28 @@ QO_HOT static double logit_eval(double* g, int n, const qo_logistic* p, const do
   const double ell = fma(-(0.5 * p->lam), pen, S);
   if (g) {
     for (int i = 0; i < m; ++i) v[i] = p->y[i] - qo_sigmoid(z[i]);
-    /* rule C2: chains of `rblock` rows, block partials added in ascending order */
-    double* T = scratch + 2 * m + n;
-    for (int i0 = 0; i0 < m; i0 += rblock) {
-      const int i1 = (i0 + rblock < m) ? i0 + rblock : m;
-      for (int j = 0; j < n; ++j) w[j] = 0.0;
+    const int rb = rblock > 0 ? rblock : qo_chain_block(m);
+    int blk = 0;
+    for (int i0 = 0; i0 < m; i0 += rb, ++blk) {
+      const int i1 = (i0 + rb < m) ? i0 + rb : m;
+      for (int j = 0; j < n; ++j) tn[j] = 0.0;
       for (int i = i0; i < i1; ++i) {
         const double ri = v[i];
-        const double* col = p->Xt + (size_t)n * i;
-        for (int j = 0; j < n; ++j) w[j] = fma(col[j], ri, w[j]);
+        const double* restrict col = p->Xt + (size_t)n * i;
+        for (int j = 0; j < n; ++j) tn[j] = fma(col[j], ri, tn[j]);
       }
-      if (i0 == 0) for (int j = 0; j < n; ++j) T[j] = w[j];
-      else for (int j = 0; j < n; ++j) T[j] = T[j] + w[j];
+      qo_combine(n, blk, i1 == m, tn, Sn, Tn);
     }
-    for (int j = 0; j < n; ++j) g[j] = fma(-p->lam, th[j], T[j]);
+    for (int j = 0; j < n; ++j) g[j] = fma(-p->lam, th[j], Tn[j]);
   }
   return ell;
 }
 
 static size_t qo_scratch_len(const qo_model* model, int n) {
-  size_t len = 4 * (size_t)n + 64;
+  size_t len = 5 * (size_t)n + 64;
   if (model->kind == QO_LOGISTIC) {
     const qo_logistic* p = (const qo_logistic*)model->params;
-    len += 2 * (size_t)p->m;
+    len += 4 * (size_t)p->m;
   }
   return len;
 }
@@ -213,14 +253,14 @@ static double qo_eval(double* g, const qo_model* model, int n, const double* th,
 
 double qo_logdensity(const qo_model* model, int n, const double* theta) {
   double* scratch = (double*)malloc(sizeof(double) * qo_scratch_len(model, n));
-  const double v = qo_eval(NULL, model, n, theta, 256, scratch);
+  const double v = qo_eval(NULL, model, n, theta, 0, scratch);
   free(scratch);
   return v;
 }
 
 double qo_dlogdensity(double* grad, const qo_model* model, int n, const double* theta) {
   double* scratch = (double*)malloc(sizeof(double) * qo_scratch_len(model, n));
-  const double v = qo_eval(grad, model, n, theta, 256, scratch);
+  const double v = qo_eval(grad, model, n, theta, 0, scratch);
   free(scratch);
   return v;
 }
@@ -230,11 +270,13 @@ QO_HOT double qo_bfgs_update(int n, int L, double* H, double* u, double* y, cons
                              const double* g_new, const double* g_old, int rblock,
                              double* scratch) {
   double* restrict t = scratch;         /* chain accumulators, one per row c */
-  double* restrict T = scratch + n;     /* block-combined row sums */
+  double* restrict T = scratch + n;     /* row sums */
   double* restrict w = scratch + 2 * n; /* c1*s[r] */
   double* restrict v = scratch + 3 * n; /* products for csum */
+  double* restrict S = scratch + 4 * n; /* super-block sums (rule C2) */
   const double* restrict sv = s;        /* s, u, H and the scratch rows never overlap */
   double* restrict uv = u;
+  const int rb = rblock > 0 ? rblock : qo_chain_block(n);
 
   /* QN.jl:36-41  y = ∇_old - ∇_new ; sᵀy */
   for (int i = 0; i < n; ++i) {
@@ -246,10 +288,11 @@ QO_HOT double qo_bfgs_update(int n, int L, double* H, double* u, double* y, cons
   const double rho = 1.0 / sy; /* QN.jl:42, no guard */
 
   /* QN.jl:44-52  t[c] = Σ_r y[r] H[c,r] ; u = t ρ ; yᵀHy.
-   * Loop nest: blocks of QO_CB rows keep their chain accumulators in registers
-   * while r runs; each row's chain is still sequential in ascending r (rule C2). */
-  for (int r0 = 0; r0 < n; r0 += rblock) {
-    const int r1 = (r0 + rblock < n) ? r0 + rblock : n;
+   * Loop nest: strips of QO_CB rows keep their chain accumulators in registers while r
+   * runs over one block; each row's chain is sequential in ascending r (rule C2). */
+  int blk = 0;
+  for (int r0 = 0; r0 < n; r0 += rb, ++blk) {
+    const int r1 = (r0 + rb < n) ? r0 + rb : n;
     for (int c0 = 0; c0 < n; c0 += QO_CB) {
       double acc[QO_CB];
       if (c0 + QO_CB <= n) {
@@ -271,8 +314,7 @@ QO_HOT double qo_bfgs_update(int n, int L, double* H, double* u, double* y, cons
         for (int k = 0; k < cb; ++k) t[c0 + k] = acc[k];
       }
     }
-    if (r0 == 0) for (int c = 0; c < n; ++c) T[c] = t[c];
-    else for (int c = 0; c < n; ++c) T[c] = T[c] + t[c];
+    qo_combine(n, blk, r1 == n, t, S, T);
   }
   for (int c = 0; c < n; ++c) {
     u[c] = T[c] * rho;
@@ -285,8 +327,9 @@ QO_HOT double qo_bfgs_update(int n, int L, double* H, double* u, double* y, cons
 
   /* QN.jl:56-67  rank-2 update fused with d = H⁺ ∇_new */
   for (int r = 0; r < n; ++r) w[r] = c1 * s[r];
-  for (int r0 = 0; r0 < n; r0 += rblock) {
-    const int r1 = (r0 + rblock < n) ? r0 + rblock : n;
+  blk = 0;
+  for (int r0 = 0; r0 < n; r0 += rb, ++blk) {
+    const int r1 = (r0 + rb < n) ? r0 + rb : n;
     for (int c0 = 0; c0 < n; c0 += QO_CB) {
       double acc[QO_CB], sc[QO_CB], nuc[QO_CB];
       const int cb = (c0 + QO_CB <= n) ? QO_CB : n - c0;
@@ -320,8 +363,7 @@ QO_HOT double qo_bfgs_update(int n, int L, double* H, double* u, double* y, cons
       }
       for (int k = 0; k < cb; ++k) t[c0 + k] = acc[k];
     }
-    if (r0 == 0) for (int c = 0; c < n; ++c) T[c] = t[c];
-    else for (int c = 0; c < n; ++c) T[c] = T[c] + t[c];
+    qo_combine(n, blk, r1 == n, t, S, T);
   }
   for (int c = 0; c < n; ++c) {
     y[c] = T[c]; /* new direction overwrites y, QN.jl:65 */
@@ -402,7 +444,7 @@ double qo_linesearch(int n, double* x_new, const double* x_old, const double* s,
                      const qo_model* model, double l0, double m, const qo_backtracking* ls,
                      int64_t* fevals) {
   double* scratch = (double*)malloc(sizeof(double) * qo_scratch_len(model, n));
-  const double a = qo_linesearch_impl(n, x_new, x_old, s, model, l0, m, ls, fevals, 256, scratch);
+  const double a = qo_linesearch_impl(n, x_new, x_old, s, model, l0, m, ls, fevals, 0, scratch);
   free(scratch);
   return a;
 }

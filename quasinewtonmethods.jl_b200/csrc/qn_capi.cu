@@ -10,12 +10,14 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/qn_cuda.h"
 #include "qn_device.cuh"
 #include "qn_objectives.cuh"
 #include "qn_resident.cuh"
+#include "qn_resident_tile.cuh"
 #include "qn_internal.h"
 
 namespace {
@@ -82,17 +84,46 @@ int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Par
   return QN_OK;
 }
 
+// The register-tile kernel evaluates the objective warp-locally; only Rosenbrock has
+// that form (qn_resident_tile.cuh).
+template <int N, int MINB>
+int launch_tile(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
+  const size_t smem = sizeof(double) * (size_t)qn::tile_smem_doubles<N>();
+  auto kern = qn::qn_resident_tile_kernel<N, MINB>;
+  int occ = 0;
+  QN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 64, smem));
+  if (occ < 1) return fail(QN_ERR_UNSUPPORTED_SIZE, "tile kernel does not fit on an SM (n=%d)", N);
+  long long grid = (long long)occ * ctx->prop.multiProcessorCount;
+  if (grid > p.batch) grid = p.batch;
+  p.counter = qn_next_counter(ctx, st);
+  kern<<<(unsigned)grid, 64, smem, st>>>(p);
+  QN_CUDA_TRY(cudaGetLastError());
+  ctx->last_path = 0;
+  ctx->last_grid = (int)grid;
+  ctx->last_block = 64;
+  ctx->last_smem = (int)smem;
+  ctx->last_launches = 1;
+  return QN_OK;
+}
+
 template <class Obj>
 int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Params& op,
                   uint32_t flags, cudaStream_t st) {
   const int n = p.n;
-  if (!(flags & QN_FLAG_FORCE_SMEM)) {
-    switch (n) {
+  if constexpr (Obj::kRegisterPaths) {
+    if (!(flags & QN_FLAG_FORCE_SMEM)) {
+      switch (n) {
 #define QN_REG_CASE(N, BLOCK, MINB) \
   case N: return launch_resident<Obj, N, BLOCK, MINB>(ctx, p, op, st);
+#define QN_TILE_CASE(N, MINB) \
+  case N:                      \
+    if constexpr (std::is_same<Obj, qn::Rosenbrock>::value) return launch_tile<N, MINB>(ctx, p, st); \
+    break;
 #include "qn_reg_sizes.inc"
 #undef QN_REG_CASE
-      default: break;
+#undef QN_TILE_CASE
+        default: break;
+      }
     }
   }
   if (n <= 256) return launch_resident<Obj, 0, 256, 1>(ctx, p, op, st);
@@ -109,14 +140,14 @@ int dispatch_model(qn_context* ctx, const qn_model* model, qn::BatchParams& p, u
         return fail(QN_ERR_INVALID_ARGUMENT, "dense Gaussian model has n=%d, call has n=%d",
                     model->n, p.n);
       qn::DenseGaussian::Params op{model->d_a, model->d_b};
-      return dispatch_size<qn::DenseGaussian>(ctx, p, op, flags | QN_FLAG_FORCE_SMEM, st);
+      return dispatch_size<qn::DenseGaussian>(ctx, p, op, flags, st);
     }
     case QN_OBJ_LOGISTIC: {
       if (model->n != p.n)
         return fail(QN_ERR_INVALID_ARGUMENT, "logistic model has n=%d, call has n=%d", model->n,
                     p.n);
       qn::Logistic::Params op{model->m, model->d_a, model->d_b, model->d_c, model->lam};
-      return dispatch_size<qn::Logistic>(ctx, p, op, flags | QN_FLAG_FORCE_SMEM, st);
+      return dispatch_size<qn::Logistic>(ctx, p, op, flags, st);
     }
     default:
       return fail(QN_ERR_UNREGISTERED_OBJECTIVE,
@@ -345,7 +376,7 @@ int32_t qn_bfgs_optimize_batched_device_f64(qn_context* ctx, const qn_model* mod
     return fail(QN_ERR_INVALID_ARGUMENT, "ntrace > 0 needs trace_out");
   if (batch == 0) return QN_OK;
   QN_CUDA_TRY(cudaSetDevice(ctx->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  cudaStream_t st = (cudaStream_t)stream; // used literally: NULL is the CUDA default stream
 
   qn::BatchParams p{};
   p.n = n;

@@ -47,6 +47,35 @@ struct BatchParams {
   unsigned long long* counter; // persistent-grid work queue
 };
 
+// Rule C2: a row sum over K terms is cut into balanced blocks of
+// ceil(K / ceil(K/16)) <= 16 consecutive terms; one sequential FMA chain per block,
+// block partials added in ascending order (in super-blocks of 16 blocks for K > 256).
+__host__ __device__ constexpr int chain_block(int K) {
+  return K <= 0 ? 1 : (K + (K + 15) / 16 - 1) / ((K + 15) / 16);
+}
+
+// Blocked row sum of rule C2 for one row: term(r) returns the two fma operands through
+// references.  Handles the two-level (super-block) combine for any K.
+template <class F>
+__device__ __forceinline__ double chain_rowsum(int K, F&& term) {
+  const int rb = chain_block(K);
+  double T = 0.0, S = 0.0;
+  int blk = 0;
+  for (int r0 = 0; r0 < K; r0 += rb, ++blk) {
+    const int r1 = min(r0 + rb, K);
+    double t = 0.0;
+#pragma unroll 4
+    for (int r = r0; r < r1; ++r) {
+      double a, b;
+      term(r, a, b);
+      t = fma(a, b, t);
+    }
+    S = ((blk & 15) == 0) ? t : S + t;
+    if ((blk & 15) == 15 || r1 == K) T = (blk < 16) ? S : T + S;
+  }
+  return T;
+}
+
 // nanmin / nanmax, QN.jl:152-153
 __device__ __forceinline__ double nanmin(double a, double b) { return a < b ? a : (isnan(b) ? a : b); }
 __device__ __forceinline__ double nanmax(double a, double b) { return a < b ? b : (isnan(a) ? b : a); }

@@ -51,7 +51,7 @@ extern "C" int32_t qn_bfgs_optimize_batched_multi_f64(
         ctx, models[g], n, s.count, (const double*)(s.base + s.o_theta), n, ls, tol, max_iter,
         nullptr, 0, 0, (double*)(s.base + s.o_x), (double*)(s.base + s.o_g),
         (double*)(s.base + s.o_ell), (int32_t*)(s.base + s.o_it), (int32_t*)(s.base + s.o_fe),
-        (int32_t*)(s.base + s.o_st), 0, nullptr, flags, nullptr);
+        (int32_t*)(s.base + s.o_st), 0, nullptr, flags, ctx->stream);
     if (rc) return rc;
   }
   // phase 2: gather

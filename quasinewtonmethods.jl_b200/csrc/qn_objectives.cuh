@@ -23,6 +23,7 @@ namespace qn {
 struct Rosenbrock {
   struct Params {};
   static constexpr int kKind = QN_OBJ_ROSENBROCK;
+  static constexpr bool kRegisterPaths = true; // instantiate the register-resident kernels
   __host__ __device__ static int scratch_doubles(int, const Params&) { return 0; }
 
   template <bool GRAD>
@@ -63,6 +64,7 @@ struct DenseGaussian {
     const double* lambda; // n×n column-major, ld = n
   };
   static constexpr int kKind = QN_OBJ_DENSE_GAUSSIAN;
+  static constexpr bool kRegisterPaths = false; // n = 128 class: shared-memory-resident only
   __host__ __device__ static int scratch_doubles(int n, const Params&) { return (n + 31) & ~31; }
 
   template <bool GRAD>
@@ -78,16 +80,10 @@ struct DenseGaussian {
     double z = 0.0;
     if (c < n) {
       const double* row = p.lambda + c;
-      int r = 0;
-      for (; r + 4 <= n; r += 4) {
-        const double l0 = __ldg(row + (size_t)n * r), l1 = __ldg(row + (size_t)n * (r + 1));
-        const double l2 = __ldg(row + (size_t)n * (r + 2)), l3 = __ldg(row + (size_t)n * (r + 3));
-        z = fma(l0, ds[r], z);
-        z = fma(l1, ds[r + 1], z);
-        z = fma(l2, ds[r + 2], z);
-        z = fma(l3, ds[r + 3], z);
-      }
-      for (; r < n; ++r) z = fma(__ldg(row + (size_t)n * r), ds[r], z);
+      z = chain_rowsum(n, [&](int r, double& a, double& b) {
+        a = __ldg(row + (size_t)n * r);
+        b = ds[r];
+      });
     }
     const double q = t.csum(d * z, n);
     if (GRAD) g = -z;
@@ -108,6 +104,7 @@ struct Logistic {
     double lam;
   };
   static constexpr int kKind = QN_OBJ_LOGISTIC;
+  static constexpr bool kRegisterPaths = false;
   __host__ __device__ static int scratch_doubles(int, const Params& p) { return 2 * ((p.m + 31) & ~31); }
 
   __device__ __forceinline__ static double softplus(double z) {
@@ -126,10 +123,11 @@ struct Logistic {
     double* vs = t.scratch;                     // yᵢzᵢ - softplus(zᵢ)
     double* rs = t.scratch + ((m + 31) & ~31);  // yᵢ - σ(zᵢ)
     for (int i = c; i < m; i += nthr) {
-      double z = 0.0;
       const double* col = p.X + i;
-#pragma unroll 4
-      for (int j = 0; j < n; ++j) z = fma(__ldg(col + (size_t)m * j), t.xs[j], z);
+      const double z = chain_rowsum(n, [&](int j, double& a, double& b) {
+        a = __ldg(col + (size_t)m * j);
+        b = t.xs[j];
+      });
       const double yi = __ldg(p.y + i);
       vs[i] = yi * z - softplus(z);
       if (GRAD) rs[i] = yi - sigmoid(z);
@@ -144,17 +142,12 @@ struct Logistic {
     const double S = warp_butterfly(pp);
     const double ell = fma(-(0.5 * p.lam), pen, S);
     if (GRAD) {
-      double T = 0.0;
       if (c < n) {
-        // rule C2: chains of 256 rows, block partials added in ascending order
-        for (int i0 = 0; i0 < m; i0 += 256) {
-          const int i1 = (i0 + 256 < m) ? i0 + 256 : m;
-          double w = 0.0;
-          const double* col = p.Xt + c;
-#pragma unroll 4
-          for (int i = i0; i < i1; ++i) w = fma(__ldg(col + (size_t)n * i), rs[i], w);
-          T = (i0 == 0) ? w : T + w;
-        }
+        const double* col = p.Xt + c;
+        const double T = chain_rowsum(m, [&](int i, double& a, double& b) {
+          a = __ldg(col + (size_t)n * i);
+          b = rs[i];
+        });
         g = fma(-p.lam, th, T);
       }
     }

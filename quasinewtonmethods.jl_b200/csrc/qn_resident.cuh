@@ -1,17 +1,17 @@
-// qn_resident.cuh — the resident BFGS kernel: one CTA owns one problem for its
-// whole run (QN.jl:237-292 entirely on the device), B⁻¹ never leaves the SM.
+// qn_resident.cuh — resident BFGS kernels, thread-per-row layout: one CTA owns one
+// problem for its whole run (QN.jl:237-292 entirely on the device), B⁻¹ never leaves
+// the SM.
 //
 // Thread c owns element c of every vector and ROW c of B⁻¹ (the reference's
 // unit-stride index, QN.jl:48,61-62).  Two storage policies for the row:
 //
-//   NREG > 0  register-resident: n = NREG is a compile-time constant and the
-//             row lives in NREG fp64 registers (n = 60: 120 of the thread's
-//             registers).  B⁻¹ costs no shared-memory or HBM traffic at all; the
-//             only shared-memory reads of the two O(n²) passes are warp-wide
-//             BROADCASTS of the vectors.  Bound: the FP64 pipe.
+//   NREG > 0  register-resident, n = NREG compile-time, row in NREG fp64 registers.
+//             Used for small n (<= 32); for 33..64 the register-TILE kernel in
+//             qn_resident_tile.cuh is faster (it re-uses every shared-memory
+//             broadcast for four rows).
 //   NREG == 0 shared-memory-resident: runtime n, B⁻¹ in shared memory in the
-//             reference's own column-major layout H[c + n r]; a warp's access
-//             to one column is 32 consecutive doubles (conflict-free).
+//             reference's own column-major layout H[c + n r]; a warp's access to one
+//             column is 32 consecutive doubles (conflict-free).
 //             Bound: shared-memory bandwidth (24 n² bytes per iteration).
 //
 // The grid is persistent: gridDim = (#SMs × resident CTAs per SM) and CTAs pull
@@ -52,6 +52,75 @@ __host__ __device__ inline ResidentSmem resident_smem_layout(int n, bool h_in_sm
   return L;
 }
 
+// linesearch!  QN.jl:165-232.  Every thread of the team runs the same scalar code on
+// identical values, so control flow is uniform.  x, s: this thread's elements of
+// x_old and the search direction.  Returns α (0 = failure, QN.jl:193).
+template <class Obj>
+__device__ __forceinline__ double team_linesearch(Team& tm, const typename Obj::Params& op,
+                                                  const LsParams& ls, const double x,
+                                                  const double s, const double l0,
+                                                  const double m, int& fevals) {
+  double lx0 = l0, lx1 = l0;
+  double a1 = 1.0, a2 = 1.0;
+  double dummy;
+  // step!: x_new = x_old + α s (one fma, rule C3), then logdensity. QN.jl:157-162
+  tm.xs[tm.c] = fma(a1, s, x);
+  __syncthreads();
+  lx1 = Obj::template eval<false>(tm, op, dummy);
+  ++fevals;
+  int iterfinite = 0;
+  while (!isfinite(lx1) && iterfinite < 52) { // QN.jl:178-184
+    ++iterfinite;
+    a1 = a2;
+    a2 = 0.5 * a2;
+    tm.xs[tm.c] = fma(a2, s, x);
+    __syncthreads();
+    lx1 = Obj::template eval<false>(tm, op, dummy);
+    ++fevals;
+  }
+  long long iteration = 0;
+  while (!(lx1 >= fma(a2 * ls.c1, m, l0))) { // QN.jl:187
+    ++iteration;
+    if (iteration > ls.iterations) return 0.0; // QN.jl:193
+    double at;
+    if (ls.order == 2 || iteration == 1) {
+      at = -((m * a2) * a2) / (2.0 * fma(-m, a2, lx1 - l0)); // QN.jl:205
+    } else {
+      const double denom = 1.0 / ((((a1 * a1) * a2) * a2) * (a2 - a1)); // QN.jl:207
+      const double r1 = fma(-m, a2, lx1 - l0);
+      const double r0 = fma(-m, a1, lx0 - l0);
+      const double a = ((a1 * a1) * r1 - (a2 * a2) * r0) * denom;                    // QN.jl:208
+      const double b = ((((-a1) * a1) * a1) * r1 + ((a2 * a2) * a2) * r0) * denom;   // QN.jl:209
+      if (fabs(a) <= kEps + kSqrtTol * fabs(a)) {  // QN.jl:211
+        at = m / (2.0 * b);                        // QN.jl:212
+      } else {
+        const double d = nanmax(b * b - (3.0 * a) * m, 0.0); // QN.jl:215
+        at = (sqrt(d) + b) / (-3.0 * a);                     // QN.jl:218
+      }
+    }
+    a1 = a2;                           // QN.jl:222
+    at = nanmin(at, a2 * ls.rho_hi);   // QN.jl:224
+    a2 = nanmax(at, a2 * ls.rho_lo);   // QN.jl:225
+    lx0 = lx1;                         // QN.jl:228
+    tm.xs[tm.c] = fma(a2, s, x);
+    __syncthreads();
+    lx1 = Obj::template eval<false>(tm, op, dummy);
+    ++fevals;
+  }
+  return a2;
+}
+
+__device__ __forceinline__ void write_problem_scalars(const BatchParams& p, long long j, int c,
+                                                      double result, int iters, int fevals,
+                                                      int status) {
+  if (c == 0) {
+    if (p.ell_out) p.ell_out[j] = result;
+    if (p.iters_out) p.iters_out[j] = iters;
+    if (p.fevals_out) p.fevals_out[j] = fevals;
+    if (p.status_out) p.status_out[j] = status;
+  }
+}
+
 template <class Obj, int NREG>
 __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
                                                    const typename Obj::Params& op,
@@ -61,6 +130,7 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
   const int c = tm.c;
   const bool active = c < n;
   constexpr int HR = (NREG > 0) ? NREG : 1;
+  const int rb = chain_block(n); // rule C2 block length
   double h[HR]; // row c of B⁻¹ (register policy)
   (void)h; (void)hs;
 
@@ -96,66 +166,75 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
       // ---- BFGS_update!  QN.jl:34-69
       const double sy = tm.finish(n);  // sᵀy, QN.jl:39
       const double rho = 1.0 / sy;     // QN.jl:42 (no guard)
-      // pass 1: t = Σ_r y[r] H[c,r]   QN.jl:44-49, one chain per row (rule C2)
-      double t = 0.0;
+      // pass 1: T = Σ_r y[r] H[c,r]   QN.jl:44-49: block chains, partials added in order (rule C2)
+      double T = 0.0;
       if (NREG > 0) {
+        constexpr int RB = chain_block(HR);
 #pragma unroll
-        for (int r = 0; r + 1 < HR; r += 2) {
-          const double2 yy = *reinterpret_cast<const double2*>(ys + r);
-          t = fma(yy.x, h[r], t);
-          t = fma(yy.y, h[r + 1], t);
+        for (int r0 = 0; r0 < HR; r0 += RB) {
+          double t = 0.0;
+#pragma unroll
+          for (int r = r0; r < r0 + RB && r < HR; ++r) t = fma(ys[r], h[r], t);
+          T = (r0 == 0) ? t : T + t;
         }
-        if (HR & 1) t = fma(ys[HR - 1], h[HR - 1], t);
       } else if (active) {
         const double* hrow = hs + c;
-        int r = 0;
-        for (; r + 4 <= n; r += 4) {
-          const double h0 = hrow[n * r], h1 = hrow[n * (r + 1)];
-          const double h2 = hrow[n * (r + 2)], h3 = hrow[n * (r + 3)];
-          t = fma(ys[r], h0, t);
-          t = fma(ys[r + 1], h1, t);
-          t = fma(ys[r + 2], h2, t);
-          t = fma(ys[r + 3], h3, t);
+        for (int r0 = 0; r0 < n; r0 += rb) {
+          const int r1 = min(r0 + rb, n);
+          double t = 0.0;
+#pragma unroll 4
+          for (int r = r0; r < r1; ++r) t = fma(ys[r], hrow[n * r], t);
+          T = (r0 == 0) ? t : T + t;
         }
-        for (; r < n; ++r) t = fma(ys[r], hrow[n * r], t);
       }
-      const double u = t * rho;       // B⁻¹y[c] = t ρ, QN.jl:50
+      const double u = T * rho;       // B⁻¹y[c] = t ρ, QN.jl:50
       cols[c].nu = -u;
-      const double yHy = tm.csum(t * y, n);          // QN.jl:51
+      const double yHy = tm.csum(T * y, n);          // QN.jl:51
       const double c1 = fma(yHy, rho, 1.0) * rho;    // QN.jl:54
       cols[c].w = c1 * s;                            // (c₁ s[r]), rounded once per r (rule C4)
       __syncthreads();
       // pass 2: H ← H + c₁ssᵀ - usᵀ - suᵀ fused with d = H⁺∇_new   QN.jl:56-67
       const double nu_c = -u;
-      double acc = 0.0;
+      double D = 0.0;
       if (NREG > 0) {
+        constexpr int RB = chain_block(HR);
 #pragma unroll
-        for (int r = 0; r < HR; ++r) {
-          const double2 wn = *reinterpret_cast<const double2*>(&cols[r].w);
-          const double2 sg = *reinterpret_cast<const double2*>(&cols[r].s);
-          double hh = h[r];
-          hh = fma(wn.x, s, hh);   // + (c₁ s[r]) s[c]
-          hh = fma(wn.y, s, hh);   // - u[r] s[c]
-          hh = fma(nu_c, sg.x, hh);// - u[c] s[r]
-          h[r] = hh;
-          acc = fma(hh, sg.y, acc);
+        for (int r0 = 0; r0 < HR; r0 += RB) {
+          double acc = 0.0;
+#pragma unroll
+          for (int r = r0; r < r0 + RB && r < HR; ++r) {
+            const double2 wn = *reinterpret_cast<const double2*>(&cols[r].w);
+            const double2 sg = *reinterpret_cast<const double2*>(&cols[r].s);
+            double hh = h[r];
+            hh = fma(wn.x, s, hh);   // + (c₁ s[r]) s[c]
+            hh = fma(wn.y, s, hh);   // - u[r] s[c]
+            hh = fma(nu_c, sg.x, hh);// - u[c] s[r]
+            h[r] = hh;
+            acc = fma(hh, sg.y, acc);
+          }
+          D = (r0 == 0) ? acc : D + acc;
         }
       } else if (active) {
         double* hrow = hs + c;
+        for (int r0 = 0; r0 < n; r0 += rb) {
+          const int r1 = min(r0 + rb, n);
+          double acc = 0.0;
 #pragma unroll 4
-        for (int r = 0; r < n; ++r) {
-          const double2 wn = *reinterpret_cast<const double2*>(&cols[r].w);
-          const double2 sg = *reinterpret_cast<const double2*>(&cols[r].s);
-          double hh = hrow[n * r];
-          hh = fma(wn.x, s, hh);
-          hh = fma(wn.y, s, hh);
-          hh = fma(nu_c, sg.x, hh);
-          hrow[n * r] = hh;
-          acc = fma(hh, sg.y, acc);
+          for (int r = r0; r < r1; ++r) {
+            const double2 wn = *reinterpret_cast<const double2*>(&cols[r].w);
+            const double2 sg = *reinterpret_cast<const double2*>(&cols[r].s);
+            double hh = hrow[n * r];
+            hh = fma(wn.x, s, hh);
+            hh = fma(wn.y, s, hh);
+            hh = fma(nu_c, sg.x, hh);
+            hrow[n * r] = hh;
+            acc = fma(hh, sg.y, acc);
+          }
+          D = (r0 == 0) ? acc : D + acc;
         }
       }
-      m = tm.csum(acc * g, n); // m = dᵀ∇_new, QN.jl:66-68
-      s = acc;                 // the new direction; `s, y = y, s`, QN.jl:65,268
+      m = tm.csum(D * g, n); // m = dᵀ∇_new, QN.jl:66-68
+      s = D;                 // the new direction; `s, y = y, s`, QN.jl:65,268
     }
     if (m <= 0.0) { // QN.jl:272-280: H ← I, s ← ∇_new, m ← ∇ᵀ∇
       if (NREG > 0) {
@@ -168,60 +247,7 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
       m = tm.csum(g * g, n);
     }
 
-    // ---- linesearch!  QN.jl:165-232 (every thread runs the same scalar code)
-    double alpha;
-    {
-      const LsParams& ls = p.ls;
-      double lx0 = l0, lx1 = l0;
-      double a1 = 1.0, a2 = 1.0;
-      double dummy;
-      // step!: x_new = x_old + α s (one fma, rule C3), then logdensity. QN.jl:157-162
-      tm.xs[c] = fma(a1, s, x);
-      __syncthreads();
-      lx1 = Obj::template eval<false>(tm, op, dummy);
-      ++fevals;
-      int iterfinite = 0;
-      while (!isfinite(lx1) && iterfinite < 52) { // QN.jl:178-184
-        ++iterfinite;
-        a1 = a2;
-        a2 = 0.5 * a2;
-        tm.xs[c] = fma(a2, s, x);
-        __syncthreads();
-        lx1 = Obj::template eval<false>(tm, op, dummy);
-        ++fevals;
-      }
-      long long iteration = 0;
-      bool failed = false;
-      while (!(lx1 >= fma(a2 * ls.c1, m, l0))) { // QN.jl:187
-        ++iteration;
-        if (iteration > ls.iterations) { failed = true; break; } // QN.jl:193
-        double at;
-        if (ls.order == 2 || iteration == 1) {
-          at = -((m * a2) * a2) / (2.0 * fma(-m, a2, lx1 - l0)); // QN.jl:205
-        } else {
-          const double denom = 1.0 / ((((a1 * a1) * a2) * a2) * (a2 - a1)); // QN.jl:207
-          const double r1 = fma(-m, a2, lx1 - l0);
-          const double r0 = fma(-m, a1, lx0 - l0);
-          const double a = ((a1 * a1) * r1 - (a2 * a2) * r0) * denom;                    // QN.jl:208
-          const double b = ((((-a1) * a1) * a1) * r1 + ((a2 * a2) * a2) * r0) * denom;   // QN.jl:209
-          if (fabs(a) <= kEps + kSqrtTol * fabs(a)) {  // QN.jl:211
-            at = m / (2.0 * b);                        // QN.jl:212
-          } else {
-            const double d = nanmax(b * b - (3.0 * a) * m, 0.0); // QN.jl:215
-            at = (sqrt(d) + b) / (-3.0 * a);                     // QN.jl:218
-          }
-        }
-        a1 = a2;                           // QN.jl:222
-        at = nanmin(at, a2 * ls.rho_hi);   // QN.jl:224
-        a2 = nanmax(at, a2 * ls.rho_lo);   // QN.jl:225
-        lx0 = lx1;                         // QN.jl:228
-        tm.xs[c] = fma(a2, s, x);
-        __syncthreads();
-        lx1 = Obj::template eval<false>(tm, op, dummy);
-        ++fevals;
-      }
-      alpha = failed ? 0.0 : a2;
-    }
+    const double alpha = team_linesearch<Obj>(tm, op, p.ls, x, s, l0, m, fevals); // QN.jl:283
     if (alpha == 0.0) { status = QN_LINESEARCH_FAILED; break; } // QN.jl:284
     // update_state!: s ← αs ; x_old += s   QN.jl:21-27
     s = alpha * s;
@@ -246,12 +272,7 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
       }
     }
   }
-  if (c == 0) {
-    if (p.ell_out) p.ell_out[j] = result;
-    if (p.iters_out) p.iters_out[j] = iters;
-    if (p.fevals_out) p.fevals_out[j] = fevals;
-    if (p.status_out) p.status_out[j] = status;
-  }
+  write_problem_scalars(p, j, c, result, iters, fevals, status);
 }
 
 template <class Obj, int NREG, int BLOCK, int MINB>

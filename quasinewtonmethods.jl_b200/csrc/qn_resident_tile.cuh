@@ -1,0 +1,386 @@
+// qn_resident_tile.cuh — the register-TILE resident kernel (33 <= n <= 64; the n = 60
+// headline configuration runs here).
+//
+// Why tiles.  With one thread per row of B⁻¹ every step of the two O(n²) passes needs
+// the column operands (y[r]; c₁s[r], -u[r], s[r], ∇[r]) as warp-wide shared-memory
+// broadcasts, and each broadcast feeds ONE row per thread: 300 LDS.128 per problem
+// iteration against 300 DFMA.  On B200 a broadcast LDS.128 costs 2.14 SM-cycles and a
+// warp DFMA 2.24 SMSP-cycles (tools/ubench.cu, profiles/ubench_r1.txt), so that layout is
+// bound by the shared-memory pipe (ncu: 78 % of peak wavefronts, FP64 pipe 36 %).
+// Here a thread owns an RT×CT = 4×15 register tile of B⁻¹ (rows 4q..4q+3, columns of
+// block b), so every broadcast is re-used for four rows: 16 DFMA per pair of LDS.128.
+// The 16 lanes of a half-warp share a column block, and one LDS.128 serves one distinct
+// address per half-warp at no extra cost (measured), so a warp covers two column blocks.
+//
+// Summation order.  A row sum is the sum of its column-block chains — exactly rule C2
+// of the canonical order: block length CT = chain_block(n), partials
+// added in ascending block order.  The partials of a row live in NB different threads;
+// they meet in shared memory, and the reduction that follows (yᵀB⁻¹y, m) reads them
+// straight from there, so the exchange costs no extra barrier.
+//
+// Warp-replicated vectors.  Everything that is O(n) — x, ∇, s, y, the objective, the line
+// search, the dot products — is computed by BOTH warps redundantly, each warp holding
+// the whole vector as two elements per lane (element l in `lo`, element l+32 in `hi`,
+// which is exactly the accumulator layout of the canonical reduction, rule C1).  The
+// two warps therefore only meet at the four barriers around the two tile passes; the
+// objective evaluations of the line search need no barrier and no shared memory, and
+// reductions whose inputs are ready together (ℓ₀ with sᵀy; m with the first trial ℓ)
+// share one butterfly.
+#pragma once
+
+#include "qn_resident.cuh"
+
+namespace qn {
+
+// two elements of a length-n vector per lane: lo = v[lane], hi = v[lane + 32]
+struct Pair {
+  double lo, hi;
+};
+
+// butterfly of rule C1 for two independent sums at once (same latency as one)
+__device__ __forceinline__ void warp_butterfly2(double& a, double& b) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const double ta = __shfl_xor_sync(0xffffffffu, a, off);
+    const double tb = __shfl_xor_sync(0xffffffffu, b, off);
+    a = a + ta;
+    b = b + tb;
+  }
+}
+
+// Warp-level Rosenbrock (test/runtests.jl:4-33) on a replicated vector.  Lane i < N
+// evaluates pair i: θ1 = x[i] is its own `lo`; θ2 = x[i+N] comes from the lane that
+// holds it, by one 64-bit shuffle (each lane is asked for at most one of lo/hi
+// because N <= 32).  Returns this lane's term of the @simd sum (0 for lanes >= N);
+// the caller reduces it by rule C1.  With GRAD the gradient is returned replicated.
+template <int n, bool GRAD>
+__device__ __forceinline__ double rosenbrock_warp_terms(const int lane, const Pair x, Pair& g) {
+  constexpr int N = n >> 1;
+  static_assert(N <= 32 && n > 32, "pair partner must be reachable by one shuffle");
+  // lane `src` sends x[src] (lo) when that element is a θ2 (src >= N), else x[src+32]
+  const double send = (lane >= N) ? x.lo : x.hi;
+  const int src = (lane + N < 32) ? lane + N : lane + N - 32;
+  const double t2 = __shfl_sync(0xffffffffu, send, src);
+  const double t1 = x.lo;
+  const double a = t2 - t1 * t1;
+  const double b = 1.0 - t1;
+  const double term = (lane < N) ? 100.0 * (a * a) + b * b : 0.0; // runtests.jl:9,23
+  if (GRAD) {
+    const double g1 = (400.0 * a) * t1 + 2.0 * b; // ∇[i],   runtests.jl:24
+    const double g2 = 200.0 * (t1 * t1 - t2);     // ∇[i+N], runtests.jl:25
+    // element e = i+N lives in lane src(i); send g2 back along the same route
+    const int back = (lane >= N) ? lane - N : lane + 32 - N; // the pair index whose θ2 I hold
+    const double r = __shfl_sync(0xffffffffu, g2, back & 31);
+    g.lo = (lane < N) ? g1 : r;                    // lanes >= N hold a θ2 in lo
+    g.hi = r;                                      // lanes <  N hold a θ2 (or nothing) in hi
+    if (n & 1) {                                   // tail element n-1 = 2N, runtests.jl:27-31
+      const double tail = 2.0 * (1.0 - ((2 * N < 32) ? x.lo : x.hi));
+      if (2 * N < 32) { if (lane == 2 * N) g.lo = tail; }
+      else { if (lane == 2 * N - 32) g.hi = tail; }
+    }
+  }
+  return term;
+}
+
+// finish ℓ from the reduced sum of terms: s = 0 - Σ; odd n adds the tail (runtests.jl:11-16)
+template <int n>
+__device__ __forceinline__ double rosenbrock_finish(const double sum, const Pair x) {
+  double s = 0.0 - sum;
+  if (n & 1) {
+    constexpr int N = n >> 1;
+    const double xt = __shfl_sync(0xffffffffu, (2 * N < 32) ? x.lo : x.hi, (2 * N) & 31);
+    const double d = 1.0 - xt;
+    s = -fma(d, d, -s);
+  }
+  return s;
+}
+
+template <int N>
+struct TileCfg {
+  static constexpr int RT = 4;                       // rows per thread
+  static constexpr int CT = chain_block(N);          // columns per thread = rule-C2 block
+  static constexpr int NB = (N + CT - 1) / CT;       // column blocks (<= 4)
+  static constexpr int NG = (N + RT - 1) / RT;       // row groups (<= 16)
+  static constexpr int BLOCK = 64;                   // 4 half-warps
+  static constexpr bool kFull = (N % CT == 0);       // every column block is CT wide
+  static_assert(N > 32 && N <= 64, "tile kernel covers 33..64");
+  static_assert(NB <= 4 && NG <= 16, "tile grid must fit four half-warps");
+  // shared memory (doubles); block-padded arrays hold element e at (e / CT) * 16 + e % CT
+  static constexpr int oWN = 0;                      // {c₁s, -u}[NB][16]   (double2)
+  static constexpr int oSG = oWN + 2 * 64;           // {s, ∇}[NB][16]      (double2)
+  static constexpr int oYsp = oSG + 2 * 64;          // y[NB][16]
+  static constexpr int oS = oYsp + 64;               // s by element (row operands)
+  static constexpr int oNu = oS + 64;                // -u by element
+  static constexpr int oPart = oNu + 64;             // block partials [4][64]
+  static constexpr int oEnd = oPart + 4 * 64;
+};
+
+template <int N>
+__host__ __device__ constexpr int tile_smem_doubles() { return TileCfg<N>::oEnd + 2; }
+
+template <int N>
+__device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long long j, double* smem) {
+  using C = TileCfg<N>;
+  constexpr int RT = C::RT, CT = C::CT, NB = C::NB;
+  const int t = threadIdx.x;
+  const int lane = t & 31;
+  const int warp = t >> 5;
+  const int e = t;                    // the element this thread publishes / writes out
+  const bool owner = e < N;
+  const bool hi_valid = lane + 32 < N;
+  const int b = t >> 4;               // column block of this thread's tile (one per half-warp)
+  const int q = t & 15;               // row group
+  const int row0 = RT * q;
+  const int col0 = CT * b;
+  const int slot = (e / CT) * 16 + (e % CT);
+
+  double2* WN = reinterpret_cast<double2*>(smem + C::oWN);
+  double2* SG = reinterpret_cast<double2*>(smem + C::oSG);
+  double* ysp = smem + C::oYsp;
+  double* s_arr = smem + C::oS;
+  double* nu_arr = smem + C::oNu;
+  double* part = smem + C::oPart;
+
+  double h[RT][CT]; // the tile: h[i][k] = B⁻¹[row0 + i, col0 + k]
+
+  auto mine = [&](const Pair& v) { return warp ? v.hi : v.lo; }; // element e of a replicated vector
+  auto dot = [&](const Pair& a, const Pair& bb) {                // lane accumulator of rule C1
+    double pacc = a.lo * bb.lo;
+    if (hi_valid) pacc = pacc + a.hi * bb.hi;
+    return pacc;
+  };
+  // Σ_b part[b][e'] in ascending block order (rule C2), for e' = lane and lane+32
+  auto combine = [&]() {
+    Pair T;
+    T.lo = part[lane];
+#pragma unroll
+    for (int bb = 1; bb < NB; ++bb) T.lo = T.lo + part[bb * 64 + lane];
+    T.hi = 0.0;
+    if (hi_valid) {
+      T.hi = part[lane + 32];
+#pragma unroll
+      for (int bb = 1; bb < NB; ++bb) T.hi = T.hi + part[bb * 64 + lane + 32];
+    }
+    return T;
+  };
+
+  Pair x, g, gp, s;
+  {
+    const double* th = p.theta0 + j * p.theta_stride; // copyto!(x_old, x), QN.jl:248
+    x.lo = th[lane];
+    x.hi = hi_valid ? th[lane + 32] : 0.0;
+  }
+  g.lo = g.hi = gp.lo = gp.hi = s.lo = s.hi = 0.0;
+  double result = __longlong_as_double(0x7ff8000000000000LL); // NaN, QN.jl:291
+  int iters = 0, fevals = 0, status = QN_MAX_ITER;
+
+  for (int it = 1; it <= p.max_iter; ++it) { // QN.jl:250,253
+    // ---- ℓ₀ = ∂logdensity!(∇_new, obj, x_old)  QN.jl:254, fused with y and sᵀy (QN.jl:36-41)
+    double term = rosenbrock_warp_terms<N, true>(lane, x, g);
+    Pair y;
+    y.lo = gp.lo - g.lo;
+    y.hi = gp.hi - g.hi;
+    double sy = dot(s, y);
+    warp_butterfly2(term, sy);
+    const double l0 = rosenbrock_finish<N>(term, x);
+    ++fevals;
+    if (!isfinite(l0)) { status = QN_NONFINITE; break; } // QN.jl:255
+    // maximum(abs, ∇_new) < tol, QN.jl:257 (a NaN entry makes it false)
+    const bool small = fabs(g.lo) < p.tol && (!hi_valid || fabs(g.hi) < p.tol);
+    if (__all_sync(0xffffffffu, small)) { status = QN_CONVERGED; result = l0; break; } // QN.jl:258-261
+
+    double m;
+    double lx1 = 0.0; // ℓ(x + s) of the first line-search trial (reduced together with m)
+    if (it == 1) {
+      m = -1.0; // QN.jl:263-264
+    } else {
+      // ---- BFGS_update!  QN.jl:34-69
+      if (owner) {
+        ysp[slot] = mine(y);
+        s_arr[e] = mine(s);
+        SG[slot] = make_double2(mine(s), mine(g));
+      }
+      __syncthreads(); // (a) operands of pass 1 visible; previous readers of `part` are done
+      const double rho = 1.0 / sy; // QN.jl:42 (no guard)
+      // pass 1 on the tile: t[i] = Σ_k y[col0+k] H[row0+i, col0+k]   QN.jl:44-49
+      {
+        double tt[RT];
+#pragma unroll
+        for (int i = 0; i < RT; ++i) tt[i] = 0.0;
+        const double2* yb = reinterpret_cast<const double2*>(ysp + b * 16);
+        double2 yy[(CT + 1) / 2];
+#pragma unroll
+        for (int k2 = 0; k2 < (CT + 1) / 2; ++k2) yy[k2] = yb[k2];
+#pragma unroll
+        for (int k = 0; k < CT; ++k) {
+          const double yk = (k & 1) ? yy[k >> 1].y : yy[k >> 1].x;
+          if (C::kFull || col0 + k < N) {
+#pragma unroll
+            for (int i = 0; i < RT; ++i) tt[i] = fma(yk, h[i][k], tt[i]);
+          }
+        }
+        double2* pp = reinterpret_cast<double2*>(part + b * 64 + row0);
+        pp[0] = make_double2(tt[0], tt[1]);
+        pp[1] = make_double2(tt[2], tt[3]);
+      }
+      __syncthreads(); // (b) pass-1 partials visible
+      const Pair T = combine();
+      const double yHy = warp_butterfly(dot(T, y));  // Σ_c t[c] y[c], QN.jl:51
+      const double c1 = fma(yHy, rho, 1.0) * rho;    // QN.jl:54
+      if (owner) {
+        const double nu = -(mine(T) * rho);          // -B⁻¹y[c] = -(t ρ), QN.jl:50
+        nu_arr[e] = nu;
+        WN[slot] = make_double2(c1 * mine(s), nu);   // (c₁ s[r]) rounded once per r (rule C4)
+      }
+      __syncthreads(); // (c) operands of pass 2 visible; pass-1 partials consumed
+      // pass 2 on the tile: H ← H + c₁ssᵀ - usᵀ - suᵀ fused with d = H⁺∇_new   QN.jl:56-67
+      {
+        double sc[RT], nuc[RT], acc[RT];
+        const double2 s01 = *reinterpret_cast<const double2*>(s_arr + row0);
+        const double2 s23 = *reinterpret_cast<const double2*>(s_arr + row0 + 2);
+        const double2 n01 = *reinterpret_cast<const double2*>(nu_arr + row0);
+        const double2 n23 = *reinterpret_cast<const double2*>(nu_arr + row0 + 2);
+        sc[0] = s01.x; sc[1] = s01.y; sc[2] = s23.x; sc[3] = s23.y;
+        nuc[0] = n01.x; nuc[1] = n01.y; nuc[2] = n23.x; nuc[3] = n23.y;
+#pragma unroll
+        for (int i = 0; i < RT; ++i) acc[i] = 0.0;
+        const double2* wnb = WN + b * 16;
+        const double2* sgb = SG + b * 16;
+        double2 wn = wnb[0], sg = sgb[0];
+#pragma unroll
+        for (int k = 0; k < CT; ++k) {
+          double2 wn_next = wn, sg_next = sg;
+          if (k + 1 < CT) { wn_next = wnb[k + 1]; sg_next = sgb[k + 1]; } // one step ahead
+          if (C::kFull || col0 + k < N) {
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+              double hh = h[i][k];
+              hh = fma(wn.x, sc[i], hh);   // + (c₁ s[r]) s[c]
+              hh = fma(wn.y, sc[i], hh);   // - u[r] s[c]
+              hh = fma(nuc[i], sg.x, hh);  // - u[c] s[r]
+              h[i][k] = hh;
+              acc[i] = fma(hh, sg.y, acc[i]);
+            }
+          }
+          wn = wn_next;
+          sg = sg_next;
+        }
+        double2* pp = reinterpret_cast<double2*>(part + b * 64 + row0);
+        pp[0] = make_double2(acc[0], acc[1]);
+        pp[1] = make_double2(acc[2], acc[3]);
+      }
+      __syncthreads(); // (d) pass-2 partials visible
+      s = combine();   // the new direction d = H⁺∇_new; `s, y = y, s`, QN.jl:65,268
+      // m = dᵀ∇_new (QN.jl:66-68) shares its butterfly with the first trial of the line
+      // search, ℓ(x + 1·d) (QN.jl:174), whose inputs are ready at the same time.
+      Pair xn, gdummy;
+      xn.lo = fma(1.0, s.lo, x.lo);
+      xn.hi = fma(1.0, s.hi, x.hi);
+      double tterm = rosenbrock_warp_terms<N, false>(lane, xn, gdummy);
+      m = dot(s, g);
+      warp_butterfly2(m, tterm);
+      lx1 = rosenbrock_finish<N>(tterm, xn);
+    }
+    const bool reset = (m <= 0.0);
+    if (reset) { // QN.jl:272-280: H ← I, s ← ∇_new, m ← ∇ᵀ∇
+#pragma unroll
+      for (int i = 0; i < RT; ++i)
+#pragma unroll
+        for (int k = 0; k < CT; ++k) h[i][k] = (row0 + i == col0 + k) ? 1.0 : 0.0;
+      s = g;
+      m = warp_butterfly(dot(g, g));
+    }
+
+    // ---- linesearch!  QN.jl:165-232; both warps run the same scalar code on the same values
+    double alpha;
+    {
+      const LsParams& ls = p.ls;
+      auto trial = [&](const double a) { // step! (QN.jl:157-162): x_new = x_old + a s, one fma each
+        Pair xn, gdummy;
+        xn.lo = fma(a, s.lo, x.lo);
+        xn.hi = fma(a, s.hi, x.hi);
+        const double sum = warp_butterfly(rosenbrock_warp_terms<N, false>(lane, xn, gdummy));
+        ++fevals;
+        return rosenbrock_finish<N>(sum, xn);
+      };
+      double lx0 = l0;
+      double a1 = 1.0, a2 = 1.0;
+      if (it == 1 || reset) lx1 = trial(a1); // otherwise already evaluated above
+      else ++fevals;
+      int iterfinite = 0;
+      while (!isfinite(lx1) && iterfinite < 52) { // QN.jl:178-184
+        ++iterfinite;
+        a1 = a2;
+        a2 = 0.5 * a2;
+        lx1 = trial(a2);
+      }
+      long long iteration = 0;
+      bool failed = false;
+      while (!(lx1 >= fma(a2 * ls.c1, m, l0))) { // QN.jl:187
+        ++iteration;
+        if (iteration > ls.iterations) { failed = true; break; } // QN.jl:193
+        double at;
+        if (ls.order == 2 || iteration == 1) {
+          at = -((m * a2) * a2) / (2.0 * fma(-m, a2, lx1 - l0)); // QN.jl:205
+        } else {
+          const double denom = 1.0 / ((((a1 * a1) * a2) * a2) * (a2 - a1)); // QN.jl:207
+          const double r1 = fma(-m, a2, lx1 - l0);
+          const double r0 = fma(-m, a1, lx0 - l0);
+          const double a = ((a1 * a1) * r1 - (a2 * a2) * r0) * denom;                   // QN.jl:208
+          const double bq = ((((-a1) * a1) * a1) * r1 + ((a2 * a2) * a2) * r0) * denom; // QN.jl:209
+          if (fabs(a) <= kEps + kSqrtTol * fabs(a)) {  // QN.jl:211
+            at = m / (2.0 * bq);                       // QN.jl:212
+          } else {
+            const double d = nanmax(bq * bq - (3.0 * a) * m, 0.0); // QN.jl:215
+            at = (sqrt(d) + bq) / (-3.0 * a);                      // QN.jl:218
+          }
+        }
+        a1 = a2;                           // QN.jl:222
+        at = nanmin(at, a2 * ls.rho_hi);   // QN.jl:224
+        a2 = nanmax(at, a2 * ls.rho_lo);   // QN.jl:225
+        lx0 = lx1;                         // QN.jl:228
+        lx1 = trial(a2);
+      }
+      alpha = failed ? 0.0 : a2;
+    }
+    if (alpha == 0.0) { status = QN_LINESEARCH_FAILED; break; } // QN.jl:284
+    // update_state!: s ← αs ; x_old += s   QN.jl:21-27
+    s.lo = alpha * s.lo; s.hi = alpha * s.hi;
+    x.lo = x.lo + s.lo;  x.hi = x.hi + s.hi;
+    gp = g; // ∇_old, ∇_new = ∇_new, ∇_old, QN.jl:286
+    ++iters;
+    if (p.trace != nullptr && it <= p.ntrace && owner)
+      p.trace[(j * p.ntrace + (it - 1)) * (long long)N + e] = mine(x);
+  }
+
+  if (owner) {
+    if (p.x_out) p.x_out[j * p.x_stride + e] = mine(x);
+    if (p.g_out) p.g_out[j * p.g_stride + e] = mine(g);
+  }
+  if (p.h_out && b < NB) {
+    double* ho = p.h_out + j * p.h_stride;
+#pragma unroll
+    for (int i = 0; i < RT; ++i)
+#pragma unroll
+      for (int k = 0; k < CT; ++k)
+        if (row0 + i < N && col0 + k < N) ho[(row0 + i) + (long long)p.ldh * (col0 + k)] = h[i][k];
+  }
+  write_problem_scalars(p, j, t, result, iters, fevals, status);
+}
+
+template <int N, int MINB>
+__global__ void __launch_bounds__(64, MINB)
+qn_resident_tile_kernel(const BatchParams p) {
+  extern __shared__ __align__(16) double smem[];
+  volatile long long* next = reinterpret_cast<volatile long long*>(smem + tile_smem_doubles<N>() - 2);
+  for (;;) {
+    __syncthreads(); // the previous problem's shared-memory traffic is finished
+    if (threadIdx.x == 0) *next = (long long)atomicAdd(p.counter, 1ULL);
+    __syncthreads();
+    const long long j = *next;
+    if (j >= p.batch) break;
+    tile_solve_one<N>(p, j, smem);
+  }
+}
+
+}  // namespace qn
