@@ -86,10 +86,10 @@ int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Par
 
 // The register-tile kernel evaluates the objective warp-locally; only Rosenbrock has
 // that form (qn_resident_tile.cuh).
-template <int N, int MINB>
+template <int N, int MINB, int PF>
 int launch_tile(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
   const size_t smem = sizeof(double) * (size_t)qn::tile_smem_doubles<N>();
-  auto kern = qn::qn_resident_tile_kernel<N, MINB>;
+  auto kern = qn::qn_resident_tile_kernel<N, MINB, PF>;
   int occ = 0;
   QN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 64, smem));
   if (occ < 1) return fail(QN_ERR_UNSUPPORTED_SIZE, "tile kernel does not fit on an SM (n=%d)", N);
@@ -117,7 +117,12 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
   case N: return launch_resident<Obj, N, BLOCK, MINB>(ctx, p, op, st);
 #define QN_TILE_CASE(N, MINB) \
   case N:                      \
-    if constexpr (std::is_same<Obj, qn::Rosenbrock>::value) return launch_tile<N, MINB>(ctx, p, st); \
+    if constexpr (std::is_same<Obj, qn::Rosenbrock>::value) {                                        \
+      const char* v = getenv("QN_TILE_VARIANT"); /* tuning knob, see DESIGN.md §5 */                 \
+      if (v && v[0] == '5') return launch_tile<N, 5, 2>(ctx, p, st);                                 \
+      if (v && v[0] == '4') return launch_tile<N, 4, 3>(ctx, p, st);                                 \
+      return launch_tile<N, MINB, 1>(ctx, p, st);                                                    \
+    }                                                                                                \
     break;
 #include "qn_reg_sizes.inc"
 #undef QN_REG_CASE

@@ -22,26 +22,25 @@ __global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, doubl
   if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-// conflict-free LDS.128: lane l of a warp reads the 16 bytes at (base + l)*16, so
-// a warp request is 512 consecutive bytes = 4 wavefronts of 128 B.  The window
-// base moves every load so nothing can be hoisted out of the loop.
+// conflict-free LDS.128: lane l of a warp reads the 16 bytes at (window + l)*16, so a warp
+// request is 512 consecutive bytes = 4 wavefronts of 128 B.  The window moves with every
+// load and with the loop counter, so nothing can be hoisted or folded (same pattern as
+// tools/ubench.cu, which measured 4.01 SM-cycles per such load = 127.6 B/clk/SM).
 __global__ void __launch_bounds__(256) lds_kernel(double* out, int iters) {
-  __shared__ __align__(16) double buf[4096];
-  for (int i = threadIdx.x; i < 4096; i += blockDim.x) buf[i] = (double)i;
+  __shared__ __align__(16) unsigned char buf[16384];
+  for (int i = threadIdx.x; i < 16384 / 4; i += blockDim.x) reinterpret_cast<int*>(buf)[i] = i;
   __syncthreads();
-  const double2* p = reinterpret_cast<const double2*>(buf);
+  const unsigned off = (threadIdx.x & 31) * 16;
   long long bits = 0;
-  int base = threadIdx.x;
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const double2 v = p[base & 2047];
-      base += 256 + 32 * (k & 1);
-      // integer xor keeps the loads alive without touching the FP64 pipe
-      bits ^= __double_as_longlong(v.x) ^ __double_as_longlong(v.y);
+    for (int k = 0; k < 16; ++k) {
+      const unsigned a = (off + (unsigned)(k * 528 + i * 16)) & (16384 - 16);
+      const longlong2 v = *reinterpret_cast<const longlong2*>(buf + a);
+      bits ^= v.x ^ v.y; // integer xor keeps the loads alive without touching the FP64 pipe
     }
   }
-  if (bits == 0x123456789LL) out[blockIdx.x * blockDim.x + threadIdx.x] = (double)bits;
+  if (bits == 0x1234567) out[blockIdx.x * blockDim.x + threadIdx.x] = (double)bits;
 }
 
 __global__ void __launch_bounds__(256) copy_kernel(const double2* __restrict__ src,
@@ -91,14 +90,14 @@ extern "C" int32_t qn_microbench_dfma(qn_context* ctx, double* tflops) {
 extern "C" int32_t qn_microbench_lds(qn_context* ctx, double* gbs) {
   if (!ctx || !gbs) return qn_fail(QN_ERR_INVALID_ARGUMENT, "NULL argument");
   QN_CUDA_TRY(cudaSetDevice(ctx->device));
-  const int grid = ctx->prop.multiProcessorCount * 6, block = 256, iters = 4096;
+  const int grid = ctx->prop.multiProcessorCount * 8, block = 256, iters = 2048;
   double* out = nullptr;
   QN_CUDA_TRY(cudaMalloc(&out, sizeof(double) * grid * block));
   float ms = 0;
   int rc = time_best(ctx->stream, 5, &ms, [&] { lds_kernel<<<grid, block, 0, ctx->stream>>>(out, iters); });
   cudaFree(out);
   if (rc) return rc;
-  const double bytes = (double)grid * block * iters * 8.0 * 16.0;
+  const double bytes = (double)grid * block * iters * 16.0 * 16.0;
   *gbs = bytes / (ms * 1e-3) / 1e9;
   return QN_OK;
 }

@@ -32,6 +32,16 @@
 
 namespace qn {
 
+// Optional per-phase cycle accounting (build with -DQN_PHASE_TIMING; tools/phase_timing.py).
+#ifdef QN_PHASE_TIMING
+__device__ unsigned long long g_phase_clk[16];
+#define QN_TICK(k) do { const long long _t = clock64(); if (threadIdx.x == 0 && blockIdx.x == 0) g_phase_clk[k] += (unsigned long long)(_t - _tprev); _tprev = _t; } while (0)
+#define QN_TICK_INIT long long _tprev = clock64()
+#else
+#define QN_TICK(k) do { } while (0)
+#define QN_TICK_INIT do { } while (0)
+#endif
+
 // two elements of a length-n vector per lane: lo = v[lane], hi = v[lane + 32]
 struct Pair {
   double lo, hi;
@@ -118,7 +128,7 @@ struct TileCfg {
 template <int N>
 __host__ __device__ constexpr int tile_smem_doubles() { return TileCfg<N>::oEnd + 2; }
 
-template <int N>
+template <int N, int PF>
 __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long long j, double* smem) {
   using C = TileCfg<N>;
   constexpr int RT = C::RT, CT = C::CT, NB = C::NB;
@@ -174,7 +184,9 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
   double result = __longlong_as_double(0x7ff8000000000000LL); // NaN, QN.jl:291
   int iters = 0, fevals = 0, status = QN_MAX_ITER;
 
+  QN_TICK_INIT;
   for (int it = 1; it <= p.max_iter; ++it) { // QN.jl:250,253
+    QN_TICK(0);
     // ---- ℓ₀ = ∂logdensity!(∇_new, obj, x_old)  QN.jl:254, fused with y and sᵀy (QN.jl:36-41)
     double term = rosenbrock_warp_terms<N, true>(lane, x, g);
     Pair y;
@@ -188,6 +200,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
     // maximum(abs, ∇_new) < tol, QN.jl:257 (a NaN entry makes it false)
     const bool small = fabs(g.lo) < p.tol && (!hi_valid || fabs(g.hi) < p.tol);
     if (__all_sync(0xffffffffu, small)) { status = QN_CONVERGED; result = l0; break; } // QN.jl:258-261
+    QN_TICK(1);
 
     double m;
     double lx1 = 0.0; // ℓ(x + s) of the first line-search trial (reduced together with m)
@@ -201,6 +214,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
         SG[slot] = make_double2(mine(s), mine(g));
       }
       __syncthreads(); // (a) operands of pass 1 visible; previous readers of `part` are done
+      QN_TICK(2);
       const double rho = 1.0 / sy; // QN.jl:42 (no guard)
       // pass 1 on the tile: t[i] = Σ_k y[col0+k] H[row0+i, col0+k]   QN.jl:44-49
       {
@@ -224,6 +238,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
         pp[1] = make_double2(tt[2], tt[3]);
       }
       __syncthreads(); // (b) pass-1 partials visible
+      QN_TICK(3);
       const Pair T = combine();
       const double yHy = warp_butterfly(dot(T, y));  // Σ_c t[c] y[c], QN.jl:51
       const double c1 = fma(yHy, rho, 1.0) * rho;    // QN.jl:54
@@ -233,6 +248,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
         WN[slot] = make_double2(c1 * mine(s), nu);   // (c₁ s[r]) rounded once per r (rule C4)
       }
       __syncthreads(); // (c) operands of pass 2 visible; pass-1 partials consumed
+      QN_TICK(4);
       // pass 2 on the tile: H ← H + c₁ssᵀ - usᵀ - suᵀ fused with d = H⁺∇_new   QN.jl:56-67
       {
         double sc[RT], nuc[RT], acc[RT];
@@ -246,11 +262,15 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
         for (int i = 0; i < RT; ++i) acc[i] = 0.0;
         const double2* wnb = WN + b * 16;
         const double2* sgb = SG + b * 16;
-        double2 wn = wnb[0], sg = sgb[0];
+        // operand ring: the loads of step k+PF are issued while step k computes, so the
+        // ~35-cycle shared-memory latency is covered by PF steps of 16 DFMA each
+        double2 wnr[PF + 1], sgr[PF + 1];
+#pragma unroll
+        for (int k = 0; k < PF && k < CT; ++k) { wnr[k] = wnb[k]; sgr[k] = sgb[k]; }
 #pragma unroll
         for (int k = 0; k < CT; ++k) {
-          double2 wn_next = wn, sg_next = sg;
-          if (k + 1 < CT) { wn_next = wnb[k + 1]; sg_next = sgb[k + 1]; } // one step ahead
+          if (k + PF < CT) { wnr[(k + PF) % (PF + 1)] = wnb[k + PF]; sgr[(k + PF) % (PF + 1)] = sgb[k + PF]; }
+          const double2 wn = wnr[k % (PF + 1)], sg = sgr[k % (PF + 1)];
           if (C::kFull || col0 + k < N) {
 #pragma unroll
             for (int i = 0; i < RT; ++i) {
@@ -262,14 +282,13 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
               acc[i] = fma(hh, sg.y, acc[i]);
             }
           }
-          wn = wn_next;
-          sg = sg_next;
         }
         double2* pp = reinterpret_cast<double2*>(part + b * 64 + row0);
         pp[0] = make_double2(acc[0], acc[1]);
         pp[1] = make_double2(acc[2], acc[3]);
       }
       __syncthreads(); // (d) pass-2 partials visible
+      QN_TICK(5);
       s = combine();   // the new direction d = H⁺∇_new; `s, y = y, s`, QN.jl:65,268
       // m = dᵀ∇_new (QN.jl:66-68) shares its butterfly with the first trial of the line
       // search, ℓ(x + 1·d) (QN.jl:174), whose inputs are ready at the same time.
@@ -280,6 +299,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
       m = dot(s, g);
       warp_butterfly2(m, tterm);
       lx1 = rosenbrock_finish<N>(tterm, xn);
+      QN_TICK(6);
     }
     const bool reset = (m <= 0.0);
     if (reset) { // QN.jl:272-280: H ← I, s ← ∇_new, m ← ∇ᵀ∇
@@ -343,6 +363,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
       }
       alpha = failed ? 0.0 : a2;
     }
+    QN_TICK(7);
     if (alpha == 0.0) { status = QN_LINESEARCH_FAILED; break; } // QN.jl:284
     // update_state!: s ← αs ; x_old += s   QN.jl:21-27
     s.lo = alpha * s.lo; s.hi = alpha * s.hi;
@@ -368,7 +389,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
   write_problem_scalars(p, j, t, result, iters, fevals, status);
 }
 
-template <int N, int MINB>
+template <int N, int MINB, int PF>
 __global__ void __launch_bounds__(64, MINB)
 qn_resident_tile_kernel(const BatchParams p) {
   extern __shared__ __align__(16) double smem[];
@@ -379,7 +400,7 @@ qn_resident_tile_kernel(const BatchParams p) {
     __syncthreads();
     const long long j = *next;
     if (j >= p.batch) break;
-    tile_solve_one<N>(p, j, smem);
+    tile_solve_one<N, PF>(p, j, smem);
   }
 }
 

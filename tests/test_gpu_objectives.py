@@ -1,0 +1,105 @@
+"""BASELINE.json configs[2]: dense-Gaussian and logistic-regression objectives (n = 128, B⁻¹ =
+128 KB in shared memory).  The reference ships neither objective; both are defined by
+this build with their own oracle in oracle/qn_oracle.c.
+
+Gaussian: every operation is +, x or fma, so GPU == oracle bit for bit.
+Logistic: exp/log1p come from two different math libraries (CUDA vs glibc), so parity is to a
+tolerance: objective values 1e-12 relative, gradients 1e-11, optimum 1e-8 (the north-star gate).
+"""
+import numpy as np
+import pytest
+
+from conftest import starts
+from problems import gaussian_problem, logistic_problem
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n", [5, 60, 128])
+def test_gaussian_objective_and_solve(eng, qn, ob, n):
+    mu, lam = gaussian_problem(n)
+    model = qn.DenseGaussian(mu, lam)
+    omodel = ob.OracleModel(ob.DENSE_GAUSSIAN, mu=mu, lam=lam)
+    Th = starts(n, 17, key=n)
+    ell, g = eng.logdensity_batched(model, Th, grad=True)
+    for j in range(Th.shape[1]):
+        v, gr = ob.dlogdensity(omodel, Th[:, j])
+        assert v == ell[j] and np.array_equal(gr, g[:, j])
+    # numpy cross-check of the definition itself
+    d = Th - mu[:, None]
+    assert np.allclose(ell, -0.5 * np.einsum("ij,ij->j", d, lam @ d), rtol=1e-12)
+    assert np.allclose(g, -(lam @ d), rtol=1e-11, atol=1e-12)
+    batch = 24
+    Theta = starts(n, batch, key=3 * n)
+    got = eng.optimize_batched(model, Theta, ntrace=5)
+    ref = ob.optimize_batch(omodel, Theta, ntrace=5)
+    assert eng.last_launch()["path"] == qn._lib.PATH_SMEM
+    for k in ("x", "g", "ell", "trace"):
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+    assert np.array_equal(got["iters"], ref["iters"]) and np.array_equal(got["status"], ref["status"])
+    assert (got["status"] == qn.CONVERGED).all()
+    assert np.abs(got["x"] - mu[:, None]).max() < 1e-7  # the maximiser of a Gaussian is μ
+    print("gaussian n=%d: iterations mean %.1f" % (n, got["iters"].mean()))
+
+
+@pytest.mark.parametrize("m,n", [(64, 7), (1024, 128)])
+def test_logistic_objective_and_solve(eng, qn, ob, m, n):
+    X, y, lam = logistic_problem(m, n)
+    model = qn.LogisticRegression(X, y, lam)
+    omodel = ob.OracleModel(ob.LOGISTIC, X=X, y=y, lam=lam)
+    Th = starts(n, 9, key=n)
+    ell, g = eng.logdensity_batched(model, Th, grad=True)
+    for j in range(Th.shape[1]):
+        v, gr = ob.dlogdensity(omodel, Th[:, j])
+        assert abs(v - ell[j]) <= 1e-12 * abs(v)
+        assert np.allclose(gr, g[:, j], rtol=1e-11, atol=1e-12)
+    batch = 16
+    Theta = starts(n, batch, key=5 * n)
+    got = eng.optimize_batched(model, Theta, ntrace=5)
+    ref = ob.optimize_batch(omodel, Theta, ntrace=5)
+    # |ℓ| ≈ 600 here, so once |∇| < ~1e-6 the Armijo test (QN.jl:187) compares differences below
+    # the rounding noise of ℓ itself: with tol = 1e-8 the reference algorithm ends some starts
+    # with a line-search failure (QN.jl:193) a hair short of the tolerance — in the CPU oracle
+    # exactly as on the GPU, but not for the same starts, because the two exp/log1p differ in the
+    # last bit.  Parity is therefore asserted on the starts that converge in both.
+    both = (got["status"] == qn.CONVERGED) & (ref["status"] == ob.CONVERGED)
+    assert both.mean() >= 0.7
+    assert set(np.unique(got["status"])) <= {qn.CONVERGED, qn.LINESEARCH_FAILED}
+    assert np.abs(got["x"][:, both] - ref["x"][:, both]).max() <= 1e-8   # ‖Δθ‖∞ at the optimum
+    assert np.abs(got["g"][:, both]).max() < 1e-8
+    assert np.abs(got["g"]).max() < 1e-6 and np.abs(ref["g"]).max() < 1e-6  # failures stop at the noise floor
+    assert np.abs(got["x"] - ref["x"]).max() <= 1e-6
+    scale = np.abs(ref["trace"]).max(axis=2, keepdims=True)
+    assert (np.abs(got["trace"] - ref["trace"]) / scale).max() <= 1e-12  # first five iterates
+    print("logistic %dx%d: converged GPU %d / oracle %d of %d; iterations GPU %s / oracle %s" % (
+        m, n, (got["status"] == 0).sum(), (ref["status"] == 0).sum(), batch, got["iters"][:6], ref["iters"][:6]))
+
+
+def test_model_dimension_mismatch_is_an_error(eng, qn):
+    mu, lam = gaussian_problem(8)
+    with pytest.raises(qn.QNError):
+        eng.optimize_batched(qn.DenseGaussian(mu, lam), starts(9, 2))
+
+
+def test_single_process_multi_gpu_entry(qn, ob):
+    """qn_bfgs_optimize_batched_multi_f64: problem j -> context j mod G, no communication."""
+    import ctypes as C
+    lib = qn._lib.load()
+    G = min(lib.qn_device_count(), 2)
+    for ndev in sorted({1, G}):
+        engines = [qn.Engine(d) for d in range(ndev)]
+        ctxs = (C.c_void_p * ndev)(*[e._ctx for e in engines])
+        models = (C.c_void_p * ndev)(*[e.model_handle(qn.Rosenbrock()) for e in engines])
+        n, batch = 60, 203  # ragged over 2 devices
+        Theta = starts(n, batch, key=77)
+        x = np.empty((n, batch), order="F"); g = np.empty((n, batch), order="F")
+        ell = np.empty(batch); it = np.empty(batch, np.int32); fe = np.empty(batch, np.int32); st = np.empty(batch, np.int32)
+        ls = qn.BackTracking()._c()
+        qn._lib.check(lib.qn_bfgs_optimize_batched_multi_f64(
+            ctxs, ndev, models, n, batch, Theta.ctypes.data, C.byref(ls), 1e-8, 10000, x.ctypes.data, g.ctypes.data,
+            ell.ctypes.data, it.ctypes.data, fe.ctypes.data, st.ctypes.data, 0))
+        ref = ob.optimize_batch(ob.rosenbrock(), Theta)
+        assert np.array_equal(x, ref["x"]) and np.array_equal(g, ref["g"]) and np.array_equal(ell, ref["ell"])
+        assert np.array_equal(it, ref["iters"]) and np.array_equal(st, ref["status"])
+        for e in engines:
+            e.close()
