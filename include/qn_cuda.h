@@ -185,6 +185,12 @@ int32_t qn_bfgs_optimize_batched_multi_f64(qn_context* const* ctxs, int32_t nctx
 int32_t qn_last_launch_info(qn_context* ctx, int32_t* path, int32_t* grid, int32_t* block,
                             int32_t* smem_bytes, int32_t* kernel_launches);
 
+/* Streaming (large-n) path benchmark: `iters` BFGS iterations (first two untimed) of an
+ * n-dimensional Rosenbrock problem with B⁻¹ in HBM.  gbs = achieved ALGORITHMIC bandwidth,
+ * (16 n² + 96 n) bytes per iteration / measured time. */
+int32_t qn_stream_bench_f64(qn_context* ctx, int32_t n, int32_t iters, int32_t order,
+                            double* ms_per_iter, double* gbs);
+
 /* ---- microbenchmarks that define the roofline denominators */
 /* sustained fp64 FMA rate, TFLOP/s (2 flops per DFMA), all SMs busy */
 int32_t qn_microbench_dfma(qn_context* ctx, double* tflops);

@@ -132,11 +132,45 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
     }
   }
   if (n <= 256) return launch_resident<Obj, 0, 256, 1>(ctx, p, op, st);
-  return fail(QN_ERR_UNSUPPORTED_SIZE, "n=%d: resident path supports n <= 160", n);
+  return fail(QN_ERR_UNSUPPORTED_SIZE, "n=%d does not fit the resident path", n);
 }
 
-int dispatch_model(qn_context* ctx, const qn_model* model, qn::BatchParams& p, uint32_t flags,
-                   cudaStream_t st) {
+// Large n: B⁻¹ in HBM, one problem at a time on the whole GPU (qn_stream.cu).
+int dispatch_stream(qn_context* ctx, const qn_model* model, qn::BatchParams& p,
+                    const qn_backtracking* ls, cudaStream_t st) {
+  if (model->kind != QN_OBJ_ROSENBROCK)
+    return fail(QN_ERR_UNREGISTERED_OBJECTIVE,
+                "objective kind %d has no registered device implementation on the streaming path "
+                "(n=%d); only Rosenbrock has one", model->kind, p.n);
+  // the graph cannot be captured on the legacy default stream: run on the context's stream,
+  // ordered after whatever the caller enqueued on `st`
+  cudaStream_t run = ctx->stream;
+  if (st != run) QN_CUDA_TRY(cudaStreamSynchronize(st));
+  int launches = 0;
+  for (long long j = 0; j < p.batch; ++j) {
+    double ell;
+    int it, fe, status;
+    int rc = qn_stream_solve(ctx, p.n, p.theta0 + j * p.theta_stride, ls, p.tol, p.max_iter,
+                             p.x_out ? p.x_out + j * p.x_stride : nullptr,
+                             p.g_out ? p.g_out + j * p.g_stride : nullptr,
+                             p.h_out ? p.h_out + j * p.h_stride : nullptr, p.ldh, &ell, &it, &fe,
+                             &status, p.ntrace,
+                             p.trace ? p.trace + (size_t)j * p.ntrace * p.n : nullptr, run, nullptr, 0);
+    if (rc) return rc;
+    launches += ctx->last_launches;
+    if (p.ell_out) QN_CUDA_TRY(cudaMemcpy(p.ell_out + j, &ell, sizeof ell, cudaMemcpyHostToDevice));
+    if (p.iters_out) QN_CUDA_TRY(cudaMemcpy(p.iters_out + j, &it, sizeof it, cudaMemcpyHostToDevice));
+    if (p.fevals_out) QN_CUDA_TRY(cudaMemcpy(p.fevals_out + j, &fe, sizeof fe, cudaMemcpyHostToDevice));
+    if (p.status_out) QN_CUDA_TRY(cudaMemcpy(p.status_out + j, &status, sizeof status, cudaMemcpyHostToDevice));
+  }
+  ctx->last_launches = launches;
+  return QN_OK;
+}
+
+int dispatch_model(qn_context* ctx, const qn_model* model, qn::BatchParams& p,
+                   const qn_backtracking* ls, uint32_t flags, cudaStream_t st) {
+  // resident up to n = 160 (205 KB of B⁻¹ + vectors in 227 KB of shared memory), HBM beyond
+  if ((flags & QN_FLAG_FORCE_STREAM) || p.n > 160) return dispatch_stream(ctx, model, p, ls, st);
   switch (model->kind) {
     case QN_OBJ_ROSENBROCK:
       return dispatch_size<qn::Rosenbrock>(ctx, p, qn::Rosenbrock::Params{}, flags, st);
@@ -414,7 +448,7 @@ int32_t qn_bfgs_optimize_batched_device_f64(qn_context* ctx, const qn_model* mod
   p.ntrace = ntrace;
   p.trace = trace_out;
   std::lock_guard<std::mutex> lock(ctx->mu);
-  return dispatch_model(ctx, model, p, flags, st);
+  return dispatch_model(ctx, model, p, ls, flags, st);
 }
 
 // ---- optimize!, host pointers (the call a Julia / Python user makes)
@@ -489,7 +523,7 @@ int32_t qn_bfgs_optimize_batched_f64(qn_context* ctx, const qn_model* model, int
   p.trace = ntrace ? (double*)(base + o_tr) : nullptr;
   {
     std::lock_guard<std::mutex> lock(ctx->mu);
-    rc = dispatch_model(ctx, model, p, flags, st);
+    rc = dispatch_model(ctx, model, p, ls, flags, st);
   }
   if (rc) return rc;
 

@@ -53,3 +53,9 @@ inline int qn_host_state_ld(int n, int native_w) {
   while (w < n && w < native_w) w <<= 1;
   return ((n + w - 1) / w) * w;
 }
+
+// qn_stream.cu: one large problem with B⁻¹ in HBM (device pointers; blocks until finished).
+int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_backtracking* ls,
+                    double tol, int max_iter, double* d_x_out, double* d_g_out, double* d_h_out,
+                    int ldh_out, double* ell, int* iters, int* fevals, int* status, int ntrace,
+                    double* d_trace, cudaStream_t st, float* ms_per_iter_out, int fixed_iters);

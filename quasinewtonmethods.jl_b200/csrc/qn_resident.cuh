@@ -145,7 +145,7 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
     __syncthreads();
     const double l0 = Obj::template eval<true>(tm, op, g);
     ++fevals;
-    if (!isfinite(l0)) { status = QN_NONFINITE; break; } // QN.jl:255
+    if (!isfinite(l0)) { status = QN_NONFINITE; if (!(it & 1)) g = g_prev; break; } // QN.jl:255
 
     // publish what the update needs, and test convergence, on one barrier.
     // y = ∇_old - ∇_new, QN.jl:38
@@ -248,17 +248,21 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
     }
 
     const double alpha = team_linesearch<Obj>(tm, op, p.ls, x, s, l0, m, fevals); // QN.jl:283
-    if (alpha == 0.0) { status = QN_LINESEARCH_FAILED; break; } // QN.jl:284
+    if (alpha == 0.0) { status = QN_LINESEARCH_FAILED; if (!(it & 1)) g = g_prev; break; } // QN.jl:284
     // update_state!: s ← αs ; x_old += s   QN.jl:21-27
     s = alpha * s;
     x = x + s;
-    g_prev = g; // ∇_old, ∇_new = ∇_new, ∇_old, QN.jl:286
     ++iters;
     if (p.trace != nullptr && it <= p.ntrace && active)
       p.trace[(j * p.ntrace + (it - 1)) * (long long)n + c] = x;
+    if (it == p.max_iter) { if (!(it & 1)) g = g_prev; break; } // N iterations exhausted, QN.jl:250,291
+    g_prev = g; // ∇_old, ∇_new = ∇_new, ∇_old, QN.jl:286
   }
 
-  // ---- results: θ* at offset 0 and ∇ at offset L of the state block (QN.jl:135,138)
+  // ---- results: θ* at offset 0 and ∇ at offset L of the state block (QN.jl:135,138).
+  // The reference swaps its two gradient buffers every iteration (QN.jl:286) and only
+  // copies into the canonical slot on convergence (QN.jl:258-259): after a failure in an
+  // even iteration `gradient(state)` still shows the previous iteration's ∇ (selected above).
   if (active) {
     if (p.x_out) p.x_out[j * p.x_stride + c] = x;
     if (p.g_out) p.g_out[j * p.g_stride + c] = g;

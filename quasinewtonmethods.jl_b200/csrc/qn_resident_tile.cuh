@@ -196,7 +196,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
     warp_butterfly2(term, sy);
     const double l0 = rosenbrock_finish<N>(term, x);
     ++fevals;
-    if (!isfinite(l0)) { status = QN_NONFINITE; break; } // QN.jl:255
+    if (!isfinite(l0)) { status = QN_NONFINITE; if (!(it & 1)) g = gp; break; } // QN.jl:255
     // maximum(abs, ∇_new) < tol, QN.jl:257 (a NaN entry makes it false)
     const bool small = fabs(g.lo) < p.tol && (!hi_valid || fabs(g.hi) < p.tol);
     if (__all_sync(0xffffffffu, small)) { status = QN_CONVERGED; result = l0; break; } // QN.jl:258-261
@@ -364,14 +364,16 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
       alpha = failed ? 0.0 : a2;
     }
     QN_TICK(7);
-    if (alpha == 0.0) { status = QN_LINESEARCH_FAILED; break; } // QN.jl:284
+    if (alpha == 0.0) { status = QN_LINESEARCH_FAILED; if (!(it & 1)) g = gp; break; } // QN.jl:284
     // update_state!: s ← αs ; x_old += s   QN.jl:21-27
     s.lo = alpha * s.lo; s.hi = alpha * s.hi;
     x.lo = x.lo + s.lo;  x.hi = x.hi + s.hi;
-    gp = g; // ∇_old, ∇_new = ∇_new, ∇_old, QN.jl:286
     ++iters;
     if (p.trace != nullptr && it <= p.ntrace && owner)
       p.trace[(j * p.ntrace + (it - 1)) * (long long)N + e] = mine(x);
+    // N iterations exhausted (QN.jl:250,291); which ∇ the canonical slot shows: see qn_resident.cuh
+    if (it == p.max_iter) { if (!(it & 1)) g = gp; break; }
+    gp = g; // ∇_old, ∇_new = ∇_new, ∇_old, QN.jl:286
   }
 
   if (owner) {

@@ -1,0 +1,629 @@
+// qn_stream.cu — the large-n path (BASELINE.json configs[4], n in the thousands): B⁻¹ lives
+// in HBM and one problem uses the whole GPU.
+//
+// Per BFGS iteration (QN.jl:253-288) six kernels run back to back, captured once in a CUDA
+// graph and replayed; all control flow stays on the device (a `done` flag turns the
+// remaining launches into no-ops; the host only polls it every few iterations):
+//
+//   vec_begin  (1 CTA)   ℓ₀, ∇ = ∂logdensity!(x_old); convergence; y, sᵀy, ρ        QN.jl:254-264,36-42
+//   pass1      (grid)    block partials of t = B⁻¹y                                   QN.jl:44-49
+//   vec_mid    (1 CTA)   t, u = tρ, yᵀB⁻¹y, c₁, c₁s                                   QN.jl:50-54
+//   pass2      (grid)    B⁻¹ ← B⁻¹ + c₁ssᵀ - usᵀ - suᵀ fused with partials of d = B⁻¹∇   QN.jl:56-67
+//   vec_end    (1 CTA)   d, m, reset decision, the whole line search, update_state!   QN.jl:66-68,272-286
+//   identity   (grid)    B⁻¹ ← I when vec_end asked for a reset                       QN.jl:144-148
+//
+// The two passes are pure streams over the n×n matrix: pass1 reads 8n² bytes, pass2 reads
+// and writes 16n² — the reference's own two-pass order (24n² bytes per iteration), which
+// is what keeps this path bit-identical to the oracle.  Their bound is HBM bandwidth.
+//
+// Work split of a pass: a CTA owns 512 consecutive rows (2 per thread, one 128-bit access
+// per column) and one SUPER-BLOCK of 16·rb columns (rule C2, rb = chain_block(n) = 16 at
+// n = 8192).  Inside it each thread runs the rule-C2 chains of its two rows and adds the
+// block partials in order; the per-super-block sums go to a small [nsb × n] array that the
+// next single-CTA kernel adds up in ascending order.  Every global access of a warp is 512
+// contiguous bytes; 8 independent 128-bit loads per thread are in flight.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+
+#include "qn_device.cuh"
+#include "qn_internal.h"
+
+namespace qn {
+
+constexpr int kVecThreads = 1024;
+constexpr int kPassThreads = 256;
+constexpr int kRowsPerCta = 2 * kPassThreads;
+
+struct StreamScalars {
+  double l0, sy, rho, c1, m, result;
+  int it;          // completed outer iterations
+  int iters, fevals, status;
+  int done;        // 1: the remaining kernels are no-ops
+  int skip_update; // iteration 1: m = -1, no BFGS update (QN.jl:263-264)
+  int need_reset;  // vec_end -> identity
+  int exit_it;     // iteration in which the solve ended (selects which ∇ buffer is canonical)
+};
+
+struct StreamParams {
+  int n, ld, rb, sbcols, nsb, max_iter;
+  double tol;
+  LsParams ls;
+  double* H;
+  double *x, *g, *gp, *s, *y, *nu, *w, *xs, *tmp, *dvec; // length-n vectors
+  double* partial;                                  // [nsb][n]
+  unsigned int* tile_count;                         // one arrival counter per row tile
+  int stage_in_smem;                                // vec kernels stage reductions in shared memory
+  StreamScalars* sc;
+  int ntrace;
+  double* trace; // [ntrace][n]
+};
+
+// ---- canonical csum (rule C1) by one CTA.  `stage` is an n-double scratch array (shared
+// memory when it fits, else global); `red` is one shared double.  Every thread calls it.
+__device__ __forceinline__ double cta_csum_staged(int n, const double* stage, double* red) {
+  if (threadIdx.x < 32) {
+    const int l = threadIdx.x;
+    double p = (l < n) ? stage[l] : 0.0;
+    int i = l + 32;
+    for (; i + 224 < n; i += 256) { // 8 loads in flight; the adds stay in ascending order
+      double v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = stage[i + 32 * k];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) p = p + v[k];
+    }
+    for (; i < n; i += 32) p = p + stage[i];
+    p = warp_butterfly(p);
+    if (l == 0) *red = p;
+  }
+  __syncthreads();
+  const double r = *red;
+  __syncthreads(); // stage and red may be reused right away
+  return r;
+}
+template <class F>
+__device__ __forceinline__ double cta_csum(int n, double* stage, double* red, F&& v) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) stage[i] = v(i);
+  __syncthreads();
+  return cta_csum_staged(n, stage, red);
+}
+
+// Rosenbrock (test/runtests.jl:4-33) by one CTA; writes ∇ to g when g != nullptr.
+__device__ __forceinline__ double cta_rosenbrock(int n, const double* x, double* g, double* tmp, double* red) {
+  const int N = n >> 1;
+  const double sum = cta_csum(N, tmp, red, [&](int i) {
+    const double t1 = x[i], t2 = x[i + N];
+    const double a = t2 - t1 * t1;
+    const double b = 1.0 - t1;
+    if (g) {
+      g[i] = (400.0 * a) * t1 + 2.0 * b;
+      g[i + N] = 200.0 * (t1 * t1 - t2);
+    }
+    return 100.0 * (a * a) + b * b;
+  });
+  double s = 0.0 - sum;
+  if (n & 1) {
+    const double d = 1.0 - x[n - 1];
+    s = -fma(d, d, -s);
+    if (g && threadIdx.x == 0) g[n - 1] = 2.0 * d;
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(kVecThreads) stream_vec_begin(const StreamParams p) {
+  extern __shared__ __align__(16) double vsm[];
+  __shared__ double red;
+  __shared__ int flag;
+  StreamScalars* sc = p.sc;
+  if (sc->done) return;
+  const int n = p.n;
+  const int it = sc->it + 1;
+  double* stage = p.stage_in_smem ? vsm : p.tmp;
+  const double l0 = cta_rosenbrock(n, p.x, p.g, stage, &red); // QN.jl:254
+  __syncthreads();
+  if (threadIdx.x == 0) { sc->l0 = l0; sc->fevals += 1; flag = 1; }
+  if (!isfinite(l0)) { // QN.jl:255
+    if (threadIdx.x == 0) { sc->status = QN_NONFINITE; sc->done = 1; sc->exit_it = it; }
+    return;
+  }
+  __syncthreads();
+  bool small = true; // maximum(abs, ∇) < tol, QN.jl:257
+  for (int i = threadIdx.x; i < n; i += blockDim.x) small = small && (fabs(p.g[i]) < p.tol);
+  if (!small) flag = 0;
+  __syncthreads();
+  if (flag) {
+    if (threadIdx.x == 0) { sc->status = QN_CONVERGED; sc->result = l0; sc->done = 1; sc->exit_it = it; }
+    return;
+  }
+  if (it == 1) { // QN.jl:263-264
+    if (threadIdx.x == 0) { sc->m = -1.0; sc->skip_update = 1; }
+    return;
+  }
+  // y = ∇_old - ∇_new ; sᵀy   QN.jl:36-41
+  const double sy = cta_csum(n, stage, &red, [&](int i) {
+    const double yi = p.gp[i] - p.g[i];
+    p.y[i] = yi;
+    return p.s[i] * yi;
+  });
+  if (threadIdx.x == 0) { sc->sy = sy; sc->rho = 1.0 / sy; sc->skip_update = 0; } // QN.jl:42
+}
+
+// Tail of a pass: the LAST of the nsb CTAs of a row tile to finish adds that tile's
+// super-block partials in ascending order (rule C2) — 16 SMs do this in parallel instead of
+// one.  finish(c, T) consumes the row sum.  Returns after the tile is done.
+template <class F>
+__device__ __forceinline__ void pass_tail(const StreamParams& p, F&& finish) {
+  __shared__ int is_last;
+  __threadfence(); // this CTA's partials are visible device-wide before it signs off
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(p.tile_count + blockIdx.x, 1u);
+    is_last = (prev == (unsigned)p.nsb - 1);
+    if (is_last) p.tile_count[blockIdx.x] = 0; // ready for the next pass
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int c0 = blockIdx.x * kRowsPerCta + 2 * threadIdx.x;
+  if (c0 >= p.n) return;
+  const bool two = (c0 + 1 < p.n);
+  const volatile double* part = p.partial + c0; // written by other CTAs of this launch
+  double T0 = part[0], T1 = two ? part[1] : 0.0;
+  for (int j = 1; j < p.nsb; ++j) {
+    T0 = T0 + part[(size_t)j * p.n];
+    if (two) T1 = T1 + part[(size_t)j * p.n + 1];
+  }
+  finish(c0, T0);
+  if (two) finish(c0 + 1, T1);
+}
+
+__global__ void __launch_bounds__(kVecThreads) stream_vec_mid(const StreamParams p) {
+  extern __shared__ __align__(16) double vsm[];
+  __shared__ double red;
+  StreamScalars* sc = p.sc;
+  if (sc->done || sc->skip_update) return;
+  const int n = p.n;
+  const double rho = sc->rho;
+  // pass1's tail left t[c]·y[c] in tmp and -u in nu; yᵀB⁻¹y = csum, QN.jl:51
+  double* stage = p.stage_in_smem ? vsm : p.tmp;
+  if (p.stage_in_smem) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) stage[i] = p.tmp[i];
+    __syncthreads();
+  }
+  const double yHy = cta_csum_staged(n, stage, &red);
+  const double c1 = fma(yHy, rho, 1.0) * rho; // QN.jl:54
+  for (int c = threadIdx.x; c < n; c += blockDim.x) p.w[c] = c1 * p.s[c];
+  if (threadIdx.x == 0) sc->c1 = c1;
+}
+
+__global__ void __launch_bounds__(kVecThreads) stream_vec_end(const StreamParams p) {
+  extern __shared__ __align__(16) double vsm[];
+  __shared__ double red;
+  StreamScalars* sc = p.sc;
+  if (sc->done) return;
+  const int n = p.n;
+  const int it = sc->it + 1;
+  const double l0 = sc->l0;
+  double* stage = p.stage_in_smem ? vsm : p.tmp;            // n doubles
+  double* xs = p.stage_in_smem ? vsm + ((n + 1) & ~1) : p.xs; // trial point, n doubles
+  double m;
+  if (!sc->skip_update) {
+    // pass2's tail left d in s and d[c]·∇[c] in tmp; m = dᵀ∇_new = csum, QN.jl:66-68
+    if (p.stage_in_smem) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) stage[i] = p.tmp[i];
+      __syncthreads();
+    }
+    m = cta_csum_staged(n, stage, &red);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) p.s[i] = p.dvec[i]; // `s, y = y, s`, QN.jl:65,268
+    __syncthreads();
+  } else {
+    m = sc->m;
+  }
+  int need_reset = 0;
+  if (m <= 0.0) { // QN.jl:272-280
+    need_reset = 1;
+    m = cta_csum(n, stage, &red, [&](int i) {
+      const double gi = p.g[i];
+      p.s[i] = gi;
+      return gi * gi;
+    });
+  }
+  __syncthreads();
+  // ---- linesearch!  QN.jl:165-232
+  int fevals = 0;
+  auto trial = [&](double a) { // step!, QN.jl:157-162
+    for (int i = threadIdx.x; i < n; i += blockDim.x) xs[i] = fma(a, p.s[i], p.x[i]);
+    __syncthreads();
+    ++fevals;
+    return cta_rosenbrock(n, xs, nullptr, stage, &red);
+  };
+  const LsParams& ls = p.ls;
+  double lx0 = l0, lx1;
+  double a1 = 1.0, a2 = 1.0;
+  lx1 = trial(a1);
+  int iterfinite = 0;
+  while (!isfinite(lx1) && iterfinite < 52) { // QN.jl:178-184
+    ++iterfinite;
+    a1 = a2;
+    a2 = 0.5 * a2;
+    lx1 = trial(a2);
+  }
+  long long iteration = 0;
+  bool failed = false;
+  while (!(lx1 >= fma(a2 * ls.c1, m, l0))) { // QN.jl:187
+    ++iteration;
+    if (iteration > ls.iterations) { failed = true; break; }
+    double at;
+    if (ls.order == 2 || iteration == 1) {
+      at = -((m * a2) * a2) / (2.0 * fma(-m, a2, lx1 - l0));
+    } else {
+      const double denom = 1.0 / ((((a1 * a1) * a2) * a2) * (a2 - a1));
+      const double r1 = fma(-m, a2, lx1 - l0);
+      const double r0 = fma(-m, a1, lx0 - l0);
+      const double a = ((a1 * a1) * r1 - (a2 * a2) * r0) * denom;
+      const double b = ((((-a1) * a1) * a1) * r1 + ((a2 * a2) * a2) * r0) * denom;
+      if (fabs(a) <= kEps + kSqrtTol * fabs(a)) {
+        at = m / (2.0 * b);
+      } else {
+        const double d = nanmax(b * b - (3.0 * a) * m, 0.0);
+        at = (sqrt(d) + b) / (-3.0 * a);
+      }
+    }
+    a1 = a2;
+    at = nanmin(at, a2 * ls.rho_hi);
+    a2 = nanmax(at, a2 * ls.rho_lo);
+    lx0 = lx1;
+    lx1 = trial(a2);
+  }
+  const double alpha = failed ? 0.0 : a2;
+  if (alpha == 0.0) { // QN.jl:284
+    if (threadIdx.x == 0) { sc->status = QN_LINESEARCH_FAILED; sc->done = 1; sc->fevals += fevals; sc->need_reset = 0; sc->exit_it = it; }
+    return;
+  }
+  // update_state!  QN.jl:21-27 ; ∇_old ← ∇_new  QN.jl:286
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double si = alpha * p.s[i];
+    p.s[i] = si;
+    const double xi = p.x[i] + si;
+    p.x[i] = xi;
+    if (it < p.max_iter) p.gp[i] = p.g[i];
+    if (p.trace != nullptr && it <= p.ntrace) p.trace[(size_t)(it - 1) * n + i] = xi;
+  }
+  if (threadIdx.x == 0) {
+    sc->m = m;
+    sc->it = it;
+    sc->iters += 1;
+    sc->fevals += fevals;
+    sc->need_reset = need_reset;
+    if (it >= p.max_iter) { sc->status = QN_MAX_ITER; sc->done = 1; sc->exit_it = it; }
+  }
+}
+
+// ---- pass 1: partial[sb][c] = Σ_{blocks of sb} chain_b(c),  chain_b(c) = Σ_{r in b} y[r] H[c,r]
+__global__ void __launch_bounds__(kPassThreads) stream_pass1(const StreamParams p) {
+  const StreamScalars* sc = p.sc;
+  if (sc->done || sc->skip_update) return;
+  extern __shared__ __align__(16) double sm[];
+  double* ys = sm; // y of this super-block's columns
+  const int n = p.n, ld = p.ld, rb = p.rb;
+  const int sb = blockIdx.y;
+  const int r_begin = sb * p.sbcols;
+  const int r_end = min(r_begin + p.sbcols, n);
+  for (int r = r_begin + threadIdx.x; r < r_end; r += blockDim.x) ys[r - r_begin] = p.y[r];
+  __syncthreads();
+  const int c0 = blockIdx.x * kRowsPerCta + 2 * threadIdx.x;
+  const bool two = (c0 + 1 < n);
+  const double* hp = p.H + c0;
+  double S0 = 0.0, S1 = 0.0;
+  bool first = true;
+  for (int b0 = r_begin; b0 < r_end && c0 < n; b0 += rb) {
+    const int b1 = min(b0 + rb, r_end);
+    double t0 = 0.0, t1 = 0.0;
+    int r = b0;
+    for (; r + 8 <= b1; r += 8) { // 8 independent 128-bit loads in flight
+      double2 h[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) h[k] = *reinterpret_cast<const double2*>(hp + (size_t)ld * (r + k));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const double yr = ys[r + k - r_begin];
+        t0 = fma(yr, h[k].x, t0);
+        t1 = fma(yr, h[k].y, t1);
+      }
+    }
+    for (; r < b1; ++r) {
+      const double2 h = *reinterpret_cast<const double2*>(hp + (size_t)ld * r);
+      const double yr = ys[r - r_begin];
+      t0 = fma(yr, h.x, t0);
+      t1 = fma(yr, h.y, t1);
+    }
+    S0 = first ? t0 : S0 + t0;
+    S1 = first ? t1 : S1 + t1;
+    first = false;
+  }
+  if (c0 < n) {
+    double* out = p.partial + (size_t)sb * n + c0;
+    out[0] = S0;
+    if (two) out[1] = S1;
+  }
+  const double rho = sc->rho;
+  pass_tail(p, [&](int c, double T) {
+    p.nu[c] = -(T * rho);      // -B⁻¹y[c] = -(t ρ), QN.jl:50
+    p.tmp[c] = T * p.y[c];     // term of yᵀB⁻¹y, QN.jl:51
+  });
+}
+
+// ---- pass 2: H[c,r] ← ((H + (c₁s[r])s[c]) - u[r]s[c]) - u[c]s[r] ; partials of d = H⁺∇
+__global__ void __launch_bounds__(kPassThreads) stream_pass2(const StreamParams p) {
+  const StreamScalars* sc = p.sc;
+  if (sc->done || sc->skip_update) return;
+  extern __shared__ __align__(16) double sm[];
+  double4* ops = reinterpret_cast<double4*>(sm); // {c₁s[r], -u[r], s[r], ∇[r]} per column
+  const int n = p.n, ld = p.ld, rb = p.rb;
+  const int sb = blockIdx.y;
+  const int r_begin = sb * p.sbcols;
+  const int r_end = min(r_begin + p.sbcols, n);
+  for (int r = r_begin + threadIdx.x; r < r_end; r += blockDim.x)
+    ops[r - r_begin] = make_double4(p.w[r], p.nu[r], p.s[r], p.g[r]);
+  __syncthreads();
+  const int c0 = blockIdx.x * kRowsPerCta + 2 * threadIdx.x;
+  const bool two = (c0 + 1 < n);
+  const double s0 = (c0 < n) ? p.s[c0] : 0.0, nu0 = (c0 < n) ? p.nu[c0] : 0.0;
+  const double s1 = two ? p.s[c0 + 1] : 0.0, nu1 = two ? p.nu[c0 + 1] : 0.0;
+  double* hp = p.H + c0;
+  double S0 = 0.0, S1 = 0.0;
+  bool first = true;
+  for (int b0 = r_begin; b0 < r_end && c0 < n; b0 += rb) {
+    const int b1 = min(b0 + rb, r_end);
+    double a0 = 0.0, a1 = 0.0;
+    int r = b0;
+    for (; r + 8 <= b1; r += 8) {
+      double2 h[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) h[k] = *reinterpret_cast<const double2*>(hp + (size_t)ld * (r + k));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const double4 o = ops[r + k - r_begin];
+        double h0 = h[k].x, h1 = h[k].y;
+        h0 = fma(o.x, s0, h0); h1 = fma(o.x, s1, h1);     // + (c₁ s[r]) s[c]
+        h0 = fma(o.y, s0, h0); h1 = fma(o.y, s1, h1);     // - u[r] s[c]
+        h0 = fma(nu0, o.z, h0); h1 = fma(nu1, o.z, h1);   // - u[c] s[r]
+        *reinterpret_cast<double2*>(hp + (size_t)ld * (r + k)) = make_double2(h0, h1);
+        a0 = fma(h0, o.w, a0);
+        a1 = fma(h1, o.w, a1);
+      }
+    }
+    for (; r < b1; ++r) {
+      const double2 h = *reinterpret_cast<const double2*>(hp + (size_t)ld * r);
+      const double4 o = ops[r - r_begin];
+      double h0 = h.x, h1 = h.y;
+      h0 = fma(o.x, s0, h0); h1 = fma(o.x, s1, h1);
+      h0 = fma(o.y, s0, h0); h1 = fma(o.y, s1, h1);
+      h0 = fma(nu0, o.z, h0); h1 = fma(nu1, o.z, h1);
+      *reinterpret_cast<double2*>(hp + (size_t)ld * r) = make_double2(h0, h1);
+      a0 = fma(h0, o.w, a0);
+      a1 = fma(h1, o.w, a1);
+    }
+    S0 = first ? a0 : S0 + a0;
+    S1 = first ? a1 : S1 + a1;
+    first = false;
+  }
+  if (c0 < n) {
+    double* out = p.partial + (size_t)sb * n + c0;
+    out[0] = S0;
+    if (two) out[1] = S1;
+  }
+  pass_tail(p, [&](int c, double d) {
+    p.tmp[c] = d * p.g[c]; // term of m = dᵀ∇_new, QN.jl:66
+    p.dvec[c] = d;         // the new direction (other CTAs of this launch still read s)
+  });
+}
+
+// B⁻¹ ← I (QN.jl:144-148), only when vec_end asked for it
+__global__ void __launch_bounds__(256) stream_identity(const StreamParams p) {
+  const StreamScalars* sc = p.sc;
+  if (sc->done || !sc->need_reset) return;
+  const size_t ld2 = (size_t)p.ld / 2;
+  const size_t total = ld2 * p.n; // double2 elements
+  double2* H2 = reinterpret_cast<double2*>(p.H);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / ld2, c = 2 * (i % ld2);
+    H2[i] = make_double2(c == r ? 1.0 : 0.0, c + 1 == r ? 1.0 : 0.0);
+  }
+}
+
+}  // namespace qn
+
+// -------------------------------------------------------------------------- host side
+namespace {
+
+struct StreamWork {
+  qn::StreamParams p{};
+  void* block = nullptr; // one allocation for everything but H
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  size_t vec_smem = 0;
+};
+
+int enqueue_iteration(qn_context* ctx, const qn::StreamParams& p, size_t vec_smem, cudaStream_t st) {
+  const dim3 grid((p.n + qn::kRowsPerCta - 1) / qn::kRowsPerCta, p.nsb);
+  qn::stream_vec_begin<<<1, qn::kVecThreads, vec_smem, st>>>(p);
+  qn::stream_pass1<<<grid, qn::kPassThreads, sizeof(double) * p.sbcols, st>>>(p);
+  qn::stream_vec_mid<<<1, qn::kVecThreads, vec_smem, st>>>(p);
+  qn::stream_pass2<<<grid, qn::kPassThreads, sizeof(double) * 4 * p.sbcols, st>>>(p);
+  qn::stream_vec_end<<<1, qn::kVecThreads, vec_smem, st>>>(p);
+  qn::stream_identity<<<ctx->prop.multiProcessorCount * 8, 256, 0, st>>>(p);
+  QN_CUDA_TRY(cudaGetLastError());
+  return QN_OK;
+}
+
+}  // namespace
+
+// One large problem, device-resident x0 (n doubles at theta0).  Returns when finished.
+// iters_per_check: how many iterations are enqueued between polls of the done flag.
+int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_backtracking* ls,
+                    double tol, int max_iter, double* d_x_out, double* d_g_out, double* d_h_out,
+                    int ldh_out, double* ell, int* iters, int* fevals, int* status, int ntrace,
+                    double* d_trace, cudaStream_t st, float* ms_per_iter_out, int fixed_iters) {
+  using namespace qn;
+  StreamWork w;
+  StreamParams& p = w.p;
+  p.n = n;
+  p.ld = (n + 15) & ~15;
+  p.rb = chain_block(n);
+  p.sbcols = 16 * p.rb;
+  p.nsb = (n + p.sbcols - 1) / p.sbcols;
+  p.max_iter = max_iter;
+  p.tol = tol;
+  p.ls = LsParams{ls->c1, ls->rho_hi, ls->rho_lo, (long long)ls->iterations, ls->order};
+  p.ntrace = ntrace;
+  p.trace = d_trace;
+  QN_CUDA_TRY(cudaMalloc(&p.H, sizeof(double) * (size_t)p.ld * n));
+  const size_t nv = ((size_t)n + 31) & ~(size_t)31;
+  const int row_tiles = (n + qn::kRowsPerCta - 1) / qn::kRowsPerCta;
+  const size_t words = nv * 11 + (size_t)p.nsb * n + 64 + row_tiles;
+  cudaError_t e = cudaMalloc(&w.block, sizeof(double) * words);
+  if (e != cudaSuccess) {
+    cudaFree(p.H);
+    return qn_fail(QN_ERR_CUDA, "cudaMalloc failed for the streaming work space: %s", cudaGetErrorString(e));
+  }
+  double* base = (double*)w.block;
+  p.x = base; p.g = base + nv; p.gp = base + 2 * nv; p.s = base + 3 * nv; p.y = base + 4 * nv;
+  p.nu = base + 5 * nv; p.w = base + 6 * nv; p.xs = base + 7 * nv; p.tmp = base + 8 * nv;
+  p.dvec = base + 9 * nv;
+  p.partial = base + 11 * nv;
+  p.sc = reinterpret_cast<StreamScalars*>(p.partial + (size_t)p.nsb * n);
+  p.tile_count = reinterpret_cast<unsigned int*>(p.partial + (size_t)p.nsb * n + 32);
+  // vec kernels stage their reductions (n doubles) and the trial point (n doubles) in shared memory
+  const size_t vec_smem = sizeof(double) * (2 * (((size_t)n + 1) & ~(size_t)1));
+  p.stage_in_smem = vec_smem <= (size_t)ctx->prop.sharedMemPerBlockOptin - 1024;
+  w.vec_smem = p.stage_in_smem ? vec_smem : 0;
+  int rc = QN_OK;
+  auto cleanup = [&]() {
+    if (w.exec) cudaGraphExecDestroy(w.exec);
+    if (w.graph) cudaGraphDestroy(w.graph);
+    cudaFree(w.block);
+    cudaFree(p.H);
+  };
+#define QN_TRY_CLEAN(expr)                                                                \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      cleanup();                                                                          \
+      return qn_fail(QN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                     __FILE__, __LINE__);                                                 \
+    }                                                                                     \
+  } while (0)
+  QN_TRY_CLEAN(cudaMemsetAsync(w.block, 0, sizeof(double) * words, st));
+  QN_TRY_CLEAN(cudaMemcpyAsync(p.x, d_theta0, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+  StreamScalars init{};
+  init.result = NAN;
+  init.status = QN_MAX_ITER;
+  QN_TRY_CLEAN(cudaMemcpyAsync(p.sc, &init, sizeof init, cudaMemcpyHostToDevice, st));
+  if (max_iter <= 0) {
+    init.done = 1;
+  } else {
+    // capture one iteration (6 kernels) and replay it
+    QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(double) * 4 * p.sbcols)));
+    if (w.vec_smem) {
+      QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_begin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
+      QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
+      QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_end, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
+    }
+    QN_TRY_CLEAN(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_iteration(ctx, p, w.vec_smem, st);
+    cudaError_t ce = cudaStreamEndCapture(st, &w.graph);
+    if (rc != QN_OK || ce != cudaSuccess) {
+      cleanup();
+      return rc != QN_OK ? rc : qn_fail(QN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    }
+    QN_TRY_CLEAN(cudaGraphInstantiate(&w.exec, w.graph, 0));
+    StreamScalars host{};
+    if (fixed_iters > 0) {
+      // benchmark mode: exactly fixed_iters iterations, the first two are warm-up
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      const int warm = fixed_iters > 2 ? 2 : 0;
+      for (int k = 0; k < warm; ++k) QN_TRY_CLEAN(cudaGraphLaunch(w.exec, st));
+      cudaEventRecord(e0, st);
+      for (int k = warm; k < fixed_iters; ++k) QN_TRY_CLEAN(cudaGraphLaunch(w.exec, st));
+      cudaEventRecord(e1, st);
+      QN_TRY_CLEAN(cudaMemcpyAsync(&host, p.sc, sizeof host, cudaMemcpyDeviceToHost, st));
+      QN_TRY_CLEAN(cudaStreamSynchronize(st));
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (ms_per_iter_out) *ms_per_iter_out = ms / (float)(fixed_iters - warm);
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    } else {
+      // enqueue 8 iterations at a time, then poll the done flag
+      int launched = 0;
+      for (;;) {
+        for (int k = 0; k < 8 && launched < max_iter; ++k, ++launched) QN_TRY_CLEAN(cudaGraphLaunch(w.exec, st));
+        QN_TRY_CLEAN(cudaMemcpyAsync(&host, p.sc, sizeof host, cudaMemcpyDeviceToHost, st));
+        QN_TRY_CLEAN(cudaStreamSynchronize(st));
+        if (host.done || launched >= max_iter) break;
+      }
+    }
+    init = host;
+  }
+  ctx->last_path = 2;
+  ctx->last_grid = ((n + qn::kRowsPerCta - 1) / qn::kRowsPerCta) * p.nsb;
+  ctx->last_block = qn::kPassThreads;
+  ctx->last_smem = (int)(sizeof(double) * 4 * p.sbcols);
+  ctx->last_launches = 6 * (init.it + (init.done ? 1 : 0));
+  if (d_x_out) QN_TRY_CLEAN(cudaMemcpyAsync(d_x_out, p.x, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+  // which ∇ the reference's canonical slot shows after a failure: see qn_resident.cuh
+  const double* g_src = (init.status == QN_CONVERGED || (init.exit_it & 1)) ? p.g : p.gp;
+  if (d_g_out) QN_TRY_CLEAN(cudaMemcpyAsync(d_g_out, g_src, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+  if (d_h_out)
+    QN_TRY_CLEAN(cudaMemcpy2DAsync(d_h_out, sizeof(double) * ldh_out, p.H, sizeof(double) * p.ld,
+                                   sizeof(double) * n, n, cudaMemcpyDeviceToDevice, st));
+  QN_TRY_CLEAN(cudaStreamSynchronize(st));
+  if (ell) *ell = init.result;
+  if (iters) *iters = init.iters;
+  if (fevals) *fevals = init.fevals;
+  if (status) *status = init.status;
+  cleanup();
+#undef QN_TRY_CLEAN
+  return QN_OK;
+}
+
+// Time `iters` iterations of the streaming path on a fresh n-dimensional Rosenbrock problem
+// (x0 = a fixed pseudo-random start) and report ms per iteration and the achieved ALGORITHMIC
+// bandwidth (16 n² + 96 n bytes per iteration).
+extern "C" int32_t qn_stream_bench_f64(qn_context* ctx, int32_t n, int32_t iters, int32_t order,
+                                       double* ms_per_iter, double* gbs) {
+  if (!ctx || !ms_per_iter || !gbs || n < 2 || iters < 3) return qn_fail(QN_ERR_INVALID_ARGUMENT, "bad argument");
+  QN_CUDA_TRY(cudaSetDevice(ctx->device));
+  double* h = (double*)malloc(sizeof(double) * n);
+  unsigned long long state = 88172645463325252ULL;
+  for (int i = 0; i < n; ++i) { // xorshift + sum of uniforms: a deterministic roughly normal start
+    double acc = 0;
+    for (int k = 0; k < 12; ++k) {
+      state ^= state << 13; state ^= state >> 7; state ^= state << 17;
+      acc += (double)(state >> 11) / 9007199254740992.0;
+    }
+    h[i] = acc - 6.0;
+  }
+  double* d = nullptr;
+  QN_CUDA_TRY(cudaMalloc(&d, sizeof(double) * n));
+  cudaMemcpy(d, h, sizeof(double) * n, cudaMemcpyHostToDevice);
+  free(h);
+  qn_backtracking ls;
+  qn_backtracking_default(&ls, order);
+  float ms = 0;
+  int it = 0, fe = 0, stt = 0;
+  double ell = 0;
+  int rc = qn_stream_solve(ctx, n, d, &ls, 1e-8, iters, nullptr, nullptr, nullptr, 0, &ell, &it, &fe, &stt,
+                           0, nullptr, ctx->stream, &ms, iters);
+  cudaFree(d);
+  if (rc) return rc;
+  *ms_per_iter = ms;
+  *gbs = (16.0 * n * (double)n + 96.0 * n) / (ms * 1e-3) / 1e9;
+  return QN_OK;
+}

@@ -140,9 +140,15 @@ def test_edge_cases(eng, qn, ob):
     _check(got, ref)
     assert got["status"][2] == qn.NONFINITE and np.isnan(got["ell"][2])
     assert got["status"][4] == qn.NONFINITE and got["status"][0] == qn.CONVERGED
-    # iteration cap -> NaN (QN.jl:291)
-    got = eng.optimize_batched(R, starts(10, 4), max_iter=3)
-    assert (got["status"] == qn.MAX_ITER).all() and np.isnan(got["ell"]).all() and (got["iters"] == 3).all()
+    # iteration cap -> NaN (QN.jl:291); `gradient(state)` then shows the buffer the reference's
+    # pointer swaps (QN.jl:286) leave in the canonical slot: odd cap -> latest ∇, even -> previous
+    for n, cap in ((10, 3), (10, 4), (60, 5), (60, 6), (24, 1), (24, 2)):
+        Th = starts(n, 4, key=cap)
+        got = eng.optimize_batched(R, Th, max_iter=cap, ntrace=cap)
+        ref = ob.optimize_batch(ob.rosenbrock(), Th, max_iter=cap, ntrace=cap)
+        assert (got["status"] == qn.MAX_ITER).all() and np.isnan(got["ell"]).all() and (got["iters"] == cap).all()
+        for k in ("x", "g", "trace", "fevals"):
+            assert np.array_equal(got[k], ref[k]), (n, cap, k)
     # already at the optimum: no step taken
     got = eng.optimize_batched(R, np.ones((9, 3), order="F"))
     assert (got["iters"] == 0).all() and (got["ell"] == 0).all() and (got["status"] == 0).all()

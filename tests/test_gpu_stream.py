@@ -1,0 +1,60 @@
+"""The large-n path (BASELINE.json configs[4]): B⁻¹ in HBM, fused streaming GEMV / rank-2 passes.
+Same canonical order as the resident kernels, so the comparison with the oracle is bit for bit."""
+import numpy as np
+import pytest
+
+from conftest import starts
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(got, ref):
+    for k in ("x", "g", "ell", "trace"):
+        if ref.get(k) is not None:
+            assert np.array_equal(got[k], ref[k], equal_nan=True), k
+    assert np.array_equal(got["iters"], ref["iters"])
+    assert np.array_equal(got["fevals"], ref["fevals"])
+    assert np.array_equal(got["status"], ref["status"])
+
+
+@pytest.mark.parametrize("n", [2, 17, 60, 61])
+def test_forced_stream_path_full_solves(eng, qn, ob, n):
+    """QN_FLAG_FORCE_STREAM on sizes the resident path also covers: identical bits, full solves."""
+    Theta = starts(n, 3, key=900 + n)
+    got = eng.optimize_batched(qn.Rosenbrock(), Theta, ntrace=5, flags=qn._lib.FLAG_FORCE_STREAM)
+    assert eng.last_launch()["path"] == qn._lib.PATH_STREAM
+    ref = ob.optimize_batch(ob.rosenbrock(), Theta, ntrace=5)
+    _same(got, ref)
+    assert (got["status"] == qn.CONVERGED).all()
+
+
+@pytest.mark.parametrize("n,iters", [(161, 40), (256, 40), (777, 25), (1024, 25), (2049, 12)])
+def test_large_n_first_iterations(eng, qn, ob, n, iters):
+    """n beyond the resident limit: the first `iters` iterations, iterates and all, against the
+    oracle (a full solve at these sizes takes thousands of iterations; QN.jl:250 caps at 10 000)."""
+    Theta = starts(n, 1, key=n)
+    got = eng.optimize_batched(qn.Rosenbrock(), Theta, max_iter=iters, ntrace=iters)
+    assert eng.last_launch()["path"] == qn._lib.PATH_STREAM
+    ref = ob.optimize_batch(ob.rosenbrock(), Theta, max_iter=iters, ntrace=iters)
+    _same(got, ref)
+    assert got["status"][0] == qn.MAX_ITER and np.isnan(got["ell"][0])
+
+
+def test_large_n_full_solve_and_h_writeback(eng, qn, ob):
+    n = 192
+    Theta = starts(n, 1, key=5)
+    sb = qn.BFGSStateBatch(n, 1)
+    got = eng.optimize_batched(qn.Rosenbrock(), Theta, states=sb, flags=qn._lib.FLAG_WRITE_H)
+    o = ob.optimize(ob.rosenbrock(), Theta[:, 0], L=sb.L)
+    assert got["status"][0] == qn.CONVERGED and got["iters"][0] == o["iters"]
+    assert np.array_equal(got["x"][:, 0], o["x"]) and got["ell"][0] == o["ell"]
+    L = sb.L
+    assert np.array_equal(sb.data[0, 7 * L:].reshape(n, L)[:, :n], o["state"][7 * L:].reshape(n, L)[:, :n])
+    print("n=192 full solve on the streaming path: %d iterations" % got["iters"][0])
+
+
+def test_stream_rejects_unregistered_objective(eng, qn):
+    from problems import gaussian_problem
+    mu, lam = gaussian_problem(200)
+    with pytest.raises(qn.UnregisteredObjectiveError):
+        eng.optimize_batched(qn.DenseGaussian(mu, lam), starts(200, 1))
