@@ -1,0 +1,158 @@
+# QuasiNewtonCUDA.jl — Julia-side shim over libqn_cuda.so.
+#
+# STATUS: UNTESTED.  No Julia runtime exists in the build image or on the GPU boxes
+# (SURVEY.md §0), so this file has never been executed.  It is the binding a maintainer of
+# QuasiNewtonMethods.jl would add; the Python host layer (../api.py) is the tested mirror of
+# the same C ABI, call for call.  Every ccall below matches a prototype in include/qn_cuda.h.
+#
+# Usage, mirroring the reference (README.md:52-59 of QuasiNewtonMethods.jl):
+#
+#     using QuasiNewtonMethods, QuasiNewtonCUDA
+#     state = QuasiNewtonMethods.BFGSState{60}(undef)
+#     x = randn(60)
+#     QuasiNewtonCUDA.optimize!(state, QuasiNewtonCUDA.Rosenbrock(), x)        # one problem
+#     states = [QuasiNewtonMethods.BFGSState{60}(undef) for _ in 1:65536]
+#     QuasiNewtonCUDA.optimize!(states, QuasiNewtonCUDA.Rosenbrock(), randn(60, 65536))  # batched
+#     QuasiNewtonMethods.optimum(states[1]); QuasiNewtonMethods.gradient(states[1])
+module QuasiNewtonCUDA
+
+using QuasiNewtonMethods
+using QuasiNewtonMethods: AbstractBFGSState, BFGSState, BackTracking
+
+const libqn = get(ENV, "LIBQN_CUDA", "libqn_cuda.so")
+
+# ---- errors ------------------------------------------------------------------------------
+struct QNError <: Exception
+    code::Int32
+    msg::String
+end
+Base.showerror(io::IO, e::QNError) = print(io, "libqn_cuda error ", e.code, ": ", e.msg)
+
+const QN_ERR_UNREGISTERED_OBJECTIVE = Int32(3)
+
+last_error() = unsafe_string(ccall((:qn_last_error, libqn), Cstring, ()))
+function check(rc::Int32)
+    rc == 0 && return nothing
+    # QN_ERR_UNREGISTERED_OBJECTIVE is the MethodError analogue (QuasiNewtonMethods.jl:254):
+    # an objective without a device implementation is an error, never a CPU fallback.
+    throw(QNError(rc, last_error()))
+end
+
+# ---- BackTracking{O} -> qn_backtracking (QuasiNewtonMethods.jl:72-80) ----------------------
+struct CBackTracking
+    c1::Float64
+    rho_hi::Float64
+    rho_lo::Float64
+    iterations::Int64
+    order::Int32
+    _pad::Int32
+end
+CBackTracking(ls::BackTracking{O}) where {O} =
+    CBackTracking(ls.c₁, ls.ρₕ, ls.ρₗ, ls.iterations, Int32(O), Int32(0))
+
+# ---- context (one per GPU) ----------------------------------------------------------------
+mutable struct Context
+    ptr::Ptr{Cvoid}
+    function Context(device::Integer=0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:qn_create, libqn), Int32, (Ref{Ptr{Cvoid}}, Int32), r, device))
+        ctx = new(r[])
+        finalizer(c -> ccall((:qn_destroy, libqn), Int32, (Ptr{Cvoid},), c.ptr), ctx)
+        ctx
+    end
+end
+const DEFAULT_CONTEXT = Ref{Union{Nothing,Context}}(nothing)
+default_context() = something(DEFAULT_CONTEXT[], (DEFAULT_CONTEXT[] = Context(0)))
+
+# ---- objective registry: replaces dispatch on typeof(obj) (QuasiNewtonMethods.jl:8-9) --------
+"Objectives with a registered CUDA device implementation."
+abstract type DeviceObjective end
+struct Rosenbrock <: DeviceObjective end                       # test/runtests.jl:4-33, kind 0
+struct DenseGaussian <: DeviceObjective                        # kind 1
+    μ::Vector{Float64}
+    Λ::Matrix{Float64}
+end
+struct LogisticRegression <: DeviceObjective                   # kind 2
+    X::Matrix{Float64}
+    y::Vector{Float64}
+    λ::Float64
+end
+
+function model_handle(ctx::Context, ::Rosenbrock)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:qn_model_create, libqn), Int32, (Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}), ctx.ptr, 0, r))
+    r[]
+end
+function model_handle(ctx::Context, m::DenseGaussian)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:qn_model_dense_gaussian, libqn), Int32,
+                (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+                ctx.ptr, length(m.μ), m.μ, m.Λ, r))
+    r[]
+end
+function model_handle(ctx::Context, m::LogisticRegression)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:qn_model_logistic, libqn), Int32,
+                (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Float64, Ref{Ptr{Cvoid}}),
+                ctx.ptr, size(m.X, 1), size(m.X, 2), m.X, m.y, m.λ, r))
+    r[]
+end
+# Any other objective type: an error, like the reference's MethodError at QuasiNewtonMethods.jl:254.
+model_handle(::Context, obj) =
+    throw(QNError(QN_ERR_UNREGISTERED_OBJECTIVE,
+                  "no CUDA device implementation registered for $(typeof(obj)); there is no CPU fallback"))
+free_model(h) = ccall((:qn_model_free, libqn), Int32, (Ptr{Cvoid},), h)
+
+# ---- optimize!(state, obj, x, ls, tol): QuasiNewtonMethods.jl:237 ---------------------------
+function optimize!(state::AbstractBFGSState{P,Float64,L}, obj, x::AbstractVector{Float64},
+                   ls::BackTracking=BackTracking(), tol=1e-8; ctx::Context=default_context()) where {P,L}
+    length(x) == P || throw(DimensionMismatch("x has length $(length(x)), state is BFGSState{$P}"))
+    h = model_handle(ctx, obj)
+    cls = Ref(CBackTracking(ls))
+    ell = Ref{Float64}(NaN); iters = Ref{Int32}(0); fevals = Ref{Int32}(0); status = Ref{Int32}(0)
+    GC.@preserve state obj x begin      # QuasiNewtonMethods.jl:238
+        check(ccall((:qn_bfgs_optimize_f64, libqn), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Float64}, Ref{CBackTracking}, Float64,
+                     Ptr{Float64}, Int32, Ref{Float64}, Ref{Int32}, Ref{Int32}, Ref{Int32}, UInt32),
+                    ctx.ptr, h, P, pointer(x), cls, tol, pointer(state), L, ell, iters, fevals, status, 0))
+    end
+    free_model(h)
+    ell[]   # ℓ at the optimum, or NaN (QuasiNewtonMethods.jl:261,291)
+end
+
+# ---- batched optimize!(states, obj, Θ): one problem per column of Θ ---------------------------
+# `states` is a vector of BFGSState{P}; results are written straight into each state's block
+# (θ* at offset 0, ∇ at offset L, QuasiNewtonMethods.jl:135,138), so `optimum(states[j])` and
+# `gradient(states[j])` work unchanged.  Mutable-struct states are separate heap objects, so the
+# batch goes through one contiguous staging matrix and is copied into the states afterwards.
+function optimize!(states::AbstractVector{<:BFGSState{P,Float64,L}}, obj, Θ::AbstractMatrix{Float64},
+                   ls::BackTracking=BackTracking(), tol=1e-8; ctx::Context=default_context()) where {P,L}
+    batch = size(Θ, 2)
+    (size(Θ, 1) == P && length(states) == batch) || throw(DimensionMismatch("Θ must be $P × $(length(states))"))
+    h = model_handle(ctx, obj)
+    cls = Ref(CBackTracking(ls))
+    Θc = Θ isa Matrix{Float64} ? Θ : Matrix{Float64}(Θ)
+    xs = Matrix{Float64}(undef, P, batch); gs = Matrix{Float64}(undef, P, batch)
+    ell = Vector{Float64}(undef, batch)
+    iters = Vector{Int32}(undef, batch); fevals = Vector{Int32}(undef, batch); status = Vector{Int32}(undef, batch)
+    GC.@preserve Θc xs gs ell iters fevals status begin
+        check(ccall((:qn_bfgs_optimize_batched_f64, libqn), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int64, Ptr{Float64}, Ref{CBackTracking}, Float64, Int32,
+                     Ptr{Float64}, Int64, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                     Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Float64}, UInt32),
+                    ctx.ptr, h, P, batch, Θc, cls, tol, 10_000,
+                    C_NULL, 0, 0, xs, gs, ell, iters, fevals, status, 0, C_NULL, 0))
+    end
+    free_model(h)
+    for j in 1:batch
+        st = states[j]
+        GC.@preserve st begin
+            p = pointer(st)
+            unsafe_copyto!(p, pointer(xs, (j - 1) * P + 1), P)                 # ref_x_old, offset 0
+            unsafe_copyto!(p + L * sizeof(Float64), pointer(gs, (j - 1) * P + 1), P)  # ref_∇_new, offset L
+        end
+    end
+    (ℓ = ell, iterations = iters, evaluations = fevals, status = status)
+end
+
+end # module
