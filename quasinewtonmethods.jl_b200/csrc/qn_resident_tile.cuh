@@ -115,18 +115,38 @@ struct TileCfg {
   static constexpr bool kFull = (N % CT == 0);       // every column block is CT wide
   static_assert(N > 32 && N <= 64, "tile kernel covers 33..64");
   static_assert(NB <= 4 && NG <= 16, "tile grid must fit four half-warps");
-  // shared memory (doubles); block-padded arrays hold element e at (e / CT) * 16 + e % CT
-  static constexpr int oWN = 0;                      // {c₁s, -u}[NB][16]   (double2)
-  static constexpr int oSG = oWN + 2 * 64;           // {s, ∇}[NB][16]      (double2)
-  static constexpr int oYsp = oSG + 2 * 64;          // y[NB][16]
-  static constexpr int oS = oYsp + 64;               // s by element (row operands)
-  static constexpr int oNu = oS + 64;                // -u by element
-  static constexpr int oPart = oNu + 64;             // block partials [4][64]
-  static constexpr int oEnd = oPart + 4 * 64;
+  // ---- shared memory (doubles) ----
+  // per-warp PRIVATE region (only the owning warp touches it: __syncwarp is enough)
+  static constexpr int wWN = 0;                      // {c₁s, -u}[2 blocks][16]  (double2)
+  static constexpr int wSG = wWN + 64;               // {s, ∇}[2 blocks][16]     (double2)
+  static constexpr int wYsp = wSG + 64;              // y[2 blocks][16]
+  static constexpr int wS = wYsp + 32;               // s  by element (row operands, lane-indexed)
+  static constexpr int wNu = wS + 64;                // -u by element
+  static constexpr int wX = wNu + 64;                // x_old, ∇, ∇_old, y parked here while the
+  static constexpr int wG = wX + 64;                 //   passes need the registers
+  static constexpr int wGp = wG + 64;
+  static constexpr int wY = wGp + 64;
+  static constexpr int wSize = wY + 64;
+  // shared by the two warps: block partials of pass 1 and pass 2, [4 blocks][64 rows] each
+  static constexpr int oPart1 = 2 * wSize;
+  static constexpr int oPart2 = oPart1 + 4 * 64;
+  static constexpr int oEnd = oPart2 + 4 * 64;
 };
 
 template <int N>
 __host__ __device__ constexpr int tile_smem_doubles() { return TileCfg<N>::oEnd + 2; }
+
+__device__ __forceinline__ void warp_butterfly3(double& a, double& b, double& c) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const double ta = __shfl_xor_sync(0xffffffffu, a, off);
+    const double tb = __shfl_xor_sync(0xffffffffu, b, off);
+    const double tc = __shfl_xor_sync(0xffffffffu, c, off);
+    a = a + ta;
+    b = b + tb;
+    c = c + tc;
+  }
+}
 
 template <int N, int PF>
 __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long long j, double* smem) {
@@ -135,21 +155,31 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
   const int t = threadIdx.x;
   const int lane = t & 31;
   const int warp = t >> 5;
-  const int e = t;                    // the element this thread publishes / writes out
+  const int e = t;                    // the element this thread writes out at the end
   const bool owner = e < N;
   const bool hi_valid = lane + 32 < N;
   const int b = t >> 4;               // column block of this thread's tile (one per half-warp)
+  const int hb = b & 1;               // ... counted inside this warp's private operand arrays
   const int q = t & 15;               // row group
   const int row0 = RT * q;
   const int col0 = CT * b;
-  const int slot = (e / CT) * 16 + (e % CT);
 
-  double2* WN = reinterpret_cast<double2*>(smem + C::oWN);
-  double2* SG = reinterpret_cast<double2*>(smem + C::oSG);
-  double* ysp = smem + C::oYsp;
-  double* s_arr = smem + C::oS;
-  double* nu_arr = smem + C::oNu;
-  double* part = smem + C::oPart;
+  double* pw = smem + warp * C::wSize;             // this warp's private region
+  double2* WN = reinterpret_cast<double2*>(pw + C::wWN);
+  double2* SG = reinterpret_cast<double2*>(pw + C::wSG);
+  double* ysp = pw + C::wYsp;
+  double* s_arr = pw + C::wS;
+  double* nu_arr = pw + C::wNu;
+  double* part1 = smem + C::oPart1;
+  double* part2 = smem + C::oPart2;
+
+  // slot of element el in this warp's block-padded operand arrays, or -1 when the element
+  // belongs to a column block of the other warp
+  auto slot_of = [&](const int el) {
+    const int blk = el / CT - 2 * warp;
+    return (el < N && blk >= 0 && blk < 2) ? blk * 16 + el % CT : -1;
+  };
+  const int slot_lo = slot_of(lane), slot_hi = slot_of(lane + 32);
 
   double h[RT][CT]; // the tile: h[i][k] = B⁻¹[row0 + i, col0 + k]
 
@@ -159,8 +189,10 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
     if (hi_valid) pacc = pacc + a.hi * bb.hi;
     return pacc;
   };
+  auto park = [&](const int off, const Pair& v) { pw[off + lane] = v.lo; pw[off + 32 + lane] = v.hi; };
+  auto unpark = [&](const int off) { Pair v; v.lo = pw[off + lane]; v.hi = pw[off + 32 + lane]; return v; };
   // Σ_b part[b][e'] in ascending block order (rule C2), for e' = lane and lane+32
-  auto combine = [&]() {
+  auto combine = [&](const double* part) {
     Pair T;
     T.lo = part[lane];
 #pragma unroll
@@ -174,46 +206,78 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
     return T;
   };
 
-  Pair x, g, gp, s;
+  // ---- state.  x, g: x_old and ∇ at x_old.  s: the last step α·d.  y, sy: ∇_old - ∇ and sᵀy
+  // for the coming update.  They are produced one iteration early, by the line-search trial
+  // that gets accepted (see spec_eval).
+  Pair x, g, s, y;
+  double l0, sy = 0.0;
   {
     const double* th = p.theta0 + j * p.theta_stride; // copyto!(x_old, x), QN.jl:248
     x.lo = th[lane];
     x.hi = hi_valid ? th[lane + 32] : 0.0;
+    s.lo = s.hi = y.lo = y.hi = 0.0;
+    const double term = rosenbrock_warp_terms<N, true>(lane, x, g); // QN.jl:254 of iteration 1
+    l0 = rosenbrock_finish<N>(warp_butterfly(term), x);
+    Pair zero; zero.lo = zero.hi = 0.0;
+    park(C::wGp, zero);
   }
-  g.lo = g.hi = gp.lo = gp.hi = s.lo = s.hi = 0.0;
   double result = __longlong_as_double(0x7ff8000000000000LL); // NaN, QN.jl:291
   int iters = 0, fevals = 0, status = QN_MAX_ITER;
+
+  // A line-search trial at step a along d (QN.jl:157-162), evaluated TOGETHER with what the
+  // next iteration needs if the trial is accepted: update_state! (QN.jl:21-27) gives
+  // s' = a·d, x' = x + s'; then ∂logdensity! at x' (QN.jl:254), y' = ∇ - ∇' and s'ᵀy'
+  // (QN.jl:36-41).  The trial point itself is x + a·d as ONE fma (rule C3) — the same point
+  // as x' only for a = 1.  All sums are returned un-reduced so they share one butterfly.
+  // Only ∇', the un-reduced ℓ' terms and s'ᵀy' are kept; s', x', y' are recomputed on acceptance
+  // (the same operations on the same operands: the same bits).
+  struct Spec { Pair g; double term_next, sy; };
+  auto spec_eval = [&](const double a, const Pair& d, Spec& sp, Pair& xn, double& term_trial) {
+    Pair sn, xo, yn;
+    sn.lo = a * d.lo;     sn.hi = a * d.hi;
+    xo.lo = x.lo + sn.lo; xo.hi = x.hi + sn.hi;
+    sp.term_next = rosenbrock_warp_terms<N, true>(lane, xo, sp.g);
+    if (a == 1.0) {           // x + 1·d and fma(1, d, x) are the same bits
+      xn = xo;
+      term_trial = sp.term_next;
+    } else {
+      xn.lo = fma(a, d.lo, x.lo);
+      xn.hi = fma(a, d.hi, x.hi);
+      Pair unused;
+      term_trial = rosenbrock_warp_terms<N, false>(lane, xn, unused);
+    }
+    yn.lo = g.lo - sp.g.lo; yn.hi = g.hi - sp.g.hi;
+    sp.sy = dot(sn, yn);
+  };
 
   QN_TICK_INIT;
   for (int it = 1; it <= p.max_iter; ++it) { // QN.jl:250,253
     QN_TICK(0);
-    // ---- ℓ₀ = ∂logdensity!(∇_new, obj, x_old)  QN.jl:254, fused with y and sᵀy (QN.jl:36-41)
-    double term = rosenbrock_warp_terms<N, true>(lane, x, g);
-    Pair y;
-    y.lo = gp.lo - g.lo;
-    y.hi = gp.hi - g.hi;
-    double sy = dot(s, y);
-    warp_butterfly2(term, sy);
-    const double l0 = rosenbrock_finish<N>(term, x);
-    ++fevals;
-    if (!isfinite(l0)) { status = QN_NONFINITE; if (!(it & 1)) g = gp; break; } // QN.jl:255
+    ++fevals; // the ∂logdensity! of this iteration (QN.jl:254), evaluated by the accepted trial
+    if (!isfinite(l0)) { status = QN_NONFINITE; if (!(it & 1)) g = unpark(C::wGp); break; } // QN.jl:255
     // maximum(abs, ∇_new) < tol, QN.jl:257 (a NaN entry makes it false)
     const bool small = fabs(g.lo) < p.tol && (!hi_valid || fabs(g.hi) < p.tol);
     if (__all_sync(0xffffffffu, small)) { status = QN_CONVERGED; result = l0; break; } // QN.jl:258-261
     QN_TICK(1);
 
     double m;
-    double lx1 = 0.0; // ℓ(x + s) of the first line-search trial (reduced together with m)
+    Pair d;       // search direction
+    Spec sp;      // candidate next state of the latest trial
+    Pair xn;      // the latest trial point
+    double lx1 = 0.0;
+    bool have_trial = false;
     if (it == 1) {
       m = -1.0; // QN.jl:263-264
     } else {
-      // ---- BFGS_update!  QN.jl:34-69
-      if (owner) {
-        ysp[slot] = mine(y);
-        s_arr[e] = mine(s);
-        SG[slot] = make_double2(mine(s), mine(g));
-      }
-      __syncthreads(); // (a) operands of pass 1 visible; previous readers of `part` are done
+      // ---- BFGS_update!  QN.jl:34-69.  Operands go to this warp's private arrays.
+      s_arr[lane] = s.lo;
+      s_arr[lane + 32] = s.hi;
+      if (slot_lo >= 0) { ysp[slot_lo] = y.lo; SG[slot_lo] = make_double2(s.lo, g.lo); }
+      if (slot_hi >= 0) { ysp[slot_hi] = y.hi; SG[slot_hi] = make_double2(s.hi, g.hi); }
+      park(C::wX, x);
+      park(C::wG, g);
+      park(C::wY, y);
+      __syncwarp();
       QN_TICK(2);
       const double rho = 1.0 / sy; // QN.jl:42 (no guard)
       // pass 1 on the tile: t[i] = Σ_k y[col0+k] H[row0+i, col0+k]   QN.jl:44-49
@@ -221,7 +285,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
         double tt[RT];
 #pragma unroll
         for (int i = 0; i < RT; ++i) tt[i] = 0.0;
-        const double2* yb = reinterpret_cast<const double2*>(ysp + b * 16);
+        const double2* yb = reinterpret_cast<const double2*>(ysp + hb * 16);
         double2 yy[(CT + 1) / 2];
 #pragma unroll
         for (int k2 = 0; k2 < (CT + 1) / 2; ++k2) yy[k2] = yb[k2];
@@ -233,21 +297,25 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
             for (int i = 0; i < RT; ++i) tt[i] = fma(yk, h[i][k], tt[i]);
           }
         }
-        double2* pp = reinterpret_cast<double2*>(part + b * 64 + row0);
+        double2* pp = reinterpret_cast<double2*>(part1 + b * 64 + row0);
         pp[0] = make_double2(tt[0], tt[1]);
         pp[1] = make_double2(tt[2], tt[3]);
       }
-      __syncthreads(); // (b) pass-1 partials visible
+      __syncthreads(); // pass-1 partials of both warps visible
       QN_TICK(3);
-      const Pair T = combine();
-      const double yHy = warp_butterfly(dot(T, y));  // Σ_c t[c] y[c], QN.jl:51
-      const double c1 = fma(yHy, rho, 1.0) * rho;    // QN.jl:54
-      if (owner) {
-        const double nu = -(mine(T) * rho);          // -B⁻¹y[c] = -(t ρ), QN.jl:50
-        nu_arr[e] = nu;
-        WN[slot] = make_double2(c1 * mine(s), nu);   // (c₁ s[r]) rounded once per r (rule C4)
+      {
+        const Pair T = combine(part1);
+        const Pair yv = unpark(C::wY);
+        const double yHy = warp_butterfly(dot(T, yv)); // Σ_c t[c] y[c], QN.jl:51
+        const double c1 = fma(yHy, rho, 1.0) * rho;    // QN.jl:54
+        const double nu_lo = -(T.lo * rho), nu_hi = -(T.hi * rho); // -B⁻¹y[c] = -(t ρ), QN.jl:50
+        nu_arr[lane] = nu_lo;
+        nu_arr[lane + 32] = nu_hi;
+        // (c₁ s[r]) rounded once per r (rule C4)
+        if (slot_lo >= 0) WN[slot_lo] = make_double2(c1 * s_arr[lane], nu_lo);
+        if (slot_hi >= 0) WN[slot_hi] = make_double2(c1 * s_arr[lane + 32], nu_hi);
       }
-      __syncthreads(); // (c) operands of pass 2 visible; pass-1 partials consumed
+      __syncwarp();
       QN_TICK(4);
       // pass 2 on the tile: H ← H + c₁ssᵀ - usᵀ - suᵀ fused with d = H⁺∇_new   QN.jl:56-67
       {
@@ -260,10 +328,9 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
         nuc[0] = n01.x; nuc[1] = n01.y; nuc[2] = n23.x; nuc[3] = n23.y;
 #pragma unroll
         for (int i = 0; i < RT; ++i) acc[i] = 0.0;
-        const double2* wnb = WN + b * 16;
-        const double2* sgb = SG + b * 16;
-        // operand ring: the loads of step k+PF are issued while step k computes, so the
-        // ~35-cycle shared-memory latency is covered by PF steps of 16 DFMA each
+        const double2* wnb = WN + hb * 16;
+        const double2* sgb = SG + hb * 16;
+        // operand ring: the loads of step k+PF are issued while step k computes
         double2 wnr[PF + 1], sgr[PF + 1];
 #pragma unroll
         for (int k = 0; k < PF && k < CT; ++k) { wnr[k] = wnb[k]; sgr[k] = sgb[k]; }
@@ -283,50 +350,51 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
             }
           }
         }
-        double2* pp = reinterpret_cast<double2*>(part + b * 64 + row0);
+        double2* pp = reinterpret_cast<double2*>(part2 + b * 64 + row0);
         pp[0] = make_double2(acc[0], acc[1]);
         pp[1] = make_double2(acc[2], acc[3]);
       }
-      __syncthreads(); // (d) pass-2 partials visible
+      __syncthreads(); // pass-2 partials of both warps visible
       QN_TICK(5);
-      s = combine();   // the new direction d = H⁺∇_new; `s, y = y, s`, QN.jl:65,268
-      // m = dᵀ∇_new (QN.jl:66-68) shares its butterfly with the first trial of the line
-      // search, ℓ(x + 1·d) (QN.jl:174), whose inputs are ready at the same time.
-      Pair xn, gdummy;
-      xn.lo = fma(1.0, s.lo, x.lo);
-      xn.hi = fma(1.0, s.hi, x.hi);
-      double tterm = rosenbrock_warp_terms<N, false>(lane, xn, gdummy);
-      m = dot(s, g);
-      warp_butterfly2(m, tterm);
+      d = combine(part2); // the new direction d = H⁺∇_new; `s, y = y, s`, QN.jl:65,268
+      x = unpark(C::wX);
+      g = unpark(C::wG);
+      // m = dᵀ∇_new (QN.jl:66-68) shares its butterfly with the first line-search trial
+      // ℓ(x + 1·d) (QN.jl:174) and with s'ᵀy' of the iteration that follows if it is accepted.
+      double tterm;
+      spec_eval(1.0, d, sp, xn, tterm);
+      m = dot(d, g);
+      warp_butterfly3(m, tterm, sp.sy);
+      sp.term_next = tterm;
       lx1 = rosenbrock_finish<N>(tterm, xn);
+      have_trial = true;
       QN_TICK(6);
     }
-    const bool reset = (m <= 0.0);
-    if (reset) { // QN.jl:272-280: H ← I, s ← ∇_new, m ← ∇ᵀ∇
+    if (m <= 0.0) { // QN.jl:272-280: H ← I, s ← ∇_new, m ← ∇ᵀ∇
 #pragma unroll
       for (int i = 0; i < RT; ++i)
 #pragma unroll
         for (int k = 0; k < CT; ++k) h[i][k] = (row0 + i == col0 + k) ? 1.0 : 0.0;
-      s = g;
+      d = g;
       m = warp_butterfly(dot(g, g));
+      have_trial = false;
     }
 
     // ---- linesearch!  QN.jl:165-232; both warps run the same scalar code on the same values
     double alpha;
     {
       const LsParams& ls = p.ls;
-      auto trial = [&](const double a) { // step! (QN.jl:157-162): x_new = x_old + a s, one fma each
-        Pair xn, gdummy;
-        xn.lo = fma(a, s.lo, x.lo);
-        xn.hi = fma(a, s.hi, x.hi);
-        const double sum = warp_butterfly(rosenbrock_warp_terms<N, false>(lane, xn, gdummy));
+      auto trial = [&](const double a) {
+        double tterm;
+        spec_eval(a, d, sp, xn, tterm);
+        warp_butterfly3(tterm, sp.term_next, sp.sy);
         ++fevals;
-        return rosenbrock_finish<N>(sum, xn);
+        return rosenbrock_finish<N>(tterm, xn);
       };
       double lx0 = l0;
       double a1 = 1.0, a2 = 1.0;
-      if (it == 1 || reset) lx1 = trial(a1); // otherwise already evaluated above
-      else ++fevals;
+      if (have_trial) ++fevals; // evaluated above, together with m
+      else lx1 = trial(a1);     // QN.jl:174
       int iterfinite = 0;
       while (!isfinite(lx1) && iterfinite < 52) { // QN.jl:178-184
         ++iterfinite;
@@ -351,8 +419,8 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
           if (fabs(a) <= kEps + kSqrtTol * fabs(a)) {  // QN.jl:211
             at = m / (2.0 * bq);                       // QN.jl:212
           } else {
-            const double d = nanmax(bq * bq - (3.0 * a) * m, 0.0); // QN.jl:215
-            at = (sqrt(d) + bq) / (-3.0 * a);                      // QN.jl:218
+            const double dd = nanmax(bq * bq - (3.0 * a) * m, 0.0); // QN.jl:215
+            at = (sqrt(dd) + bq) / (-3.0 * a);                      // QN.jl:218
           }
         }
         a1 = a2;                           // QN.jl:222
@@ -364,16 +432,21 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
       alpha = failed ? 0.0 : a2;
     }
     QN_TICK(7);
-    if (alpha == 0.0) { status = QN_LINESEARCH_FAILED; if (!(it & 1)) g = gp; break; } // QN.jl:284
-    // update_state!: s ← αs ; x_old += s   QN.jl:21-27
-    s.lo = alpha * s.lo; s.hi = alpha * s.hi;
-    x.lo = x.lo + s.lo;  x.hi = x.hi + s.hi;
+    if (alpha == 0.0) { status = QN_LINESEARCH_FAILED; if (!(it & 1)) g = unpark(C::wGp); break; } // QN.jl:284
+    // ---- accept: update_state! (QN.jl:21-27) and the buffer swap (QN.jl:286) were already
+    // applied to the candidate; its ∂logdensity! becomes the next iteration's (QN.jl:254).
+    s.lo = alpha * d.lo; s.hi = alpha * d.hi; // s ← αs      QN.jl:23-24
+    x.lo = x.lo + s.lo;  x.hi = x.hi + s.hi;  // x_old += s  QN.jl:25
     ++iters;
     if (p.trace != nullptr && it <= p.ntrace && owner)
       p.trace[(j * p.ntrace + (it - 1)) * (long long)N + e] = mine(x);
     // N iterations exhausted (QN.jl:250,291); which ∇ the canonical slot shows: see qn_resident.cuh
-    if (it == p.max_iter) { if (!(it & 1)) g = gp; break; }
-    gp = g; // ∇_old, ∇_new = ∇_new, ∇_old, QN.jl:286
+    if (it == p.max_iter) { if (!(it & 1)) g = unpark(C::wGp); break; }
+    park(C::wGp, g);
+    y.lo = g.lo - sp.g.lo; y.hi = g.hi - sp.g.hi; // y = ∇_old - ∇_new, QN.jl:38
+    sy = sp.sy;
+    g = sp.g;
+    l0 = (alpha == 1.0) ? lx1 : rosenbrock_finish<N>(sp.term_next, x);
   }
 
   if (owner) {
