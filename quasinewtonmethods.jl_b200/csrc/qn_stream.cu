@@ -60,6 +60,23 @@ struct StreamParams {
   double* trace; // [ntrace][n]
 };
 
+// Element-wise pass over n elements by one CTA with 8 independent loads in flight per thread
+// (a single SM sees ~700 cycles of L2 latency per dependent round trip): ld(i) loads/computes,
+// st(i, v) stores.
+template <class L, class S>
+__device__ __forceinline__ void cta_map(int n, L&& ld, S&& st) {
+  const int T = blockDim.x;
+  int i = threadIdx.x;
+  for (; i + 7 * T < n; i += 8 * T) {
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = ld(i + k * T);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) st(i + k * T, v[k]);
+  }
+  for (; i < n; i += T) st(i, ld(i));
+}
+
 // ---- canonical csum (rule C1) by one CTA.  `stage` is an n-double scratch array (shared
 // memory when it fits, else global); `red` is one shared double.  Every thread calls it.
 __device__ __forceinline__ double cta_csum_staged(int n, const double* stage, double* red) {
@@ -85,16 +102,26 @@ __device__ __forceinline__ double cta_csum_staged(int n, const double* stage, do
 }
 template <class F>
 __device__ __forceinline__ double cta_csum(int n, double* stage, double* red, F&& v) {
-  for (int i = threadIdx.x; i < n; i += blockDim.x) stage[i] = v(i);
+  // four independent elements per thread per round: the L2 loads inside v() overlap
+  const int T = blockDim.x;
+  int i = threadIdx.x;
+  for (; i + 3 * T < n; i += 4 * T) {
+    const double a = v(i), b = v(i + T), c = v(i + 2 * T), d = v(i + 3 * T);
+    stage[i] = a; stage[i + T] = b; stage[i + 2 * T] = c; stage[i + 3 * T] = d;
+  }
+  for (; i < n; i += T) stage[i] = v(i);
   __syncthreads();
   return cta_csum_staged(n, stage, red);
 }
 
-// Rosenbrock (test/runtests.jl:4-33) by one CTA; writes ∇ to g when g != nullptr.
-__device__ __forceinline__ double cta_rosenbrock(int n, const double* x, double* g, double* tmp, double* red) {
+// Rosenbrock (test/runtests.jl:4-33) by one CTA at the point X(i); writes ∇ to g when
+// g != nullptr.  X is a functor so a line-search trial can evaluate at x + a·s without
+// materialising the point (step!, QN.jl:157-162).
+template <class XF>
+__device__ __forceinline__ double cta_rosenbrock(int n, XF&& X, double* g, double* stage, double* red) {
   const int N = n >> 1;
-  const double sum = cta_csum(N, tmp, red, [&](int i) {
-    const double t1 = x[i], t2 = x[i + N];
+  const double sum = cta_csum(N, stage, red, [&](int i) {
+    const double t1 = X(i), t2 = X(i + N);
     const double a = t2 - t1 * t1;
     const double b = 1.0 - t1;
     if (g) {
@@ -105,7 +132,7 @@ __device__ __forceinline__ double cta_rosenbrock(int n, const double* x, double*
   });
   double s = 0.0 - sum;
   if (n & 1) {
-    const double d = 1.0 - x[n - 1];
+    const double d = 1.0 - X(n - 1);
     s = -fma(d, d, -s);
     if (g && threadIdx.x == 0) g[n - 1] = 2.0 * d;
   }
@@ -121,7 +148,8 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_begin(const StreamPara
   const int n = p.n;
   const int it = sc->it + 1;
   double* stage = p.stage_in_smem ? vsm : p.tmp;
-  const double l0 = cta_rosenbrock(n, p.x, p.g, stage, &red); // QN.jl:254
+  const double* xv = p.x;
+  const double l0 = cta_rosenbrock(n, [&](int i) { return xv[i]; }, p.g, stage, &red); // QN.jl:254
   __syncthreads();
   if (threadIdx.x == 0) { sc->l0 = l0; sc->fevals += 1; flag = 1; }
   if (!isfinite(l0)) { // QN.jl:255
@@ -130,7 +158,7 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_begin(const StreamPara
   }
   __syncthreads();
   bool small = true; // maximum(abs, ∇) < tol, QN.jl:257
-  for (int i = threadIdx.x; i < n; i += blockDim.x) small = small && (fabs(p.g[i]) < p.tol);
+  cta_map(n, [&](int i) { return p.g[i]; }, [&](int, double gi) { small = small && (fabs(gi) < p.tol); });
   if (!small) flag = 0;
   __syncthreads();
   if (flag) {
@@ -189,12 +217,12 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_mid(const StreamParams
   // pass1's tail left t[c]·y[c] in tmp and -u in nu; yᵀB⁻¹y = csum, QN.jl:51
   double* stage = p.stage_in_smem ? vsm : p.tmp;
   if (p.stage_in_smem) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) stage[i] = p.tmp[i];
+    cta_map(n, [&](int i) { return p.tmp[i]; }, [&](int i, double v) { stage[i] = v; });
     __syncthreads();
   }
   const double yHy = cta_csum_staged(n, stage, &red);
   const double c1 = fma(yHy, rho, 1.0) * rho; // QN.jl:54
-  for (int c = threadIdx.x; c < n; c += blockDim.x) p.w[c] = c1 * p.s[c];
+  cta_map(n, [&](int c) { return p.s[c]; }, [&](int c, double sc_) { p.w[c] = c1 * sc_; });
   if (threadIdx.x == 0) sc->c1 = c1;
 }
 
@@ -207,16 +235,15 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_end(const StreamParams
   const int it = sc->it + 1;
   const double l0 = sc->l0;
   double* stage = p.stage_in_smem ? vsm : p.tmp;            // n doubles
-  double* xs = p.stage_in_smem ? vsm + ((n + 1) & ~1) : p.xs; // trial point, n doubles
   double m;
   if (!sc->skip_update) {
     // pass2's tail left d in s and d[c]·∇[c] in tmp; m = dᵀ∇_new = csum, QN.jl:66-68
     if (p.stage_in_smem) {
-      for (int i = threadIdx.x; i < n; i += blockDim.x) stage[i] = p.tmp[i];
+      cta_map(n, [&](int i) { return p.tmp[i]; }, [&](int i, double v) { stage[i] = v; });
       __syncthreads();
     }
     m = cta_csum_staged(n, stage, &red);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) p.s[i] = p.dvec[i]; // `s, y = y, s`, QN.jl:65,268
+    cta_map(n, [&](int i) { return p.dvec[i]; }, [&](int i, double v) { p.s[i] = v; }); // `s, y = y, s`, QN.jl:65,268
     __syncthreads();
   } else {
     m = sc->m;
@@ -233,11 +260,11 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_end(const StreamParams
   __syncthreads();
   // ---- linesearch!  QN.jl:165-232
   int fevals = 0;
-  auto trial = [&](double a) { // step!, QN.jl:157-162
-    for (int i = threadIdx.x; i < n; i += blockDim.x) xs[i] = fma(a, p.s[i], p.x[i]);
-    __syncthreads();
+  const double* xv = p.x;
+  const double* sv = p.s;
+  auto trial = [&](double a) { // step! (QN.jl:157-162): x_new[i] = x_old[i] + a s[i] as one fma
     ++fevals;
-    return cta_rosenbrock(n, xs, nullptr, stage, &red);
+    return cta_rosenbrock(n, [&](int i) { return fma(a, sv[i], xv[i]); }, nullptr, stage, &red);
   };
   const LsParams& ls = p.ls;
   double lx0 = l0, lx1;
@@ -283,14 +310,12 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_end(const StreamParams
     return;
   }
   // update_state!  QN.jl:21-27 ; ∇_old ← ∇_new  QN.jl:286
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const double si = alpha * p.s[i];
-    p.s[i] = si;
-    const double xi = p.x[i] + si;
+  cta_map(n, [&](int i) { return alpha * p.s[i]; }, [&](int i, double si) { p.s[i] = si; });
+  cta_map(n, [&](int i) { return p.x[i] + p.s[i]; }, [&](int i, double xi) {
     p.x[i] = xi;
-    if (it < p.max_iter) p.gp[i] = p.g[i];
     if (p.trace != nullptr && it <= p.ntrace) p.trace[(size_t)(it - 1) * n + i] = xi;
-  }
+  });
+  if (it < p.max_iter) cta_map(n, [&](int i) { return p.g[i]; }, [&](int i, double gi) { p.gp[i] = gi; });
   if (threadIdx.x == 0) {
     sc->m = m;
     sc->it = it;
@@ -496,8 +521,8 @@ int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_bac
   p.partial = base + 11 * nv;
   p.sc = reinterpret_cast<StreamScalars*>(p.partial + (size_t)p.nsb * n);
   p.tile_count = reinterpret_cast<unsigned int*>(p.partial + (size_t)p.nsb * n + 32);
-  // vec kernels stage their reductions (n doubles) and the trial point (n doubles) in shared memory
-  const size_t vec_smem = sizeof(double) * (2 * (((size_t)n + 1) & ~(size_t)1));
+  // vec kernels stage their reductions (n doubles) in shared memory
+  const size_t vec_smem = sizeof(double) * (((size_t)n + 1) & ~(size_t)1);
   p.stage_in_smem = vec_smem <= (size_t)ctx->prop.sharedMemPerBlockOptin - 1024;
   w.vec_smem = p.stage_in_smem ? vec_smem : 0;
   int rc = QN_OK;

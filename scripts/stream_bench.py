@@ -6,7 +6,7 @@ eng = qn.default_engine()
 out = {}
 for n in [int(a) for a in sys.argv[1:]] or [8192]:
     ms, gbs = C.c_double(), C.c_double()
-    qn._lib.check(eng._lib.qn_stream_bench_f64(eng._ctx, n, 22, 2, C.byref(ms), C.byref(gbs)))
+    qn._lib.check(eng._lib.qn_stream_bench_f64(eng._ctx, n, int(os.environ.get("QN_STREAM_ITERS", "22")), 2, C.byref(ms), C.byref(gbs)))
     out[n] = dict(ms_per_iter=ms.value, algorithmic_gbs=gbs.value, physical_gbs=gbs.value * 1.5)
     print(n, out[n])
 hbm = C.c_double(); qn._lib.check(eng._lib.qn_microbench_hbm(eng._ctx, C.byref(hbm)))
