@@ -57,7 +57,17 @@ template <class Obj, int NREG, int BLOCK, int MINB>
 int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Params& op,
                     cudaStream_t st) {
   const int n = p.n;
-  const qn::ResidentSmem L = qn::resident_smem_layout<Obj>(n, NREG == 0, op);
+  // shared-memory policy: deal the rule-C2 blocks of a row out to up to 4 threads while the
+  // CTA stays within 1024 threads and the partial-sum array still fits beside B⁻¹
+  const int B = qn::resident_block_threads(n);
+  int tpr = 1;
+  if (NREG == 0 && n >= 48) {
+    for (int cand = 4; cand >= 2; cand >>= 1) {
+      const size_t need = sizeof(double) * (size_t)qn::resident_smem_layout<Obj>(n, true, cand, op).total;
+      if (B * cand <= 1024 && need <= (size_t)ctx->prop.sharedMemPerBlockOptin) { tpr = cand; break; }
+    }
+  }
+  const qn::ResidentSmem L = qn::resident_smem_layout<Obj>(n, NREG == 0, tpr, op);
   const size_t smem = sizeof(double) * (size_t)L.total;
   if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin)
     return fail(QN_ERR_UNSUPPORTED_SIZE,
@@ -66,7 +76,7 @@ int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Par
                 n, smem, (size_t)ctx->prop.sharedMemPerBlockOptin);
   auto kern = qn::qn_resident_kernel<Obj, NREG, BLOCK, MINB>;
   QN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int block = (NREG > 0) ? BLOCK : qn::resident_block_threads(n);
+  const int block = (NREG > 0) ? BLOCK : B * tpr;
   int occ = 0;
   QN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
   if (occ < 1) return fail(QN_ERR_UNSUPPORTED_SIZE, "resident kernel does not fit on an SM (n=%d)", n);
@@ -131,7 +141,7 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
       }
     }
   }
-  if (n <= 256) return launch_resident<Obj, 0, 256, 1>(ctx, p, op, st);
+  if (n <= 256) return launch_resident<Obj, 0, 1024, 1>(ctx, p, op, st);
   return fail(QN_ERR_UNSUPPORTED_SIZE, "n=%d does not fit the resident path", n);
 }
 

@@ -97,8 +97,11 @@ struct Team {
   double* red;  // two staging buffers of `stride` doubles each
   int stride;
   int phase;
-  double* xs;      // the point the objective is evaluated at (n doubles, shared)
+  double* xs;      // the point the objective is evaluated at (shared, nvec doubles)
+  int nvec;        // length of the per-element shared arrays (threads >= nvec own no element)
   double* scratch; // objective scratch (shared)
+  double* part;    // [rule-C2 blocks][nvec] block partials, present when tpr > 1
+  int tpr;         // threads per row: blockDim = nvec * tpr (1 = one thread per element)
 
   // canonical csum (rule C1) split around a barrier the caller provides
   __device__ __forceinline__ void stage(double v) {
@@ -111,6 +114,42 @@ struct Team {
     for (int i = lane + 32; i < count; i += 32) p = p + r[i];
     return warp_butterfly(p);
   }
+  // Rule-C2 row sum over K terms for every row c < n, using ALL threads of the team: the
+  // blocks of row (c mod nvec) are dealt out to its tpr threads, the partials meet in `part`,
+  // and the owner (c < n) adds them in ascending order.  term(row, r, a, b) yields the two fma
+  // operands.  Returns the row sum in the owner thread (0 elsewhere).  Contains a barrier
+  // when tpr > 1; the next use of `part` must be separated from this one by another barrier.
+  template <class F>
+  __device__ __forceinline__ double rowsum(int K, F&& term) {
+    if (tpr == 1) {
+      if (c >= n) return 0.0;
+      const int row = c;
+      return chain_rowsum(K, [&](int r, double& a, double& b) { term(row, r, a, b); });
+    }
+    const int rb = chain_block(K);
+    const int row = c % nvec, hgrp = c / nvec;
+    if (row < n) {
+      for (int r0 = hgrp * rb, blk = hgrp; r0 < K; r0 += tpr * rb, blk += tpr) {
+        const int r1 = min(r0 + rb, K);
+        double t = 0.0;
+#pragma unroll 4
+        for (int r = r0; r < r1; ++r) {
+          double a, b;
+          term(row, r, a, b);
+          t = fma(a, b, t);
+        }
+        part[blk * nvec + row] = t;
+      }
+    }
+    __syncthreads();
+    double T = 0.0;
+    if (c < n) {
+      T = part[c];
+      for (int r0 = rb, blk = 1; r0 < K; r0 += rb, ++blk) T = T + part[blk * nvec + c];
+    }
+    return T;
+  }
+
   // Thread c contributes v when c < count.  Result is identical in every thread.
   // Two staging buffers alternate, so the barrier inside the NEXT csum is what
   // protects this one's buffer from being overwritten while a slow warp reads.

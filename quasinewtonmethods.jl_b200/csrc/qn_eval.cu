@@ -21,6 +21,9 @@ qn_eval_kernel(int n, long long batch, const double* __restrict__ theta, double*
   tm.stride = B;
   tm.phase = 0;
   tm.xs = smem + 2 * B;
+  tm.nvec = B;
+  tm.tpr = 1;
+  tm.part = nullptr;
   tm.scratch = smem + 3 * B;
   for (long long j = blockIdx.x; j < batch; j += gridDim.x) {
     __syncthreads();

@@ -77,14 +77,13 @@ struct DenseGaussian {
       ds[c] = d;
     }
     __syncthreads();
-    double z = 0.0;
-    if (c < n) {
-      const double* row = p.lambda + c;
-      z = chain_rowsum(n, [&](int r, double& a, double& b) {
-        a = __ldg(row + (size_t)n * r);
-        b = ds[r];
-      });
-    }
+    // z = Λ(θ-μ): rule-C2 row sums, the blocks of a row shared by the team's tpr threads
+    // (K = n <= 256: one super-block).  The csum below is the barrier after this use of `part`.
+    const double* lam = p.lambda;
+    const double z = t.rowsum(n, [&](int row, int r, double& a, double& b) {
+      a = __ldg(lam + row + (size_t)n * r);
+      b = ds[r];
+    });
     const double q = t.csum(d * z, n);
     if (GRAD) g = -z;
     return -0.5 * q;

@@ -32,21 +32,25 @@ struct __align__(16) Pass2Col {
 
 __host__ __device__ inline int resident_block_threads(int n) { return (n + 31) & ~31; }
 
-// shared memory carve-up (in doubles)
+// shared memory carve-up (in doubles).  tpr = threads per row of B⁻¹ (shared-memory policy
+// only): the rule-C2 blocks of a row are dealt out to tpr threads, whose block partials meet
+// in `part` ([blocks][B]).
 struct ResidentSmem {
-  int red, xs, ys, cols, scratch, h, total;
+  int red, xs, ys, cols, scratch, part, h, total;
 };
 template <class Obj>
-__host__ __device__ inline ResidentSmem resident_smem_layout(int n, bool h_in_smem,
+__host__ __device__ inline ResidentSmem resident_smem_layout(int n, bool h_in_smem, int tpr,
                                                              const typename Obj::Params& op) {
   const int B = resident_block_threads(n);
+  const int nblocks = (n + chain_block(n) - 1) / chain_block(n);
   ResidentSmem L;
   int o = 0;
   L.cols = o; o += 4 * B;   // Pass2Col[B], 16-byte aligned at offset 0
   L.ys = o;   o += B;
   L.xs = o;   o += B;
-  L.red = o;  o += 2 * B;
+  L.red = o;  o += 2 * B * tpr;
   L.scratch = o; o += Obj::scratch_doubles(n, op);
+  L.part = o; o += (tpr > 1) ? nblocks * B : 0;
   L.h = o;    o += h_in_smem ? n * n : 0;
   L.total = o + 2; // + problem index broadcast slot
   return L;
@@ -64,7 +68,7 @@ __device__ __forceinline__ double team_linesearch(Team& tm, const typename Obj::
   double a1 = 1.0, a2 = 1.0;
   double dummy;
   // step!: x_new = x_old + α s (one fma, rule C3), then logdensity. QN.jl:157-162
-  tm.xs[tm.c] = fma(a1, s, x);
+  if (tm.c < tm.nvec) tm.xs[tm.c] = fma(a1, s, x);
   __syncthreads();
   lx1 = Obj::template eval<false>(tm, op, dummy);
   ++fevals;
@@ -73,7 +77,7 @@ __device__ __forceinline__ double team_linesearch(Team& tm, const typename Obj::
     ++iterfinite;
     a1 = a2;
     a2 = 0.5 * a2;
-    tm.xs[tm.c] = fma(a2, s, x);
+    if (tm.c < tm.nvec) tm.xs[tm.c] = fma(a2, s, x);
     __syncthreads();
     lx1 = Obj::template eval<false>(tm, op, dummy);
     ++fevals;
@@ -102,7 +106,7 @@ __device__ __forceinline__ double team_linesearch(Team& tm, const typename Obj::
     at = nanmin(at, a2 * ls.rho_hi);   // QN.jl:224
     a2 = nanmax(at, a2 * ls.rho_lo);   // QN.jl:225
     lx0 = lx1;                         // QN.jl:228
-    tm.xs[tm.c] = fma(a2, s, x);
+    if (tm.c < tm.nvec) tm.xs[tm.c] = fma(a2, s, x);
     __syncthreads();
     lx1 = Obj::template eval<false>(tm, op, dummy);
     ++fevals;
@@ -125,10 +129,17 @@ template <class Obj, int NREG>
 __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
                                                    const typename Obj::Params& op,
                                                    const long long j, Team& tm, double* ys,
-                                                   Pass2Col* cols, double* hs) {
+                                                   Pass2Col* cols, double* hs, double* part) {
   const int n = (NREG > 0) ? NREG : p.n;
-  const int c = tm.c;
+  const int c = tm.c;          // thread index: the owner of element c when c < n
   const bool active = c < n;
+  // shared-memory policy: tpr threads share a row; thread c works on row c mod B and on the
+  // rule-C2 blocks hgrp, hgrp + tpr, ... of it
+  const int B = resident_block_threads(n);
+  const int tpr = (NREG > 0) ? 1 : (int)blockDim.x / B;
+  const int row = (NREG > 0) ? c : c % B;
+  const int hgrp = (NREG > 0) ? 0 : c / B;
+  (void)part; (void)row; (void)hgrp; (void)tpr;
   constexpr int HR = (NREG > 0) ? NREG : 1;
   const int rb = chain_block(n); // rule C2 block length
   double h[HR]; // row c of B⁻¹ (register policy)
@@ -141,7 +152,7 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
 
   for (int it = 1; it <= p.max_iter; ++it) { // QN.jl:250,253
     // ---- ℓ₀ = ∂logdensity!(∇_new, obj, x_old)   QN.jl:254
-    tm.xs[c] = x;
+    if (c < B) tm.xs[c] = x;
     __syncthreads();
     const double l0 = Obj::template eval<true>(tm, op, g);
     ++fevals;
@@ -150,9 +161,11 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
     // publish what the update needs, and test convergence, on one barrier.
     // y = ∇_old - ∇_new, QN.jl:38
     const double y = g_prev - g;
-    ys[c] = y;
-    cols[c].s = s;
-    cols[c].g = g;
+    if (c < B) {
+      ys[c] = y;
+      cols[c].s = s;
+      cols[c].g = g;
+    }
     tm.stage(s * y);
     // maximum(abs, ∇_new) < tol, QN.jl:257 (a NaN entry makes it false)
     const int conv = __syncthreads_and(!active || fabs(g) < p.tol);
@@ -177,21 +190,39 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
           for (int r = r0; r < r0 + RB && r < HR; ++r) t = fma(ys[r], h[r], t);
           T = (r0 == 0) ? t : T + t;
         }
-      } else if (active) {
-        const double* hrow = hs + c;
-        for (int r0 = 0; r0 < n; r0 += rb) {
-          const int r1 = min(r0 + rb, n);
-          double t = 0.0;
+      } else if (tpr == 1) {
+        if (active) {
+          const double* hrow = hs + c;
+          for (int r0 = 0; r0 < n; r0 += rb) {
+            const int r1 = min(r0 + rb, n);
+            double t = 0.0;
 #pragma unroll 4
-          for (int r = r0; r < r1; ++r) t = fma(ys[r], hrow[n * r], t);
-          T = (r0 == 0) ? t : T + t;
+            for (int r = r0; r < r1; ++r) t = fma(ys[r], hrow[n * r], t);
+            T = (r0 == 0) ? t : T + t;
+          }
+        }
+      } else {
+        if (row < n) {
+          const double* hrow = hs + row;
+          for (int r0 = hgrp * rb, blk = hgrp; r0 < n; r0 += tpr * rb, blk += tpr) {
+            const int r1 = min(r0 + rb, n);
+            double t = 0.0;
+#pragma unroll 4
+            for (int r = r0; r < r1; ++r) t = fma(ys[r], hrow[n * r], t);
+            part[blk * B + row] = t;
+          }
+        }
+        __syncthreads();
+        if (active) { // block partials in ascending order (rule C2)
+          T = part[c];
+          for (int r0 = rb, blk = 1; r0 < n; r0 += rb, ++blk) T = T + part[blk * B + c];
         }
       }
       const double u = T * rho;       // B⁻¹y[c] = t ρ, QN.jl:50
-      cols[c].nu = -u;
+      if (c < B) cols[c].nu = -u;
       const double yHy = tm.csum(T * y, n);          // QN.jl:51
       const double c1 = fma(yHy, rho, 1.0) * rho;    // QN.jl:54
-      cols[c].w = c1 * s;                            // (c₁ s[r]), rounded once per r (rule C4)
+      if (c < B) cols[c].w = c1 * s;                 // (c₁ s[r]), rounded once per r (rule C4)
       __syncthreads();
       // pass 2: H ← H + c₁ssᵀ - usᵀ - suᵀ fused with d = H⁺∇_new   QN.jl:56-67
       const double nu_c = -u;
@@ -214,23 +245,51 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
           }
           D = (r0 == 0) ? acc : D + acc;
         }
-      } else if (active) {
-        double* hrow = hs + c;
-        for (int r0 = 0; r0 < n; r0 += rb) {
-          const int r1 = min(r0 + rb, n);
-          double acc = 0.0;
+      } else if (tpr == 1) {
+        if (active) {
+          double* hrow = hs + c;
+          for (int r0 = 0; r0 < n; r0 += rb) {
+            const int r1 = min(r0 + rb, n);
+            double acc = 0.0;
 #pragma unroll 4
-          for (int r = r0; r < r1; ++r) {
-            const double2 wn = *reinterpret_cast<const double2*>(&cols[r].w);
-            const double2 sg = *reinterpret_cast<const double2*>(&cols[r].s);
-            double hh = hrow[n * r];
-            hh = fma(wn.x, s, hh);
-            hh = fma(wn.y, s, hh);
-            hh = fma(nu_c, sg.x, hh);
-            hrow[n * r] = hh;
-            acc = fma(hh, sg.y, acc);
+            for (int r = r0; r < r1; ++r) {
+              const double2 wn = *reinterpret_cast<const double2*>(&cols[r].w);
+              const double2 sg = *reinterpret_cast<const double2*>(&cols[r].s);
+              double hh = hrow[n * r];
+              hh = fma(wn.x, s, hh);
+              hh = fma(wn.y, s, hh);
+              hh = fma(nu_c, sg.x, hh);
+              hrow[n * r] = hh;
+              acc = fma(hh, sg.y, acc);
+            }
+            D = (r0 == 0) ? acc : D + acc;
           }
-          D = (r0 == 0) ? acc : D + acc;
+        }
+      } else {
+        if (row < n) {
+          const double s_row = cols[row].s, nu_row = cols[row].nu; // published by the row's owner
+          double* hrow = hs + row;
+          for (int r0 = hgrp * rb, blk = hgrp; r0 < n; r0 += tpr * rb, blk += tpr) {
+            const int r1 = min(r0 + rb, n);
+            double acc = 0.0;
+#pragma unroll 4
+            for (int r = r0; r < r1; ++r) {
+              const double2 wn = *reinterpret_cast<const double2*>(&cols[r].w);
+              const double2 sg = *reinterpret_cast<const double2*>(&cols[r].s);
+              double hh = hrow[n * r];
+              hh = fma(wn.x, s_row, hh);
+              hh = fma(wn.y, s_row, hh);
+              hh = fma(nu_row, sg.x, hh);
+              hrow[n * r] = hh;
+              acc = fma(hh, sg.y, acc);
+            }
+            part[blk * B + row] = acc;
+          }
+        }
+        __syncthreads();
+        if (active) {
+          D = part[c];
+          for (int r0 = rb, blk = 1; r0 < n; r0 += rb, ++blk) D = D + part[blk * B + c];
         }
       }
       m = tm.csum(D * g, n); // m = dᵀ∇_new, QN.jl:66-68
@@ -282,18 +341,23 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
 template <class Obj, int NREG, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
 qn_resident_kernel(const BatchParams p, const typename Obj::Params op) {
+  // launch: blockDim = resident_block_threads(n) * tpr (tpr = 1 for the register policy)
   extern __shared__ __align__(16) double smem[];
   const int n = (NREG > 0) ? NREG : p.n;
-  const ResidentSmem L = resident_smem_layout<Obj>(n, NREG == 0, op);
+  const int tpr = (NREG > 0) ? 1 : (int)blockDim.x / resident_block_threads(n);
+  const ResidentSmem L = resident_smem_layout<Obj>(n, NREG == 0, tpr, op);
 
   Team tm;
   tm.n = n;
   tm.c = threadIdx.x;
   tm.lane = threadIdx.x & 31;
   tm.red = smem + L.red;
-  tm.stride = resident_block_threads(n);
+  tm.stride = resident_block_threads(n) * tpr;
   tm.phase = 0;
   tm.xs = smem + L.xs;
+  tm.nvec = resident_block_threads(n);
+  tm.tpr = tpr;
+  tm.part = smem + L.part;
   tm.scratch = smem + L.scratch;
   double* ys = smem + L.ys;
   Pass2Col* cols = reinterpret_cast<Pass2Col*>(smem + L.cols);
@@ -306,7 +370,7 @@ qn_resident_kernel(const BatchParams p, const typename Obj::Params op) {
     __syncthreads();
     const long long j = *next;
     if (j >= p.batch) break;
-    resident_solve_one<Obj, NREG>(p, op, j, tm, ys, cols, hs);
+    resident_solve_one<Obj, NREG>(p, op, j, tm, ys, cols, hs, smem + L.part);
   }
 }
 
