@@ -64,6 +64,11 @@ enum {
 #define QN_FLAG_FORCE_SMEM 0x2u   /* use the shared-memory-resident kernel even where the
                                      register-resident one exists (testing/ablation) */
 #define QN_FLAG_FORCE_STREAM 0x4u /* use the HBM streaming path regardless of n */
+#define QN_FLAG_ONE_PASS 0x8u     /* streaming path only: one-pass deferred-update variant (16 n²
+                                     instead of 24 n² bytes per iteration).  Same mathematics as
+                                     QN.jl:34-69 but NOT the reference's rounding: iterates agree
+                                     with the default mode to ~1e-14 relative over the first
+                                     iterations, optima to a few 1e-8 */
 
 /* BackTracking{O}(c₁, ρₕ, ρₗ, iterations): QN.jl:72-80.  order = O ∈ {2,3}. */
 typedef struct {
@@ -189,7 +194,7 @@ int32_t qn_last_launch_info(qn_context* ctx, int32_t* path, int32_t* grid, int32
  * n-dimensional Rosenbrock problem with B⁻¹ in HBM.  gbs = achieved ALGORITHMIC bandwidth,
  * (16 n² + 96 n) bytes per iteration / measured time. */
 int32_t qn_stream_bench_f64(qn_context* ctx, int32_t n, int32_t iters, int32_t order,
-                            double* ms_per_iter, double* gbs);
+                            uint32_t flags, double* ms_per_iter, double* gbs);
 
 /* ---- microbenchmarks that define the roofline denominators */
 /* sustained fp64 FMA rate, TFLOP/s (2 flops per DFMA), all SMs busy */

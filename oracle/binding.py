@@ -16,6 +16,7 @@ _SO = os.path.join(_HERE, "libqn_oracle.so")
 ROSENBROCK, DENSE_GAUSSIAN, LOGISTIC = 0, 1, 2
 CONVERGED, NONFINITE, LINESEARCH_FAILED, MAX_ITER = 0, 1, 2, 3
 RBLOCK = 0  # canonical rule C2 blocks (qo_chain_block)
+ONEPASS = -1  # rblock value selecting the one-pass deferred-update variant (not the reference order)
 
 
 class Backtracking(C.Structure):

@@ -17,7 +17,7 @@ CONVERGED, NONFINITE, LINESEARCH_FAILED, MAX_ITER = range(4)
 # objective kinds
 OBJ_ROSENBROCK, OBJ_DENSE_GAUSSIAN, OBJ_LOGISTIC = range(3)
 # flags
-FLAG_WRITE_H, FLAG_FORCE_SMEM, FLAG_FORCE_STREAM = 0x1, 0x2, 0x4
+FLAG_WRITE_H, FLAG_FORCE_SMEM, FLAG_FORCE_STREAM, FLAG_ONE_PASS = 0x1, 0x2, 0x4, 0x8
 # execution paths reported by qn_last_launch_info
 PATH_REGISTER, PATH_SMEM, PATH_STREAM = 0, 1, 2
 
@@ -76,7 +76,7 @@ SIGNATURES = {
     "qn_microbench_dfma": (C.c_int32, [_vp, _dp]),
     "qn_microbench_lds": (C.c_int32, [_vp, _dp]),
     "qn_microbench_hbm": (C.c_int32, [_vp, _dp]),
-    "qn_stream_bench_f64": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp]),
+    "qn_stream_bench_f64": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, _dp, _dp]),
 }
 
 _lib = None

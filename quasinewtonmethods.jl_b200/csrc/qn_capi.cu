@@ -147,7 +147,7 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
 
 // Large n: B⁻¹ in HBM, one problem at a time on the whole GPU (qn_stream.cu).
 int dispatch_stream(qn_context* ctx, const qn_model* model, qn::BatchParams& p,
-                    const qn_backtracking* ls, cudaStream_t st) {
+                    const qn_backtracking* ls, uint32_t flags, cudaStream_t st) {
   if (model->kind != QN_OBJ_ROSENBROCK)
     return fail(QN_ERR_UNREGISTERED_OBJECTIVE,
                 "objective kind %d has no registered device implementation on the streaming path "
@@ -165,7 +165,8 @@ int dispatch_stream(qn_context* ctx, const qn_model* model, qn::BatchParams& p,
                              p.g_out ? p.g_out + j * p.g_stride : nullptr,
                              p.h_out ? p.h_out + j * p.h_stride : nullptr, p.ldh, &ell, &it, &fe,
                              &status, p.ntrace,
-                             p.trace ? p.trace + (size_t)j * p.ntrace * p.n : nullptr, run, nullptr, 0);
+                             p.trace ? p.trace + (size_t)j * p.ntrace * p.n : nullptr, run, nullptr, 0,
+                             (flags & QN_FLAG_ONE_PASS) ? 1 : 0);
     if (rc) return rc;
     launches += ctx->last_launches;
     if (p.ell_out) QN_CUDA_TRY(cudaMemcpy(p.ell_out + j, &ell, sizeof ell, cudaMemcpyHostToDevice));
@@ -180,7 +181,7 @@ int dispatch_stream(qn_context* ctx, const qn_model* model, qn::BatchParams& p,
 int dispatch_model(qn_context* ctx, const qn_model* model, qn::BatchParams& p,
                    const qn_backtracking* ls, uint32_t flags, cudaStream_t st) {
   // resident up to n = 160 (205 KB of B⁻¹ + vectors in 227 KB of shared memory), HBM beyond
-  if ((flags & QN_FLAG_FORCE_STREAM) || p.n > 160) return dispatch_stream(ctx, model, p, ls, st);
+  if ((flags & QN_FLAG_FORCE_STREAM) || p.n > 160) return dispatch_stream(ctx, model, p, ls, flags, st);
   switch (model->kind) {
     case QN_OBJ_ROSENBROCK:
       return dispatch_size<qn::Rosenbrock>(ctx, p, qn::Rosenbrock::Params{}, flags, st);

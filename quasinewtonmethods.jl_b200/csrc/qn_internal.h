@@ -58,4 +58,5 @@ inline int qn_host_state_ld(int n, int native_w) {
 int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_backtracking* ls,
                     double tol, int max_iter, double* d_x_out, double* d_g_out, double* d_h_out,
                     int ldh_out, double* ell, int* iters, int* fevals, int* status, int ntrace,
-                    double* d_trace, cudaStream_t st, float* ms_per_iter_out, int fixed_iters);
+                    double* d_trace, cudaStream_t st, float* ms_per_iter_out, int fixed_iters,
+                    int onepass);

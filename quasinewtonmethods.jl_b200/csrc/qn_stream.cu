@@ -44,6 +44,8 @@ struct StreamScalars {
   int skip_update; // iteration 1: m = -1, no BFGS update (QN.jl:263-264)
   int need_reset;  // vec_end -> identity
   int exit_it;     // iteration in which the solve ended (selects which ∇ buffer is canonical)
+  int pending;     // one-pass mode: the rank-2 update (ps, pu, pc1) is not yet applied to H
+  double pc1;
 };
 
 struct StreamParams {
@@ -52,6 +54,9 @@ struct StreamParams {
   LsParams ls;
   double* H;
   double *x, *g, *gp, *s, *y, *nu, *w, *xs, *tmp, *dvec; // length-n vectors
+  double *ps, *pu, *tvec, *wvec;                          // one-pass mode: pending s, u; t = Hy, w = H∇
+  double* partial2;                                        // one-pass mode: second [nsb][n] array
+  int onepass;
   double* partial;                                  // [nsb][n]
   unsigned int* tile_count;                         // one arrival counter per row tile
   int stage_in_smem;                                // vec kernels stage reductions in shared memory
@@ -226,31 +231,17 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_mid(const StreamParams
   if (threadIdx.x == 0) sc->c1 = c1;
 }
 
-__global__ void __launch_bounds__(kVecThreads) stream_vec_end(const StreamParams p) {
-  extern __shared__ __align__(16) double vsm[];
-  __shared__ double red;
-  StreamScalars* sc = p.sc;
-  if (sc->done) return;
+// Second half of an iteration, shared by the two-pass and the one-pass mode: the reset
+// decision (QN.jl:272-280), the whole line search (QN.jl:165-232), update_state! (QN.jl:21-27)
+// and the bookkeeping.  Runs in one CTA; s holds the direction, m = dᵀ∇.
+__device__ __forceinline__ void stream_finish_iteration(const StreamParams& p, StreamScalars* sc, const int it,
+                                                        const double l0, double m, double* stage, double* redp) {
   const int n = p.n;
-  const int it = sc->it + 1;
-  const double l0 = sc->l0;
-  double* stage = p.stage_in_smem ? vsm : p.tmp;            // n doubles
-  double m;
-  if (!sc->skip_update) {
-    // pass2's tail left d in s and d[c]·∇[c] in tmp; m = dᵀ∇_new = csum, QN.jl:66-68
-    if (p.stage_in_smem) {
-      cta_map(n, [&](int i) { return p.tmp[i]; }, [&](int i, double v) { stage[i] = v; });
-      __syncthreads();
-    }
-    m = cta_csum_staged(n, stage, &red);
-    cta_map(n, [&](int i) { return p.dvec[i]; }, [&](int i, double v) { p.s[i] = v; }); // `s, y = y, s`, QN.jl:65,268
-    __syncthreads();
-  } else {
-    m = sc->m;
-  }
+  double& red = *redp;
   int need_reset = 0;
   if (m <= 0.0) { // QN.jl:272-280
     need_reset = 1;
+    if (threadIdx.x == 0) sc->pending = 0; // one-pass mode: the reset discards the pending update
     m = cta_csum(n, stage, &red, [&](int i) {
       const double gi = p.g[i];
       p.s[i] = gi;
@@ -324,6 +315,32 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_end(const StreamParams
     sc->need_reset = need_reset;
     if (it >= p.max_iter) { sc->status = QN_MAX_ITER; sc->done = 1; sc->exit_it = it; }
   }
+}
+
+
+__global__ void __launch_bounds__(kVecThreads) stream_vec_end(const StreamParams p) {
+  extern __shared__ __align__(16) double vsm[];
+  __shared__ double red;
+  StreamScalars* sc = p.sc;
+  if (sc->done) return;
+  const int n = p.n;
+  const int it = sc->it + 1;
+  const double l0 = sc->l0;
+  double* stage = p.stage_in_smem ? vsm : p.tmp;            // n doubles
+  double m;
+  if (!sc->skip_update) {
+    // pass2's tail left d in s and d[c]·∇[c] in tmp; m = dᵀ∇_new = csum, QN.jl:66-68
+    if (p.stage_in_smem) {
+      cta_map(n, [&](int i) { return p.tmp[i]; }, [&](int i, double v) { stage[i] = v; });
+      __syncthreads();
+    }
+    m = cta_csum_staged(n, stage, &red);
+    cta_map(n, [&](int i) { return p.dvec[i]; }, [&](int i, double v) { p.s[i] = v; }); // `s, y = y, s`, QN.jl:65,268
+    __syncthreads();
+  } else {
+    m = sc->m;
+  }
+  stream_finish_iteration(p, sc, it, l0, m, stage, &red);
 }
 
 // ---- pass 1: partial[sb][c] = Σ_{blocks of sb} chain_b(c),  chain_b(c) = Σ_{r in b} y[r] H[c,r]
@@ -446,6 +463,167 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass2(const StreamParams 
   });
 }
 
+// ---- one-pass mode: ONE sweep applies the pending update of the previous
+// iteration and accumulates both GEMVs, t = H y and w = H ∇ (rule C2 chains, same tiling as
+// pass1/pass2).  16 n² bytes per iteration instead of 24 n²; not the reference's rounding.
+__global__ void __launch_bounds__(kPassThreads) stream_pass_one(const StreamParams p) {
+  const StreamScalars* sc = p.sc;
+  if (sc->done || sc->skip_update) return;
+  extern __shared__ __align__(16) double sm[];
+  double4* ops = reinterpret_cast<double4*>(sm);         // {pc₁ps[r], -pu[r], ps[r], 0} per column
+  double2* yg = reinterpret_cast<double2*>(sm + 4 * p.sbcols); // {y[r], ∇[r]}
+  const int n = p.n, ld = p.ld, rb = p.rb;
+  const int sb = blockIdx.y;
+  const int r_begin = sb * p.sbcols;
+  const int r_end = min(r_begin + p.sbcols, n);
+  const bool pending = sc->pending != 0;
+  const double pc1 = sc->pc1;
+  for (int r = r_begin + threadIdx.x; r < r_end; r += blockDim.x) {
+    const double psr = p.ps[r];
+    ops[r - r_begin] = make_double4(pc1 * psr, -p.pu[r], psr, 0.0);
+    yg[r - r_begin] = make_double2(p.y[r], p.g[r]);
+  }
+  __syncthreads();
+  const int c0 = blockIdx.x * kRowsPerCta + 2 * threadIdx.x;
+  const bool two = (c0 + 1 < n);
+  const double s0 = (c0 < n) ? p.ps[c0] : 0.0, nu0 = (c0 < n) ? -p.pu[c0] : 0.0;
+  const double s1 = two ? p.ps[c0 + 1] : 0.0, nu1 = two ? -p.pu[c0 + 1] : 0.0;
+  double* hp = p.H + c0;
+  double St0 = 0.0, St1 = 0.0, Sw0 = 0.0, Sw1 = 0.0;
+  bool first = true;
+  for (int b0 = r_begin; b0 < r_end && c0 < n; b0 += rb) {
+    const int b1 = min(b0 + rb, r_end);
+    double t0 = 0.0, t1 = 0.0, w0 = 0.0, w1 = 0.0;
+    int r = b0;
+    for (; r + 8 <= b1; r += 8) {
+      double2 h[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) h[k] = *reinterpret_cast<const double2*>(hp + (size_t)ld * (r + k));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        double h0 = h[k].x, h1 = h[k].y;
+        if (pending) {
+          const double4 o = ops[r + k - r_begin];
+          h0 = fma(o.x, s0, h0); h1 = fma(o.x, s1, h1);
+          h0 = fma(o.y, s0, h0); h1 = fma(o.y, s1, h1);
+          h0 = fma(nu0, o.z, h0); h1 = fma(nu1, o.z, h1);
+          *reinterpret_cast<double2*>(hp + (size_t)ld * (r + k)) = make_double2(h0, h1);
+        }
+        const double2 q = yg[r + k - r_begin];
+        t0 = fma(q.x, h0, t0); t1 = fma(q.x, h1, t1);
+        w0 = fma(h0, q.y, w0); w1 = fma(h1, q.y, w1);
+      }
+    }
+    for (; r < b1; ++r) {
+      const double2 h = *reinterpret_cast<const double2*>(hp + (size_t)ld * r);
+      double h0 = h.x, h1 = h.y;
+      if (pending) {
+        const double4 o = ops[r - r_begin];
+        h0 = fma(o.x, s0, h0); h1 = fma(o.x, s1, h1);
+        h0 = fma(o.y, s0, h0); h1 = fma(o.y, s1, h1);
+        h0 = fma(nu0, o.z, h0); h1 = fma(nu1, o.z, h1);
+        *reinterpret_cast<double2*>(hp + (size_t)ld * r) = make_double2(h0, h1);
+      }
+      const double2 q = yg[r - r_begin];
+      t0 = fma(q.x, h0, t0); t1 = fma(q.x, h1, t1);
+      w0 = fma(h0, q.y, w0); w1 = fma(h1, q.y, w1);
+    }
+    St0 = first ? t0 : St0 + t0; St1 = first ? t1 : St1 + t1;
+    Sw0 = first ? w0 : Sw0 + w0; Sw1 = first ? w1 : Sw1 + w1;
+    first = false;
+  }
+  if (c0 < n) {
+    double* o1 = p.partial + (size_t)sb * n + c0;
+    double* o2 = p.partial2 + (size_t)sb * n + c0;
+    o1[0] = St0; o2[0] = Sw0;
+    if (two) { o1[1] = St1; o2[1] = Sw1; }
+  }
+  // tail: the last CTA of a row tile adds both sets of super-block partials in order
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(p.tile_count + blockIdx.x, 1u);
+    is_last = (prev == (unsigned)p.nsb - 1);
+    if (is_last) p.tile_count[blockIdx.x] = 0;
+  }
+  __syncthreads();
+  if (!is_last || c0 >= n) return;
+  __threadfence();
+  const volatile double* p1 = p.partial + c0;
+  const volatile double* p2 = p.partial2 + c0;
+  double T0 = p1[0], T1 = two ? p1[1] : 0.0, W0 = p2[0], W1 = two ? p2[1] : 0.0;
+  for (int j = 1; j < p.nsb; ++j) {
+    T0 = T0 + p1[(size_t)j * n]; W0 = W0 + p2[(size_t)j * n];
+    if (two) { T1 = T1 + p1[(size_t)j * n + 1]; W1 = W1 + p2[(size_t)j * n + 1]; }
+  }
+  p.tvec[c0] = T0; p.wvec[c0] = W0;
+  if (two) { p.tvec[c0 + 1] = T1; p.wvec[c0 + 1] = W1; }
+}
+
+// one-pass mode: everything after the sweep, in one CTA
+__global__ void __launch_bounds__(kVecThreads) stream_vec_after(const StreamParams p) {
+  extern __shared__ __align__(16) double vsm[];
+  __shared__ double red;
+  StreamScalars* sc = p.sc;
+  if (sc->done) return;
+  const int n = p.n;
+  const int it = sc->it + 1;
+  const double l0 = sc->l0;
+  double* stage = p.stage_in_smem ? vsm : p.tmp;
+  double m;
+  if (!sc->skip_update) {
+    const double rho = sc->rho;
+    const double yHy = cta_csum(n, stage, &red, [&](int c) { // u = tρ ; Σ t[c] y[c]   QN.jl:50-51
+      const double T = p.tvec[c];
+      p.nu[c] = T * rho; // u itself in this mode
+      return T * p.y[c];
+    });
+    const double c1 = fma(yHy, rho, 1.0) * rho; // QN.jl:54
+    const double sg = cta_csum(n, stage, &red, [&](int c) { return p.s[c] * p.g[c]; });
+    const double ug = cta_csum(n, stage, &red, [&](int c) { return p.nu[c] * p.g[c]; });
+    // d = ((w + (c₁ s)(sᵀ∇)) - u (sᵀ∇)) - s (uᵀ∇) ; m = dᵀ∇ ; this update becomes the pending one
+    m = cta_csum(n, stage, &red, [&](int c) {
+      const double sc_ = p.s[c], uc = p.nu[c];
+      double d = fma(c1 * sc_, sg, p.wvec[c]);
+      d = fma(-uc, sg, d);
+      d = fma(-sc_, ug, d);
+      p.ps[c] = sc_;
+      p.pu[c] = uc;
+      p.s[c] = d; // `s, y = y, s`, QN.jl:65,268
+      return d * p.g[c];
+    });
+    if (threadIdx.x == 0) { sc->pc1 = c1; sc->pending = 1; sc->c1 = c1; }
+    __syncthreads();
+  } else {
+    m = sc->m;
+  }
+  stream_finish_iteration(p, sc, it, l0, m, stage, &red);
+}
+
+// one-pass mode, end of the solve: apply the pending update so H is the true B⁻¹
+__global__ void __launch_bounds__(kPassThreads) stream_flush_pending(const StreamParams p) {
+  const StreamScalars* sc = p.sc;
+  if (!sc->pending) return;
+  const int n = p.n, ld = p.ld;
+  const double pc1 = sc->pc1;
+  const int c0 = blockIdx.x * kRowsPerCta + 2 * threadIdx.x;
+  if (c0 >= n) return;
+  const bool two = (c0 + 1 < n);
+  const double s0 = p.ps[c0], nu0 = -p.pu[c0];
+  const double s1 = two ? p.ps[c0 + 1] : 0.0, nu1 = two ? -p.pu[c0 + 1] : 0.0;
+  const int r_begin = blockIdx.y * p.sbcols, r_end = min(r_begin + p.sbcols, n);
+  for (int r = r_begin; r < r_end; ++r) {
+    double2* hp = reinterpret_cast<double2*>(p.H + c0 + (size_t)ld * r);
+    const double psr = p.ps[r], wr = pc1 * psr, nur = -p.pu[r];
+    double2 h = *hp;
+    h.x = fma(wr, s0, h.x); h.y = fma(wr, s1, h.y);
+    h.x = fma(nur, s0, h.x); h.y = fma(nur, s1, h.y);
+    h.x = fma(nu0, psr, h.x); h.y = fma(nu1, psr, h.y);
+    *hp = h;
+  }
+}
+
 // B⁻¹ ← I (QN.jl:144-148), only when vec_end asked for it
 __global__ void __launch_bounds__(256) stream_identity(const StreamParams p) {
   const StreamScalars* sc = p.sc;
@@ -475,10 +653,15 @@ struct StreamWork {
 int enqueue_iteration(qn_context* ctx, const qn::StreamParams& p, size_t vec_smem, cudaStream_t st) {
   const dim3 grid((p.n + qn::kRowsPerCta - 1) / qn::kRowsPerCta, p.nsb);
   qn::stream_vec_begin<<<1, qn::kVecThreads, vec_smem, st>>>(p);
-  qn::stream_pass1<<<grid, qn::kPassThreads, sizeof(double) * p.sbcols, st>>>(p);
-  qn::stream_vec_mid<<<1, qn::kVecThreads, vec_smem, st>>>(p);
-  qn::stream_pass2<<<grid, qn::kPassThreads, sizeof(double) * 4 * p.sbcols, st>>>(p);
-  qn::stream_vec_end<<<1, qn::kVecThreads, vec_smem, st>>>(p);
+  if (p.onepass) {
+    qn::stream_pass_one<<<grid, qn::kPassThreads, sizeof(double) * 6 * p.sbcols, st>>>(p);
+    qn::stream_vec_after<<<1, qn::kVecThreads, vec_smem, st>>>(p);
+  } else {
+    qn::stream_pass1<<<grid, qn::kPassThreads, sizeof(double) * p.sbcols, st>>>(p);
+    qn::stream_vec_mid<<<1, qn::kVecThreads, vec_smem, st>>>(p);
+    qn::stream_pass2<<<grid, qn::kPassThreads, sizeof(double) * 4 * p.sbcols, st>>>(p);
+    qn::stream_vec_end<<<1, qn::kVecThreads, vec_smem, st>>>(p);
+  }
   qn::stream_identity<<<ctx->prop.multiProcessorCount * 8, 256, 0, st>>>(p);
   QN_CUDA_TRY(cudaGetLastError());
   return QN_OK;
@@ -491,7 +674,8 @@ int enqueue_iteration(qn_context* ctx, const qn::StreamParams& p, size_t vec_sme
 int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_backtracking* ls,
                     double tol, int max_iter, double* d_x_out, double* d_g_out, double* d_h_out,
                     int ldh_out, double* ell, int* iters, int* fevals, int* status, int ntrace,
-                    double* d_trace, cudaStream_t st, float* ms_per_iter_out, int fixed_iters) {
+                    double* d_trace, cudaStream_t st, float* ms_per_iter_out, int fixed_iters,
+                    int onepass) {
   using namespace qn;
   StreamWork w;
   StreamParams& p = w.p;
@@ -508,7 +692,7 @@ int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_bac
   QN_CUDA_TRY(cudaMalloc(&p.H, sizeof(double) * (size_t)p.ld * n));
   const size_t nv = ((size_t)n + 31) & ~(size_t)31;
   const int row_tiles = (n + qn::kRowsPerCta - 1) / qn::kRowsPerCta;
-  const size_t words = nv * 11 + (size_t)p.nsb * n + 64 + row_tiles;
+  const size_t words = nv * 15 + 2 * (size_t)p.nsb * n + 64 + row_tiles;
   cudaError_t e = cudaMalloc(&w.block, sizeof(double) * words);
   if (e != cudaSuccess) {
     cudaFree(p.H);
@@ -518,9 +702,12 @@ int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_bac
   p.x = base; p.g = base + nv; p.gp = base + 2 * nv; p.s = base + 3 * nv; p.y = base + 4 * nv;
   p.nu = base + 5 * nv; p.w = base + 6 * nv; p.xs = base + 7 * nv; p.tmp = base + 8 * nv;
   p.dvec = base + 9 * nv;
-  p.partial = base + 11 * nv;
-  p.sc = reinterpret_cast<StreamScalars*>(p.partial + (size_t)p.nsb * n);
-  p.tile_count = reinterpret_cast<unsigned int*>(p.partial + (size_t)p.nsb * n + 32);
+  p.ps = base + 10 * nv; p.pu = base + 11 * nv; p.tvec = base + 12 * nv; p.wvec = base + 13 * nv;
+  p.partial = base + 15 * nv;
+  p.partial2 = p.partial + (size_t)p.nsb * n;
+  p.sc = reinterpret_cast<StreamScalars*>(p.partial2 + (size_t)p.nsb * n);
+  p.tile_count = reinterpret_cast<unsigned int*>(p.partial2 + (size_t)p.nsb * n + 32);
+  p.onepass = onepass;
   // vec kernels stage their reductions (n doubles) in shared memory
   const size_t vec_smem = sizeof(double) * (((size_t)n + 1) & ~(size_t)1);
   p.stage_in_smem = vec_smem <= (size_t)ctx->prop.sharedMemPerBlockOptin - 1024;
@@ -557,6 +744,7 @@ int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_bac
       QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_begin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
       QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
       QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_end, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
+      QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_after, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
     }
     QN_TRY_CLEAN(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     rc = enqueue_iteration(ctx, p, w.vec_smem, st);
@@ -600,11 +788,15 @@ int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_bac
   ctx->last_grid = ((n + qn::kRowsPerCta - 1) / qn::kRowsPerCta) * p.nsb;
   ctx->last_block = qn::kPassThreads;
   ctx->last_smem = (int)(sizeof(double) * 4 * p.sbcols);
-  ctx->last_launches = 6 * (init.it + (init.done ? 1 : 0));
+  ctx->last_launches = (onepass ? 4 : 6) * (init.it + (init.done ? 1 : 0));
   if (d_x_out) QN_TRY_CLEAN(cudaMemcpyAsync(d_x_out, p.x, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
   // which ∇ the reference's canonical slot shows after a failure: see qn_resident.cuh
   const double* g_src = (init.status == QN_CONVERGED || (init.exit_it & 1)) ? p.g : p.gp;
   if (d_g_out) QN_TRY_CLEAN(cudaMemcpyAsync(d_g_out, g_src, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+  if (d_h_out && onepass) { // the stored matrix lags one update behind: apply it
+    const dim3 grid((n + qn::kRowsPerCta - 1) / qn::kRowsPerCta, p.nsb);
+    qn::stream_flush_pending<<<grid, qn::kPassThreads, 0, st>>>(p);
+  }
   if (d_h_out)
     QN_TRY_CLEAN(cudaMemcpy2DAsync(d_h_out, sizeof(double) * ldh_out, p.H, sizeof(double) * p.ld,
                                    sizeof(double) * n, n, cudaMemcpyDeviceToDevice, st));
@@ -622,7 +814,7 @@ int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_bac
 // (x0 = a fixed pseudo-random start) and report ms per iteration and the achieved ALGORITHMIC
 // bandwidth (16 n² + 96 n bytes per iteration).
 extern "C" int32_t qn_stream_bench_f64(qn_context* ctx, int32_t n, int32_t iters, int32_t order,
-                                       double* ms_per_iter, double* gbs) {
+                                       uint32_t flags, double* ms_per_iter, double* gbs) {
   if (!ctx || !ms_per_iter || !gbs || n < 2 || iters < 3) return qn_fail(QN_ERR_INVALID_ARGUMENT, "bad argument");
   QN_CUDA_TRY(cudaSetDevice(ctx->device));
   double* h = (double*)malloc(sizeof(double) * n);
@@ -645,7 +837,7 @@ extern "C" int32_t qn_stream_bench_f64(qn_context* ctx, int32_t n, int32_t iters
   int it = 0, fe = 0, stt = 0;
   double ell = 0;
   int rc = qn_stream_solve(ctx, n, d, &ls, 1e-8, iters, nullptr, nullptr, nullptr, 0, &ell, &it, &fe, &stt,
-                           0, nullptr, ctx->stream, &ms, iters);
+                           0, nullptr, ctx->stream, &ms, iters, (flags & QN_FLAG_ONE_PASS) ? 1 : 0);
   cudaFree(d);
   if (rc) return rc;
   *ms_per_iter = ms;

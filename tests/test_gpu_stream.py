@@ -58,3 +58,37 @@ def test_stream_rejects_unregistered_objective(eng, qn):
     mu, lam = gaussian_problem(200)
     with pytest.raises(qn.UnregisteredObjectiveError):
         eng.optimize_batched(qn.DenseGaussian(mu, lam), starts(200, 1))
+
+
+@pytest.mark.parametrize("n,iters", [(60, 0), (61, 0), (200, 60), (1024, 20)])
+def test_one_pass_mode(eng, qn, ob, n, iters):
+    """QN_FLAG_ONE_PASS (deferred update, 16 n² bytes per iteration): bit for bit equal to ITS oracle
+    (oracle rblock = ONEPASS), and within the north-star tolerances of the reference order:
+    first five iterates 1e-12 relative, max|∇| < 1e-8; the optimum agrees to 5e-8 (two valid runs
+    stopped at max|∇| < 1e-8 can differ by ~2·tol/λ_min = 5e-8 on Rosenbrock)."""
+    flags = qn._lib.FLAG_FORCE_STREAM | qn._lib.FLAG_ONE_PASS
+    Theta = starts(n, 2, key=70 + n)
+    kw = dict(max_iter=iters) if iters else {}
+    nt = iters if iters else 5
+    got = eng.optimize_batched(qn.Rosenbrock(), Theta, ntrace=nt, flags=flags, **kw)
+    own = ob.optimize_batch(ob.rosenbrock(), Theta, ntrace=nt, rblock=ob.ONEPASS, **kw)
+    _same(got, own)
+    ref = ob.optimize_batch(ob.rosenbrock(), Theta, ntrace=nt, **kw)
+    scale = np.abs(ref["trace"][:, :5]).max(axis=2, keepdims=True)
+    assert (np.abs(got["trace"][:, :5] - ref["trace"][:, :5]) / scale).max() <= 1e-12
+    if not iters:
+        assert (got["status"] == qn.CONVERGED).all()
+        assert np.abs(got["g"]).max() < 1e-8
+        assert np.abs(got["x"] - ref["x"]).max() <= 5e-8
+        print("one-pass n=%d: iterations %s vs reference order %s" % (n, got["iters"], ref["iters"]))
+
+
+def test_one_pass_h_writeback(eng, qn, ob):
+    n = 40
+    Theta = starts(n, 1, key=8)
+    sb = qn.BFGSStateBatch(n, 1)
+    eng.optimize_batched(qn.Rosenbrock(), Theta, states=sb,
+                         flags=qn._lib.FLAG_WRITE_H | qn._lib.FLAG_FORCE_STREAM | qn._lib.FLAG_ONE_PASS)
+    o = ob.optimize(ob.rosenbrock(), Theta[:, 0], L=sb.L, rblock=ob.ONEPASS)
+    L = sb.L
+    assert np.array_equal(sb.data[0, 7 * L:].reshape(n, L)[:, :n], o["state"][7 * L:].reshape(n, L)[:, :n])
