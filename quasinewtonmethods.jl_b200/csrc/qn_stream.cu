@@ -119,6 +119,62 @@ __device__ __forceinline__ double cta_csum(int n, double* stage, double* red, F&
   return cta_csum_staged(n, stage, red);
 }
 
+// Reduce K staged arrays (array k has cnt[k] elements at stage + k*ns) by rule C1, warp k on
+// array k, so the K sequential chains run side by side.  Contains the barriers around it.
+template <int K>
+__device__ __forceinline__ void cta_reduce_multi(const int (&cnt)[K], const double* stage, int ns, double* red,
+                                                 double (&out)[K]) {
+  __syncthreads();
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (w < K) {
+    const int n = cnt[w];
+    const double* st = stage + w * ns;
+    double p = (l < n) ? st[l] : 0.0;
+    int j = l + 32;
+    for (; j + 224 < n; j += 256) {
+      double x[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = st[j + 32 * k];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) p = p + x[k];
+    }
+    for (; j < n; j += 32) p = p + st[j];
+    p = warp_butterfly(p);
+    if (l == 0) red[w] = p;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) out[k] = red[k];
+  __syncthreads();
+}
+
+// K independent canonical csums at once: v(i, out[K]) produces the K values of element i;
+// warp k reduces array k, so the K sequential chains run side by side.  stage: K*ns doubles.
+template <int K, class F>
+__device__ __forceinline__ void cta_csum_multi(int n, double* stage, int ns, double* red, F&& v, double (&out)[K]) {
+  const int T = blockDim.x;
+  int i = threadIdx.x;
+  for (; i + 3 * T < n; i += 4 * T) { // four independent elements per thread per round
+    double a[4][K];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v(i + q * T, a[q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int k = 0; k < K; ++k) stage[k * ns + i + q * T] = a[q][k];
+  }
+  for (; i < n; i += T) {
+    double a[K];
+    v(i, a);
+#pragma unroll
+    for (int k = 0; k < K; ++k) stage[k * ns + i] = a[k];
+  }
+  int cnt[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) cnt[k] = n;
+  cta_reduce_multi<K>(cnt, stage, ns, red, out);
+}
+
 // Rosenbrock (test/runtests.jl:4-33) by one CTA at the point X(i); writes ∇ to g when
 // g != nullptr.  X is a functor so a line-search trial can evaluate at x + a·s without
 // materialising the point (step!, QN.jl:157-162).
@@ -477,6 +533,7 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass_one(const StreamPara
   const int r_begin = sb * p.sbcols;
   const int r_end = min(r_begin + p.sbcols, n);
   const bool pending = sc->pending != 0;
+  const bool reset = sc->need_reset != 0; // B⁻¹ ← I (QN.jl:144-148) is folded into this sweep
   const double pc1 = sc->pc1;
   for (int r = r_begin + threadIdx.x; r < r_end; r += blockDim.x) {
     const double psr = p.ps[r];
@@ -498,10 +555,13 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass_one(const StreamPara
     for (; r + 8 <= b1; r += 8) {
       double2 h[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) h[k] = *reinterpret_cast<const double2*>(hp + (size_t)ld * (r + k));
+      for (int k = 0; k < 8; ++k)
+        h[k] = reset ? make_double2(c0 == r + k ? 1.0 : 0.0, c0 + 1 == r + k ? 1.0 : 0.0)
+                     : *reinterpret_cast<const double2*>(hp + (size_t)ld * (r + k));
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         double h0 = h[k].x, h1 = h[k].y;
+        if (reset) *reinterpret_cast<double2*>(hp + (size_t)ld * (r + k)) = h[k];
         if (pending) {
           const double4 o = ops[r + k - r_begin];
           h0 = fma(o.x, s0, h0); h1 = fma(o.x, s1, h1);
@@ -515,8 +575,10 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass_one(const StreamPara
       }
     }
     for (; r < b1; ++r) {
-      const double2 h = *reinterpret_cast<const double2*>(hp + (size_t)ld * r);
+      const double2 h = reset ? make_double2(c0 == r ? 1.0 : 0.0, c0 + 1 == r ? 1.0 : 0.0)
+                              : *reinterpret_cast<const double2*>(hp + (size_t)ld * r);
       double h0 = h.x, h1 = h.y;
+      if (reset) *reinterpret_cast<double2*>(hp + (size_t)ld * r) = h;
       if (pending) {
         const double4 o = ops[r - r_begin];
         h0 = fma(o.x, s0, h0); h1 = fma(o.x, s1, h1);
@@ -561,29 +623,37 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass_one(const StreamPara
   if (two) { p.tvec[c0 + 1] = T1; p.wvec[c0 + 1] = W1; }
 }
 
-// one-pass mode: everything after the sweep, in one CTA
-__global__ void __launch_bounds__(kVecThreads) stream_vec_after(const StreamParams p) {
+// one-pass mode: everything between two sweeps, in one CTA — the O(n) part of iteration `it`
+// after its sweep (u, yᵀB⁻¹y, c₁, d, m; reset decision; line search; update_state!), then the
+// head of iteration it+1 (∂logdensity!, convergence, y, sᵀy).  Independent reductions share a
+// round: {yᵀB⁻¹y, sᵀ∇, uᵀ∇} and {ℓ, sᵀy}.
+__global__ void __launch_bounds__(kVecThreads) stream_vec_onepass(const StreamParams p) {
   extern __shared__ __align__(16) double vsm[];
-  __shared__ double red;
+  __shared__ double red[4];
+  __shared__ int flag;
   StreamScalars* sc = p.sc;
   if (sc->done) return;
   const int n = p.n;
-  const int it = sc->it + 1;
+  const int ns = (n + 1) & ~1;
+  int it = sc->it + 1;
   const double l0 = sc->l0;
-  double* stage = p.stage_in_smem ? vsm : p.tmp;
+  double* stage = p.stage_in_smem ? vsm : p.tmp; // 3*ns doubles
   double m;
   if (!sc->skip_update) {
     const double rho = sc->rho;
-    const double yHy = cta_csum(n, stage, &red, [&](int c) { // u = tρ ; Σ t[c] y[c]   QN.jl:50-51
-      const double T = p.tvec[c];
-      p.nu[c] = T * rho; // u itself in this mode
-      return T * p.y[c];
-    });
-    const double c1 = fma(yHy, rho, 1.0) * rho; // QN.jl:54
-    const double sg = cta_csum(n, stage, &red, [&](int c) { return p.s[c] * p.g[c]; });
-    const double ug = cta_csum(n, stage, &red, [&](int c) { return p.nu[c] * p.g[c]; });
+    double r3[3];
+    cta_csum_multi<3>(n, stage, ns, red, [&](int c, double (&o)[3]) {
+      const double T = p.tvec[c], gc = p.g[c];
+      const double u = T * rho;   // B⁻¹y[c] = tρ, QN.jl:50
+      p.nu[c] = u;
+      o[0] = T * p.y[c];          // term of yᵀB⁻¹y, QN.jl:51
+      o[1] = p.s[c] * gc;         // term of sᵀ∇
+      o[2] = u * gc;              // term of uᵀ∇
+    }, r3);
+    const double c1 = fma(r3[0], rho, 1.0) * rho; // QN.jl:54
+    const double sg = r3[1], ug = r3[2];
     // d = ((w + (c₁ s)(sᵀ∇)) - u (sᵀ∇)) - s (uᵀ∇) ; m = dᵀ∇ ; this update becomes the pending one
-    m = cta_csum(n, stage, &red, [&](int c) {
+    m = cta_csum(n, stage, red, [&](int c) {
       const double sc_ = p.s[c], uc = p.nu[c];
       double d = fma(c1 * sc_, sg, p.wvec[c]);
       d = fma(-uc, sg, d);
@@ -598,7 +668,73 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_after(const StreamPara
   } else {
     m = sc->m;
   }
-  stream_finish_iteration(p, sc, it, l0, m, stage, &red);
+  stream_finish_iteration(p, sc, it, l0, m, stage, red);
+  __syncthreads();
+  if (sc->done) return;
+  // ---- head of iteration it+1: ℓ₀, ∇ = ∂logdensity!(x_old) fused with y and sᵀy   QN.jl:254,36-41
+  it = it + 1;
+  const int N = n >> 1;
+  {
+    // stage the ℓ terms (N of them) and the sᵀy terms (n, in element order) in one sweep
+    double* st0 = stage;
+    double* st1 = stage + ns;
+    const int T = blockDim.x;
+    for (int i0 = threadIdx.x; i0 < N; i0 += 2 * T) {
+      double t1[2], t2[2], gp1[2], gp2[2], s1[2], s2[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int i = i0 + q * T;
+        if (i < N) { t1[q] = p.x[i]; t2[q] = p.x[i + N]; gp1[q] = p.gp[i]; gp2[q] = p.gp[i + N]; s1[q] = p.s[i]; s2[q] = p.s[i + N]; }
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int i = i0 + q * T;
+        if (i < N) {
+          const double a = t2[q] - t1[q] * t1[q];
+          const double b = 1.0 - t1[q];
+          const double g1 = (400.0 * a) * t1[q] + 2.0 * b, g2 = 200.0 * (t1[q] * t1[q] - t2[q]);
+          const double y1 = gp1[q] - g1, y2 = gp2[q] - g2; // y = ∇_old - ∇_new, QN.jl:38
+          p.g[i] = g1; p.g[i + N] = g2;
+          p.y[i] = y1; p.y[i + N] = y2;
+          st0[i] = 100.0 * (a * a) + b * b;
+          st1[i] = s1[q] * y1;
+          st1[i + N] = s2[q] * y2;
+        }
+      }
+    }
+  }
+  double tail_d = 0.0;
+  if (n & 1) {
+    tail_d = 1.0 - p.x[n - 1];
+    if (threadIdx.x == 0) {
+      const double gt = 2.0 * tail_d, yt = p.gp[n - 1] - gt;
+      p.g[n - 1] = gt;
+      p.y[n - 1] = yt;
+      stage[ns + n - 1] = p.s[n - 1] * yt;
+    }
+  }
+  double r2[2];
+  const int cnt2[2] = {N, n};
+  cta_reduce_multi<2>(cnt2, stage, ns, red, r2);
+  double lnew = 0.0 - r2[0];
+  if (n & 1) lnew = -fma(tail_d, tail_d, -lnew);
+  const double sy = r2[1];
+  __syncthreads();
+  if (threadIdx.x == 0) { sc->l0 = lnew; sc->fevals += 1; flag = 1; }
+  if (!isfinite(lnew)) { // QN.jl:255
+    if (threadIdx.x == 0) { sc->status = QN_NONFINITE; sc->done = 1; sc->exit_it = it; }
+    return;
+  }
+  __syncthreads();
+  bool small = true; // maximum(abs, ∇) < tol, QN.jl:257
+  cta_map(n, [&](int i) { return p.g[i]; }, [&](int, double gi) { small = small && (fabs(gi) < p.tol); });
+  if (!small) flag = 0;
+  __syncthreads();
+  if (flag) {
+    if (threadIdx.x == 0) { sc->status = QN_CONVERGED; sc->result = lnew; sc->done = 1; sc->exit_it = it; }
+    return;
+  }
+  if (threadIdx.x == 0) { sc->sy = sy; sc->rho = 1.0 / sy; sc->skip_update = 0; } // QN.jl:39,42
 }
 
 // one-pass mode, end of the solve: apply the pending update so H is the true B⁻¹
@@ -652,10 +788,12 @@ struct StreamWork {
 
 int enqueue_iteration(qn_context* ctx, const qn::StreamParams& p, size_t vec_smem, cudaStream_t st) {
   const dim3 grid((p.n + qn::kRowsPerCta - 1) / qn::kRowsPerCta, p.nsb);
-  qn::stream_vec_begin<<<1, qn::kVecThreads, vec_smem, st>>>(p);
-  if (p.onepass) {
+  if (!p.onepass) qn::stream_vec_begin<<<1, qn::kVecThreads, vec_smem, st>>>(p);
+  if (p.onepass) { // two kernels per iteration; the head of iteration 1 ran before the graph
     qn::stream_pass_one<<<grid, qn::kPassThreads, sizeof(double) * 6 * p.sbcols, st>>>(p);
-    qn::stream_vec_after<<<1, qn::kVecThreads, vec_smem, st>>>(p);
+    qn::stream_vec_onepass<<<1, qn::kVecThreads, vec_smem, st>>>(p);
+    QN_CUDA_TRY(cudaGetLastError());
+    return QN_OK;
   } else {
     qn::stream_pass1<<<grid, qn::kPassThreads, sizeof(double) * p.sbcols, st>>>(p);
     qn::stream_vec_mid<<<1, qn::kVecThreads, vec_smem, st>>>(p);
@@ -692,7 +830,7 @@ int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_bac
   QN_CUDA_TRY(cudaMalloc(&p.H, sizeof(double) * (size_t)p.ld * n));
   const size_t nv = ((size_t)n + 31) & ~(size_t)31;
   const int row_tiles = (n + qn::kRowsPerCta - 1) / qn::kRowsPerCta;
-  const size_t words = nv * 15 + 2 * (size_t)p.nsb * n + 64 + row_tiles;
+  const size_t words = nv * 18 + 2 * (size_t)p.nsb * n + 64 + row_tiles;
   cudaError_t e = cudaMalloc(&w.block, sizeof(double) * words);
   if (e != cudaSuccess) {
     cudaFree(p.H);
@@ -701,15 +839,15 @@ int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_bac
   double* base = (double*)w.block;
   p.x = base; p.g = base + nv; p.gp = base + 2 * nv; p.s = base + 3 * nv; p.y = base + 4 * nv;
   p.nu = base + 5 * nv; p.w = base + 6 * nv; p.xs = base + 7 * nv; p.tmp = base + 8 * nv;
-  p.dvec = base + 9 * nv;
-  p.ps = base + 10 * nv; p.pu = base + 11 * nv; p.tvec = base + 12 * nv; p.wvec = base + 13 * nv;
-  p.partial = base + 15 * nv;
+  p.dvec = base + 12 * nv; // tmp spans 8..11 (three staged arrays when shared memory is too small)
+  p.ps = base + 13 * nv; p.pu = base + 14 * nv; p.tvec = base + 15 * nv; p.wvec = base + 16 * nv;
+  p.partial = base + 18 * nv;
   p.partial2 = p.partial + (size_t)p.nsb * n;
   p.sc = reinterpret_cast<StreamScalars*>(p.partial2 + (size_t)p.nsb * n);
   p.tile_count = reinterpret_cast<unsigned int*>(p.partial2 + (size_t)p.nsb * n + 32);
   p.onepass = onepass;
-  // vec kernels stage their reductions (n doubles) in shared memory
-  const size_t vec_smem = sizeof(double) * (((size_t)n + 1) & ~(size_t)1);
+  // vec kernels stage their reductions in shared memory (n doubles; three arrays in one-pass mode)
+  const size_t vec_smem = sizeof(double) * (onepass ? 3 : 1) * (((size_t)n + 1) & ~(size_t)1);
   p.stage_in_smem = vec_smem <= (size_t)ctx->prop.sharedMemPerBlockOptin - 1024;
   w.vec_smem = p.stage_in_smem ? vec_smem : 0;
   int rc = QN_OK;
@@ -744,7 +882,7 @@ int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_bac
       QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_begin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
       QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
       QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_end, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
-      QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_after, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
+      QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_onepass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
     }
     QN_TRY_CLEAN(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     rc = enqueue_iteration(ctx, p, w.vec_smem, st);
@@ -754,6 +892,7 @@ int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_bac
       return rc != QN_OK ? rc : qn_fail(QN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
     }
     QN_TRY_CLEAN(cudaGraphInstantiate(&w.exec, w.graph, 0));
+    if (onepass) qn::stream_vec_begin<<<1, qn::kVecThreads, w.vec_smem, st>>>(p); // head of iteration 1
     StreamScalars host{};
     if (fixed_iters > 0) {
       // benchmark mode: exactly fixed_iters iterations, the first two are warm-up
@@ -788,7 +927,7 @@ int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_bac
   ctx->last_grid = ((n + qn::kRowsPerCta - 1) / qn::kRowsPerCta) * p.nsb;
   ctx->last_block = qn::kPassThreads;
   ctx->last_smem = (int)(sizeof(double) * 4 * p.sbcols);
-  ctx->last_launches = (onepass ? 4 : 6) * (init.it + (init.done ? 1 : 0));
+  ctx->last_launches = onepass ? 1 + 2 * (init.it + (init.done ? 1 : 0)) : 6 * (init.it + (init.done ? 1 : 0));
   if (d_x_out) QN_TRY_CLEAN(cudaMemcpyAsync(d_x_out, p.x, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
   // which ∇ the reference's canonical slot shows after a failure: see qn_resident.cuh
   const double* g_src = (init.status == QN_CONVERGED || (init.exit_it & 1)) ? p.g : p.gp;
