@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("QN_EXTRA_NVCC", "").split()
 
 
 def _nvcc():

@@ -22,10 +22,12 @@
 // block partials in order; the per-super-block sums go to a small [nsb × n] array that the
 // next single-CTA kernel adds up in ascending order.  Every global access of a warp is 512
 // contiguous bytes; 8 independent 128-bit loads per thread are in flight.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 #include "qn_device.cuh"
 #include "qn_internal.h"
@@ -35,6 +37,25 @@ namespace qn {
 constexpr int kVecThreads = 1024;
 constexpr int kPassThreads = 256;
 constexpr int kRowsPerCta = 2 * kPassThreads;
+
+// B⁻¹ is streamed: every element is read once and written at most once per sweep; the cache
+// hint of those accesses is a kernel template parameter (0: default, 1: .cs evict-first,
+// 2: .lu / .cg, 3: .cv / .wt).  scripts/exp_stream_hints.sh measures the combinations.
+template <int HINT>
+__device__ __forceinline__ double2 ld_h(const double* ptr) {
+  if (HINT == 1) return __ldcs(reinterpret_cast<const double2*>(ptr));
+  if (HINT == 2) return __ldlu(reinterpret_cast<const double2*>(ptr));
+  if (HINT == 3) return __ldcv(reinterpret_cast<const double2*>(ptr));
+  if (HINT == 4) return __ldcg(reinterpret_cast<const double2*>(ptr));
+  return *reinterpret_cast<const double2*>(ptr);
+}
+template <int HINT>
+__device__ __forceinline__ void st_h(double* ptr, const double2 v) {
+  if (HINT == 1) __stcs(reinterpret_cast<double2*>(ptr), v);
+  else if (HINT == 2) __stcg(reinterpret_cast<double2*>(ptr), v);
+  else if (HINT == 3) __stwt(reinterpret_cast<double2*>(ptr), v);
+  else *reinterpret_cast<double2*>(ptr) = v;
+}
 
 struct StreamScalars {
   double l0, sy, rho, c1, m, result;
@@ -46,6 +67,7 @@ struct StreamScalars {
   int exit_it;     // iteration in which the solve ended (selects which ∇ buffer is canonical)
   int pending;     // one-pass mode: the rank-2 update (ps, pu, pc1) is not yet applied to H
   double pc1;
+  int spec;        // cluster vector kernel: evaluate the lower-clamp chain of step sizes speculatively
 };
 
 struct StreamParams {
@@ -400,6 +422,7 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_end(const StreamParams
 }
 
 // ---- pass 1: partial[sb][c] = Σ_{blocks of sb} chain_b(c),  chain_b(c) = Σ_{r in b} y[r] H[c,r]
+template <int LDH, int STH>
 __global__ void __launch_bounds__(kPassThreads) stream_pass1(const StreamParams p) {
   const StreamScalars* sc = p.sc;
   if (sc->done || sc->skip_update) return;
@@ -423,7 +446,7 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass1(const StreamParams 
     for (; r + 8 <= b1; r += 8) { // 8 independent 128-bit loads in flight
       double2 h[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) h[k] = *reinterpret_cast<const double2*>(hp + (size_t)ld * (r + k));
+      for (int k = 0; k < 8; ++k) h[k] = ld_h<LDH>(hp + (size_t)ld * (r + k));
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const double yr = ys[r + k - r_begin];
@@ -432,7 +455,7 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass1(const StreamParams 
       }
     }
     for (; r < b1; ++r) {
-      const double2 h = *reinterpret_cast<const double2*>(hp + (size_t)ld * r);
+      const double2 h = ld_h<LDH>(hp + (size_t)ld * r);
       const double yr = ys[r - r_begin];
       t0 = fma(yr, h.x, t0);
       t1 = fma(yr, h.y, t1);
@@ -454,6 +477,7 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass1(const StreamParams 
 }
 
 // ---- pass 2: H[c,r] ← ((H + (c₁s[r])s[c]) - u[r]s[c]) - u[c]s[r] ; partials of d = H⁺∇
+template <int LDH, int STH>
 __global__ void __launch_bounds__(kPassThreads) stream_pass2(const StreamParams p) {
   const StreamScalars* sc = p.sc;
   if (sc->done || sc->skip_update) return;
@@ -480,7 +504,7 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass2(const StreamParams 
     for (; r + 8 <= b1; r += 8) {
       double2 h[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) h[k] = *reinterpret_cast<const double2*>(hp + (size_t)ld * (r + k));
+      for (int k = 0; k < 8; ++k) h[k] = ld_h<LDH>(hp + (size_t)ld * (r + k));
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const double4 o = ops[r + k - r_begin];
@@ -488,19 +512,19 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass2(const StreamParams 
         h0 = fma(o.x, s0, h0); h1 = fma(o.x, s1, h1);     // + (c₁ s[r]) s[c]
         h0 = fma(o.y, s0, h0); h1 = fma(o.y, s1, h1);     // - u[r] s[c]
         h0 = fma(nu0, o.z, h0); h1 = fma(nu1, o.z, h1);   // - u[c] s[r]
-        *reinterpret_cast<double2*>(hp + (size_t)ld * (r + k)) = make_double2(h0, h1);
+        st_h<STH>(hp + (size_t)ld * (r + k), make_double2(h0, h1));
         a0 = fma(h0, o.w, a0);
         a1 = fma(h1, o.w, a1);
       }
     }
     for (; r < b1; ++r) {
-      const double2 h = *reinterpret_cast<const double2*>(hp + (size_t)ld * r);
+      const double2 h = ld_h<LDH>(hp + (size_t)ld * r);
       const double4 o = ops[r - r_begin];
       double h0 = h.x, h1 = h.y;
       h0 = fma(o.x, s0, h0); h1 = fma(o.x, s1, h1);
       h0 = fma(o.y, s0, h0); h1 = fma(o.y, s1, h1);
       h0 = fma(nu0, o.z, h0); h1 = fma(nu1, o.z, h1);
-      *reinterpret_cast<double2*>(hp + (size_t)ld * r) = make_double2(h0, h1);
+      st_h<STH>(hp + (size_t)ld * r, make_double2(h0, h1));
       a0 = fma(h0, o.w, a0);
       a1 = fma(h1, o.w, a1);
     }
@@ -522,6 +546,7 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass2(const StreamParams 
 // ---- one-pass mode: ONE sweep applies the pending update of the previous
 // iteration and accumulates both GEMVs, t = H y and w = H ∇ (rule C2 chains, same tiling as
 // pass1/pass2).  16 n² bytes per iteration instead of 24 n²; not the reference's rounding.
+template <int LDH, int STH>
 __global__ void __launch_bounds__(kPassThreads) stream_pass_one(const StreamParams p) {
   const StreamScalars* sc = p.sc;
   if (sc->done || sc->skip_update) return;
@@ -557,17 +582,17 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass_one(const StreamPara
 #pragma unroll
       for (int k = 0; k < 8; ++k)
         h[k] = reset ? make_double2(c0 == r + k ? 1.0 : 0.0, c0 + 1 == r + k ? 1.0 : 0.0)
-                     : *reinterpret_cast<const double2*>(hp + (size_t)ld * (r + k));
+                     : ld_h<LDH>(hp + (size_t)ld * (r + k));
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         double h0 = h[k].x, h1 = h[k].y;
-        if (reset) *reinterpret_cast<double2*>(hp + (size_t)ld * (r + k)) = h[k];
+        if (reset) st_h<STH>(hp + (size_t)ld * (r + k), h[k]);
         if (pending) {
           const double4 o = ops[r + k - r_begin];
           h0 = fma(o.x, s0, h0); h1 = fma(o.x, s1, h1);
           h0 = fma(o.y, s0, h0); h1 = fma(o.y, s1, h1);
           h0 = fma(nu0, o.z, h0); h1 = fma(nu1, o.z, h1);
-          *reinterpret_cast<double2*>(hp + (size_t)ld * (r + k)) = make_double2(h0, h1);
+          st_h<STH>(hp + (size_t)ld * (r + k), make_double2(h0, h1));
         }
         const double2 q = yg[r + k - r_begin];
         t0 = fma(q.x, h0, t0); t1 = fma(q.x, h1, t1);
@@ -576,15 +601,15 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass_one(const StreamPara
     }
     for (; r < b1; ++r) {
       const double2 h = reset ? make_double2(c0 == r ? 1.0 : 0.0, c0 + 1 == r ? 1.0 : 0.0)
-                              : *reinterpret_cast<const double2*>(hp + (size_t)ld * r);
+                              : ld_h<LDH>(hp + (size_t)ld * r);
       double h0 = h.x, h1 = h.y;
-      if (reset) *reinterpret_cast<double2*>(hp + (size_t)ld * r) = h;
+      if (reset) st_h<STH>(hp + (size_t)ld * r, h);
       if (pending) {
         const double4 o = ops[r - r_begin];
         h0 = fma(o.x, s0, h0); h1 = fma(o.x, s1, h1);
         h0 = fma(o.y, s0, h0); h1 = fma(o.y, s1, h1);
         h0 = fma(nu0, o.z, h0); h1 = fma(nu1, o.z, h1);
-        *reinterpret_cast<double2*>(hp + (size_t)ld * r) = make_double2(h0, h1);
+        st_h<STH>(hp + (size_t)ld * r, make_double2(h0, h1));
       }
       const double2 q = yg[r - r_begin];
       t0 = fma(q.x, h0, t0); t1 = fma(q.x, h1, t1);
@@ -737,6 +762,339 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_onepass(const StreamPa
   if (threadIdx.x == 0) { sc->sy = sy; sc->rho = 1.0 / sy; sc->skip_update = 0; } // QN.jl:39,42
 }
 
+// ---- one-pass mode, cluster form of stream_vec_onepass.  The O(n) work between two sweeps
+// is latency-bound in a single CTA (every dependent round is an L2 round trip through one
+// SM); here a thread-block CLUSTER of kCluCtas CTAs keeps the whole state in REGISTERS — a
+// thread owns PPT Rosenbrock pairs (i, i+N) — and only the rule-C1 reductions leave the
+// thread: every term is stored through distributed shared memory into the CTA that reduces
+// that array (array k -> cluster rank k), one warp there runs the sequential lane chains, and
+// the result is read back by everyone.  Two cluster barriers per round of reductions.
+// Same operations on the same operands as stream_vec_onepass: the same bits.
+constexpr int kCluCtas = 8;
+constexpr int kCluThreads = 512;
+
+struct CluShared {
+  double red;            // this rank's reduction result
+  int flags[kCluCtas];   // rank 0: per-CTA votes
+  int all;               // rank 0: the combined vote
+};
+
+// rank k reduces the cnt[k] staged terms in ITS `stage` by rule C1; every thread gets all K sums.
+// vote < 0: no vote; otherwise the CTAs' votes (CTA-uniform 0/1) are and-ed into *vote_out.
+template <int K>
+__device__ __forceinline__ void cluster_reduce(cooperative_groups::cluster_group& cl, const int (&cnt)[K],
+                                               const double* stage, CluShared* sh, double (&out)[K],
+                                               int vote = -1, int* vote_out = nullptr) {
+  const unsigned rank = cl.block_rank();
+  if (vote >= 0 && threadIdx.x == 0) cl.map_shared_rank(sh, 0)->flags[rank] = vote;
+  cl.sync(); // every term (and vote) has landed in its reducer's shared memory
+  if (rank < K && threadIdx.x < 32) {
+    const int l = threadIdx.x, n = cnt[rank];
+    double p = (l < n) ? stage[l] : 0.0;
+    int j = l + 32;
+    if (j + 224 < n) { // the loads of the next eight terms are in flight while these eight are added
+      double x[8], z[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = stage[j + 32 * k];
+      j += 256;
+      for (; j + 224 < n; j += 256) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) z[k] = stage[j + 32 * k];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) p = p + x[k];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = z[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) p = p + x[k];
+    }
+    for (; j < n; j += 32) p = p + stage[j];
+    p = warp_butterfly(p);
+    if (l == 0) sh->red = p;
+  }
+  if (vote >= 0 && rank == 0 && threadIdx.x == 32) {
+    int a = 1;
+#pragma unroll
+    for (int k = 0; k < kCluCtas; ++k) a &= sh->flags[k];
+    sh->all = a;
+  }
+  cl.sync();
+#pragma unroll
+  for (int k = 0; k < K; ++k) out[k] = cl.map_shared_rank(sh, k)->red;
+  if (vote >= 0) *vote_out = cl.map_shared_rank(sh, 0)->all;
+}
+
+template <int PPT>
+__global__ void __cluster_dims__(kCluCtas, 1, 1) __launch_bounds__(kCluThreads)
+stream_vec_onepass_cluster(const StreamParams p) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
+  extern __shared__ __align__(16) double vsm[]; // ns doubles: the array this rank reduces
+  __shared__ CluShared sh;
+  StreamScalars* sc = p.sc;
+  if (sc->done) return; // cluster-uniform: nobody writes sc before the first cluster barrier
+  const int n = p.n, N = n >> 1;
+  const unsigned rank = cl.block_rank();
+  const int tau = (int)rank * kCluThreads + (int)threadIdx.x;
+  const bool leader = (tau == 0);
+  constexpr int NE = 2 * PPT + 1; // elements of this thread: PPT pairs (i, i+N) and the odd tail
+  int idx[NE];
+  bool ok[NE], mine[NE];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int i = tau + k * kCluCtas * kCluThreads;
+    idx[2 * k] = i; idx[2 * k + 1] = i + N;
+    ok[2 * k] = ok[2 * k + 1] = mine[2 * k] = mine[2 * k + 1] = (i < N);
+  }
+  idx[NE - 1] = n - 1;
+  ok[NE - 1] = (n & 1) != 0;     // the tail element is replicated in every thread
+  mine[NE - 1] = ok[NE - 1] && leader; // ... and stored by one
+  double* st[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) st[k] = cl.map_shared_rank(vsm, k);
+
+  double x[NE], g[NE], s[NE], y[NE];
+#pragma unroll
+  for (int j = 0; j < NE; ++j) {
+    x[j] = g[j] = s[j] = y[j] = 0.0;
+    if (ok[j]) { x[j] = p.x[idx[j]]; g[j] = p.g[idx[j]]; s[j] = p.s[idx[j]]; y[j] = p.y[idx[j]]; }
+  }
+  int it = sc->it + 1;
+  const double l0 = sc->l0;
+  const int skip_update = sc->skip_update;
+  int fevals = 0;
+  double m;
+  if (!skip_update) {
+    const double rho = sc->rho;
+    double T[NE], W[NE], u[NE];
+#pragma unroll
+    for (int j = 0; j < NE; ++j) {
+      T[j] = W[j] = 0.0;
+      if (ok[j]) { T[j] = p.tvec[idx[j]]; W[j] = p.wvec[idx[j]]; }
+    }
+#pragma unroll
+    for (int j = 0; j < NE; ++j) {
+      u[j] = T[j] * rho; // B⁻¹y[c] = tρ, QN.jl:50
+      if (mine[j]) {
+        st[0][idx[j]] = T[j] * y[j]; // term of yᵀB⁻¹y, QN.jl:51
+        st[1][idx[j]] = s[j] * g[j]; // term of sᵀ∇
+        st[2][idx[j]] = u[j] * g[j]; // term of uᵀ∇
+      }
+    }
+    double r3[3];
+    const int cnt3[3] = {n, n, n};
+    cluster_reduce<3>(cl, cnt3, vsm, &sh, r3);
+    const double c1 = fma(r3[0], rho, 1.0) * rho; // QN.jl:54
+    const double sg = r3[1], ug = r3[2];
+    // d = ((w + (c₁ s)(sᵀ∇)) - u (sᵀ∇)) - s (uᵀ∇) ; m = dᵀ∇ ; this update becomes the pending one
+#pragma unroll
+    for (int j = 0; j < NE; ++j) {
+      double d = fma(c1 * s[j], sg, W[j]);
+      d = fma(-u[j], sg, d);
+      d = fma(-s[j], ug, d);
+      if (mine[j]) {
+        p.ps[idx[j]] = s[j];
+        p.pu[idx[j]] = u[j];
+        st[0][idx[j]] = d * g[j];
+      }
+      s[j] = d; // `s, y = y, s`, QN.jl:65,268
+    }
+    double r1[1];
+    const int cnt1[1] = {n};
+    cluster_reduce<1>(cl, cnt1, vsm, &sh, r1);
+    m = r1[0];
+    if (leader) { sc->pc1 = c1; sc->pending = 1; sc->c1 = c1; }
+  } else {
+    m = sc->m;
+  }
+  int need_reset = 0;
+  if (m <= 0.0) { // QN.jl:272-280
+    need_reset = 1;
+    if (leader) sc->pending = 0; // the reset discards the pending update
+#pragma unroll
+    for (int j = 0; j < NE; ++j) {
+      s[j] = g[j];
+      if (mine[j]) st[0][idx[j]] = g[j] * g[j];
+    }
+    double r1[1];
+    const int cnt1[1] = {n};
+    cluster_reduce<1>(cl, cnt1, vsm, &sh, r1);
+    m = r1[0];
+  }
+  // ---- linesearch!  QN.jl:165-232 (the same scalar code on the same values in every thread)
+  // A trial step! (QN.jl:157-162): x + a s as one fma, then ℓ.  Far from the optimum the
+  // backtracking sequence is the lower-clamp chain a, aρₗ, aρₗ², … (QN.jl:225), so a round
+  // evaluates the next three links of that chain as well — rank k reduces candidate k — and a
+  // later trial whose step is bit-equal to a cached candidate costs no round at all.
+  const LsParams& ls = p.ls;
+  const int spec = sc->spec;
+  double ca[4], cv[4];
+  int ncache = 0;
+  auto trial = [&](const double a) {
+    ++fevals;
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+      if (k < ncache && ca[k] == a) return cv[k];
+    ca[0] = a;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) ca[k] = ca[k - 1] * ls.rho_lo;
+    const int nc = spec ? 4 : 1;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c < nc) {
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+          if (mine[2 * k]) {
+            const double t1 = fma(ca[c], s[2 * k], x[2 * k]), t2 = fma(ca[c], s[2 * k + 1], x[2 * k + 1]);
+            const double aa = t2 - t1 * t1;
+            const double bb = 1.0 - t1;
+            st[c][idx[2 * k]] = 100.0 * (aa * aa) + bb * bb;
+          }
+        }
+      }
+    }
+    double r4[4];
+    if (spec) {
+      const int cnt4[4] = {N, N, N, N};
+      cluster_reduce<4>(cl, cnt4, vsm, &sh, r4);
+    } else {
+      double r1[1];
+      const int cnt1[1] = {N};
+      cluster_reduce<1>(cl, cnt1, vsm, &sh, r1);
+      r4[0] = r1[0];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      double v = 0.0 - r4[c < nc ? c : 0];
+      if (n & 1) {
+        const double d = 1.0 - fma(ca[c], s[NE - 1], x[NE - 1]);
+        v = -fma(d, d, -v);
+      }
+      cv[c] = v;
+    }
+    ncache = nc;
+    return cv[0];
+  };
+  double lx0 = l0, lx1;
+  double a1 = 1.0, a2 = 1.0;
+  lx1 = trial(a1);
+  int iterfinite = 0;
+  while (!isfinite(lx1) && iterfinite < 52) { // QN.jl:178-184
+    ++iterfinite;
+    a1 = a2;
+    a2 = 0.5 * a2;
+    lx1 = trial(a2);
+  }
+  long long iteration = 0;
+  bool failed = false;
+  while (!(lx1 >= fma(a2 * ls.c1, m, l0))) { // QN.jl:187
+    ++iteration;
+    if (iteration > ls.iterations) { failed = true; break; }
+    double at;
+    if (ls.order == 2 || iteration == 1) {
+      at = -((m * a2) * a2) / (2.0 * fma(-m, a2, lx1 - l0));
+    } else {
+      const double denom = 1.0 / ((((a1 * a1) * a2) * a2) * (a2 - a1));
+      const double q1 = fma(-m, a2, lx1 - l0);
+      const double q0 = fma(-m, a1, lx0 - l0);
+      const double a = ((a1 * a1) * q1 - (a2 * a2) * q0) * denom;
+      const double b = ((((-a1) * a1) * a1) * q1 + ((a2 * a2) * a2) * q0) * denom;
+      if (fabs(a) <= kEps + kSqrtTol * fabs(a)) {
+        at = m / (2.0 * b);
+      } else {
+        const double d = nanmax(b * b - (3.0 * a) * m, 0.0);
+        at = (sqrt(d) + b) / (-3.0 * a);
+      }
+    }
+    a1 = a2;
+    at = nanmin(at, a2 * ls.rho_hi);
+    a2 = nanmax(at, a2 * ls.rho_lo);
+    lx0 = lx1;
+    lx1 = trial(a2);
+  }
+  const double alpha = failed ? 0.0 : a2;
+  if (alpha == 0.0) { // QN.jl:284
+    if (leader) { sc->status = QN_LINESEARCH_FAILED; sc->done = 1; sc->fevals += fevals; sc->need_reset = 0; sc->exit_it = it; }
+#pragma unroll
+    for (int j = 0; j < NE; ++j) if (mine[j]) p.s[idx[j]] = s[j];
+    cl.sync(); // nobody leaves while its shared memory may still be read remotely
+    return;
+  }
+  // update_state!  QN.jl:21-27 ; ∇_old ← ∇_new  QN.jl:286
+  const bool last = (it >= p.max_iter);
+#pragma unroll
+  for (int j = 0; j < NE; ++j) {
+    s[j] = alpha * s[j];
+    x[j] = x[j] + s[j];
+    if (mine[j]) {
+      p.s[idx[j]] = s[j];
+      p.x[idx[j]] = x[j];
+      if (p.trace != nullptr && it <= p.ntrace) p.trace[(size_t)(it - 1) * n + idx[j]] = x[j];
+      if (!last) p.gp[idx[j]] = g[j];
+    }
+  }
+  if (last) {
+    if (leader) {
+      sc->m = m; sc->it = it; sc->iters += 1; sc->fevals += fevals; sc->need_reset = need_reset;
+      sc->status = QN_MAX_ITER; sc->done = 1; sc->exit_it = it;
+    }
+    cl.sync();
+    return;
+  }
+  // ---- head of iteration it+1: ℓ₀, ∇ = ∂logdensity!(x_old) fused with y and sᵀy   QN.jl:254,36-41
+  const int it_done = it;
+  it = it + 1;
+  bool small = true;
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const double t1 = x[2 * k], t2 = x[2 * k + 1];
+    const double aa = t2 - t1 * t1;
+    const double bb = 1.0 - t1;
+    const double g1 = (400.0 * aa) * t1 + 2.0 * bb, g2 = 200.0 * (t1 * t1 - t2);
+    const double y1 = g[2 * k] - g1, y2 = g[2 * k + 1] - g2; // y = ∇_old - ∇_new, QN.jl:38
+    if (mine[2 * k]) {
+      p.g[idx[2 * k]] = g1; p.g[idx[2 * k + 1]] = g2;
+      p.y[idx[2 * k]] = y1; p.y[idx[2 * k + 1]] = y2;
+      st[0][idx[2 * k]] = 100.0 * (aa * aa) + bb * bb;
+      st[1][idx[2 * k]] = s[2 * k] * y1;
+      st[1][idx[2 * k + 1]] = s[2 * k + 1] * y2;
+      small = small && (fabs(g1) < p.tol) && (fabs(g2) < p.tol); // maximum(abs, ∇) < tol, QN.jl:257
+    }
+  }
+  double tail_d = 0.0;
+  if (n & 1) {
+    tail_d = 1.0 - x[NE - 1];
+    const double gt = 2.0 * tail_d, yt = g[NE - 1] - gt;
+    if (mine[NE - 1]) {
+      p.g[n - 1] = gt;
+      p.y[n - 1] = yt;
+      st[1][n - 1] = s[NE - 1] * yt;
+    }
+    small = small && (fabs(gt) < p.tol);
+  }
+  const int cta_small = __syncthreads_and(small ? 1 : 0);
+  double r2[2];
+  const int cnt2[2] = {N, n};
+  int all_small = 0;
+  cluster_reduce<2>(cl, cnt2, vsm, &sh, r2, cta_small, &all_small);
+  double lnew = 0.0 - r2[0];
+  if (n & 1) lnew = -fma(tail_d, tail_d, -lnew);
+  const double sy = r2[1];
+  if (leader) {
+    sc->m = m; sc->it = it_done; sc->iters += 1; sc->fevals += fevals + 1; sc->need_reset = need_reset;
+    sc->spec = (fevals > 1); // this line search backtracked: expect the next one to
+    sc->l0 = lnew;
+    if (!isfinite(lnew)) { // QN.jl:255
+      sc->status = QN_NONFINITE; sc->done = 1; sc->exit_it = it;
+    } else if (all_small) {
+      sc->status = QN_CONVERGED; sc->result = lnew; sc->done = 1; sc->exit_it = it;
+    } else {
+      sc->sy = sy; sc->rho = 1.0 / sy; sc->skip_update = 0; // QN.jl:39,42
+    }
+  }
+  cl.sync();
+}
+
 // one-pass mode, end of the solve: apply the pending update so H is the true B⁻¹
 __global__ void __launch_bounds__(kPassThreads) stream_flush_pending(const StreamParams p) {
   const StreamScalars* sc = p.sc;
@@ -784,20 +1142,46 @@ struct StreamWork {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   size_t vec_smem = 0;
+  int clu_ppt = 0;      // one-pass mode: pairs per thread of the cluster vector kernel (0: single-CTA kernel)
+  size_t clu_smem = 0;
 };
 
-int enqueue_iteration(qn_context* ctx, const qn::StreamParams& p, size_t vec_smem, cudaStream_t st) {
+using PassKernel = void (*)(const qn::StreamParams);
+#define QN_PASS_ROW(name, l) { name<l, 0>, name<l, 1>, name<l, 2>, name<l, 3> }
+#define QN_PASS_TABLE(name) { QN_PASS_ROW(name, 0), QN_PASS_ROW(name, 1), QN_PASS_ROW(name, 2), QN_PASS_ROW(name, 3), QN_PASS_ROW(name, 4) }
+PassKernel const kPass1Tab[5][4] = QN_PASS_TABLE(qn::stream_pass1);
+PassKernel const kPass2Tab[5][4] = QN_PASS_TABLE(qn::stream_pass2);
+PassKernel const kPassOneTab[5][4] = QN_PASS_TABLE(qn::stream_pass_one);
+
+// cache hints of the B⁻¹ accesses per kernel: measured defaults (gpurun_out/hints2.txt, n = 8192:
+// pass2 .lu loads + .cs stores 356 -> 316 µs per iteration; one-pass sweep .cg loads 216 -> 206 µs),
+// overridable for experiments (scripts/exp_stream_hints.sh)
+int hint_env(const char* name, int dflt, int hi) {
+  const char* v = getenv(name);
+  if (!v) return dflt;
+  const int k = atoi(v);
+  return (k < 0 || k > hi) ? dflt : k;
+}
+PassKernel pass1_kernel() { return kPass1Tab[hint_env("QN_HINT_P1_LD", 0, 4)][0]; }
+PassKernel pass2_kernel() { return kPass2Tab[hint_env("QN_HINT_P2_LD", 2, 4)][hint_env("QN_HINT_P2_ST", 1, 3)]; }
+PassKernel pass_one_kernel() { return kPassOneTab[hint_env("QN_HINT_ONE_LD", 4, 4)][hint_env("QN_HINT_ONE_ST", 0, 3)]; }
+
+int enqueue_iteration(qn_context* ctx, const qn::StreamParams& p, size_t vec_smem, cudaStream_t st, int clu_ppt = 0,
+                      size_t clu_smem = 0) {
   const dim3 grid((p.n + qn::kRowsPerCta - 1) / qn::kRowsPerCta, p.nsb);
   if (!p.onepass) qn::stream_vec_begin<<<1, qn::kVecThreads, vec_smem, st>>>(p);
   if (p.onepass) { // two kernels per iteration; the head of iteration 1 ran before the graph
-    qn::stream_pass_one<<<grid, qn::kPassThreads, sizeof(double) * 6 * p.sbcols, st>>>(p);
-    qn::stream_vec_onepass<<<1, qn::kVecThreads, vec_smem, st>>>(p);
+    pass_one_kernel()<<<grid, qn::kPassThreads, sizeof(double) * 6 * p.sbcols, st>>>(p);
+    if (clu_ppt == 1) qn::stream_vec_onepass_cluster<1><<<qn::kCluCtas, qn::kCluThreads, clu_smem, st>>>(p);
+    else if (clu_ppt == 2) qn::stream_vec_onepass_cluster<2><<<qn::kCluCtas, qn::kCluThreads, clu_smem, st>>>(p);
+    else if (clu_ppt == 3) qn::stream_vec_onepass_cluster<3><<<qn::kCluCtas, qn::kCluThreads, clu_smem, st>>>(p);
+    else qn::stream_vec_onepass<<<1, qn::kVecThreads, vec_smem, st>>>(p);
     QN_CUDA_TRY(cudaGetLastError());
     return QN_OK;
   } else {
-    qn::stream_pass1<<<grid, qn::kPassThreads, sizeof(double) * p.sbcols, st>>>(p);
+    pass1_kernel()<<<grid, qn::kPassThreads, sizeof(double) * p.sbcols, st>>>(p);
     qn::stream_vec_mid<<<1, qn::kVecThreads, vec_smem, st>>>(p);
-    qn::stream_pass2<<<grid, qn::kPassThreads, sizeof(double) * 4 * p.sbcols, st>>>(p);
+    pass2_kernel()<<<grid, qn::kPassThreads, sizeof(double) * 4 * p.sbcols, st>>>(p);
     qn::stream_vec_end<<<1, qn::kVecThreads, vec_smem, st>>>(p);
   }
   qn::stream_identity<<<ctx->prop.multiProcessorCount * 8, 256, 0, st>>>(p);
@@ -871,12 +1255,13 @@ int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_bac
   StreamScalars init{};
   init.result = NAN;
   init.status = QN_MAX_ITER;
+  init.spec = 1;
   QN_TRY_CLEAN(cudaMemcpyAsync(p.sc, &init, sizeof init, cudaMemcpyHostToDevice, st));
   if (max_iter <= 0) {
     init.done = 1;
   } else {
     // capture one iteration (6 kernels) and replay it
-    QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    QN_TRY_CLEAN(cudaFuncSetAttribute(pass2_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(sizeof(double) * 4 * p.sbcols)));
     if (w.vec_smem) {
       QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_begin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
@@ -884,8 +1269,22 @@ int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_bac
       QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_end, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
       QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_onepass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
     }
+    if (onepass && !getenv("QN_STREAM_NO_CLUSTER")) {
+      // the cluster vector kernel: a thread owns up to 3 Rosenbrock pairs; a rank stages n doubles
+      const int pairs = n >> 1, cap = qn::kCluCtas * qn::kCluThreads;
+      const int ppt = pairs <= cap ? 1 : (pairs + cap - 1) / cap;
+      const size_t smem = sizeof(double) * (((size_t)n + 1) & ~(size_t)1);
+      if (ppt <= 3 && smem + 1024 <= (size_t)ctx->prop.sharedMemPerBlockOptin) {
+        w.clu_ppt = ppt;
+        w.clu_smem = smem;
+        const int ismem = (int)smem;
+        if (ppt == 1) QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_onepass_cluster<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ismem));
+        if (ppt == 2) QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_onepass_cluster<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ismem));
+        if (ppt == 3) QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_onepass_cluster<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ismem));
+      }
+    }
     QN_TRY_CLEAN(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    rc = enqueue_iteration(ctx, p, w.vec_smem, st);
+    rc = enqueue_iteration(ctx, p, w.vec_smem, st, w.clu_ppt, w.clu_smem);
     cudaError_t ce = cudaStreamEndCapture(st, &w.graph);
     if (rc != QN_OK || ce != cudaSuccess) {
       cleanup();

@@ -60,7 +60,7 @@ def test_stream_rejects_unregistered_objective(eng, qn):
         eng.optimize_batched(qn.DenseGaussian(mu, lam), starts(200, 1))
 
 
-@pytest.mark.parametrize("n,iters", [(60, 0), (61, 0), (200, 60), (1024, 20)])
+@pytest.mark.parametrize("n,iters", [(60, 0), (61, 0), (200, 60), (1024, 20), (8193, 6), (9001, 6), (16500, 4)])
 def test_one_pass_mode(eng, qn, ob, n, iters):
     """QN_FLAG_ONE_PASS (deferred update, 16 n² bytes per iteration): bit for bit equal to ITS oracle
     (oracle rblock = ONEPASS), and within the north-star tolerances of the reference order:
@@ -81,6 +81,19 @@ def test_one_pass_mode(eng, qn, ob, n, iters):
         assert np.abs(got["g"]).max() < 1e-8
         assert np.abs(got["x"] - ref["x"]).max() <= 5e-8
         print("one-pass n=%d: iterations %s vs reference order %s" % (n, got["iters"], ref["iters"]))
+
+
+@pytest.mark.parametrize("n,iters", [(61, 0), (200, 60)])
+def test_one_pass_mode_single_cta_fallback(eng, qn, ob, n, iters, monkeypatch):
+    """The single-CTA vector kernel (used when n is beyond the cluster kernel's reach) gives the same bits."""
+    monkeypatch.setenv("QN_STREAM_NO_CLUSTER", "1")
+    flags = qn._lib.FLAG_FORCE_STREAM | qn._lib.FLAG_ONE_PASS
+    Theta = starts(n, 2, key=70 + n)
+    kw = dict(max_iter=iters) if iters else {}
+    nt = iters if iters else 5
+    got = eng.optimize_batched(qn.Rosenbrock(), Theta, ntrace=nt, flags=flags, **kw)
+    own = ob.optimize_batch(ob.rosenbrock(), Theta, ntrace=nt, rblock=ob.ONEPASS, **kw)
+    _same(got, own)
 
 
 def test_one_pass_h_writeback(eng, qn, ob):
