@@ -3,6 +3,8 @@
 // file: every entry either runs a CUDA kernel or returns an error.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -53,30 +55,39 @@ unsigned long long* qn_next_counter(qn_context* ctx, cudaStream_t st) {
 namespace {
 
 // ---- kernel launchers ------------------------------------------------------
-template <class Obj, int NREG, int BLOCK, int MINB>
+template <class Obj, int NREG, int BLOCK, int MINB, int PAIRN = 0>
 int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Params& op,
                     cudaStream_t st) {
   const int n = p.n;
-  // shared-memory policy: deal the rule-C2 blocks of a row out to up to 4 threads while the
-  // CTA stays within 1024 threads and the partial-sum array still fits beside B⁻¹
+  // shared-memory policy: a thread owns a PAIR of rows of B⁻¹ (one 16-byte access per column)
+  // and the rule-C2 column blocks are dealt out to G thread groups of B/2 threads, as many as
+  // the CTA's thread limit and the partial-sum array beside B⁻¹ allow
   const int B = qn::resident_block_threads(n);
-  int tpr = 1;
-  if (NREG == 0 && n >= 48) {
-    for (int cand = 4; cand >= 2; cand >>= 1) {
+  int nthreads = (NREG > 0) ? BLOCK : B;
+  if (PAIRN > 0) { // pair-register policy: one rule-C2 block per thread
+    nthreads = (B / 2) * ((n + qn::chain_block(n) - 1) / qn::chain_block(n));
+  } else if (NREG == 0 && n >= 48) {
+    const int half = B / 2;
+    const int nblocks = (n + qn::chain_block(n) - 1) / qn::chain_block(n);
+    for (int G = std::min(nblocks, BLOCK / half); G >= 2; --G) {
+      const int cand = ((G * half + 31) / 32) * 32;
+      if (cand <= B) break;
       const size_t need = sizeof(double) * (size_t)qn::resident_smem_layout<Obj>(n, true, cand, op).total;
-      if (B * cand <= 1024 && need <= (size_t)ctx->prop.sharedMemPerBlockOptin) { tpr = cand; break; }
+      if (cand <= BLOCK && need <= (size_t)ctx->prop.sharedMemPerBlockOptin) { nthreads = cand; break; }
     }
   }
-  const qn::ResidentSmem L = qn::resident_smem_layout<Obj>(n, NREG == 0, tpr, op);
+  if (NREG == 0 && PAIRN == 0 && BLOCK > 512 && nthreads <= 512) // the 512-thread build may use 128 registers
+    return launch_resident<Obj, 0, 512, 1>(ctx, p, op, st);
+  const qn::ResidentSmem L = qn::resident_smem_layout<Obj>(n, NREG == 0 && PAIRN == 0, nthreads, op);
   const size_t smem = sizeof(double) * (size_t)L.total;
   if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin)
     return fail(QN_ERR_UNSUPPORTED_SIZE,
                 "n=%d needs %zu bytes of shared memory per problem; the device allows %zu "
                 "(use the streaming path)",
                 n, smem, (size_t)ctx->prop.sharedMemPerBlockOptin);
-  auto kern = qn::qn_resident_kernel<Obj, NREG, BLOCK, MINB>;
+  auto kern = qn::qn_resident_kernel<Obj, NREG, BLOCK, MINB, PAIRN>;
   QN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int block = (NREG > 0) ? BLOCK : B * tpr;
+  const int block = nthreads;
   int occ = 0;
   QN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
   if (occ < 1) return fail(QN_ERR_UNSUPPORTED_SIZE, "resident kernel does not fit on an SM (n=%d)", n);
@@ -86,7 +97,7 @@ int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Par
   p.counter = qn_next_counter(ctx, st);
   kern<<<(unsigned)grid, block, smem, st>>>(p, op);
   QN_CUDA_TRY(cudaGetLastError());
-  ctx->last_path = (NREG > 0) ? 0 : 1;
+  ctx->last_path = (NREG > 0 || PAIRN > 0) ? 0 : 1;
   ctx->last_grid = (int)grid;
   ctx->last_block = block;
   ctx->last_smem = (int)smem;
@@ -140,6 +151,10 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
         default: break;
       }
     }
+  }
+  // n = 128 (BASELINE.json configs[2], [3]): B⁻¹ as 2×16 register tiles of 512 threads, any objective
+  if constexpr (Obj::kPairRegister) {
+    if (n == 128 && !(flags & QN_FLAG_FORCE_SMEM)) return launch_resident<Obj, 0, 512, 1, 128>(ctx, p, op, st);
   }
   if (n <= 256) return launch_resident<Obj, 0, 1024, 1>(ctx, p, op, st);
   return fail(QN_ERR_UNSUPPORTED_SIZE, "n=%d does not fit the resident path", n);

@@ -54,6 +54,27 @@ __host__ __device__ constexpr int chain_block(int K) {
   return K <= 0 ? 1 : (K + (K + 15) / 16 - 1) / ((K + 15) / 16);
 }
 
+// One rule-C2 block: a sequential fma chain over r0 <= r < r1 from +0.0.  The operands of eight
+// steps are fetched before their fmas run, so eight (global-memory) loads are in flight.
+template <class F>
+__device__ __forceinline__ double block_chain(int r0, int r1, F&& term) {
+  double t = 0.0;
+  int r = r0;
+  for (; r + 8 <= r1; r += 8) {
+    double a[8], b[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) term(r + k, a[k], b[k]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t = fma(a[k], b[k], t);
+  }
+  for (; r < r1; ++r) {
+    double a, b;
+    term(r, a, b);
+    t = fma(a, b, t);
+  }
+  return t;
+}
+
 // Blocked row sum of rule C2 for one row: term(r) returns the two fma operands through
 // references.  Handles the two-level (super-block) combine for any K.
 template <class F>
@@ -63,17 +84,26 @@ __device__ __forceinline__ double chain_rowsum(int K, F&& term) {
   int blk = 0;
   for (int r0 = 0; r0 < K; r0 += rb, ++blk) {
     const int r1 = min(r0 + rb, K);
-    double t = 0.0;
-#pragma unroll 4
-    for (int r = r0; r < r1; ++r) {
-      double a, b;
-      term(r, a, b);
-      t = fma(a, b, t);
-    }
+    const double t = block_chain(r0, r1, term);
     S = ((blk & 15) == 0) ? t : S + t;
     if ((blk & 15) == 15 || r1 == K) T = (blk < 16) ? S : T + S;
   }
   return T;
+}
+
+// One rule-C2 SUPER-block (16 blocks) of a row sum over K terms: block partials added in order.
+template <class F>
+__device__ __forceinline__ double superblock_sum(int K, int sb, F&& term) {
+  const int rb = chain_block(K);
+  double S = 0.0;
+  const int rend = min(K, (sb + 1) * 16 * rb);
+  bool first = true;
+  for (int r0 = sb * 16 * rb; r0 < rend; r0 += rb) {
+    const double t = block_chain(r0, min(r0 + rb, rend), term);
+    S = first ? t : S + t;
+    first = false;
+  }
+  return S;
 }
 
 // nanmin / nanmax, QN.jl:152-153
@@ -105,7 +135,7 @@ struct Team {
 
   // canonical csum (rule C1) split around a barrier the caller provides
   __device__ __forceinline__ void stage(double v) {
-    red[phase * stride + c] = v;
+    if (c < stride) red[phase * stride + c] = v;
   }
   __device__ __forceinline__ double finish(int count) {
     const double* r = red + phase * stride;
@@ -128,17 +158,10 @@ struct Team {
     }
     const int rb = chain_block(K);
     const int row = c % nvec, hgrp = c / nvec;
-    if (row < n) {
+    if (row < n && hgrp < tpr) {
       for (int r0 = hgrp * rb, blk = hgrp; r0 < K; r0 += tpr * rb, blk += tpr) {
         const int r1 = min(r0 + rb, K);
-        double t = 0.0;
-#pragma unroll 4
-        for (int r = r0; r < r1; ++r) {
-          double a, b;
-          term(row, r, a, b);
-          t = fma(a, b, t);
-        }
-        part[blk * nvec + row] = t;
+        part[blk * nvec + row] = block_chain(r0, r1, [&](int r, double& a, double& b) { term(row, r, a, b); });
       }
     }
     __syncthreads();

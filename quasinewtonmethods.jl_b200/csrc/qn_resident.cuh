@@ -32,14 +32,16 @@ struct __align__(16) Pass2Col {
 
 __host__ __device__ inline int resident_block_threads(int n) { return (n + 31) & ~31; }
 
-// shared memory carve-up (in doubles).  tpr = threads per row of B⁻¹ (shared-memory policy
-// only): the rule-C2 blocks of a row are dealt out to tpr threads, whose block partials meet
-// in `part` ([blocks][B]).
+// shared memory carve-up (in doubles).  nthreads = blockDim.x.  Shared-memory policy: B⁻¹ is
+// stored column-major with an EVEN column stride (resident_ldh) so a thread's pair of rows is one
+// 16-byte access; with nthreads > B the rule-C2 blocks of the rows are dealt out to thread
+// groups whose block partials meet in `part` ([blocks][B]).
 struct ResidentSmem {
   int red, xs, ys, cols, scratch, part, h, total;
 };
+__host__ __device__ inline int resident_ldh(int n) { return (n + 1) & ~1; }
 template <class Obj>
-__host__ __device__ inline ResidentSmem resident_smem_layout(int n, bool h_in_smem, int tpr,
+__host__ __device__ inline ResidentSmem resident_smem_layout(int n, bool h_in_smem, int nthreads,
                                                              const typename Obj::Params& op) {
   const int B = resident_block_threads(n);
   const int nblocks = (n + chain_block(n) - 1) / chain_block(n);
@@ -48,10 +50,10 @@ __host__ __device__ inline ResidentSmem resident_smem_layout(int n, bool h_in_sm
   L.cols = o; o += 4 * B;   // Pass2Col[B], 16-byte aligned at offset 0
   L.ys = o;   o += B;
   L.xs = o;   o += B;
-  L.red = o;  o += 2 * B * tpr;
+  L.red = o;  o += 2 * B;
   L.scratch = o; o += Obj::scratch_doubles(n, op);
-  L.part = o; o += (tpr > 1) ? nblocks * B : 0;
-  L.h = o;    o += h_in_smem ? n * n : 0;
+  L.part = o; o += (nthreads > B) ? nblocks * B : 0;
+  L.h = o;    o += h_in_smem ? resident_ldh(n) * n : 0;
   L.total = o + 2; // + problem index broadcast slot
   return L;
 }
@@ -125,25 +127,37 @@ __device__ __forceinline__ void write_problem_scalars(const BatchParams& p, long
   }
 }
 
-template <class Obj, int NREG>
+// PAIRN > 0 (with NREG == 0): the "pair" policy with n = PAIRN at compile time and every
+// thread's 2 × rb tile of B⁻¹ (two rows, one rule-C2 block) in REGISTERS; needs
+// blockDim = (B/2) · #blocks so that a thread owns exactly one block.
+template <class Obj, int NREG, int PAIRN = 0>
 __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
                                                    const typename Obj::Params& op,
                                                    const long long j, Team& tm, double* ys,
                                                    Pass2Col* cols, double* hs, double* part) {
-  const int n = (NREG > 0) ? NREG : p.n;
+  const int n = (NREG > 0) ? NREG : (PAIRN > 0 ? PAIRN : p.n);
   const int c = tm.c;          // thread index: the owner of element c when c < n
   const bool active = c < n;
-  // shared-memory policy: tpr threads share a row; thread c works on row c mod B and on the
-  // rule-C2 blocks hgrp, hgrp + tpr, ... of it
+  // shared-memory policy with more threads than elements ("pair" policy): thread c works on the
+  // two rows 2·(c mod B/2), +1 and on the rule-C2 blocks bgrp, bgrp + G, ... of them
   const int B = resident_block_threads(n);
-  const int tpr = (NREG > 0) ? 1 : (int)blockDim.x / B;
-  const int row = (NREG > 0) ? c : c % B;
-  const int hgrp = (NREG > 0) ? 0 : c / B;
-  (void)part; (void)row; (void)hgrp; (void)tpr;
+  const bool multi = (NREG == 0) && ((int)blockDim.x > B || PAIRN > 0);
+  const int half = B >> 1;
+  const int G = (NREG > 0) ? 1 : (int)blockDim.x / half;
+  const int row0 = (NREG > 0) ? c : 2 * (c % half);
+  const int bgrp = (NREG > 0) ? 0 : c / half;
+  const int ldh = (NREG > 0) ? 0 : resident_ldh(n);
+  (void)part; (void)multi; (void)G; (void)row0; (void)bgrp; (void)ldh;
   constexpr int HR = (NREG > 0) ? NREG : 1;
   const int rb = chain_block(n); // rule C2 block length
   double h[HR]; // row c of B⁻¹ (register policy)
   (void)h; (void)hs;
+  constexpr int PRB = (PAIRN > 0) ? chain_block(PAIRN) : 1;
+  double hp[2][PRB]; // rows row0, row0+1 × the columns of block bgrp (pair-register policy)
+  (void)hp;
+  const int pcol0 = bgrp * PRB;                       // first column of this thread's block
+  const int pcols = (PAIRN > 0) ? min(PRB, n - pcol0) : 0; // ... and how many it has
+  (void)pcol0; (void)pcols;
 
   double x = active ? p.theta0[j * p.theta_stride + c] : 0.0; // copyto!(x_old, x), QN.jl:248
   double g = 0.0, g_prev = 0.0, s = 0.0;
@@ -190,26 +204,49 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
           for (int r = r0; r < r0 + RB && r < HR; ++r) t = fma(ys[r], h[r], t);
           T = (r0 == 0) ? t : T + t;
         }
-      } else if (tpr == 1) {
+      } else if (PAIRN > 0) {
+        if (row0 < n) {
+          double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+          for (int k = 0; k < PRB; ++k) {
+            if (k < pcols) {
+              const double yr = ys[pcol0 + k];
+              t0 = fma(yr, hp[0][k], t0);
+              t1 = fma(yr, hp[1][k], t1);
+            }
+          }
+          *reinterpret_cast<double2*>(part + bgrp * B + row0) = make_double2(t0, t1);
+        }
+        __syncthreads();
+        if (active) { // block partials in ascending order (rule C2)
+          T = part[c];
+          for (int r0 = rb, blk = 1; r0 < n; r0 += rb, ++blk) T = T + part[blk * B + c];
+        }
+      } else if (!multi) {
         if (active) {
           const double* hrow = hs + c;
           for (int r0 = 0; r0 < n; r0 += rb) {
             const int r1 = min(r0 + rb, n);
             double t = 0.0;
 #pragma unroll 4
-            for (int r = r0; r < r1; ++r) t = fma(ys[r], hrow[n * r], t);
+            for (int r = r0; r < r1; ++r) t = fma(ys[r], hrow[ldh * r], t);
             T = (r0 == 0) ? t : T + t;
           }
         }
       } else {
-        if (row < n) {
-          const double* hrow = hs + row;
-          for (int r0 = hgrp * rb, blk = hgrp; r0 < n; r0 += tpr * rb, blk += tpr) {
+        if (bgrp < G && row0 < n) {
+          const double* hrow = hs + row0;
+          for (int r0 = bgrp * rb, blk = bgrp; r0 < n; r0 += G * rb, blk += G) {
             const int r1 = min(r0 + rb, n);
-            double t = 0.0;
-#pragma unroll 4
-            for (int r = r0; r < r1; ++r) t = fma(ys[r], hrow[n * r], t);
-            part[blk * B + row] = t;
+            double t0 = 0.0, t1 = 0.0;
+#pragma unroll 8
+            for (int r = r0; r < r1; ++r) {
+              const double yr = ys[r];
+              const double2 hh = *reinterpret_cast<const double2*>(hrow + ldh * r);
+              t0 = fma(yr, hh.x, t0);
+              t1 = fma(yr, hh.y, t1);
+            }
+            *reinterpret_cast<double2*>(part + blk * B + row0) = make_double2(t0, t1);
           }
         }
         __syncthreads();
@@ -222,7 +259,10 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
       if (c < B) cols[c].nu = -u;
       const double yHy = tm.csum(T * y, n);          // QN.jl:51
       const double c1 = fma(yHy, rho, 1.0) * rho;    // QN.jl:54
-      if (c < B) cols[c].w = c1 * s;                 // (c₁ s[r]), rounded once per r (rule C4)
+      if (c < B) {
+        cols[c].w = c1 * s;                          // (c₁ s[r]), rounded once per r (rule C4)
+        if (multi) { ys[c] = s; tm.xs[c] = -u; }     // row operands of a pair as one 16-byte read
+      }                                              //   (y and the point are dead until the line search)
       __syncthreads();
       // pass 2: H ← H + c₁ssᵀ - usᵀ - suᵀ fused with d = H⁺∇_new   QN.jl:56-67
       const double nu_c = -u;
@@ -245,7 +285,33 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
           }
           D = (r0 == 0) ? acc : D + acc;
         }
-      } else if (tpr == 1) {
+      } else if (PAIRN > 0) {
+        if (row0 < n) {
+          const double2 sAB = *reinterpret_cast<const double2*>(ys + row0);  // s of the pair (see below)
+          const double2 nAB = *reinterpret_cast<const double2*>(tm.xs + row0); // -u of the pair
+          double accA = 0.0, accB = 0.0;
+#pragma unroll
+          for (int k = 0; k < PRB; ++k) {
+            if (k < pcols) {
+              const double2 wn = *reinterpret_cast<const double2*>(&cols[pcol0 + k].w);
+              const double2 sg = *reinterpret_cast<const double2*>(&cols[pcol0 + k].s);
+              double ha = hp[0][k], hb = hp[1][k];
+              ha = fma(wn.x, sAB.x, ha);  hb = fma(wn.x, sAB.y, hb);   // + (c₁ s[r]) s[c]
+              ha = fma(wn.y, sAB.x, ha);  hb = fma(wn.y, sAB.y, hb);   // - u[r] s[c]
+              ha = fma(nAB.x, sg.x, ha);  hb = fma(nAB.y, sg.x, hb);   // - u[c] s[r]
+              hp[0][k] = ha; hp[1][k] = hb;
+              accA = fma(ha, sg.y, accA);
+              accB = fma(hb, sg.y, accB);
+            }
+          }
+          *reinterpret_cast<double2*>(part + bgrp * B + row0) = make_double2(accA, accB);
+        }
+        __syncthreads();
+        if (active) {
+          D = part[c];
+          for (int r0 = rb, blk = 1; r0 < n; r0 += rb, ++blk) D = D + part[blk * B + c];
+        }
+      } else if (!multi) {
         if (active) {
           double* hrow = hs + c;
           for (int r0 = 0; r0 < n; r0 += rb) {
@@ -255,35 +321,39 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
             for (int r = r0; r < r1; ++r) {
               const double2 wn = *reinterpret_cast<const double2*>(&cols[r].w);
               const double2 sg = *reinterpret_cast<const double2*>(&cols[r].s);
-              double hh = hrow[n * r];
+              double hh = hrow[ldh * r];
               hh = fma(wn.x, s, hh);
               hh = fma(wn.y, s, hh);
               hh = fma(nu_c, sg.x, hh);
-              hrow[n * r] = hh;
+              hrow[ldh * r] = hh;
               acc = fma(hh, sg.y, acc);
             }
             D = (r0 == 0) ? acc : D + acc;
           }
         }
       } else {
-        if (row < n) {
-          const double s_row = cols[row].s, nu_row = cols[row].nu; // published by the row's owner
-          double* hrow = hs + row;
-          for (int r0 = hgrp * rb, blk = hgrp; r0 < n; r0 += tpr * rb, blk += tpr) {
+        if (bgrp < G && row0 < n) {
+          // row operands of the pair, published by the rows' owners (zero beyond n)
+          const double2 sAB = *reinterpret_cast<const double2*>(ys + row0);
+          const double2 nAB = *reinterpret_cast<const double2*>(tm.xs + row0);
+          const double sA = sAB.x, sB = sAB.y, nuA = nAB.x, nuB = nAB.y;
+          double* hrow = hs + row0;
+          for (int r0 = bgrp * rb, blk = bgrp; r0 < n; r0 += G * rb, blk += G) {
             const int r1 = min(r0 + rb, n);
-            double acc = 0.0;
+            double accA = 0.0, accB = 0.0;
 #pragma unroll 4
             for (int r = r0; r < r1; ++r) {
               const double2 wn = *reinterpret_cast<const double2*>(&cols[r].w);
               const double2 sg = *reinterpret_cast<const double2*>(&cols[r].s);
-              double hh = hrow[n * r];
-              hh = fma(wn.x, s_row, hh);
-              hh = fma(wn.y, s_row, hh);
-              hh = fma(nu_row, sg.x, hh);
-              hrow[n * r] = hh;
-              acc = fma(hh, sg.y, acc);
+              double2 hh = *reinterpret_cast<const double2*>(hrow + ldh * r);
+              hh.x = fma(wn.x, sA, hh.x);  hh.y = fma(wn.x, sB, hh.y);   // + (c₁ s[r]) s[c]
+              hh.x = fma(wn.y, sA, hh.x);  hh.y = fma(wn.y, sB, hh.y);   // - u[r] s[c]
+              hh.x = fma(nuA, sg.x, hh.x); hh.y = fma(nuB, sg.x, hh.y);  // - u[c] s[r]
+              *reinterpret_cast<double2*>(hrow + ldh * r) = hh;
+              accA = fma(hh.x, sg.y, accA);
+              accB = fma(hh.y, sg.y, accB);
             }
-            part[blk * B + row] = acc;
+            *reinterpret_cast<double2*>(part + blk * B + row0) = make_double2(accA, accB);
           }
         }
         __syncthreads();
@@ -299,8 +369,14 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
       if (NREG > 0) {
 #pragma unroll
         for (int r = 0; r < HR; ++r) h[r] = (r == c) ? 1.0 : 0.0;
+      } else if (PAIRN > 0) {
+#pragma unroll
+        for (int k = 0; k < PRB; ++k) {
+          hp[0][k] = (row0 == pcol0 + k) ? 1.0 : 0.0;
+          hp[1][k] = (row0 + 1 == pcol0 + k) ? 1.0 : 0.0;
+        }
       } else if (active) {
-        for (int r = 0; r < n; ++r) hs[c + n * r] = (r == c) ? 1.0 : 0.0;
+        for (int r = 0; r < n; ++r) hs[c + ldh * r] = (r == c) ? 1.0 : 0.0;
       }
       s = g;
       m = tm.csum(g * g, n);
@@ -322,47 +398,62 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
   // The reference swaps its two gradient buffers every iteration (QN.jl:286) and only
   // copies into the canonical slot on convergence (QN.jl:258-259): after a failure in an
   // even iteration `gradient(state)` still shows the previous iteration's ∇ (selected above).
+  if (PAIRN > 0 && p.h_out && row0 < n) {
+    double* ho = p.h_out + j * p.h_stride;
+#pragma unroll
+    for (int k = 0; k < PRB; ++k) {
+      if (k < pcols) {
+        ho[row0 + (long long)p.ldh * (pcol0 + k)] = hp[0][k];
+        if (row0 + 1 < n) ho[row0 + 1 + (long long)p.ldh * (pcol0 + k)] = hp[1][k];
+      }
+    }
+  }
   if (active) {
     if (p.x_out) p.x_out[j * p.x_stride + c] = x;
     if (p.g_out) p.g_out[j * p.g_stride + c] = g;
-    if (p.h_out) {
+    if (p.h_out && PAIRN == 0) {
       double* ho = p.h_out + j * p.h_stride + c;
       if (NREG > 0) {
 #pragma unroll
         for (int r = 0; r < HR; ++r) ho[(long long)p.ldh * r] = h[r];
       } else {
-        for (int r = 0; r < n; ++r) ho[(long long)p.ldh * r] = hs[c + n * r];
+        for (int r = 0; r < n; ++r) ho[(long long)p.ldh * r] = hs[c + ldh * r];
       }
     }
   }
   write_problem_scalars(p, j, c, result, iters, fevals, status);
 }
 
-template <class Obj, int NREG, int BLOCK, int MINB>
+template <class Obj, int NREG, int BLOCK, int MINB, int PAIRN = 0>
 __global__ void __launch_bounds__(BLOCK, MINB)
 qn_resident_kernel(const BatchParams p, const typename Obj::Params op) {
-  // launch: blockDim = resident_block_threads(n) * tpr (tpr = 1 for the register policy)
+  // launch: blockDim >= resident_block_threads(n); see launch_resident for the policy
   extern __shared__ __align__(16) double smem[];
-  const int n = (NREG > 0) ? NREG : p.n;
-  const int tpr = (NREG > 0) ? 1 : (int)blockDim.x / resident_block_threads(n);
-  const ResidentSmem L = resident_smem_layout<Obj>(n, NREG == 0, tpr, op);
+  const int n = (NREG > 0) ? NREG : (PAIRN > 0 ? PAIRN : p.n);
+  const int B = resident_block_threads(n);
+  const ResidentSmem L = resident_smem_layout<Obj>(n, NREG == 0 && PAIRN == 0, (int)blockDim.x, op);
 
   Team tm;
   tm.n = n;
   tm.c = threadIdx.x;
   tm.lane = threadIdx.x & 31;
   tm.red = smem + L.red;
-  tm.stride = resident_block_threads(n) * tpr;
+  tm.stride = B;
   tm.phase = 0;
   tm.xs = smem + L.xs;
-  tm.nvec = resident_block_threads(n);
-  tm.tpr = tpr;
+  tm.nvec = B;
+  tm.tpr = (NREG > 0) ? 1 : (int)blockDim.x / B;
   tm.part = smem + L.part;
   tm.scratch = smem + L.scratch;
   double* ys = smem + L.ys;
   Pass2Col* cols = reinterpret_cast<Pass2Col*>(smem + L.cols);
   double* hs = smem + L.h;
   volatile long long* next = reinterpret_cast<volatile long long*>(smem + L.total - 2);
+  if (NREG == 0 && PAIRN == 0) { // the padding row of an odd-n B⁻¹ is read and written by its pair: keep it finite
+    const int ldh = resident_ldh(n);
+    if (ldh > n)
+      for (int r = threadIdx.x; r < n; r += blockDim.x) hs[n + ldh * r] = 0.0;
+  }
 
   for (;;) {
     __syncthreads(); // previous problem's last reads of shared memory are done
@@ -370,7 +461,7 @@ qn_resident_kernel(const BatchParams p, const typename Obj::Params op) {
     __syncthreads();
     const long long j = *next;
     if (j >= p.batch) break;
-    resident_solve_one<Obj, NREG>(p, op, j, tm, ys, cols, hs, smem + L.part);
+    resident_solve_one<Obj, NREG, PAIRN>(p, op, j, tm, ys, cols, hs, smem + L.part);
   }
 }
 

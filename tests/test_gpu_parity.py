@@ -78,6 +78,17 @@ def test_ragged_sizes_smem_path(eng, qn, ob, n):
     _check(got, ref)
 
 
+def test_n128_both_resident_policies(eng, qn, ob):
+    """n = 128 runs with B⁻¹ as 2x16 register tiles of 512 threads by default and in shared memory
+    (row pairs, column blocks dealt out to thread groups) under QN_FLAG_FORCE_SMEM: same bits."""
+    Theta = starts(128, 8, key=1280)
+    ref = ob.optimize_batch(ob.rosenbrock(), Theta, ntrace=5)
+    for flags, path in ((0, qn._lib.PATH_REGISTER), (qn._lib.FLAG_FORCE_SMEM, qn._lib.PATH_SMEM)):
+        got = eng.optimize_batched(qn.Rosenbrock(), Theta, ntrace=5, flags=flags)
+        assert eng.last_launch()["path"] == path
+        _check(got, ref)
+
+
 def test_committed_oracle_vectors(eng, qn):
     """Against the committed fixtures (no oracle call): tests/golden/oracle_vectors.npz."""
     v = np.load(os.path.join(GOLDEN, "oracle_vectors.npz"))
@@ -169,8 +180,9 @@ def test_edge_cases(eng, qn, ob):
 def test_state_blocks_and_h_writeback(eng, qn, ob):
     """Results land in BFGSState layout (QN.jl:135,138): θ* at 0, ∇ at L; with QN_FLAG_WRITE_H the
     final B⁻¹ at 7L equals the oracle's bit for bit."""
-    for n, flags in ((60, 0), (60, qn._lib.FLAG_FORCE_SMEM), (24, 0)):
-        batch = 16
+    for n, flags in ((60, 0), (60, qn._lib.FLAG_FORCE_SMEM), (24, 0), (61, qn._lib.FLAG_FORCE_SMEM),
+                     (128, 0), (128, qn._lib.FLAG_FORCE_SMEM), (159, 0)):
+        batch = 16 if n < 100 else 3
         Theta = starts(n, batch, key=n + 1)
         sb = qn.BFGSStateBatch(n, batch)
         sb.data[:] = np.nan
