@@ -185,6 +185,24 @@ int32_t qn_bfgs_optimize_batched_multi_f64(qn_context* const* ctxs, int32_t nctx
                                            int32_t* fevals_out, int32_t* status_out,
                                            uint32_t flags);
 
+/* Row-sharded large-n mode (BASELINE.json configs[4], "optional row-sharded
+ * 8-GPU mode"): ONE problem on up to 8 GPUs of one process.  Context g holds the rows of its
+ * 512-row tiles of B⁻¹ (QN.jl:48,61: the unit-stride index c) and a replica of every O(n) vector;
+ * the row sums of each sweep are exchanged with peer stores over NVLink and per-shard epoch flags
+ * inside the kernels — no host or NCCL call inside an iteration — and every reduction is
+ * replicated, so the result is the single-GPU result bit for bit.  Replaces the same reference
+ * call as qn_bfgs_optimize_f64: optimize!(state, obj, x, ls, tol), QN.jl:237-292.
+ * Host pointers.  h_out (n × ldh, column-major) may be NULL; trace_out is ntrace × n.
+ * bench_iters > 0: run exactly that many iterations (first two untimed) and report
+ * *ms_per_iter; otherwise iterate to convergence / max_iter. */
+int32_t qn_bfgs_optimize_rowsharded_f64(qn_context* const* ctxs, int32_t nctx,
+                                        const qn_model* model, int32_t n, const double* theta0,
+                                        const qn_backtracking* ls, double tol, int32_t max_iter,
+                                        double* x_out, double* g_out, double* h_out, int32_t ldh,
+                                        double* ell_out, int32_t* iters_out, int32_t* fevals_out,
+                                        int32_t* status_out, int32_t ntrace, double* trace_out,
+                                        uint32_t flags, int32_t bench_iters, double* ms_per_iter);
+
 /* How the last optimize call on this context was executed:
  * path 0 = register-resident, 1 = shared-memory-resident, 2 = HBM streaming. */
 int32_t qn_last_launch_info(qn_context* ctx, int32_t* path, int32_t* grid, int32_t* block,

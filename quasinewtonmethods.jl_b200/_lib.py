@@ -72,6 +72,9 @@ SIGNATURES = {
     "qn_bfgs_optimize_batched_multi_f64": (C.c_int32, [
         C.POINTER(_vp), C.c_int32, C.POINTER(_vp), C.c_int32, C.c_int64, _vp,
         C.POINTER(Backtracking), C.c_double, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint32]),
+    "qn_bfgs_optimize_rowsharded_f64": (C.c_int32, [
+        C.POINTER(_vp), C.c_int32, _vp, C.c_int32, _vp, C.POINTER(Backtracking), C.c_double, C.c_int32,
+        _vp, _vp, _vp, C.c_int32, _dp, _ip, _ip, _ip, C.c_int32, _vp, C.c_uint32, C.c_int32, _dp]),
     "qn_last_launch_info": (C.c_int32, [_vp, _ip, _ip, _ip, _ip, _ip]),
     "qn_microbench_dfma": (C.c_int32, [_vp, _dp]),
     "qn_microbench_lds": (C.c_int32, [_vp, _dp]),

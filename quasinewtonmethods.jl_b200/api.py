@@ -27,7 +27,7 @@ from ._lib import (CONVERGED, LINESEARCH_FAILED, MAX_ITER, NONFINITE, QNError,
 __all__ = [
     "BFGSState", "BFGSStateBatch", "BackTracking", "Rosenbrock", "DenseGaussian",
     "LogisticRegression", "optimize_", "optimize", "optimum", "gradient", "logdensity",
-    "dlogdensity_", "Engine", "default_engine", "QNError", "UnregisteredObjectiveError",
+    "dlogdensity_", "Engine", "default_engine", "optimize_rowsharded", "QNError", "UnregisteredObjectiveError",
     "CONVERGED", "NONFINITE", "LINESEARCH_FAILED", "MAX_ITER",
 ]
 
@@ -292,6 +292,32 @@ class Engine:
         g = np.empty((n, batch), order="F") if grad else None
         _lib.check(self._lib.qn_logdensity_batched_f64(self._ctx, h, n, batch, _ptr(Theta), _ptr(ell), _ptr(g)))
         return (ell, g) if grad else ell
+
+
+def optimize_rowsharded(engines, obj, theta, ls=None, tol=1e-8, max_iter=MAX_ITER_DEFAULT, ntrace=0,
+                        flags=0, want_h=False, bench_iters=0):
+    """ONE large problem on several GPUs: engine g holds the rows of its row tiles of B⁻¹
+    (qn_bfgs_optimize_rowsharded_f64).  Same result as one GPU, bit for bit.
+    Returns a dict like Engine.optimize_batched with batch = 1 (plus 'H', 'ms_per_iter')."""
+    theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1)
+    n = theta.size
+    ls = ls or BackTracking()
+    lsc = ls._c()
+    lib = engines[0]._lib
+    h = engines[0].model_handle(obj)
+    ctxs = (C.c_void_p * len(engines))(*[e._ctx for e in engines])
+    x = np.empty(n); g = np.empty(n)
+    H = np.zeros((n, n), order="F") if want_h else None
+    ell = C.c_double(float("nan")); it = C.c_int32(0); fe = C.c_int32(0); st = C.c_int32(0)
+    ms = C.c_double(0.0)
+    trace = np.full((ntrace, n), np.nan) if ntrace else None
+    _lib.check(lib.qn_bfgs_optimize_rowsharded_f64(
+        ctxs, len(engines), h, n, _ptr(theta), C.byref(lsc), tol, max_iter, _ptr(x), _ptr(g), _ptr(H), n,
+        C.byref(ell), C.byref(it), C.byref(fe), C.byref(st), ntrace, _ptr(trace), flags, bench_iters,
+        C.byref(ms)))
+    return dict(x=x[:, None], g=g[:, None], ell=np.array([ell.value]), iters=np.array([it.value], dtype=np.int32),
+                fevals=np.array([fe.value], dtype=np.int32), status=np.array([st.value], dtype=np.int32),
+                trace=None if trace is None else trace[None], H=H, ms_per_iter=ms.value)
 
 
 _engines = {}

@@ -140,6 +140,7 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
   case N:                      \
     if constexpr (std::is_same<Obj, qn::Rosenbrock>::value) {                                        \
       const char* v = getenv("QN_TILE_VARIANT"); /* tuning knob, see DESIGN.md §5 */                 \
+      if (v && v[0] == '7') return launch_tile<N, 7, 1>(ctx, p, st);                                 \
       if (v && v[0] == '5') return launch_tile<N, 5, 2>(ctx, p, st);                                 \
       if (v && v[0] == '4') return launch_tile<N, 4, 3>(ctx, p, st);                                 \
       return launch_tile<N, MINB, 1>(ctx, p, st);                                                    \

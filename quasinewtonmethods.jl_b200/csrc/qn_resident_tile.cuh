@@ -120,17 +120,22 @@ struct TileCfg {
   static constexpr int wWN = 0;                      // {c₁s, -u}[2 blocks][16]  (double2)
   static constexpr int wSG = wWN + 64;               // {s, ∇}[2 blocks][16]     (double2)
   static constexpr int wYsp = wSG + 64;              // y[2 blocks][16]
-  static constexpr int wS = wYsp + 32;               // s  by element (row operands, lane-indexed)
-  static constexpr int wNu = wS + 64;                // -u by element
-  static constexpr int wX = wNu + 64;                // x_old, ∇, ∇_old, y parked here while the
+  static constexpr int wS = wYsp + 32;               // s  by element (row operands), in the
+  static constexpr int wNu = wS + 80;                // -u by element           quad layout below
+  static constexpr int wX = wNu + 80;                // x_old, ∇, ∇_old, y parked here while the
   static constexpr int wG = wX + 64;                 //   passes need the registers
   static constexpr int wGp = wG + 64;
   static constexpr int wY = wGp + 64;
   static constexpr int wSize = wY + 64;
-  // shared by the two warps: block partials of pass 1 and pass 2, [4 blocks][64 rows] each
+  // shared by the two warps: block partials of pass 1 and pass 2, [4 blocks][80] each.
+  // Quad layout of a 64-element vector: element e = 4q+i sits at quad(e) = (i>>1)·40 + 2q + (i&1),
+  // so a thread's four rows are two consecutive-by-q 16-byte words (conflict-free LDS/STS.128),
+  // and a warp's by-element access (e = lane) touches banks 0-15 and 16-31 once each.
+  static constexpr int kQuad = 80;
   static constexpr int oPart1 = 2 * wSize;
-  static constexpr int oPart2 = oPart1 + 4 * 64;
-  static constexpr int oEnd = oPart2 + 4 * 64;
+  static constexpr int oPart2 = oPart1 + 4 * kQuad;
+  static constexpr int oEnd = oPart2 + 4 * kQuad;
+  __host__ __device__ static constexpr int quad(int e) { return ((e & 3) >> 1) * 40 + 2 * (e >> 2) + (e & 1); }
 };
 
 template <int N>
@@ -180,6 +185,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
     return (el < N && blk >= 0 && blk < 2) ? blk * 16 + el % CT : -1;
   };
   const int slot_lo = slot_of(lane), slot_hi = slot_of(lane + 32);
+  const int q_lo = C::quad(lane), q_hi = C::quad(lane + 32); // quad-layout index of this lane's elements
 
   double h[RT][CT]; // the tile: h[i][k] = B⁻¹[row0 + i, col0 + k]
 
@@ -194,14 +200,14 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
   // Σ_b part[b][e'] in ascending block order (rule C2), for e' = lane and lane+32
   auto combine = [&](const double* part) {
     Pair T;
-    T.lo = part[lane];
+    T.lo = part[q_lo];
 #pragma unroll
-    for (int bb = 1; bb < NB; ++bb) T.lo = T.lo + part[bb * 64 + lane];
+    for (int bb = 1; bb < NB; ++bb) T.lo = T.lo + part[bb * C::kQuad + q_lo];
     T.hi = 0.0;
     if (hi_valid) {
-      T.hi = part[lane + 32];
+      T.hi = part[q_hi];
 #pragma unroll
-      for (int bb = 1; bb < NB; ++bb) T.hi = T.hi + part[bb * 64 + lane + 32];
+      for (int bb = 1; bb < NB; ++bb) T.hi = T.hi + part[bb * C::kQuad + q_hi];
     }
     return T;
   };
@@ -270,8 +276,8 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
       m = -1.0; // QN.jl:263-264
     } else {
       // ---- BFGS_update!  QN.jl:34-69.  Operands go to this warp's private arrays.
-      s_arr[lane] = s.lo;
-      s_arr[lane + 32] = s.hi;
+      s_arr[q_lo] = s.lo;
+      s_arr[q_hi] = s.hi;
       if (slot_lo >= 0) { ysp[slot_lo] = y.lo; SG[slot_lo] = make_double2(s.lo, g.lo); }
       if (slot_hi >= 0) { ysp[slot_hi] = y.hi; SG[slot_hi] = make_double2(s.hi, g.hi); }
       park(C::wX, x);
@@ -297,9 +303,9 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
             for (int i = 0; i < RT; ++i) tt[i] = fma(yk, h[i][k], tt[i]);
           }
         }
-        double2* pp = reinterpret_cast<double2*>(part1 + b * 64 + row0);
-        pp[0] = make_double2(tt[0], tt[1]);
-        pp[1] = make_double2(tt[2], tt[3]);
+        double* pp = part1 + b * C::kQuad + 2 * q;
+        *reinterpret_cast<double2*>(pp) = make_double2(tt[0], tt[1]);
+        *reinterpret_cast<double2*>(pp + 40) = make_double2(tt[2], tt[3]);
       }
       __syncthreads(); // pass-1 partials of both warps visible
       QN_TICK(3);
@@ -309,21 +315,21 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
         const double yHy = warp_butterfly(dot(T, yv)); // Σ_c t[c] y[c], QN.jl:51
         const double c1 = fma(yHy, rho, 1.0) * rho;    // QN.jl:54
         const double nu_lo = -(T.lo * rho), nu_hi = -(T.hi * rho); // -B⁻¹y[c] = -(t ρ), QN.jl:50
-        nu_arr[lane] = nu_lo;
-        nu_arr[lane + 32] = nu_hi;
+        nu_arr[q_lo] = nu_lo;
+        nu_arr[q_hi] = nu_hi;
         // (c₁ s[r]) rounded once per r (rule C4)
-        if (slot_lo >= 0) WN[slot_lo] = make_double2(c1 * s_arr[lane], nu_lo);
-        if (slot_hi >= 0) WN[slot_hi] = make_double2(c1 * s_arr[lane + 32], nu_hi);
+        if (slot_lo >= 0) WN[slot_lo] = make_double2(c1 * s_arr[q_lo], nu_lo);
+        if (slot_hi >= 0) WN[slot_hi] = make_double2(c1 * s_arr[q_hi], nu_hi);
       }
       __syncwarp();
       QN_TICK(4);
       // pass 2 on the tile: H ← H + c₁ssᵀ - usᵀ - suᵀ fused with d = H⁺∇_new   QN.jl:56-67
       {
         double sc[RT], nuc[RT], acc[RT];
-        const double2 s01 = *reinterpret_cast<const double2*>(s_arr + row0);
-        const double2 s23 = *reinterpret_cast<const double2*>(s_arr + row0 + 2);
-        const double2 n01 = *reinterpret_cast<const double2*>(nu_arr + row0);
-        const double2 n23 = *reinterpret_cast<const double2*>(nu_arr + row0 + 2);
+        const double2 s01 = *reinterpret_cast<const double2*>(s_arr + 2 * q);
+        const double2 s23 = *reinterpret_cast<const double2*>(s_arr + 40 + 2 * q);
+        const double2 n01 = *reinterpret_cast<const double2*>(nu_arr + 2 * q);
+        const double2 n23 = *reinterpret_cast<const double2*>(nu_arr + 40 + 2 * q);
         sc[0] = s01.x; sc[1] = s01.y; sc[2] = s23.x; sc[3] = s23.y;
         nuc[0] = n01.x; nuc[1] = n01.y; nuc[2] = n23.x; nuc[3] = n23.y;
 #pragma unroll
@@ -350,9 +356,9 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
             }
           }
         }
-        double2* pp = reinterpret_cast<double2*>(part2 + b * 64 + row0);
-        pp[0] = make_double2(acc[0], acc[1]);
-        pp[1] = make_double2(acc[2], acc[3]);
+        double* pp = part2 + b * C::kQuad + 2 * q;
+        *reinterpret_cast<double2*>(pp) = make_double2(acc[0], acc[1]);
+        *reinterpret_cast<double2*>(pp + 40) = make_double2(acc[2], acc[3]);
       }
       __syncthreads(); // pass-2 partials of both warps visible
       QN_TICK(5);
@@ -464,8 +470,9 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
   write_problem_scalars(p, j, t, result, iters, fevals, status);
 }
 
+// registers per thread: 168 lets 6 CTAs stay resident; MINB = 7 asks for 144 (experiment)
 template <int N, int MINB, int PF>
-__global__ void __launch_bounds__(64, MINB)
+__global__ void __launch_bounds__(64) __maxnreg__(MINB >= 7 ? 144 : (MINB == 6 ? 168 : (MINB == 5 ? 200 : 255)))
 qn_resident_tile_kernel(const BatchParams p) {
   extern __shared__ __align__(16) double smem[];
   volatile long long* next = reinterpret_cast<volatile long long*>(smem + tile_smem_doubles<N>() - 2);

@@ -25,6 +25,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -77,6 +78,8 @@ struct StreamParams {
   double* H;
   double *x, *g, *gp, *s, *y, *nu, *w, *xs, *tmp, *dvec; // length-n vectors
   double *ps, *pu, *tvec, *wvec;                          // one-pass mode: pending s, u; t = Hy, w = H∇
+  double* tmp2;                                           // pass2's terms of dᵀ∇ (tmp holds pass1's)
+  int nvstride;                                           // distance between consecutive work vectors
   double* partial2;                                        // one-pass mode: second [nsb][n] array
   int onepass;
   double* partial;                                  // [nsb][n]
@@ -85,7 +88,56 @@ struct StreamParams {
   StreamScalars* sc;
   int ntrace;
   double* trace; // [ntrace][n]
+  // ---- row-sharded mode: this GPU holds rows [row0, row0 + 512·ntiles) of
+  // B⁻¹ (H points at that slab, column stride ld) and every vector replicated.  A sweep's row
+  // sums are stored into EVERY replica through peer pointers (same layout on each GPU:
+  // peer address = peer_base[g] + (address - base)), then the shard raises its flag on every
+  // peer; the vector kernel that consumes them spins on its LOCAL flags.  nshard = 1: one GPU.
+  int nshard, shard, tile0, ntiles;
+  double* base;
+  double* peer_base[8];
+  unsigned int* tiles_done;  // local: row tiles of the current sweep that have been broadcast
+  unsigned int* flags;       // local: flags[2·g + w] = last epoch shard g finished sweep w
 };
+
+constexpr int kMaxShards = 8;
+
+// store v at `ptr` (an address inside this GPU's work block) in every replica
+__device__ __forceinline__ void bstore(const StreamParams& p, double* ptr, double v) {
+  if (p.nshard == 1) { *ptr = v; return; }
+  const ptrdiff_t off = ptr - p.base;
+  for (int g = 0; g < p.nshard; ++g) p.peer_base[g][off] = v;
+}
+// after a CTA has broadcast the sums of one row tile: count it, and when it was this shard's
+// last tile publish the epoch on every peer (which = 0: pass1 / the one-pass sweep, 1: pass2)
+__device__ __forceinline__ void shard_signal(const StreamParams& p, int which, unsigned epoch) {
+  if (p.nshard == 1) return;
+  __threadfence_system(); // this thread's peer stores are visible system-wide
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(p.tiles_done, 1u);
+    if (done == (unsigned)p.ntiles - 1) {
+      *p.tiles_done = 0;
+      __threadfence_system();
+      const ptrdiff_t off = reinterpret_cast<double*>(p.flags) - p.base;
+      for (int g = 0; g < p.nshard; ++g) {
+        volatile unsigned* f = reinterpret_cast<volatile unsigned*>(p.peer_base[g] + off);
+        f[2 * p.shard + which] = epoch;
+      }
+    }
+  }
+}
+// the consumer side: wait until every shard has published `epoch` for sweep `which`
+__device__ __forceinline__ void shard_wait(const StreamParams& p, int which, unsigned epoch) {
+  if (p.nshard == 1) return;
+  if ((int)threadIdx.x < p.nshard) {
+    const volatile unsigned* f = p.flags + 2 * threadIdx.x + which;
+    while (*f < epoch) { }
+  }
+  __threadfence_system();
+  __syncthreads();
+}
+
 
 // Element-wise pass over n elements by one CTA with 8 independent loads in flight per thread
 // (a single SM sees ~700 cycles of L2 latency per dependent round trip): ld(i) loads/computes,
@@ -265,7 +317,7 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_begin(const StreamPara
 // super-block partials in ascending order (rule C2) — 16 SMs do this in parallel instead of
 // one.  finish(c, T) consumes the row sum.  Returns after the tile is done.
 template <class F>
-__device__ __forceinline__ void pass_tail(const StreamParams& p, F&& finish) {
+__device__ __forceinline__ void pass_tail(const StreamParams& p, int which, unsigned epoch, F&& finish) {
   __shared__ int is_last;
   __threadfence(); // this CTA's partials are visible device-wide before it signs off
   __syncthreads();
@@ -277,17 +329,19 @@ __device__ __forceinline__ void pass_tail(const StreamParams& p, F&& finish) {
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  const int c0 = blockIdx.x * kRowsPerCta + 2 * threadIdx.x;
-  if (c0 >= p.n) return;
-  const bool two = (c0 + 1 < p.n);
-  const volatile double* part = p.partial + c0; // written by other CTAs of this launch
-  double T0 = part[0], T1 = two ? part[1] : 0.0;
-  for (int j = 1; j < p.nsb; ++j) {
-    T0 = T0 + part[(size_t)j * p.n];
-    if (two) T1 = T1 + part[(size_t)j * p.n + 1];
+  const int c0 = (p.tile0 + blockIdx.x) * kRowsPerCta + 2 * threadIdx.x;
+  if (c0 < p.n) {
+    const bool two = (c0 + 1 < p.n);
+    const volatile double* part = p.partial + c0; // written by other CTAs of this launch
+    double T0 = part[0], T1 = two ? part[1] : 0.0;
+    for (int j = 1; j < p.nsb; ++j) {
+      T0 = T0 + part[(size_t)j * p.n];
+      if (two) T1 = T1 + part[(size_t)j * p.n + 1];
+    }
+    finish(c0, T0);
+    if (two) finish(c0 + 1, T1);
   }
-  finish(c0, T0);
-  if (two) finish(c0 + 1, T1);
+  shard_signal(p, which, epoch); // row-sharded mode: this tile's sums are in every replica
 }
 
 __global__ void __launch_bounds__(kVecThreads) stream_vec_mid(const StreamParams p) {
@@ -297,6 +351,7 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_mid(const StreamParams
   if (sc->done || sc->skip_update) return;
   const int n = p.n;
   const double rho = sc->rho;
+  shard_wait(p, 0, (unsigned)sc->it + 1u); // row-sharded mode: every shard's slice of t has arrived
   // pass1's tail left t[c]·y[c] in tmp and -u in nu; yᵀB⁻¹y = csum, QN.jl:51
   double* stage = p.stage_in_smem ? vsm : p.tmp;
   if (p.stage_in_smem) {
@@ -407,12 +462,13 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_end(const StreamParams
   double* stage = p.stage_in_smem ? vsm : p.tmp;            // n doubles
   double m;
   if (!sc->skip_update) {
-    // pass2's tail left d in s and d[c]·∇[c] in tmp; m = dᵀ∇_new = csum, QN.jl:66-68
+    shard_wait(p, 1, (unsigned)it); // row-sharded mode: every shard's slice of d has arrived
+    // pass2's tail left d in dvec and d[c]·∇[c] in tmp2; m = dᵀ∇_new = csum, QN.jl:66-68
     if (p.stage_in_smem) {
-      cta_map(n, [&](int i) { return p.tmp[i]; }, [&](int i, double v) { stage[i] = v; });
+      cta_map(n, [&](int i) { return p.tmp2[i]; }, [&](int i, double v) { stage[i] = v; });
       __syncthreads();
     }
-    m = cta_csum_staged(n, stage, &red);
+    m = cta_csum_staged(n, p.stage_in_smem ? stage : p.tmp2, &red);
     cta_map(n, [&](int i) { return p.dvec[i]; }, [&](int i, double v) { p.s[i] = v; }); // `s, y = y, s`, QN.jl:65,268
     __syncthreads();
   } else {
@@ -434,9 +490,9 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass1(const StreamParams 
   const int r_end = min(r_begin + p.sbcols, n);
   for (int r = r_begin + threadIdx.x; r < r_end; r += blockDim.x) ys[r - r_begin] = p.y[r];
   __syncthreads();
-  const int c0 = blockIdx.x * kRowsPerCta + 2 * threadIdx.x;
+  const int c0 = (p.tile0 + blockIdx.x) * kRowsPerCta + 2 * threadIdx.x;
   const bool two = (c0 + 1 < n);
-  const double* hp = p.H + c0;
+  const double* hp = p.H + (c0 - p.tile0 * kRowsPerCta);
   double S0 = 0.0, S1 = 0.0;
   bool first = true;
   for (int b0 = r_begin; b0 < r_end && c0 < n; b0 += rb) {
@@ -470,9 +526,9 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass1(const StreamParams 
     if (two) out[1] = S1;
   }
   const double rho = sc->rho;
-  pass_tail(p, [&](int c, double T) {
-    p.nu[c] = -(T * rho);      // -B⁻¹y[c] = -(t ρ), QN.jl:50
-    p.tmp[c] = T * p.y[c];     // term of yᵀB⁻¹y, QN.jl:51
+  pass_tail(p, 0, (unsigned)sc->it + 1u, [&](int c, double T) {
+    bstore(p, p.nu + c, -(T * rho));     // -B⁻¹y[c] = -(t ρ), QN.jl:50
+    bstore(p, p.tmp + c, T * p.y[c]);    // term of yᵀB⁻¹y, QN.jl:51
   });
 }
 
@@ -490,11 +546,11 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass2(const StreamParams 
   for (int r = r_begin + threadIdx.x; r < r_end; r += blockDim.x)
     ops[r - r_begin] = make_double4(p.w[r], p.nu[r], p.s[r], p.g[r]);
   __syncthreads();
-  const int c0 = blockIdx.x * kRowsPerCta + 2 * threadIdx.x;
+  const int c0 = (p.tile0 + blockIdx.x) * kRowsPerCta + 2 * threadIdx.x;
   const bool two = (c0 + 1 < n);
   const double s0 = (c0 < n) ? p.s[c0] : 0.0, nu0 = (c0 < n) ? p.nu[c0] : 0.0;
   const double s1 = two ? p.s[c0 + 1] : 0.0, nu1 = two ? p.nu[c0 + 1] : 0.0;
-  double* hp = p.H + c0;
+  double* hp = p.H + (c0 - p.tile0 * kRowsPerCta);
   double S0 = 0.0, S1 = 0.0;
   bool first = true;
   for (int b0 = r_begin; b0 < r_end && c0 < n; b0 += rb) {
@@ -537,9 +593,9 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass2(const StreamParams 
     out[0] = S0;
     if (two) out[1] = S1;
   }
-  pass_tail(p, [&](int c, double d) {
-    p.tmp[c] = d * p.g[c]; // term of m = dᵀ∇_new, QN.jl:66
-    p.dvec[c] = d;         // the new direction (other CTAs of this launch still read s)
+  pass_tail(p, 1, (unsigned)sc->it + 1u, [&](int c, double d) {
+    bstore(p, p.tmp2 + c, d * p.g[c]); // term of m = dᵀ∇_new, QN.jl:66
+    bstore(p, p.dvec + c, d);          // the new direction (other CTAs of this launch still read s)
   });
 }
 
@@ -566,11 +622,11 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass_one(const StreamPara
     yg[r - r_begin] = make_double2(p.y[r], p.g[r]);
   }
   __syncthreads();
-  const int c0 = blockIdx.x * kRowsPerCta + 2 * threadIdx.x;
+  const int c0 = (p.tile0 + blockIdx.x) * kRowsPerCta + 2 * threadIdx.x;
   const bool two = (c0 + 1 < n);
   const double s0 = (c0 < n) ? p.ps[c0] : 0.0, nu0 = (c0 < n) ? -p.pu[c0] : 0.0;
   const double s1 = two ? p.ps[c0 + 1] : 0.0, nu1 = two ? -p.pu[c0 + 1] : 0.0;
-  double* hp = p.H + c0;
+  double* hp = p.H + (c0 - p.tile0 * kRowsPerCta);
   double St0 = 0.0, St1 = 0.0, Sw0 = 0.0, Sw1 = 0.0;
   bool first = true;
   for (int b0 = r_begin; b0 < r_end && c0 < n; b0 += rb) {
@@ -635,17 +691,23 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass_one(const StreamPara
     if (is_last) p.tile_count[blockIdx.x] = 0;
   }
   __syncthreads();
-  if (!is_last || c0 >= n) return;
+  if (!is_last) return;
   __threadfence();
-  const volatile double* p1 = p.partial + c0;
-  const volatile double* p2 = p.partial2 + c0;
-  double T0 = p1[0], T1 = two ? p1[1] : 0.0, W0 = p2[0], W1 = two ? p2[1] : 0.0;
-  for (int j = 1; j < p.nsb; ++j) {
-    T0 = T0 + p1[(size_t)j * n]; W0 = W0 + p2[(size_t)j * n];
-    if (two) { T1 = T1 + p1[(size_t)j * n + 1]; W1 = W1 + p2[(size_t)j * n + 1]; }
+  if (c0 < n) {
+    const volatile double* p1 = p.partial + c0;
+    const volatile double* p2 = p.partial2 + c0;
+    double T0 = p1[0], T1 = two ? p1[1] : 0.0, W0 = p2[0], W1 = two ? p2[1] : 0.0;
+    for (int j = 1; j < p.nsb; ++j) {
+      T0 = T0 + p1[(size_t)j * n]; W0 = W0 + p2[(size_t)j * n];
+      if (two) { T1 = T1 + p1[(size_t)j * n + 1]; W1 = W1 + p2[(size_t)j * n + 1]; }
+    }
+    // row-sharded mode: the consumer may still be reading the previous iteration's sums on a
+    // peer, so t and w alternate between two buffers by iteration parity
+    const int par = (p.nshard > 1) ? ((sc->it + 1) & 1) * p.nvstride * 2 : 0;
+    bstore(p, p.tvec + par + c0, T0); bstore(p, p.wvec + par + c0, W0);
+    if (two) { bstore(p, p.tvec + par + c0 + 1, T1); bstore(p, p.wvec + par + c0 + 1, W1); }
   }
-  p.tvec[c0] = T0; p.wvec[c0] = W0;
-  if (two) { p.tvec[c0 + 1] = T1; p.wvec[c0 + 1] = W1; }
+  shard_signal(p, 0, (unsigned)sc->it + 1u);
 }
 
 // one-pass mode: everything between two sweeps, in one CTA — the O(n) part of iteration `it`
@@ -666,9 +728,13 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_onepass(const StreamPa
   double m;
   if (!sc->skip_update) {
     const double rho = sc->rho;
+    shard_wait(p, 0, (unsigned)it);
+    const int par = (p.nshard > 1) ? (it & 1) * p.nvstride * 2 : 0;
+    const double* tv = p.tvec + par;
+    const double* wv = p.wvec + par;
     double r3[3];
     cta_csum_multi<3>(n, stage, ns, red, [&](int c, double (&o)[3]) {
-      const double T = p.tvec[c], gc = p.g[c];
+      const double T = tv[c], gc = p.g[c];
       const double u = T * rho;   // B⁻¹y[c] = tρ, QN.jl:50
       p.nu[c] = u;
       o[0] = T * p.y[c];          // term of yᵀB⁻¹y, QN.jl:51
@@ -680,7 +746,7 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_onepass(const StreamPa
     // d = ((w + (c₁ s)(sᵀ∇)) - u (sᵀ∇)) - s (uᵀ∇) ; m = dᵀ∇ ; this update becomes the pending one
     m = cta_csum(n, stage, red, [&](int c) {
       const double sc_ = p.s[c], uc = p.nu[c];
-      double d = fma(c1 * sc_, sg, p.wvec[c]);
+      double d = fma(c1 * sc_, sg, wv[c]);
       d = fma(-uc, sg, d);
       d = fma(-sc_, ug, d);
       p.ps[c] = sc_;
@@ -866,11 +932,13 @@ stream_vec_onepass_cluster(const StreamParams p) {
   double m;
   if (!skip_update) {
     const double rho = sc->rho;
+    shard_wait(p, 0, (unsigned)it); // row-sharded mode: every shard's slices of t and w have arrived
+    const int par = (p.nshard > 1) ? (it & 1) * p.nvstride * 2 : 0;
     double T[NE], W[NE], u[NE];
 #pragma unroll
     for (int j = 0; j < NE; ++j) {
       T[j] = W[j] = 0.0;
-      if (ok[j]) { T[j] = p.tvec[idx[j]]; W[j] = p.wvec[idx[j]]; }
+      if (ok[j]) { T[j] = p.tvec[par + idx[j]]; W[j] = p.wvec[par + idx[j]]; }
     }
 #pragma unroll
     for (int j = 0; j < NE; ++j) {
@@ -1101,14 +1169,14 @@ __global__ void __launch_bounds__(kPassThreads) stream_flush_pending(const Strea
   if (!sc->pending) return;
   const int n = p.n, ld = p.ld;
   const double pc1 = sc->pc1;
-  const int c0 = blockIdx.x * kRowsPerCta + 2 * threadIdx.x;
+  const int c0 = (p.tile0 + blockIdx.x) * kRowsPerCta + 2 * threadIdx.x;
   if (c0 >= n) return;
   const bool two = (c0 + 1 < n);
   const double s0 = p.ps[c0], nu0 = -p.pu[c0];
   const double s1 = two ? p.ps[c0 + 1] : 0.0, nu1 = two ? -p.pu[c0 + 1] : 0.0;
   const int r_begin = blockIdx.y * p.sbcols, r_end = min(r_begin + p.sbcols, n);
   for (int r = r_begin; r < r_end; ++r) {
-    double2* hp = reinterpret_cast<double2*>(p.H + c0 + (size_t)ld * r);
+    double2* hp = reinterpret_cast<double2*>(p.H + (c0 - p.tile0 * kRowsPerCta) + (size_t)ld * r);
     const double psr = p.ps[r], wr = pc1 * psr, nur = -p.pu[r];
     double2 h = *hp;
     h.x = fma(wr, s0, h.x); h.y = fma(wr, s1, h.y);
@@ -1126,7 +1194,7 @@ __global__ void __launch_bounds__(256) stream_identity(const StreamParams p) {
   const size_t total = ld2 * p.n; // double2 elements
   double2* H2 = reinterpret_cast<double2*>(p.H);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = i / ld2, c = 2 * (i % ld2);
+    const size_t r = i / ld2, c = 2 * (i % ld2) + (size_t)p.tile0 * kRowsPerCta; // global row of the slab's entry
     H2[i] = make_double2(c == r ? 1.0 : 0.0, c + 1 == r ? 1.0 : 0.0);
   }
 }
@@ -1166,43 +1234,55 @@ PassKernel pass1_kernel() { return kPass1Tab[hint_env("QN_HINT_P1_LD", 0, 4)][0]
 PassKernel pass2_kernel() { return kPass2Tab[hint_env("QN_HINT_P2_LD", 2, 4)][hint_env("QN_HINT_P2_ST", 1, 3)]; }
 PassKernel pass_one_kernel() { return kPassOneTab[hint_env("QN_HINT_ONE_LD", 4, 4)][hint_env("QN_HINT_ONE_ST", 0, 3)]; }
 
-int enqueue_iteration(qn_context* ctx, const qn::StreamParams& p, size_t vec_smem, cudaStream_t st, int clu_ppt = 0,
-                      size_t clu_smem = 0) {
-  const dim3 grid((p.n + qn::kRowsPerCta - 1) / qn::kRowsPerCta, p.nsb);
-  if (!p.onepass) qn::stream_vec_begin<<<1, qn::kVecThreads, vec_smem, st>>>(p);
+int enqueue_iteration(qn_context* ctx, const StreamWork& w, cudaStream_t st) {
+  const qn::StreamParams& p = w.p;
+  const dim3 grid(p.ntiles, p.nsb);
   if (p.onepass) { // two kernels per iteration; the head of iteration 1 ran before the graph
     pass_one_kernel()<<<grid, qn::kPassThreads, sizeof(double) * 6 * p.sbcols, st>>>(p);
-    if (clu_ppt == 1) qn::stream_vec_onepass_cluster<1><<<qn::kCluCtas, qn::kCluThreads, clu_smem, st>>>(p);
-    else if (clu_ppt == 2) qn::stream_vec_onepass_cluster<2><<<qn::kCluCtas, qn::kCluThreads, clu_smem, st>>>(p);
-    else if (clu_ppt == 3) qn::stream_vec_onepass_cluster<3><<<qn::kCluCtas, qn::kCluThreads, clu_smem, st>>>(p);
-    else qn::stream_vec_onepass<<<1, qn::kVecThreads, vec_smem, st>>>(p);
+    if (w.clu_ppt == 1) qn::stream_vec_onepass_cluster<1><<<qn::kCluCtas, qn::kCluThreads, w.clu_smem, st>>>(p);
+    else if (w.clu_ppt == 2) qn::stream_vec_onepass_cluster<2><<<qn::kCluCtas, qn::kCluThreads, w.clu_smem, st>>>(p);
+    else if (w.clu_ppt == 3) qn::stream_vec_onepass_cluster<3><<<qn::kCluCtas, qn::kCluThreads, w.clu_smem, st>>>(p);
+    else qn::stream_vec_onepass<<<1, qn::kVecThreads, w.vec_smem, st>>>(p);
     QN_CUDA_TRY(cudaGetLastError());
     return QN_OK;
-  } else {
-    pass1_kernel()<<<grid, qn::kPassThreads, sizeof(double) * p.sbcols, st>>>(p);
-    qn::stream_vec_mid<<<1, qn::kVecThreads, vec_smem, st>>>(p);
-    pass2_kernel()<<<grid, qn::kPassThreads, sizeof(double) * 4 * p.sbcols, st>>>(p);
-    qn::stream_vec_end<<<1, qn::kVecThreads, vec_smem, st>>>(p);
   }
+  qn::stream_vec_begin<<<1, qn::kVecThreads, w.vec_smem, st>>>(p);
+  pass1_kernel()<<<grid, qn::kPassThreads, sizeof(double) * p.sbcols, st>>>(p);
+  qn::stream_vec_mid<<<1, qn::kVecThreads, w.vec_smem, st>>>(p);
+  pass2_kernel()<<<grid, qn::kPassThreads, sizeof(double) * 4 * p.sbcols, st>>>(p);
+  qn::stream_vec_end<<<1, qn::kVecThreads, w.vec_smem, st>>>(p);
   qn::stream_identity<<<ctx->prop.multiProcessorCount * 8, 256, 0, st>>>(p);
   QN_CUDA_TRY(cudaGetLastError());
   return QN_OK;
 }
 
-}  // namespace
+void stream_release(StreamWork& w) {
+  if (w.exec) cudaGraphExecDestroy(w.exec);
+  if (w.graph) cudaGraphDestroy(w.graph);
+  if (w.block) cudaFree(w.block);
+  if (w.p.H) cudaFree(w.p.H);
+  w = StreamWork{};
+}
 
-// One large problem, device-resident x0 (n doubles at theta0).  Returns when finished.
-// iters_per_check: how many iterations are enqueued between polls of the done flag.
-int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_backtracking* ls,
-                    double tol, int max_iter, double* d_x_out, double* d_g_out, double* d_h_out,
-                    int ldh_out, double* ell, int* iters, int* fevals, int* status, int ntrace,
-                    double* d_trace, cudaStream_t st, float* ms_per_iter_out, int fixed_iters,
-                    int onepass) {
+#define QN_TRY_REL(expr)                                                                  \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      return qn_fail(QN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                     __FILE__, __LINE__);                                                 \
+    }                                                                                     \
+  } while (0)
+
+// Allocate and lay out the work space of one GPU (shard `shard` of `nshard`: row tiles
+// [tile0, tile0 + ntiles) of B⁻¹), initialise it and capture one iteration into a graph.
+// The caller fills peer_base[] for nshard > 1 BEFORE calling stream_capture.
+int stream_setup(qn_context* ctx, StreamWork& w, int n, const double* theta0, bool theta_on_host,
+                 const qn_backtracking* ls, double tol, int max_iter, int ntrace, double* d_trace,
+                 int onepass, int shard, int nshard, cudaStream_t st) {
   using namespace qn;
-  StreamWork w;
   StreamParams& p = w.p;
+  QN_TRY_REL(cudaSetDevice(ctx->device));
   p.n = n;
-  p.ld = (n + 15) & ~15;
   p.rb = chain_block(n);
   p.sbcols = 16 * p.rb;
   p.nsb = (n + p.sbcols - 1) / p.sbcols;
@@ -1211,140 +1291,298 @@ int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_bac
   p.ls = LsParams{ls->c1, ls->rho_hi, ls->rho_lo, (long long)ls->iterations, ls->order};
   p.ntrace = ntrace;
   p.trace = d_trace;
-  QN_CUDA_TRY(cudaMalloc(&p.H, sizeof(double) * (size_t)p.ld * n));
+  p.onepass = onepass;
+  const int row_tiles = (n + kRowsPerCta - 1) / kRowsPerCta;
+  p.nshard = nshard;
+  p.shard = shard;
+  p.tile0 = (int)((long long)row_tiles * shard / nshard);
+  p.ntiles = (int)((long long)row_tiles * (shard + 1) / nshard) - p.tile0;
+  const int rows_local = std::min(n, (p.tile0 + p.ntiles) * kRowsPerCta) - p.tile0 * kRowsPerCta;
+  p.ld = (rows_local + 15) & ~15;
+  QN_TRY_REL(cudaMalloc(&p.H, sizeof(double) * (size_t)p.ld * n));
   const size_t nv = ((size_t)n + 31) & ~(size_t)31;
-  const int row_tiles = (n + qn::kRowsPerCta - 1) / qn::kRowsPerCta;
-  const size_t words = nv * 18 + 2 * (size_t)p.nsb * n + 64 + row_tiles;
+  p.nvstride = (int)nv;
+  const size_t words = nv * 22 + 2 * (size_t)p.nsb * n + 128 + row_tiles;
   cudaError_t e = cudaMalloc(&w.block, sizeof(double) * words);
-  if (e != cudaSuccess) {
-    cudaFree(p.H);
+  if (e != cudaSuccess)
     return qn_fail(QN_ERR_CUDA, "cudaMalloc failed for the streaming work space: %s", cudaGetErrorString(e));
-  }
   double* base = (double*)w.block;
+  p.base = base;
+  for (int g = 0; g < kMaxShards; ++g) p.peer_base[g] = base;
   p.x = base; p.g = base + nv; p.gp = base + 2 * nv; p.s = base + 3 * nv; p.y = base + 4 * nv;
   p.nu = base + 5 * nv; p.w = base + 6 * nv; p.xs = base + 7 * nv; p.tmp = base + 8 * nv;
   p.dvec = base + 12 * nv; // tmp spans 8..11 (three staged arrays when shared memory is too small)
-  p.ps = base + 13 * nv; p.pu = base + 14 * nv; p.tvec = base + 15 * nv; p.wvec = base + 16 * nv;
-  p.partial = base + 18 * nv;
+  p.ps = base + 13 * nv; p.pu = base + 14 * nv;
+  p.tvec = base + 15 * nv; p.wvec = base + 16 * nv; // and their odd-iteration copies at 17, 18 (row-sharded mode)
+  p.tmp2 = base + 19 * nv;
+  p.partial = base + 22 * nv;
   p.partial2 = p.partial + (size_t)p.nsb * n;
-  p.sc = reinterpret_cast<StreamScalars*>(p.partial2 + (size_t)p.nsb * n);
-  p.tile_count = reinterpret_cast<unsigned int*>(p.partial2 + (size_t)p.nsb * n + 32);
-  p.onepass = onepass;
+  double* tail = p.partial2 + (size_t)p.nsb * n;
+  p.sc = reinterpret_cast<StreamScalars*>(tail);          // 32 doubles reserved
+  p.flags = reinterpret_cast<unsigned int*>(tail + 32);   // 2·kMaxShards words
+  p.tiles_done = reinterpret_cast<unsigned int*>(tail + 48);
+  p.tile_count = reinterpret_cast<unsigned int*>(tail + 64);
+  static_assert(sizeof(StreamScalars) <= 32 * sizeof(double), "scalars overflow their slot");
   // vec kernels stage their reductions in shared memory (n doubles; three arrays in one-pass mode)
   const size_t vec_smem = sizeof(double) * (onepass ? 3 : 1) * (((size_t)n + 1) & ~(size_t)1);
   p.stage_in_smem = vec_smem <= (size_t)ctx->prop.sharedMemPerBlockOptin - 1024;
   w.vec_smem = p.stage_in_smem ? vec_smem : 0;
-  int rc = QN_OK;
-  auto cleanup = [&]() {
-    if (w.exec) cudaGraphExecDestroy(w.exec);
-    if (w.graph) cudaGraphDestroy(w.graph);
-    cudaFree(w.block);
-    cudaFree(p.H);
-  };
-#define QN_TRY_CLEAN(expr)                                                                \
-  do {                                                                                    \
-    cudaError_t _e = (expr);                                                              \
-    if (_e != cudaSuccess) {                                                              \
-      cleanup();                                                                          \
-      return qn_fail(QN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
-                     __FILE__, __LINE__);                                                 \
-    }                                                                                     \
-  } while (0)
-  QN_TRY_CLEAN(cudaMemsetAsync(w.block, 0, sizeof(double) * words, st));
-  QN_TRY_CLEAN(cudaMemcpyAsync(p.x, d_theta0, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+  QN_TRY_REL(cudaMemsetAsync(w.block, 0, sizeof(double) * words, st));
+  QN_TRY_REL(cudaMemcpyAsync(p.x, theta0, sizeof(double) * n, theta_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
   StreamScalars init{};
   init.result = NAN;
   init.status = QN_MAX_ITER;
   init.spec = 1;
-  QN_TRY_CLEAN(cudaMemcpyAsync(p.sc, &init, sizeof init, cudaMemcpyHostToDevice, st));
-  if (max_iter <= 0) {
-    init.done = 1;
-  } else {
-    // capture one iteration (6 kernels) and replay it
-    QN_TRY_CLEAN(cudaFuncSetAttribute(pass2_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(sizeof(double) * 4 * p.sbcols)));
-    if (w.vec_smem) {
-      QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_begin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
-      QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
-      QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_end, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
-      QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_onepass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
-    }
-    if (onepass && !getenv("QN_STREAM_NO_CLUSTER")) {
-      // the cluster vector kernel: a thread owns up to 3 Rosenbrock pairs; a rank stages n doubles
-      const int pairs = n >> 1, cap = qn::kCluCtas * qn::kCluThreads;
-      const int ppt = pairs <= cap ? 1 : (pairs + cap - 1) / cap;
-      const size_t smem = sizeof(double) * (((size_t)n + 1) & ~(size_t)1);
-      if (ppt <= 3 && smem + 1024 <= (size_t)ctx->prop.sharedMemPerBlockOptin) {
-        w.clu_ppt = ppt;
-        w.clu_smem = smem;
-        const int ismem = (int)smem;
-        if (ppt == 1) QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_onepass_cluster<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ismem));
-        if (ppt == 2) QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_onepass_cluster<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ismem));
-        if (ppt == 3) QN_TRY_CLEAN(cudaFuncSetAttribute(qn::stream_vec_onepass_cluster<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ismem));
-      }
-    }
-    QN_TRY_CLEAN(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    rc = enqueue_iteration(ctx, p, w.vec_smem, st, w.clu_ppt, w.clu_smem);
-    cudaError_t ce = cudaStreamEndCapture(st, &w.graph);
-    if (rc != QN_OK || ce != cudaSuccess) {
-      cleanup();
-      return rc != QN_OK ? rc : qn_fail(QN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-    }
-    QN_TRY_CLEAN(cudaGraphInstantiate(&w.exec, w.graph, 0));
-    if (onepass) qn::stream_vec_begin<<<1, qn::kVecThreads, w.vec_smem, st>>>(p); // head of iteration 1
-    StreamScalars host{};
-    if (fixed_iters > 0) {
-      // benchmark mode: exactly fixed_iters iterations, the first two are warm-up
-      cudaEvent_t e0 = nullptr, e1 = nullptr;
-      cudaEventCreate(&e0);
-      cudaEventCreate(&e1);
-      const int warm = fixed_iters > 2 ? 2 : 0;
-      for (int k = 0; k < warm; ++k) QN_TRY_CLEAN(cudaGraphLaunch(w.exec, st));
-      cudaEventRecord(e0, st);
-      for (int k = warm; k < fixed_iters; ++k) QN_TRY_CLEAN(cudaGraphLaunch(w.exec, st));
-      cudaEventRecord(e1, st);
-      QN_TRY_CLEAN(cudaMemcpyAsync(&host, p.sc, sizeof host, cudaMemcpyDeviceToHost, st));
-      QN_TRY_CLEAN(cudaStreamSynchronize(st));
-      float ms = 0;
-      cudaEventElapsedTime(&ms, e0, e1);
-      if (ms_per_iter_out) *ms_per_iter_out = ms / (float)(fixed_iters - warm);
-      cudaEventDestroy(e0);
-      cudaEventDestroy(e1);
-    } else {
-      // enqueue 8 iterations at a time, then poll the done flag
-      int launched = 0;
-      for (;;) {
-        for (int k = 0; k < 8 && launched < max_iter; ++k, ++launched) QN_TRY_CLEAN(cudaGraphLaunch(w.exec, st));
-        QN_TRY_CLEAN(cudaMemcpyAsync(&host, p.sc, sizeof host, cudaMemcpyDeviceToHost, st));
-        QN_TRY_CLEAN(cudaStreamSynchronize(st));
-        if (host.done || launched >= max_iter) break;
-      }
-    }
-    init = host;
+  if (max_iter <= 0) init.done = 1;
+  QN_TRY_REL(cudaMemcpyAsync(p.sc, &init, sizeof init, cudaMemcpyHostToDevice, st));
+  QN_TRY_REL(cudaStreamSynchronize(st)); // `init` is a stack variable
+  return QN_OK;
+}
+
+int stream_capture(qn_context* ctx, StreamWork& w, cudaStream_t st) {
+  const qn::StreamParams& p = w.p;
+  const int n = p.n;
+  QN_TRY_REL(cudaSetDevice(ctx->device));
+  QN_TRY_REL(cudaFuncSetAttribute(pass2_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(sizeof(double) * 4 * p.sbcols)));
+  if (w.vec_smem) {
+    QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_begin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
+    QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
+    QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_end, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
+    QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_onepass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
   }
+  if (p.onepass && !getenv("QN_STREAM_NO_CLUSTER")) {
+    // the cluster vector kernel: a thread owns up to 3 Rosenbrock pairs; a rank stages n doubles
+    const int pairs = n >> 1, cap = qn::kCluCtas * qn::kCluThreads;
+    const int ppt = pairs <= cap ? 1 : (pairs + cap - 1) / cap;
+    const size_t smem = sizeof(double) * (((size_t)n + 1) & ~(size_t)1);
+    if (ppt <= 3 && smem + 1024 <= (size_t)ctx->prop.sharedMemPerBlockOptin) {
+      w.clu_ppt = ppt;
+      w.clu_smem = smem;
+      const int ismem = (int)smem;
+      if (ppt == 1) QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_onepass_cluster<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ismem));
+      if (ppt == 2) QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_onepass_cluster<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ismem));
+      if (ppt == 3) QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_onepass_cluster<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ismem));
+    }
+  }
+  QN_TRY_REL(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  const int rc = enqueue_iteration(ctx, w, st);
+  const cudaError_t ce = cudaStreamEndCapture(st, &w.graph);
+  if (rc != QN_OK) return rc;
+  if (ce != cudaSuccess) return qn_fail(QN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+  QN_TRY_REL(cudaGraphInstantiate(&w.exec, w.graph, 0));
+  if (p.onepass) qn::stream_vec_begin<<<1, qn::kVecThreads, w.vec_smem, st>>>(p); // head of iteration 1
+  QN_TRY_REL(cudaGetLastError());
+  return QN_OK;
+}
+
+// Replay the iteration graph on every shard until the device says done (or exactly fixed_iters
+// times, timed on shard 0, the first two untimed).  The shards advance in lock step through their
+// flags; shard 0's scalars are everybody's.
+int stream_run(qn_context* const* ctxs, StreamWork* ws, cudaStream_t* sts, int G, int max_iter,
+               int fixed_iters, float* ms_per_iter_out, qn::StreamScalars& host) {
+  auto launch_all = [&]() -> int {
+    for (int g = 0; g < G; ++g) {
+      if (G > 1) QN_TRY_REL(cudaSetDevice(ctxs[g]->device));
+      QN_TRY_REL(cudaGraphLaunch(ws[g].exec, sts[g]));
+    }
+    return QN_OK;
+  };
+  int rc;
+  if (fixed_iters > 0) {
+    QN_TRY_REL(cudaSetDevice(ctxs[0]->device));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int warm = fixed_iters > 2 ? 2 : 0;
+    for (int k = 0; k < warm; ++k) if ((rc = launch_all())) return rc;
+    QN_TRY_REL(cudaSetDevice(ctxs[0]->device));
+    cudaEventRecord(e0, sts[0]);
+    for (int k = warm; k < fixed_iters; ++k) if ((rc = launch_all())) return rc;
+    QN_TRY_REL(cudaSetDevice(ctxs[0]->device));
+    cudaEventRecord(e1, sts[0]);
+    QN_TRY_REL(cudaMemcpyAsync(&host, ws[0].p.sc, sizeof host, cudaMemcpyDeviceToHost, sts[0]));
+    for (int g = G - 1; g >= 0; --g) {
+      QN_TRY_REL(cudaSetDevice(ctxs[g]->device));
+      QN_TRY_REL(cudaStreamSynchronize(sts[g]));
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms_per_iter_out) *ms_per_iter_out = ms / (float)(fixed_iters - warm);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return QN_OK;
+  }
+  // enqueue 8 iterations at a time, then poll the done flag
+  int launched = 0;
+  for (;;) {
+    for (int k = 0; k < 8 && launched < max_iter; ++k, ++launched) if ((rc = launch_all())) return rc;
+    QN_TRY_REL(cudaSetDevice(ctxs[0]->device));
+    QN_TRY_REL(cudaMemcpyAsync(&host, ws[0].p.sc, sizeof host, cudaMemcpyDeviceToHost, sts[0]));
+    QN_TRY_REL(cudaStreamSynchronize(sts[0]));
+    if (host.done || launched >= max_iter) break;
+  }
+  for (int g = G - 1; g >= 1; --g) {
+    QN_TRY_REL(cudaSetDevice(ctxs[g]->device));
+    QN_TRY_REL(cudaStreamSynchronize(sts[g]));
+  }
+  QN_TRY_REL(cudaSetDevice(ctxs[0]->device));
+  return QN_OK;
+}
+
+}  // namespace
+
+// One large problem, device-resident x0 (n doubles at theta0).  Returns when finished.
+int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_backtracking* ls,
+                    double tol, int max_iter, double* d_x_out, double* d_g_out, double* d_h_out,
+                    int ldh_out, double* ell, int* iters, int* fevals, int* status, int ntrace,
+                    double* d_trace, cudaStream_t st, float* ms_per_iter_out, int fixed_iters,
+                    int onepass) {
+  using namespace qn;
+  StreamWork w;
+  StreamScalars host{};
+  host.result = NAN;
+  host.status = QN_MAX_ITER;
+  int rc = stream_setup(ctx, w, n, d_theta0, false, ls, tol, max_iter, ntrace, d_trace, onepass, 0, 1, st);
+  if (rc == QN_OK && max_iter > 0) rc = stream_capture(ctx, w, st);
+  if (rc == QN_OK && max_iter > 0) rc = stream_run(&ctx, &w, &st, 1, max_iter, fixed_iters, ms_per_iter_out, host);
+  if (rc != QN_OK) { stream_release(w); return rc; }
+  const StreamParams& p = w.p;
   ctx->last_path = 2;
-  ctx->last_grid = ((n + qn::kRowsPerCta - 1) / qn::kRowsPerCta) * p.nsb;
+  ctx->last_grid = p.ntiles * p.nsb;
   ctx->last_block = qn::kPassThreads;
   ctx->last_smem = (int)(sizeof(double) * 4 * p.sbcols);
-  ctx->last_launches = onepass ? 1 + 2 * (init.it + (init.done ? 1 : 0)) : 6 * (init.it + (init.done ? 1 : 0));
-  if (d_x_out) QN_TRY_CLEAN(cudaMemcpyAsync(d_x_out, p.x, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-  // which ∇ the reference's canonical slot shows after a failure: see qn_resident.cuh
-  const double* g_src = (init.status == QN_CONVERGED || (init.exit_it & 1)) ? p.g : p.gp;
-  if (d_g_out) QN_TRY_CLEAN(cudaMemcpyAsync(d_g_out, g_src, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-  if (d_h_out && onepass) { // the stored matrix lags one update behind: apply it
-    const dim3 grid((n + qn::kRowsPerCta - 1) / qn::kRowsPerCta, p.nsb);
-    qn::stream_flush_pending<<<grid, qn::kPassThreads, 0, st>>>(p);
-  }
-  if (d_h_out)
-    QN_TRY_CLEAN(cudaMemcpy2DAsync(d_h_out, sizeof(double) * ldh_out, p.H, sizeof(double) * p.ld,
+  ctx->last_launches = onepass ? 1 + 2 * (host.it + (host.done ? 1 : 0)) : 6 * (host.it + (host.done ? 1 : 0));
+  auto finish = [&]() -> int {
+    if (d_x_out) QN_TRY_REL(cudaMemcpyAsync(d_x_out, p.x, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    // which ∇ the reference's canonical slot shows after a failure: see qn_resident.cuh
+    const double* g_src = (host.status == QN_CONVERGED || (host.exit_it & 1)) ? p.g : p.gp;
+    if (d_g_out) QN_TRY_REL(cudaMemcpyAsync(d_g_out, g_src, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    if (d_h_out && onepass) { // the stored matrix lags one update behind: apply it
+      const dim3 grid(p.ntiles, p.nsb);
+      qn::stream_flush_pending<<<grid, qn::kPassThreads, 0, st>>>(p);
+    }
+    if (d_h_out)
+      QN_TRY_REL(cudaMemcpy2DAsync(d_h_out, sizeof(double) * ldh_out, p.H, sizeof(double) * p.ld,
                                    sizeof(double) * n, n, cudaMemcpyDeviceToDevice, st));
-  QN_TRY_CLEAN(cudaStreamSynchronize(st));
-  if (ell) *ell = init.result;
-  if (iters) *iters = init.iters;
-  if (fevals) *fevals = init.fevals;
-  if (status) *status = init.status;
-  cleanup();
-#undef QN_TRY_CLEAN
+    QN_TRY_REL(cudaStreamSynchronize(st));
+    return QN_OK;
+  };
+  rc = finish();
+  stream_release(w);
+  if (rc != QN_OK) return rc;
+  if (ell) *ell = host.result;
+  if (iters) *iters = host.iters;
+  if (fevals) *fevals = host.fevals;
+  if (status) *status = host.status;
+  return QN_OK;
+}
+
+// Row-sharded large-n mode (BASELINE.json configs[4]): ONE problem on G GPUs of one
+// process.  GPU g holds the rows of its row tiles of B⁻¹ and a replica of every vector; each sweep's
+// row sums are stored straight into all replicas over NVLink (peer stores) and announced with
+// per-shard epoch flags, so the only exchange per sweep is n doubles per vector and no host or NCCL
+// call sits inside an iteration.  All O(n) work — the rule-C1 reductions, the line search, the
+// objective — is replicated, so every GPU holds bit-identical scalars and the result is the
+// single-GPU result bit for bit.  Host pointers in, host pointers out.
+extern "C" int32_t qn_bfgs_optimize_rowsharded_f64(
+    qn_context* const* ctxs, int32_t nctx, const qn_model* model, int32_t n, const double* theta0,
+    const qn_backtracking* ls, double tol, int32_t max_iter, double* x_out, double* g_out, double* h_out,
+    int32_t ldh, double* ell_out, int32_t* iters_out, int32_t* fevals_out, int32_t* status_out,
+    int32_t ntrace, double* trace_out, uint32_t flags, int32_t bench_iters, double* ms_per_iter) {
+  using namespace qn;
+  if (!ctxs || nctx < 1 || nctx > kMaxShards) return qn_fail(QN_ERR_INVALID_ARGUMENT, "need 1..%d contexts", kMaxShards);
+  if (!model || n < 2 || !theta0 || !ls) return qn_fail(QN_ERR_INVALID_ARGUMENT, "bad argument");
+  if (model->kind != QN_OBJ_ROSENBROCK)
+    return qn_fail(QN_ERR_UNREGISTERED_OBJECTIVE, "objective kind %d has no registered device implementation on the "
+                   "streaming path; only Rosenbrock has one", model->kind);
+  if (h_out && ldh < n) return qn_fail(QN_ERR_INVALID_ARGUMENT, "ldh < n");
+  const int onepass = (flags & QN_FLAG_ONE_PASS) ? 1 : 0;
+  const int row_tiles = (n + kRowsPerCta - 1) / kRowsPerCta;
+  const int G = std::min((int)nctx, row_tiles); // a shard owns at least one 512-row tile
+  for (int g = 0; g < G; ++g) if (!ctxs[g]) return qn_fail(QN_ERR_INVALID_ARGUMENT, "NULL context %d", g);
+  // peer access between every pair of distinct devices
+  for (int a = 0; a < G; ++a)
+    for (int b = 0; b < G; ++b) {
+      if (ctxs[a]->device == ctxs[b]->device) continue;
+      int can = 0;
+      QN_CUDA_TRY(cudaDeviceCanAccessPeer(&can, ctxs[a]->device, ctxs[b]->device));
+      if (!can) return qn_fail(QN_ERR_CUDA, "device %d cannot access device %d (no peer path)", ctxs[a]->device, ctxs[b]->device);
+      QN_CUDA_TRY(cudaSetDevice(ctxs[a]->device));
+      const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[b]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return qn_fail(QN_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", ctxs[a]->device, ctxs[b]->device, cudaGetErrorString(e));
+      (void)cudaGetLastError();
+    }
+  StreamWork ws[kMaxShards];
+  cudaStream_t sts[kMaxShards];
+  double* d_trace = nullptr;
+  auto release_all = [&]() {
+    for (int g = 0; g < G; ++g) { cudaSetDevice(ctxs[g]->device); stream_release(ws[g]); }
+    cudaSetDevice(ctxs[0]->device);
+    if (d_trace) cudaFree(d_trace);
+  };
+  int rc = QN_OK;
+  if (ntrace > 0 && trace_out) {
+    QN_CUDA_TRY(cudaSetDevice(ctxs[0]->device));
+    QN_CUDA_TRY(cudaMalloc(&d_trace, sizeof(double) * (size_t)ntrace * n));
+    QN_CUDA_TRY(cudaMemset(d_trace, 0, sizeof(double) * (size_t)ntrace * n));
+  }
+  for (int g = 0; g < G && rc == QN_OK; ++g) {
+    sts[g] = ctxs[g]->stream;
+    rc = stream_setup(ctxs[g], ws[g], n, theta0, true, ls, tol, max_iter, g == 0 ? ntrace : 0,
+                      g == 0 ? d_trace : nullptr, onepass, g, G, sts[g]);
+  }
+  for (int g = 0; g < G && rc == QN_OK; ++g) {
+    for (int k = 0; k < G; ++k) ws[g].p.peer_base[k] = ws[k].p.base;
+    if (max_iter > 0) rc = stream_capture(ctxs[g], ws[g], sts[g]);
+  }
+  StreamScalars host{};
+  host.result = NAN;
+  host.status = QN_MAX_ITER;
+  float ms = 0;
+  if (rc == QN_OK && max_iter > 0) rc = stream_run(ctxs, ws, sts, G, max_iter, bench_iters, &ms, host);
+  if (rc != QN_OK) { release_all(); return rc; }
+  auto finish = [&]() -> int {
+    const StreamParams& p0 = ws[0].p;
+    QN_TRY_REL(cudaSetDevice(ctxs[0]->device));
+    if (x_out) QN_TRY_REL(cudaMemcpyAsync(x_out, p0.x, sizeof(double) * n, cudaMemcpyDeviceToHost, sts[0]));
+    const double* g_src = (host.status == QN_CONVERGED || (host.exit_it & 1)) ? p0.g : p0.gp;
+    if (g_out) QN_TRY_REL(cudaMemcpyAsync(g_out, g_src, sizeof(double) * n, cudaMemcpyDeviceToHost, sts[0]));
+    if (trace_out && d_trace)
+      QN_TRY_REL(cudaMemcpyAsync(trace_out, d_trace, sizeof(double) * (size_t)ntrace * n, cudaMemcpyDeviceToHost, sts[0]));
+    QN_TRY_REL(cudaStreamSynchronize(sts[0]));
+    if (h_out) {
+      for (int g = 0; g < G; ++g) { // every shard returns its slab of rows
+        const StreamParams& p = ws[g].p;
+        QN_TRY_REL(cudaSetDevice(ctxs[g]->device));
+        if (onepass) {
+          const dim3 grid(p.ntiles, p.nsb);
+          qn::stream_flush_pending<<<grid, qn::kPassThreads, 0, sts[g]>>>(p);
+        }
+        const int row0 = p.tile0 * kRowsPerCta;
+        const int rows = std::min(n, (p.tile0 + p.ntiles) * kRowsPerCta) - row0;
+        QN_TRY_REL(cudaMemcpy2DAsync(h_out + row0, sizeof(double) * ldh, p.H, sizeof(double) * p.ld,
+                                     sizeof(double) * rows, n, cudaMemcpyDeviceToHost, sts[g]));
+        QN_TRY_REL(cudaStreamSynchronize(sts[g]));
+      }
+    }
+    return QN_OK;
+  };
+  rc = finish();
+  for (int g = 0; g < G; ++g) {
+    ctxs[g]->last_path = 2;
+    ctxs[g]->last_grid = ws[g].p.ntiles * ws[g].p.nsb;
+    ctxs[g]->last_block = kPassThreads;
+    ctxs[g]->last_launches = onepass ? 1 + 2 * (host.it + (host.done ? 1 : 0)) : 6 * (host.it + (host.done ? 1 : 0));
+  }
+  release_all();
+  if (rc != QN_OK) return rc;
+  if (ell_out) *ell_out = host.result;
+  if (iters_out) *iters_out = host.iters;
+  if (fevals_out) *fevals_out = host.fevals;
+  if (status_out) *status_out = host.status;
+  if (ms_per_iter) *ms_per_iter = ms;
   return QN_OK;
 }
 

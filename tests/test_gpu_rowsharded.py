@@ -1,0 +1,58 @@
+"""Row-sharded large-n mode: one problem, B⁻¹ split by row tiles over several
+contexts, row sums exchanged by peer stores + epoch flags inside the kernels.  The shards may sit on
+distinct GPUs (used when the box has them) or share one GPU — the exchange logic is the same — and
+the result must equal the oracle's, i.e. the single-GPU result, bit for bit."""
+import numpy as np
+import pytest
+
+from conftest import starts
+
+pytestmark = pytest.mark.gpu
+
+
+def _engines(qn, G):
+    ndev = qn._lib.load().qn_device_count()
+    return [qn.Engine(g % max(ndev, 1)) for g in range(G)]
+
+
+def _same(got, ref):
+    for k in ("x", "g", "ell", "trace"):
+        if ref.get(k) is not None and got.get(k) is not None:
+            assert np.array_equal(got[k], ref[k], equal_nan=True), k
+    assert np.array_equal(got["iters"], ref["iters"])
+    assert np.array_equal(got["fevals"], ref["fevals"])
+    assert np.array_equal(got["status"], ref["status"])
+
+
+@pytest.mark.parametrize("G", [2, 3])
+@pytest.mark.parametrize("n,iters", [(1100, 20), (2049, 12)])
+def test_rowsharded_two_pass_first_iterations(qn, ob, G, n, iters):
+    engs = _engines(qn, G)
+    Theta = starts(n, 1, key=n)
+    got = qn.optimize_rowsharded(engs, qn.Rosenbrock(), Theta[:, 0], max_iter=iters, ntrace=iters)
+    ref = ob.optimize_batch(ob.rosenbrock(), Theta, max_iter=iters, ntrace=iters)
+    _same(got, ref)
+
+
+@pytest.mark.parametrize("G", [2, 4])
+def test_rowsharded_one_pass_and_h(qn, ob, G):
+    n, iters = 2100, 15
+    engs = _engines(qn, G)
+    Theta = starts(n, 1, key=n)
+    got = qn.optimize_rowsharded(engs, qn.Rosenbrock(), Theta[:, 0], max_iter=iters, ntrace=iters,
+                                 flags=qn._lib.FLAG_ONE_PASS, want_h=True)
+    own = ob.optimize_batch(ob.rosenbrock(), Theta, max_iter=iters, ntrace=iters, rblock=ob.ONEPASS)
+    _same(got, own)
+    o = ob.optimize(ob.rosenbrock(), Theta[:, 0], max_iter=iters, L=n, rblock=ob.ONEPASS)
+    # state[7L + c + L r] = B⁻¹[c, r] (QN.jl:123-133); got["H"][c, r] likewise (column-major, ldh = n)
+    assert np.array_equal(got["H"], o["state"][7 * n:].reshape(n, n).T)
+
+
+def test_rowsharded_full_solve_small(qn, ob):
+    """More tiles than a full solve needs to be quick: n = 1030 (3 row tiles), two-pass, to convergence."""
+    n = 1030
+    engs = _engines(qn, 3)
+    Theta = starts(n, 1, key=77)
+    got = qn.optimize_rowsharded(engs, qn.Rosenbrock(), Theta[:, 0], ntrace=5, max_iter=400)
+    ref = ob.optimize_batch(ob.rosenbrock(), Theta, ntrace=5, max_iter=400)
+    _same(got, ref)
