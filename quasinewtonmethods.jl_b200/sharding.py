@@ -45,3 +45,19 @@ def all_gather_results(local, batch, rank, world, dist):
         parts = [b.numpy()[..., :len(shard_columns(batch, r, world))] for r, b in enumerate(bufs)]
         out[k] = gather(parts, batch)
     return out
+
+
+ROWS_PER_TILE = 512  # kRowsPerCta of csrc/qn_stream.cu: 256 threads x 2 rows
+
+
+def row_tile_partition(n, nshard):
+    """The row-sharded large-n mode's split of B⁻¹ (qn_bfgs_optimize_rowsharded_f64, stream_setup in
+    csrc/qn_stream.cu): shard g of G owns the 512-row tiles [T*g//G, T*(g+1)//G) with
+    T = ceil(n/512) and G = min(nshard, T).  Returns [(row_begin, row_end)] per shard."""
+    tiles = (n + ROWS_PER_TILE - 1) // ROWS_PER_TILE
+    G = min(int(nshard), tiles)
+    out = []
+    for g in range(G):
+        t0, t1 = tiles * g // G, tiles * (g + 1) // G
+        out.append((t0 * ROWS_PER_TILE, min(n, t1 * ROWS_PER_TILE)))
+    return out
