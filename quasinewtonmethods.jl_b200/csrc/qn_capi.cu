@@ -20,6 +20,7 @@
 #include "qn_objectives.cuh"
 #include "qn_resident.cuh"
 #include "qn_resident_tile.cuh"
+#include "qn_resident_packed.cuh"
 #include "qn_internal.h"
 
 namespace {
@@ -127,12 +128,48 @@ int launch_tile(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
   return QN_OK;
 }
 
+// n = 8, 16, 32 (Rosenbrock): several problems per warp (qn_resident_packed.cuh)
+template <int N, int RPT, int MINB>
+int launch_packed(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
+  using C = qn::PackedCfg<N, RPT>;
+  const size_t smem = sizeof(double) * (size_t)C::kSmemDoubles;
+  auto kern = qn::qn_resident_packed_kernel<N, RPT, MINB>;
+  const int block = C::kWarps * 32;
+  int occ = 0;
+  QN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
+  if (occ < 1) return fail(QN_ERR_UNSUPPORTED_SIZE, "packed kernel does not fit on an SM (n=%d)", N);
+  long long grid = (long long)occ * ctx->prop.multiProcessorCount;
+  const long long need = (p.batch + C::kWarps * C::kSub - 1) / (C::kWarps * C::kSub);
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  p.counter = qn_next_counter(ctx, st);
+  kern<<<(unsigned)grid, block, smem, st>>>(p);
+  QN_CUDA_TRY(cudaGetLastError());
+  ctx->last_path = 0;
+  ctx->last_grid = (int)grid;
+  ctx->last_block = block;
+  ctx->last_smem = (int)smem;
+  ctx->last_launches = 1;
+  return QN_OK;
+}
+
 template <class Obj>
 int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Params& op,
                   uint32_t flags, cudaStream_t st) {
   const int n = p.n;
   if constexpr (Obj::kRegisterPaths) {
     if (!(flags & QN_FLAG_FORCE_SMEM)) {
+      if constexpr (std::is_same<Obj, qn::Rosenbrock>::value) {
+        if (!getenv("QN_NO_PACK")) { // A/B knob: the thread-per-row kernels stay available
+          const char* v = getenv("QN_PACK_VARIANT"); // tuning knob: rows per lane
+          const int rpt = v ? atoi(v) : 0;
+          // defaults measured on B200 (2^18 problems): n = 8: 2 rows per lane 8.2e9 it/s (1: 6.7e9);
+          // n = 16: 2 rows 3.7e9 (1: 2.8e9, 4: 3.3e9); n = 32: 2 rows 1.14e9 (thread per row: 0.90e9)
+          if (n == 8) return rpt == 1 ? launch_packed<8, 1, 8>(ctx, p, st) : rpt == 4 ? launch_packed<8, 4, 4>(ctx, p, st) : launch_packed<8, 2, 6>(ctx, p, st);
+          if (n == 16) return rpt == 1 ? launch_packed<16, 1, 6>(ctx, p, st) : rpt == 4 ? launch_packed<16, 4, 2>(ctx, p, st) : launch_packed<16, 2, 4>(ctx, p, st);
+          if (n == 32) return launch_packed<32, 2, 2>(ctx, p, st);
+        }
+      }
       switch (n) {
 #define QN_REG_CASE(N, BLOCK, MINB) \
   case N: return launch_resident<Obj, N, BLOCK, MINB>(ctx, p, op, st);

@@ -410,6 +410,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
       }
       long long iteration = 0;
       bool failed = false;
+      QN_TICK(10);                               // timing build: start of the Armijo loop
       while (!(lx1 >= fma(a2 * ls.c1, m, l0))) { // QN.jl:187
         ++iteration;
         if (iteration > ls.iterations) { failed = true; break; } // QN.jl:193
@@ -433,7 +434,9 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
         at = nanmin(at, a2 * ls.rho_hi);   // QN.jl:224
         a2 = nanmax(at, a2 * ls.rho_lo);   // QN.jl:225
         lx0 = lx1;                         // QN.jl:228
+        QN_TICK(8);                        // timing build: interpolation of an extra trial
         lx1 = trial(a2);
+        QN_TICK(9);                        // timing build: evaluation + butterfly of an extra trial
       }
       alpha = failed ? 0.0 : a2;
     }

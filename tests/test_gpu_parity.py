@@ -78,6 +78,26 @@ def test_ragged_sizes_smem_path(eng, qn, ob, n):
     _check(got, ref)
 
 
+@pytest.mark.parametrize("n,variant", [(8, "1"), (8, "2"), (8, "4"), (16, "1"), (16, "2"), (16, "4"), (32, "2")])
+@pytest.mark.parametrize("order", [2, 3])
+def test_packed_small_n(eng, qn, ob, n, variant, order, monkeypatch):
+    """n = 8, 16: several problems per warp (qn_resident_packed.cuh), ragged batch sizes so that
+    sub-groups run dry at different times, iteration caps, traces; and the thread-per-row kernel
+    (QN_NO_PACK) gives the same bits."""
+    monkeypatch.setenv("QN_PACK_VARIANT", variant)  # rows per lane (qn_capi.cu dispatch_size)
+    ls = qn.BackTracking[order]()
+    ols = ob.backtracking(order)
+    for batch, kw in ((1, {}), (7, {}), (133, {}), (64, dict(max_iter=3)), (64, dict(max_iter=4))):
+        Theta = starts(n, batch, key=1000 * n + batch)
+        ref = ob.optimize_batch(ob.rosenbrock(), Theta, ls=ols, ntrace=5, **kw)
+        got = eng.optimize_batched(qn.Rosenbrock(), Theta, ls=ls, ntrace=5, **kw)
+        _check(got, ref)
+        monkeypatch.setenv("QN_NO_PACK", "1")
+        got2 = eng.optimize_batched(qn.Rosenbrock(), Theta, ls=ls, ntrace=5, **kw)
+        monkeypatch.delenv("QN_NO_PACK")
+        _check(got2, ref)
+
+
 def test_n128_both_resident_policies(eng, qn, ob):
     """n = 128 runs with B⁻¹ as 2x16 register tiles of 512 threads by default and in shared memory
     (row pairs, column blocks dealt out to thread groups) under QN_FLAG_FORCE_SMEM: same bits."""
@@ -180,7 +200,7 @@ def test_edge_cases(eng, qn, ob):
 def test_state_blocks_and_h_writeback(eng, qn, ob):
     """Results land in BFGSState layout (QN.jl:135,138): θ* at 0, ∇ at L; with QN_FLAG_WRITE_H the
     final B⁻¹ at 7L equals the oracle's bit for bit."""
-    for n, flags in ((60, 0), (60, qn._lib.FLAG_FORCE_SMEM), (24, 0), (61, qn._lib.FLAG_FORCE_SMEM),
+    for n, flags in ((60, 0), (60, qn._lib.FLAG_FORCE_SMEM), (24, 0), (8, 0), (16, 0), (61, qn._lib.FLAG_FORCE_SMEM),
                      (128, 0), (128, qn._lib.FLAG_FORCE_SMEM), (159, 0)):
         batch = 16 if n < 100 else 3
         Theta = starts(n, batch, key=n + 1)
