@@ -242,7 +242,9 @@ int dispatch_model(qn_context* ctx, const qn_model* model, qn::BatchParams& p,
       if (model->n != p.n)
         return fail(QN_ERR_INVALID_ARGUMENT, "dense Gaussian model has n=%d, call has n=%d",
                     model->n, p.n);
-      qn::DenseGaussian::Params op{model->d_a, model->d_b};
+      qn::DenseGaussian::Params op{model->d_a, model->d_b, 0};
+      // register-pair policy (n = 128): shared memory is free, keep Λ there (128 KB of the 227 KB)
+      if (p.n == 128 && !(flags & QN_FLAG_FORCE_SMEM) && !getenv("QN_NO_LAMBDA_SMEM")) op.lam_in_smem = 1;
       return dispatch_size<qn::DenseGaussian>(ctx, p, op, flags, st);
     }
     case QN_OBJ_LOGISTIC: {

@@ -26,6 +26,7 @@ struct Rosenbrock {
   static constexpr bool kRegisterPaths = true; // instantiate the register-resident kernels
   static constexpr bool kPairRegister = true;  // n = 128: B⁻¹ in 2×16 register tiles
   __host__ __device__ static int scratch_doubles(int, const Params&) { return 0; }
+  __device__ static void prologue(Team&, const Params&) {}
 
   template <bool GRAD>
   __device__ __forceinline__ static double eval(Team& t, const Params&, double& g) {
@@ -63,11 +64,24 @@ struct DenseGaussian {
   struct Params {
     const double* mu;     // n
     const double* lambda; // n×n column-major, ld = n
+    int lam_in_smem;      // the launcher found room for Λ beside the problem's shared memory
   };
   static constexpr int kKind = QN_OBJ_DENSE_GAUSSIAN;
   static constexpr bool kRegisterPaths = false; // no thread-per-row / 4×15-tile instantiations
   static constexpr bool kPairRegister = true;   // n = 128: B⁻¹ in 2×16 register tiles
-  __host__ __device__ static int scratch_doubles(int n, const Params&) { return (n + 31) & ~31; }
+  // θ-μ (B doubles), then Λ itself when B⁻¹ lives in registers and the 227 KB of shared memory
+  // are free: every CTA solves many problems against the same Λ, so it is fetched from L2 once
+  // per CTA instead of once per objective evaluation (128 KB at n = 128).
+  __host__ __device__ static int scratch_doubles(int n, const Params& p) {
+    return ((n + 31) & ~31) + (p.lam_in_smem ? n * n : 0);
+  }
+  __device__ static void prologue(Team& t, const Params& p) {
+    if (!p.lam_in_smem) return;
+    double* ls = t.scratch + ((t.n + 31) & ~31);
+    const int total = t.n * t.n;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) ls[i] = __ldg(p.lambda + i);
+    __syncthreads();
+  }
 
   template <bool GRAD>
   __device__ __forceinline__ static double eval(Team& t, const Params& p, double& g) {
@@ -81,11 +95,20 @@ struct DenseGaussian {
     __syncthreads();
     // z = Λ(θ-μ): rule-C2 row sums, the blocks of a row shared by the team's tpr threads
     // (K = n <= 256: one super-block).  The csum below is the barrier after this use of `part`.
-    const double* lam = p.lambda;
-    const double z = t.rowsum(n, [&](int row, int r, double& a, double& b) {
-      a = __ldg(lam + row + (size_t)n * r);
-      b = ds[r];
-    });
+    double z;
+    if (p.lam_in_smem) {
+      const double* lam = t.scratch + ((n + 31) & ~31);
+      z = t.rowsum(n, [&](int row, int r, double& a, double& b) {
+        a = lam[row + n * r];
+        b = ds[r];
+      });
+    } else {
+      const double* lam = p.lambda;
+      z = t.rowsum(n, [&](int row, int r, double& a, double& b) {
+        a = __ldg(lam + row + (size_t)n * r);
+        b = ds[r];
+      });
+    }
     const double q = t.csum(d * z, n);
     if (GRAD) g = -z;
     return -0.5 * q;
@@ -118,6 +141,7 @@ struct Logistic {
     return 2 * ((p.m + 31) & ~31) + nsb(p.m) * ((n + 31) & ~31);
   }
 
+  __device__ static void prologue(Team&, const Params&) {}
   __device__ __forceinline__ static double softplus(double z) {
     return z > 0.0 ? z + log1p(exp(-z)) : log1p(exp(z));
   }

@@ -449,6 +449,7 @@ qn_resident_kernel(const BatchParams p, const typename Obj::Params op) {
   Pass2Col* cols = reinterpret_cast<Pass2Col*>(smem + L.cols);
   double* hs = smem + L.h;
   volatile long long* next = reinterpret_cast<volatile long long*>(smem + L.total - 2);
+  Obj::prologue(tm, op); // once per CTA: e.g. the dense Gaussian's Λ into shared memory
   if (NREG == 0 && PAIRN == 0) { // the padding row of an odd-n B⁻¹ is read and written by its pair: keep it finite
     const int ldh = resident_ldh(n);
     if (ldh > n)
