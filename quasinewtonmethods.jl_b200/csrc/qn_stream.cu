@@ -94,6 +94,7 @@ struct StreamParams {
   // peer address = peer_base[g] + (address - base)), then the shard raises its flag on every
   // peer; the vector kernel that consumes them spins on its LOCAL flags.  nshard = 1: one GPU.
   int nshard, shard, tile0, ntiles;
+  int fused2; // two-pass mode in three kernels: pass1 (+ yᵀB⁻¹y, c₁), pass2 (c₁s on the fly), cluster kernel
   double* base;
   double* peer_base[8];
   unsigned int* tiles_done;  // local: row tiles of the current sweep that have been broadcast
@@ -109,23 +110,30 @@ __device__ __forceinline__ void bstore(const StreamParams& p, double* ptr, doubl
   for (int g = 0; g < p.nshard; ++g) p.peer_base[g][off] = v;
 }
 // after a CTA has broadcast the sums of one row tile: count it, and when it was this shard's
-// last tile publish the epoch on every peer (which = 0: pass1 / the one-pass sweep, 1: pass2)
-__device__ __forceinline__ void shard_signal(const StreamParams& p, int which, unsigned epoch) {
-  if (p.nshard == 1) return;
-  __threadfence_system(); // this thread's peer stores are visible system-wide
+// last tile publish the epoch on every peer (which = 0: pass1 / the one-pass sweep, 1: pass2).
+// Returns (to every thread of the CTA) whether this CTA completed the shard's last tile.
+__device__ __forceinline__ bool shard_signal(const StreamParams& p, int which, unsigned epoch, bool count_always = false) {
+  if (p.nshard == 1 && !count_always) return false;
+  __shared__ int last_tile;
+  __threadfence_system(); // this thread's (peer) stores are visible system-wide
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned done = atomicAdd(p.tiles_done, 1u);
-    if (done == (unsigned)p.ntiles - 1) {
+    last_tile = (done == (unsigned)p.ntiles - 1);
+    if (last_tile) {
       *p.tiles_done = 0;
       __threadfence_system();
-      const ptrdiff_t off = reinterpret_cast<double*>(p.flags) - p.base;
-      for (int g = 0; g < p.nshard; ++g) {
-        volatile unsigned* f = reinterpret_cast<volatile unsigned*>(p.peer_base[g] + off);
-        f[2 * p.shard + which] = epoch;
+      if (p.nshard > 1) {
+        const ptrdiff_t off = reinterpret_cast<double*>(p.flags) - p.base;
+        for (int g = 0; g < p.nshard; ++g) {
+          volatile unsigned* f = reinterpret_cast<volatile unsigned*>(p.peer_base[g] + off);
+          f[2 * p.shard + which] = epoch;
+        }
       }
     }
   }
+  __syncthreads();
+  return last_tile != 0;
 }
 // the consumer side: wait until every shard has published `epoch` for sweep `which`
 __device__ __forceinline__ void shard_wait(const StreamParams& p, int which, unsigned epoch) {
@@ -317,7 +325,8 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_begin(const StreamPara
 // super-block partials in ascending order (rule C2) — 16 SMs do this in parallel instead of
 // one.  finish(c, T) consumes the row sum.  Returns after the tile is done.
 template <class F>
-__device__ __forceinline__ void pass_tail(const StreamParams& p, int which, unsigned epoch, F&& finish) {
+__device__ __forceinline__ bool pass_tail(const StreamParams& p, int which, unsigned epoch, F&& finish,
+                                          bool count_always = false) {
   __shared__ int is_last;
   __threadfence(); // this CTA's partials are visible device-wide before it signs off
   __syncthreads();
@@ -327,7 +336,7 @@ __device__ __forceinline__ void pass_tail(const StreamParams& p, int which, unsi
     if (is_last) p.tile_count[blockIdx.x] = 0; // ready for the next pass
   }
   __syncthreads();
-  if (!is_last) return;
+  if (!is_last) return false;
   __threadfence();
   const int c0 = (p.tile0 + blockIdx.x) * kRowsPerCta + 2 * threadIdx.x;
   if (c0 < p.n) {
@@ -341,7 +350,7 @@ __device__ __forceinline__ void pass_tail(const StreamParams& p, int which, unsi
     finish(c0, T0);
     if (two) finish(c0 + 1, T1);
   }
-  shard_signal(p, which, epoch); // row-sharded mode: this tile's sums are in every replica
+  return shard_signal(p, which, epoch, count_always); // row-sharded mode: this tile's sums are in every replica
 }
 
 __global__ void __launch_bounds__(kVecThreads) stream_vec_mid(const StreamParams p) {
@@ -430,7 +439,7 @@ __device__ __forceinline__ void stream_finish_iteration(const StreamParams& p, S
   }
   const double alpha = failed ? 0.0 : a2;
   if (alpha == 0.0) { // QN.jl:284
-    if (threadIdx.x == 0) { sc->status = QN_LINESEARCH_FAILED; sc->done = 1; sc->fevals += fevals; sc->need_reset = 0; sc->exit_it = it; }
+    if (threadIdx.x == 0) { sc->status = QN_LINESEARCH_FAILED; sc->done = 1; sc->fevals += fevals; sc->need_reset = need_reset; sc->exit_it = it; }
     return;
   }
   // update_state!  QN.jl:21-27 ; ∇_old ← ∇_new  QN.jl:286
@@ -477,9 +486,15 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_end(const StreamParams
   stream_finish_iteration(p, sc, it, l0, m, stage, &red);
 }
 
+#ifndef QN_PASS2_MINB
+#define QN_PASS2_MINB 2
+#endif
+#ifndef QN_PASS1_MINB
+#define QN_PASS1_MINB 4
+#endif
 // ---- pass 1: partial[sb][c] = Σ_{blocks of sb} chain_b(c),  chain_b(c) = Σ_{r in b} y[r] H[c,r]
 template <int LDH, int STH>
-__global__ void __launch_bounds__(kPassThreads) stream_pass1(const StreamParams p) {
+__global__ void __launch_bounds__(kPassThreads, QN_PASS1_MINB) stream_pass1(const StreamParams p) {
   const StreamScalars* sc = p.sc;
   if (sc->done || sc->skip_update) return;
   extern __shared__ __align__(16) double sm[];
@@ -490,6 +505,7 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass1(const StreamParams 
   const int r_end = min(r_begin + p.sbcols, n);
   for (int r = r_begin + threadIdx.x; r < r_end; r += blockDim.x) ys[r - r_begin] = p.y[r];
   __syncthreads();
+  const bool reset = p.fused2 && sc->need_reset != 0; // B⁻¹ ← I (QN.jl:144-148) folded into the sweeps
   const int c0 = (p.tile0 + blockIdx.x) * kRowsPerCta + 2 * threadIdx.x;
   const bool two = (c0 + 1 < n);
   const double* hp = p.H + (c0 - p.tile0 * kRowsPerCta);
@@ -502,7 +518,9 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass1(const StreamParams 
     for (; r + 8 <= b1; r += 8) { // 8 independent 128-bit loads in flight
       double2 h[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) h[k] = ld_h<LDH>(hp + (size_t)ld * (r + k));
+      for (int k = 0; k < 8; ++k)
+        h[k] = reset ? make_double2(c0 == r + k ? 1.0 : 0.0, c0 + 1 == r + k ? 1.0 : 0.0)
+                     : ld_h<LDH>(hp + (size_t)ld * (r + k));
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const double yr = ys[r + k - r_begin];
@@ -511,7 +529,8 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass1(const StreamParams 
       }
     }
     for (; r < b1; ++r) {
-      const double2 h = ld_h<LDH>(hp + (size_t)ld * r);
+      const double2 h = reset ? make_double2(c0 == r ? 1.0 : 0.0, c0 + 1 == r ? 1.0 : 0.0)
+                              : ld_h<LDH>(hp + (size_t)ld * r);
       const double yr = ys[r - r_begin];
       t0 = fma(yr, h.x, t0);
       t1 = fma(yr, h.y, t1);
@@ -526,15 +545,40 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass1(const StreamParams 
     if (two) out[1] = S1;
   }
   const double rho = sc->rho;
-  pass_tail(p, 0, (unsigned)sc->it + 1u, [&](int c, double T) {
+  const unsigned epoch = (unsigned)sc->it + 1u;
+  const bool last_tile = pass_tail(p, 0, epoch, [&](int c, double T) {
     bstore(p, p.nu + c, -(T * rho));     // -B⁻¹y[c] = -(t ρ), QN.jl:50
     bstore(p, p.tmp + c, T * p.y[c]);    // term of yᵀB⁻¹y, QN.jl:51
-  });
+  }, p.fused2 != 0);
+  if (!p.fused2 || !last_tile) return;
+  // fused two-pass mode: the CTA that completed this GPU's last row tile stands in for vec_mid —
+  // once every shard's slice has arrived, yᵀB⁻¹y = csum of the terms (rule C1, one warp), then c₁
+  shard_wait(p, 0, epoch);
+  if (threadIdx.x < 32) {
+    const int l = threadIdx.x;
+    const volatile double* tv = p.tmp; // written by other CTAs (and peers) during this launch
+    double acc = (l < n) ? tv[l] : 0.0;
+    int j = l + 32;
+    for (; j + 224 < n; j += 256) {
+      double x[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = tv[j + 32 * k];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc = acc + x[k];
+    }
+    for (; j < n; j += 32) acc = acc + tv[j];
+    const double yHy = warp_butterfly(acc);
+    if (l == 0) p.sc->c1 = fma(yHy, rho, 1.0) * rho; // QN.jl:54
+  }
 }
 
 // ---- pass 2: H[c,r] ← ((H + (c₁s[r])s[c]) - u[r]s[c]) - u[c]s[r] ; partials of d = H⁺∇
+// Residency matters for these sweeps, and FEWER resident CTAs are better: each CTA walks its own
+// 4 KB-per-column stream, and 2 CTAs per SM (296 concurrent streams, all 128 registers spent on loads
+// in flight) beat 3 or 4 (measured at n = 8192, gpurun_out/minb.txt: pass2 172 µs at 2 CTAs/SM
+// against 207 µs at 3-4; the one-pass sweep 201 / 245 / 253 µs per iteration at 2 / 3 / 4).
 template <int LDH, int STH>
-__global__ void __launch_bounds__(kPassThreads) stream_pass2(const StreamParams p) {
+__global__ void __launch_bounds__(kPassThreads, QN_PASS2_MINB) stream_pass2(const StreamParams p) {
   const StreamScalars* sc = p.sc;
   if (sc->done || sc->skip_update) return;
   extern __shared__ __align__(16) double sm[];
@@ -543,8 +587,12 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass2(const StreamParams 
   const int sb = blockIdx.y;
   const int r_begin = sb * p.sbcols;
   const int r_end = min(r_begin + p.sbcols, n);
-  for (int r = r_begin + threadIdx.x; r < r_end; r += blockDim.x)
-    ops[r - r_begin] = make_double4(p.w[r], p.nu[r], p.s[r], p.g[r]);
+  const bool reset = p.fused2 && sc->need_reset != 0;
+  const double c1 = sc->c1;
+  for (int r = r_begin + threadIdx.x; r < r_end; r += blockDim.x) {
+    const double sr = p.s[r];
+    ops[r - r_begin] = make_double4(p.fused2 ? c1 * sr : p.w[r], p.nu[r], sr, p.g[r]); // (c₁ s[r]) once per r (rule C4)
+  }
   __syncthreads();
   const int c0 = (p.tile0 + blockIdx.x) * kRowsPerCta + 2 * threadIdx.x;
   const bool two = (c0 + 1 < n);
@@ -560,7 +608,9 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass2(const StreamParams 
     for (; r + 8 <= b1; r += 8) {
       double2 h[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) h[k] = ld_h<LDH>(hp + (size_t)ld * (r + k));
+      for (int k = 0; k < 8; ++k)
+        h[k] = reset ? make_double2(c0 == r + k ? 1.0 : 0.0, c0 + 1 == r + k ? 1.0 : 0.0)
+                     : ld_h<LDH>(hp + (size_t)ld * (r + k));
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const double4 o = ops[r + k - r_begin];
@@ -574,7 +624,8 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass2(const StreamParams 
       }
     }
     for (; r < b1; ++r) {
-      const double2 h = ld_h<LDH>(hp + (size_t)ld * r);
+      const double2 h = reset ? make_double2(c0 == r ? 1.0 : 0.0, c0 + 1 == r ? 1.0 : 0.0)
+                              : ld_h<LDH>(hp + (size_t)ld * r);
       const double4 o = ops[r - r_begin];
       double h0 = h.x, h1 = h.y;
       h0 = fma(o.x, s0, h0); h1 = fma(o.x, s1, h1);
@@ -602,8 +653,11 @@ __global__ void __launch_bounds__(kPassThreads) stream_pass2(const StreamParams 
 // ---- one-pass mode: ONE sweep applies the pending update of the previous
 // iteration and accumulates both GEMVs, t = H y and w = H ∇ (rule C2 chains, same tiling as
 // pass1/pass2).  16 n² bytes per iteration instead of 24 n²; not the reference's rounding.
+#ifndef QN_PASSONE_MINB
+#define QN_PASSONE_MINB 2
+#endif
 template <int LDH, int STH>
-__global__ void __launch_bounds__(kPassThreads) stream_pass_one(const StreamParams p) {
+__global__ void __launch_bounds__(kPassThreads, QN_PASSONE_MINB) stream_pass_one(const StreamParams p) {
   const StreamScalars* sc = p.sc;
   if (sc->done || sc->skip_update) return;
   extern __shared__ __align__(16) double sm[];
@@ -890,9 +944,12 @@ __device__ __forceinline__ void cluster_reduce(cooperative_groups::cluster_group
   if (vote >= 0) *vote_out = cl.map_shared_rank(sh, 0)->all;
 }
 
-template <int PPT>
+// ONEPASS = false: the same kernel between pass2 of iteration `it` and pass1 of iteration it+1 of
+// the two-pass (reference-order) mode — it replaces vec_end + vec_begin: d and the terms of m
+// come from pass2's tail instead of being formed here.
+template <int PPT, bool ONEPASS>
 __global__ void __cluster_dims__(kCluCtas, 1, 1) __launch_bounds__(kCluThreads)
-stream_vec_onepass_cluster(const StreamParams p) {
+stream_vec_cluster(const StreamParams p) {
   namespace cg = cooperative_groups;
   cg::cluster_group cl = cg::this_cluster();
   extern __shared__ __align__(16) double vsm[]; // ns doubles: the array this rank reduces
@@ -930,7 +987,7 @@ stream_vec_onepass_cluster(const StreamParams p) {
   const int skip_update = sc->skip_update;
   int fevals = 0;
   double m;
-  if (!skip_update) {
+  if (!skip_update && ONEPASS) {
     const double rho = sc->rho;
     shard_wait(p, 0, (unsigned)it); // row-sharded mode: every shard's slices of t and w have arrived
     const int par = (p.nshard > 1) ? (it & 1) * p.nvstride * 2 : 0;
@@ -972,13 +1029,26 @@ stream_vec_onepass_cluster(const StreamParams p) {
     cluster_reduce<1>(cl, cnt1, vsm, &sh, r1);
     m = r1[0];
     if (leader) { sc->pc1 = c1; sc->pending = 1; sc->c1 = c1; }
+  } else if (!skip_update) {
+    // two-pass mode: pass2's tail left the new direction in dvec (`s, y = y, s`, QN.jl:65,268);
+    // m = dᵀ∇_new = csum of d[c]·∇[c], QN.jl:66-68
+    shard_wait(p, 1, (unsigned)it); // row-sharded mode: every shard's slice of d has arrived
+#pragma unroll
+    for (int j = 0; j < NE; ++j) {
+      s[j] = ok[j] ? p.dvec[idx[j]] : 0.0;
+      if (mine[j]) st[0][idx[j]] = s[j] * g[j];
+    }
+    double r1[1];
+    const int cnt1[1] = {n};
+    cluster_reduce<1>(cl, cnt1, vsm, &sh, r1);
+    m = r1[0];
   } else {
     m = sc->m;
   }
   int need_reset = 0;
   if (m <= 0.0) { // QN.jl:272-280
     need_reset = 1;
-    if (leader) sc->pending = 0; // the reset discards the pending update
+    if (leader && ONEPASS) sc->pending = 0; // the reset discards the pending update
 #pragma unroll
     for (int j = 0; j < NE; ++j) {
       s[j] = g[j];
@@ -1082,7 +1152,7 @@ stream_vec_onepass_cluster(const StreamParams p) {
   }
   const double alpha = failed ? 0.0 : a2;
   if (alpha == 0.0) { // QN.jl:284
-    if (leader) { sc->status = QN_LINESEARCH_FAILED; sc->done = 1; sc->fevals += fevals; sc->need_reset = 0; sc->exit_it = it; }
+    if (leader) { sc->status = QN_LINESEARCH_FAILED; sc->done = 1; sc->fevals += fevals; sc->need_reset = need_reset; sc->exit_it = it; }
 #pragma unroll
     for (int j = 0; j < NE; ++j) if (mine[j]) p.s[idx[j]] = s[j];
     cl.sync(); // nobody leaves while its shared memory may still be read remotely
@@ -1187,9 +1257,10 @@ __global__ void __launch_bounds__(kPassThreads) stream_flush_pending(const Strea
 }
 
 // B⁻¹ ← I (QN.jl:144-148), only when vec_end asked for it
+template <bool AT_EXIT>
 __global__ void __launch_bounds__(256) stream_identity(const StreamParams p) {
   const StreamScalars* sc = p.sc;
-  if (sc->done || !sc->need_reset) return;
+  if ((!AT_EXIT && sc->done) || !sc->need_reset) return;
   const size_t ld2 = (size_t)p.ld / 2;
   const size_t total = ld2 * p.n; // double2 elements
   double2* H2 = reinterpret_cast<double2*>(p.H);
@@ -1234,15 +1305,28 @@ PassKernel pass1_kernel() { return kPass1Tab[hint_env("QN_HINT_P1_LD", 0, 4)][0]
 PassKernel pass2_kernel() { return kPass2Tab[hint_env("QN_HINT_P2_LD", 2, 4)][hint_env("QN_HINT_P2_ST", 1, 3)]; }
 PassKernel pass_one_kernel() { return kPassOneTab[hint_env("QN_HINT_ONE_LD", 4, 4)][hint_env("QN_HINT_ONE_ST", 0, 3)]; }
 
+// extra dynamic shared memory for pass1, a residency knob (bytes): QN_P1_PAD_KB
+size_t pass1_pad() { return (size_t)hint_env("QN_P1_PAD_KB", 0, 200) * 1024; }
+using VecKernel = void (*)(const qn::StreamParams);
+VecKernel cluster_kernel(int ppt, bool onepass) {
+  if (onepass) return ppt == 1 ? qn::stream_vec_cluster<1, true> : ppt == 2 ? qn::stream_vec_cluster<2, true> : qn::stream_vec_cluster<3, true>;
+  return ppt == 1 ? qn::stream_vec_cluster<1, false> : ppt == 2 ? qn::stream_vec_cluster<2, false> : qn::stream_vec_cluster<3, false>;
+}
+
 int enqueue_iteration(qn_context* ctx, const StreamWork& w, cudaStream_t st) {
   const qn::StreamParams& p = w.p;
   const dim3 grid(p.ntiles, p.nsb);
   if (p.onepass) { // two kernels per iteration; the head of iteration 1 ran before the graph
     pass_one_kernel()<<<grid, qn::kPassThreads, sizeof(double) * 6 * p.sbcols, st>>>(p);
-    if (w.clu_ppt == 1) qn::stream_vec_onepass_cluster<1><<<qn::kCluCtas, qn::kCluThreads, w.clu_smem, st>>>(p);
-    else if (w.clu_ppt == 2) qn::stream_vec_onepass_cluster<2><<<qn::kCluCtas, qn::kCluThreads, w.clu_smem, st>>>(p);
-    else if (w.clu_ppt == 3) qn::stream_vec_onepass_cluster<3><<<qn::kCluCtas, qn::kCluThreads, w.clu_smem, st>>>(p);
+    if (w.clu_ppt) cluster_kernel(w.clu_ppt, true)<<<qn::kCluCtas, qn::kCluThreads, w.clu_smem, st>>>(p);
     else qn::stream_vec_onepass<<<1, qn::kVecThreads, w.vec_smem, st>>>(p);
+    QN_CUDA_TRY(cudaGetLastError());
+    return QN_OK;
+  }
+  if (p.fused2) { // three kernels per iteration; the head of iteration 1 ran before the graph
+    pass1_kernel()<<<grid, qn::kPassThreads, sizeof(double) * p.sbcols + pass1_pad(), st>>>(p);
+    pass2_kernel()<<<grid, qn::kPassThreads, sizeof(double) * 4 * p.sbcols, st>>>(p);
+    cluster_kernel(w.clu_ppt, false)<<<qn::kCluCtas, qn::kCluThreads, w.clu_smem, st>>>(p);
     QN_CUDA_TRY(cudaGetLastError());
     return QN_OK;
   }
@@ -1251,7 +1335,7 @@ int enqueue_iteration(qn_context* ctx, const StreamWork& w, cudaStream_t st) {
   qn::stream_vec_mid<<<1, qn::kVecThreads, w.vec_smem, st>>>(p);
   pass2_kernel()<<<grid, qn::kPassThreads, sizeof(double) * 4 * p.sbcols, st>>>(p);
   qn::stream_vec_end<<<1, qn::kVecThreads, w.vec_smem, st>>>(p);
-  qn::stream_identity<<<ctx->prop.multiProcessorCount * 8, 256, 0, st>>>(p);
+  qn::stream_identity<false><<<ctx->prop.multiProcessorCount * 8, 256, 0, st>>>(p);
   QN_CUDA_TRY(cudaGetLastError());
   return QN_OK;
 }
@@ -1345,13 +1429,16 @@ int stream_capture(qn_context* ctx, StreamWork& w, cudaStream_t st) {
   QN_TRY_REL(cudaSetDevice(ctx->device));
   QN_TRY_REL(cudaFuncSetAttribute(pass2_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(sizeof(double) * 4 * p.sbcols)));
+  if (pass1_pad())
+    QN_TRY_REL(cudaFuncSetAttribute(pass1_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(sizeof(double) * p.sbcols + pass1_pad())));
   if (w.vec_smem) {
     QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_begin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
     QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
     QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_end, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
     QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_onepass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
   }
-  if (p.onepass && !getenv("QN_STREAM_NO_CLUSTER")) {
+  if (!getenv("QN_STREAM_NO_CLUSTER")) {
     // the cluster vector kernel: a thread owns up to 3 Rosenbrock pairs; a rank stages n doubles
     const int pairs = n >> 1, cap = qn::kCluCtas * qn::kCluThreads;
     const int ppt = pairs <= cap ? 1 : (pairs + cap - 1) / cap;
@@ -1359,10 +1446,8 @@ int stream_capture(qn_context* ctx, StreamWork& w, cudaStream_t st) {
     if (ppt <= 3 && smem + 1024 <= (size_t)ctx->prop.sharedMemPerBlockOptin) {
       w.clu_ppt = ppt;
       w.clu_smem = smem;
-      const int ismem = (int)smem;
-      if (ppt == 1) QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_onepass_cluster<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ismem));
-      if (ppt == 2) QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_onepass_cluster<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ismem));
-      if (ppt == 3) QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_onepass_cluster<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ismem));
+      QN_TRY_REL(cudaFuncSetAttribute(cluster_kernel(ppt, p.onepass != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (!p.onepass) w.p.fused2 = 1;
     }
   }
   QN_TRY_REL(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -1371,7 +1456,7 @@ int stream_capture(qn_context* ctx, StreamWork& w, cudaStream_t st) {
   if (rc != QN_OK) return rc;
   if (ce != cudaSuccess) return qn_fail(QN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
   QN_TRY_REL(cudaGraphInstantiate(&w.exec, w.graph, 0));
-  if (p.onepass) qn::stream_vec_begin<<<1, qn::kVecThreads, w.vec_smem, st>>>(p); // head of iteration 1
+  if (p.onepass || p.fused2) qn::stream_vec_begin<<<1, qn::kVecThreads, w.vec_smem, st>>>(p); // head of iteration 1
   QN_TRY_REL(cudaGetLastError());
   return QN_OK;
 }
@@ -1452,8 +1537,13 @@ int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_bac
   ctx->last_grid = p.ntiles * p.nsb;
   ctx->last_block = qn::kPassThreads;
   ctx->last_smem = (int)(sizeof(double) * 4 * p.sbcols);
-  ctx->last_launches = onepass ? 1 + 2 * (host.it + (host.done ? 1 : 0)) : 6 * (host.it + (host.done ? 1 : 0));
+  {
+    const int its = host.it + (host.done ? 1 : 0);
+    ctx->last_launches = onepass ? 1 + 2 * its : p.fused2 ? 1 + 3 * its : 6 * its;
+  }
   auto finish = [&]() -> int {
+    if (d_h_out && host.need_reset) // the solve ended between a reset decision (QN.jl:272-280) and the next sweep
+      qn::stream_identity<true><<<ctx->prop.multiProcessorCount * 8, 256, 0, st>>>(p);
     if (d_x_out) QN_TRY_REL(cudaMemcpyAsync(d_x_out, p.x, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     // which ∇ the reference's canonical slot shows after a failure: see qn_resident.cuh
     const double* g_src = (host.status == QN_CONVERGED || (host.exit_it & 1)) ? p.g : p.gp;
@@ -1556,6 +1646,7 @@ extern "C" int32_t qn_bfgs_optimize_rowsharded_f64(
       for (int g = 0; g < G; ++g) { // every shard returns its slab of rows
         const StreamParams& p = ws[g].p;
         QN_TRY_REL(cudaSetDevice(ctxs[g]->device));
+        if (host.need_reset) qn::stream_identity<true><<<ctxs[g]->prop.multiProcessorCount * 8, 256, 0, sts[g]>>>(p);
         if (onepass) {
           const dim3 grid(p.ntiles, p.nsb);
           qn::stream_flush_pending<<<grid, qn::kPassThreads, 0, sts[g]>>>(p);
@@ -1574,7 +1665,8 @@ extern "C" int32_t qn_bfgs_optimize_rowsharded_f64(
     ctxs[g]->last_path = 2;
     ctxs[g]->last_grid = ws[g].p.ntiles * ws[g].p.nsb;
     ctxs[g]->last_block = kPassThreads;
-    ctxs[g]->last_launches = onepass ? 1 + 2 * (host.it + (host.done ? 1 : 0)) : 6 * (host.it + (host.done ? 1 : 0));
+    const int its = host.it + (host.done ? 1 : 0);
+    ctxs[g]->last_launches = onepass ? 1 + 2 * its : ws[g].p.fused2 ? 1 + 3 * its : 6 * its;
   }
   release_all();
   if (rc != QN_OK) return rc;
