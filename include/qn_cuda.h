@@ -56,7 +56,8 @@ enum {
 enum {
   QN_OBJ_ROSENBROCK = 0,     /* test/runtests.jl:4-33 */
   QN_OBJ_DENSE_GAUSSIAN = 1, /* build-defined, DESIGN.md §6 */
-  QN_OBJ_LOGISTIC = 2        /* build-defined, DESIGN.md §6 */
+  QN_OBJ_LOGISTIC = 2,       /* build-defined, DESIGN.md §6 */
+  QN_OBJ_USER = 100          /* the build's plug-in objective, include/qn_objective.cuh */
 };
 
 /* ---- flags ------------------------------------------------------------ */
@@ -116,6 +117,13 @@ int32_t qn_model_dense_gaussian(qn_context* ctx, int32_t n, const double* mu,
 /* ℓ(θ) = Σᵢ [yᵢ zᵢ - log(1+e^{zᵢ})] - ½ λ ‖θ‖²,  z = Xθ;  X: m×n column-major */
 int32_t qn_model_logistic(qn_context* ctx, int32_t m, int32_t n, const double* X,
                           const double* y, double lam, qn_model** model);
+/* The device-objective extension point: the library is built with ONE
+ * user-supplied objective (include/qn_objective.cuh; `QN_USER_OBJECTIVE=my.cuh python build.py`),
+ * the analogue of adding `logdensity` / `∂logdensity!` methods for a new type (QN.jl:8-9).
+ * `params` is an opaque blob of `bytes` bytes that is copied to the device and handed to the
+ * objective; n = 0 accepts any dimension.  A library built without a user objective returns
+ * QN_ERR_UNREGISTERED_OBJECTIVE. */
+int32_t qn_model_user(qn_context* ctx, int32_t n, const void* params, size_t bytes, qn_model** model);
 int32_t qn_model_free(qn_model* model);
 
 /* logdensity(obj, θ) and ∂logdensity!(∇, obj, θ) evaluated on the device for a

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libqn_cuda.so")
+# QN_LIBRARY_PATH: a library built with a plug-in objective (include/qn_objective.cuh)
+SO_PATH = os.environ.get("QN_LIBRARY_PATH") or os.path.join(_HERE, "libqn_cuda.so")
 
 # error codes (include/qn_cuda.h)
 OK, ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_UNREGISTERED_OBJECTIVE, ERR_UNSUPPORTED_SIZE, ERR_NO_DEVICE = range(6)
@@ -16,6 +17,7 @@ OK, ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_UNREGISTERED_OBJECTIVE, ERR_UNSUPPORTED_
 CONVERGED, NONFINITE, LINESEARCH_FAILED, MAX_ITER = range(4)
 # objective kinds
 OBJ_ROSENBROCK, OBJ_DENSE_GAUSSIAN, OBJ_LOGISTIC = range(3)
+OBJ_USER = 100
 # flags
 FLAG_WRITE_H, FLAG_FORCE_SMEM, FLAG_FORCE_STREAM, FLAG_ONE_PASS = 0x1, 0x2, 0x4, 0x8
 # execution paths reported by qn_last_launch_info
@@ -57,6 +59,7 @@ SIGNATURES = {
     "qn_model_create": (C.c_int32, [_vp, C.c_int32, C.POINTER(_vp)]),
     "qn_model_dense_gaussian": (C.c_int32, [_vp, C.c_int32, _vp, _vp, C.POINTER(_vp)]),
     "qn_model_logistic": (C.c_int32, [_vp, C.c_int32, C.c_int32, _vp, _vp, C.c_double, C.POINTER(_vp)]),
+    "qn_model_user": (C.c_int32, [_vp, C.c_int32, _vp, C.c_size_t, C.POINTER(_vp)]),
     "qn_model_free": (C.c_int32, [_vp]),
     "qn_logdensity_batched_f64": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int64, _vp, _vp, _vp]),
     "qn_bfgs_optimize_batched_f64": (C.c_int32, [

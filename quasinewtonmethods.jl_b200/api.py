@@ -26,7 +26,7 @@ from ._lib import (CONVERGED, LINESEARCH_FAILED, MAX_ITER, NONFINITE, QNError,
 
 __all__ = [
     "BFGSState", "BFGSStateBatch", "BackTracking", "Rosenbrock", "DenseGaussian",
-    "LogisticRegression", "optimize_", "optimize", "optimum", "gradient", "logdensity",
+    "LogisticRegression", "UserObjective", "optimize_", "optimize", "optimum", "gradient", "logdensity",
     "dlogdensity_", "Engine", "default_engine", "optimize_rowsharded", "QNError", "UnregisteredObjectiveError",
     "CONVERGED", "NONFINITE", "LINESEARCH_FAILED", "MAX_ITER",
 ]
@@ -118,6 +118,27 @@ class LogisticRegression:
         m, n = self.X.shape
         _lib.check(_lib.load().qn_model_logistic(engine._ctx, m, n, _ptr(self.X), _ptr(self.y),
                                                  self.lam, C.byref(h)))
+        return h
+
+
+class UserObjective:
+    """The build's plug-in device objective (include/qn_objective.cuh, QN_OBJ_USER): `params` is the
+    opaque parameter blob (a numpy array) the objective's `make` interprets; n = 0 accepts any n.
+    Needs a library built with QN_USER_OBJECTIVE, selected with QN_LIBRARY_PATH; the stock library
+    answers with UnregisteredObjectiveError (no CPU fallback)."""
+    kind = _lib.OBJ_USER
+
+    def __init__(self, params, n=0):
+        self.params = np.ascontiguousarray(params)
+        self.n = int(n)
+
+    def _key(self):
+        return ("user", id(self))
+
+    def _register(self, engine):
+        h = C.c_void_p()
+        _lib.check(_lib.load().qn_model_user(engine._ctx, self.n, _ptr(self.params), self.params.nbytes,
+                                             C.byref(h)))
         return h
 
 

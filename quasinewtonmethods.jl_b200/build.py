@@ -46,15 +46,27 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source into quasinewtonmethods.jl_b200/libqn_cuda.so."""
+    """Compile every CUDA source into quasinewtonmethods.jl_b200/libqn_cuda.so.
+
+    QN_USER_OBJECTIVE=/abs/path/my.cuh builds a library WITH that plug-in objective
+    (include/qn_objective.cuh) into QN_SO_OUT (default: libqn_cuda_user.so next to the stock
+    library); the stock libqn_cuda.so is left alone."""
+    user = os.environ.get("QN_USER_OBJECTIVE")
+    if user:
+        return _build(os.environ.get("QN_SO_OUT", os.path.join(HERE, "libqn_cuda_user.so")), "build_user",
+                      ["-DQN_USER_OBJECTIVE_HEADER=\"%s\"" % os.path.abspath(user)], verbose)
     if not force and not _stale():
         return SO
+    return _build(SO, "build", [], verbose)
+
+
+def _build(so, subdir, extra, verbose):
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(os.path.join(HERE, subdir), exist_ok=True)
     for src in _sources():
-        obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        obj = os.path.join(HERE, subdir, os.path.basename(src) + ".o")
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
         objs.append(obj)
     failed = False
@@ -65,8 +77,8 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
-    return SO
+    subprocess.check_call([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", so] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    return so
 
 
 if __name__ == "__main__":

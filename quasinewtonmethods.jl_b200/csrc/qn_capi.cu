@@ -18,6 +18,9 @@
 #include "../../include/qn_cuda.h"
 #include "qn_device.cuh"
 #include "qn_objectives.cuh"
+#ifdef QN_USER_OBJECTIVE_HEADER
+#include QN_USER_OBJECTIVE_HEADER  // the build's plug-in objective (include/qn_objective.cuh)
+#endif
 #include "qn_resident.cuh"
 #include "qn_resident_tile.cuh"
 #include "qn_resident_packed.cuh"
@@ -254,6 +257,10 @@ int dispatch_model(qn_context* ctx, const qn_model* model, qn::BatchParams& p,
       qn::Logistic::Params op{model->m, model->d_a, model->d_b, model->d_c, model->lam};
       return dispatch_size<qn::Logistic>(ctx, p, op, flags, st);
     }
+#ifdef QN_USER_OBJECTIVE_HEADER
+    case QN_OBJ_USER:
+      return dispatch_size<qn::UserObjective>(ctx, p, qn::UserObjective::make(model->d_a, model->bytes, p.n), flags, st);
+#endif
     default:
       return fail(QN_ERR_UNREGISTERED_OBJECTIVE,
                   "objective kind %d has no registered device implementation", model->kind);
@@ -446,6 +453,33 @@ int32_t qn_model_logistic(qn_context* ctx, int32_t mrows, int32_t n, const doubl
   }
   *out = m;
   return QN_OK;
+}
+
+int32_t qn_model_user(qn_context* ctx, int32_t n, const void* params, size_t bytes, qn_model** out) {
+  if (!ctx || !out || n < 0 || (bytes > 0 && !params)) return fail(QN_ERR_INVALID_ARGUMENT, "bad argument");
+  *out = nullptr;
+#ifndef QN_USER_OBJECTIVE_HEADER
+  return fail(QN_ERR_UNREGISTERED_OBJECTIVE,
+              "this libqn_cuda.so was built without a user objective (include/qn_objective.cuh: "
+              "QN_USER_OBJECTIVE=my.cuh python build.py); there is no CPU fallback");
+#else
+  QN_CUDA_TRY(cudaSetDevice(ctx->device));
+  qn_model* m = new qn_model;
+  m->ctx = ctx;
+  m->kind = QN_OBJ_USER;
+  m->n = n;
+  m->bytes = bytes;
+  if (bytes > 0) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&m->d_a), bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(m->d_a, params, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      qn_model_free(m);
+      return fail(QN_ERR_CUDA, "uploading the user objective's parameters failed: %s", cudaGetErrorString(e));
+    }
+  }
+  *out = m;
+  return QN_OK;
+#endif
 }
 
 int32_t qn_model_free(qn_model* m) {

@@ -4,6 +4,9 @@
 #include "qn_device.cuh"
 #include "qn_internal.h"
 #include "qn_objectives.cuh"
+#ifdef QN_USER_OBJECTIVE_HEADER
+#include QN_USER_OBJECTIVE_HEADER
+#endif
 
 namespace qn {
 
@@ -91,6 +94,12 @@ extern "C" int32_t qn_logdensity_batched_f64(qn_context* ctx, const qn_model* mo
           ctx, n, batch, d_theta, d_ell, d_grad,
           qn::Logistic::Params{model->m, model->d_a, model->d_b, model->d_c, model->lam}, st);
       break;
+#ifdef QN_USER_OBJECTIVE_HEADER
+    case QN_OBJ_USER:
+      rc = qn::launch_eval<qn::UserObjective>(ctx, n, batch, d_theta, d_ell, d_grad,
+                                              qn::UserObjective::make(model->d_a, model->bytes, n), st);
+      break;
+#endif
     default:
       rc = qn_fail(QN_ERR_UNREGISTERED_OBJECTIVE,
                    "objective kind %d has no registered device implementation", model->kind);

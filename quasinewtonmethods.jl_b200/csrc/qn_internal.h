@@ -40,6 +40,7 @@ struct qn_model {
   double* d_b = nullptr; // gaussian: lambda  | logistic: Xt
   double* d_c = nullptr; //                   | logistic: y
   double lam = 0.0;
+  size_t bytes = 0;      // user objective: size of the parameter blob at d_a
 };
 
 // grow the context's device staging buffer (caller holds ctx->mu or is single-threaded)
