@@ -1286,24 +1286,33 @@ struct StreamWork {
 };
 
 using PassKernel = void (*)(const qn::StreamParams);
-#define QN_PASS_ROW(name, l) { name<l, 0>, name<l, 1>, name<l, 2>, name<l, 3> }
-#define QN_PASS_TABLE(name) { QN_PASS_ROW(name, 0), QN_PASS_ROW(name, 1), QN_PASS_ROW(name, 2), QN_PASS_ROW(name, 3), QN_PASS_ROW(name, 4) }
-PassKernel const kPass1Tab[5][4] = QN_PASS_TABLE(qn::stream_pass1);
-PassKernel const kPass2Tab[5][4] = QN_PASS_TABLE(qn::stream_pass2);
-PassKernel const kPassOneTab[5][4] = QN_PASS_TABLE(qn::stream_pass_one);
 
-// cache hints of the B⁻¹ accesses per kernel: measured defaults (gpurun_out/hints2.txt, n = 8192:
-// pass2 .lu loads + .cs stores 356 -> 316 µs per iteration; one-pass sweep .cg loads 216 -> 206 µs),
-// overridable for experiments (scripts/exp_stream_hints.sh)
+// cache hints of the B⁻¹ accesses per kernel: measured defaults (profiles/r1_stream_cache_hints.txt,
+// n = 8192: pass2 .lu loads + .cs stores 356 -> 316 µs per iteration; one-pass sweep .cg loads
+// 216 -> 206 µs).  The full 5×4 sweep of hints was run once (scripts/exp_stream_hints.sh, git
+// history); the combinations worth keeping are instantiated and selectable for A/B runs.
 int hint_env(const char* name, int dflt, int hi) {
   const char* v = getenv(name);
   if (!v) return dflt;
   const int k = atoi(v);
   return (k < 0 || k > hi) ? dflt : k;
 }
-PassKernel pass1_kernel() { return kPass1Tab[hint_env("QN_HINT_P1_LD", 0, 4)][0]; }
-PassKernel pass2_kernel() { return kPass2Tab[hint_env("QN_HINT_P2_LD", 2, 4)][hint_env("QN_HINT_P2_ST", 1, 3)]; }
-PassKernel pass_one_kernel() { return kPassOneTab[hint_env("QN_HINT_ONE_LD", 4, 4)][hint_env("QN_HINT_ONE_ST", 0, 3)]; }
+PassKernel pass1_kernel() {
+  return hint_env("QN_HINT_P1_LD", 0, 4) == 4 ? qn::stream_pass1<4, 0> : qn::stream_pass1<0, 0>;
+}
+PassKernel pass2_kernel() {
+  const int ld = hint_env("QN_HINT_P2_LD", 2, 4), st = hint_env("QN_HINT_P2_ST", 1, 3);
+  if (ld == 0 && st == 0) return qn::stream_pass2<0, 0>; // no hints
+  if (ld == 0) return qn::stream_pass2<0, 1>;            // .cs stores only
+  if (st == 0) return qn::stream_pass2<2, 0>;            // .lu loads only
+  return qn::stream_pass2<2, 1>;                         // default: .lu loads + .cs stores
+}
+PassKernel pass_one_kernel() {
+  const int ld = hint_env("QN_HINT_ONE_LD", 4, 4);
+  if (ld == 0) return qn::stream_pass_one<0, 0>;         // no hints
+  if (ld == 1) return qn::stream_pass_one<1, 0>;         // .cs loads
+  return qn::stream_pass_one<4, 0>;                      // default: .cg loads
+}
 
 // extra dynamic shared memory for pass1, a residency knob (bytes): QN_P1_PAD_KB
 size_t pass1_pad() { return (size_t)hint_env("QN_P1_PAD_KB", 0, 200) * 1024; }
