@@ -493,8 +493,8 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_end(const StreamParams
 #define QN_PASS1_MINB 4
 #endif
 // ---- pass 1: partial[sb][c] = Σ_{blocks of sb} chain_b(c),  chain_b(c) = Σ_{r in b} y[r] H[c,r]
-template <int LDH, int STH>
-__global__ void __launch_bounds__(kPassThreads, QN_PASS1_MINB) stream_pass1(const StreamParams p) {
+template <int LDH, int STH, int DEPTH = 8>
+__global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASS1_MINB) stream_pass1(const StreamParams p) {
   const StreamScalars* sc = p.sc;
   if (sc->done || sc->skip_update) return;
   extern __shared__ __align__(16) double sm[];
@@ -515,14 +515,14 @@ __global__ void __launch_bounds__(kPassThreads, QN_PASS1_MINB) stream_pass1(cons
     const int b1 = min(b0 + rb, r_end);
     double t0 = 0.0, t1 = 0.0;
     int r = b0;
-    for (; r + 8 <= b1; r += 8) { // 8 independent 128-bit loads in flight
-      double2 h[8];
+    for (; r + DEPTH <= b1; r += DEPTH) { // 8 independent 128-bit loads in flight
+      double2 h[DEPTH];
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
+      for (int k = 0; k < DEPTH; ++k)
         h[k] = reset ? make_double2(c0 == r + k ? 1.0 : 0.0, c0 + 1 == r + k ? 1.0 : 0.0)
                      : ld_h<LDH>(hp + (size_t)ld * (r + k));
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < DEPTH; ++k) {
         const double yr = ys[r + k - r_begin];
         t0 = fma(yr, h[k].x, t0);
         t1 = fma(yr, h[k].y, t1);
@@ -577,8 +577,8 @@ __global__ void __launch_bounds__(kPassThreads, QN_PASS1_MINB) stream_pass1(cons
 // 4 KB-per-column stream, and 2 CTAs per SM (296 concurrent streams, all 128 registers spent on loads
 // in flight) beat 3 or 4 (measured at n = 8192, gpurun_out/minb.txt: pass2 172 µs at 2 CTAs/SM
 // against 207 µs at 3-4; the one-pass sweep 201 / 245 / 253 µs per iteration at 2 / 3 / 4).
-template <int LDH, int STH>
-__global__ void __launch_bounds__(kPassThreads, QN_PASS2_MINB) stream_pass2(const StreamParams p) {
+template <int LDH, int STH, int DEPTH = 8>
+__global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASS2_MINB) stream_pass2(const StreamParams p) {
   const StreamScalars* sc = p.sc;
   if (sc->done || sc->skip_update) return;
   extern __shared__ __align__(16) double sm[];
@@ -605,14 +605,14 @@ __global__ void __launch_bounds__(kPassThreads, QN_PASS2_MINB) stream_pass2(cons
     const int b1 = min(b0 + rb, r_end);
     double a0 = 0.0, a1 = 0.0;
     int r = b0;
-    for (; r + 8 <= b1; r += 8) {
-      double2 h[8];
+    for (; r + DEPTH <= b1; r += DEPTH) {
+      double2 h[DEPTH];
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
+      for (int k = 0; k < DEPTH; ++k)
         h[k] = reset ? make_double2(c0 == r + k ? 1.0 : 0.0, c0 + 1 == r + k ? 1.0 : 0.0)
                      : ld_h<LDH>(hp + (size_t)ld * (r + k));
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < DEPTH; ++k) {
         const double4 o = ops[r + k - r_begin];
         double h0 = h[k].x, h1 = h[k].y;
         h0 = fma(o.x, s0, h0); h1 = fma(o.x, s1, h1);     // + (c₁ s[r]) s[c]
@@ -656,8 +656,8 @@ __global__ void __launch_bounds__(kPassThreads, QN_PASS2_MINB) stream_pass2(cons
 #ifndef QN_PASSONE_MINB
 #define QN_PASSONE_MINB 2
 #endif
-template <int LDH, int STH>
-__global__ void __launch_bounds__(kPassThreads, QN_PASSONE_MINB) stream_pass_one(const StreamParams p) {
+template <int LDH, int STH, int DEPTH = 8>
+__global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASSONE_MINB) stream_pass_one(const StreamParams p) {
   const StreamScalars* sc = p.sc;
   if (sc->done || sc->skip_update) return;
   extern __shared__ __align__(16) double sm[];
@@ -687,14 +687,14 @@ __global__ void __launch_bounds__(kPassThreads, QN_PASSONE_MINB) stream_pass_one
     const int b1 = min(b0 + rb, r_end);
     double t0 = 0.0, t1 = 0.0, w0 = 0.0, w1 = 0.0;
     int r = b0;
-    for (; r + 8 <= b1; r += 8) {
-      double2 h[8];
+    for (; r + DEPTH <= b1; r += DEPTH) {
+      double2 h[DEPTH];
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
+      for (int k = 0; k < DEPTH; ++k)
         h[k] = reset ? make_double2(c0 == r + k ? 1.0 : 0.0, c0 + 1 == r + k ? 1.0 : 0.0)
                      : ld_h<LDH>(hp + (size_t)ld * (r + k));
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < DEPTH; ++k) {
         double h0 = h[k].x, h1 = h[k].y;
         if (reset) st_h<STH>(hp + (size_t)ld * (r + k), h[k]);
         if (pending) {
@@ -1297,17 +1297,28 @@ int hint_env(const char* name, int dflt, int hi) {
   const int k = atoi(v);
   return (k < 0 || k > hi) ? dflt : k;
 }
-PassKernel pass1_kernel() {
+// deep = 16 instead of 8 loads in flight per thread (a whole rule-C2 block): for grids that leave
+// most SMs with at most one CTA — the shards of the row-sharded mode — where each thread's walk
+// over its 256 columns is a chain of exposed memory latencies
+bool sweep_deep(const qn_context* ctx, const qn::StreamParams& p) {
+  const int v = hint_env("QN_SWEEP_DEPTH", 0, 16);
+  if (v) return v == 16;
+  return p.ntiles * p.nsb < 2 * ctx->prop.multiProcessorCount;
+}
+PassKernel pass1_kernel(bool deep = false) {
+  if (deep) return qn::stream_pass1<0, 0, 16>;
   return hint_env("QN_HINT_P1_LD", 0, 4) == 4 ? qn::stream_pass1<4, 0> : qn::stream_pass1<0, 0>;
 }
-PassKernel pass2_kernel() {
+PassKernel pass2_kernel(bool deep = false) {
+  if (deep) return qn::stream_pass2<2, 1, 16>;
   const int ld = hint_env("QN_HINT_P2_LD", 2, 4), st = hint_env("QN_HINT_P2_ST", 1, 3);
   if (ld == 0 && st == 0) return qn::stream_pass2<0, 0>; // no hints
   if (ld == 0) return qn::stream_pass2<0, 1>;            // .cs stores only
   if (st == 0) return qn::stream_pass2<2, 0>;            // .lu loads only
   return qn::stream_pass2<2, 1>;                         // default: .lu loads + .cs stores
 }
-PassKernel pass_one_kernel() {
+PassKernel pass_one_kernel(bool deep = false) {
+  if (deep) return qn::stream_pass_one<4, 0, 16>;
   const int ld = hint_env("QN_HINT_ONE_LD", 4, 4);
   if (ld == 0) return qn::stream_pass_one<0, 0>;         // no hints
   if (ld == 1) return qn::stream_pass_one<1, 0>;         // .cs loads
@@ -1325,24 +1336,25 @@ VecKernel cluster_kernel(int ppt, bool onepass) {
 int enqueue_iteration(qn_context* ctx, const StreamWork& w, cudaStream_t st) {
   const qn::StreamParams& p = w.p;
   const dim3 grid(p.ntiles, p.nsb);
+  const bool deep = sweep_deep(ctx, p);
   if (p.onepass) { // two kernels per iteration; the head of iteration 1 ran before the graph
-    pass_one_kernel()<<<grid, qn::kPassThreads, sizeof(double) * 6 * p.sbcols, st>>>(p);
+    pass_one_kernel(deep)<<<grid, qn::kPassThreads, sizeof(double) * 6 * p.sbcols, st>>>(p);
     if (w.clu_ppt) cluster_kernel(w.clu_ppt, true)<<<qn::kCluCtas, qn::kCluThreads, w.clu_smem, st>>>(p);
     else qn::stream_vec_onepass<<<1, qn::kVecThreads, w.vec_smem, st>>>(p);
     QN_CUDA_TRY(cudaGetLastError());
     return QN_OK;
   }
   if (p.fused2) { // three kernels per iteration; the head of iteration 1 ran before the graph
-    pass1_kernel()<<<grid, qn::kPassThreads, sizeof(double) * p.sbcols + pass1_pad(), st>>>(p);
-    pass2_kernel()<<<grid, qn::kPassThreads, sizeof(double) * 4 * p.sbcols, st>>>(p);
+    pass1_kernel(deep)<<<grid, qn::kPassThreads, sizeof(double) * p.sbcols + pass1_pad(), st>>>(p);
+    pass2_kernel(deep)<<<grid, qn::kPassThreads, sizeof(double) * 4 * p.sbcols, st>>>(p);
     cluster_kernel(w.clu_ppt, false)<<<qn::kCluCtas, qn::kCluThreads, w.clu_smem, st>>>(p);
     QN_CUDA_TRY(cudaGetLastError());
     return QN_OK;
   }
   qn::stream_vec_begin<<<1, qn::kVecThreads, w.vec_smem, st>>>(p);
-  pass1_kernel()<<<grid, qn::kPassThreads, sizeof(double) * p.sbcols, st>>>(p);
+  pass1_kernel(deep)<<<grid, qn::kPassThreads, sizeof(double) * p.sbcols, st>>>(p);
   qn::stream_vec_mid<<<1, qn::kVecThreads, w.vec_smem, st>>>(p);
-  pass2_kernel()<<<grid, qn::kPassThreads, sizeof(double) * 4 * p.sbcols, st>>>(p);
+  pass2_kernel(deep)<<<grid, qn::kPassThreads, sizeof(double) * 4 * p.sbcols, st>>>(p);
   qn::stream_vec_end<<<1, qn::kVecThreads, w.vec_smem, st>>>(p);
   qn::stream_identity<false><<<ctx->prop.multiProcessorCount * 8, 256, 0, st>>>(p);
   QN_CUDA_TRY(cudaGetLastError());
@@ -1436,10 +1448,11 @@ int stream_capture(qn_context* ctx, StreamWork& w, cudaStream_t st) {
   const qn::StreamParams& p = w.p;
   const int n = p.n;
   QN_TRY_REL(cudaSetDevice(ctx->device));
-  QN_TRY_REL(cudaFuncSetAttribute(pass2_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize,
+  const bool deep = sweep_deep(ctx, p);
+  QN_TRY_REL(cudaFuncSetAttribute(pass2_kernel(deep), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(sizeof(double) * 4 * p.sbcols)));
   if (pass1_pad())
-    QN_TRY_REL(cudaFuncSetAttribute(pass1_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize,
+    QN_TRY_REL(cudaFuncSetAttribute(pass1_kernel(deep), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(sizeof(double) * p.sbcols + pass1_pad())));
   if (w.vec_smem) {
     QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_begin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
