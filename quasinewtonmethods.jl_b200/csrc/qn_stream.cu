@@ -36,8 +36,8 @@
 namespace qn {
 
 constexpr int kVecThreads = 1024;
-constexpr int kPassThreads = 256;
-constexpr int kRowsPerCta = 2 * kPassThreads;
+constexpr int kPassThreads = 256;             // most threads of a sweep CTA (2 rows each)
+constexpr int kShardRows = 2 * kPassThreads;  // the row-sharded mode splits B⁻¹ in units of 512 rows
 
 // B⁻¹ is streamed: every element is read once and written at most once per sweep; the cache
 // hint of those accesses is a kernel template parameter (0: default, 1: .cs evict-first,
@@ -93,7 +93,9 @@ struct StreamParams {
   // sums are stored into EVERY replica through peer pointers (same layout on each GPU:
   // peer address = peer_base[g] + (address - base)), then the shard raises its flag on every
   // peer; the vector kernel that consumes them spins on its LOCAL flags.  nshard = 1: one GPU.
-  int nshard, shard, tile0, ntiles;
+  int nshard, shard;
+  int row0, rows;   // this GPU's slab: rows [row0, row0 + rows) of B⁻¹ (all of them when nshard = 1)
+  int ntiles;       // CTA row tiles of a sweep on this GPU: 2·blockDim rows each
   int fused2; // two-pass mode in three kernels: pass1 (+ yᵀB⁻¹y, c₁), pass2 (c₁s on the fly), cluster kernel
   double* base;
   double* peer_base[8];
@@ -338,7 +340,7 @@ __device__ __forceinline__ bool pass_tail(const StreamParams& p, int which, unsi
   __syncthreads();
   if (!is_last) return false;
   __threadfence();
-  const int c0 = (p.tile0 + blockIdx.x) * kRowsPerCta + 2 * threadIdx.x;
+  const int c0 = p.row0 + (int)(blockIdx.x * 2 * blockDim.x) + 2 * (int)threadIdx.x;
   if (c0 < p.n) {
     const bool two = (c0 + 1 < p.n);
     const volatile double* part = p.partial + c0; // written by other CTAs of this launch
@@ -506,9 +508,9 @@ __global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASS1_MINB) s
   for (int r = r_begin + threadIdx.x; r < r_end; r += blockDim.x) ys[r - r_begin] = p.y[r];
   __syncthreads();
   const bool reset = p.fused2 && sc->need_reset != 0; // B⁻¹ ← I (QN.jl:144-148) folded into the sweeps
-  const int c0 = (p.tile0 + blockIdx.x) * kRowsPerCta + 2 * threadIdx.x;
+  const int c0 = p.row0 + (int)(blockIdx.x * 2 * blockDim.x) + 2 * (int)threadIdx.x;
   const bool two = (c0 + 1 < n);
-  const double* hp = p.H + (c0 - p.tile0 * kRowsPerCta);
+  const double* hp = p.H + (c0 - p.row0);
   double S0 = 0.0, S1 = 0.0;
   bool first = true;
   for (int b0 = r_begin; b0 < r_end && c0 < n; b0 += rb) {
@@ -594,11 +596,11 @@ __global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASS2_MINB) s
     ops[r - r_begin] = make_double4(p.fused2 ? c1 * sr : p.w[r], p.nu[r], sr, p.g[r]); // (c₁ s[r]) once per r (rule C4)
   }
   __syncthreads();
-  const int c0 = (p.tile0 + blockIdx.x) * kRowsPerCta + 2 * threadIdx.x;
+  const int c0 = p.row0 + (int)(blockIdx.x * 2 * blockDim.x) + 2 * (int)threadIdx.x;
   const bool two = (c0 + 1 < n);
   const double s0 = (c0 < n) ? p.s[c0] : 0.0, nu0 = (c0 < n) ? p.nu[c0] : 0.0;
   const double s1 = two ? p.s[c0 + 1] : 0.0, nu1 = two ? p.nu[c0 + 1] : 0.0;
-  double* hp = p.H + (c0 - p.tile0 * kRowsPerCta);
+  double* hp = p.H + (c0 - p.row0);
   double S0 = 0.0, S1 = 0.0;
   bool first = true;
   for (int b0 = r_begin; b0 < r_end && c0 < n; b0 += rb) {
@@ -676,11 +678,11 @@ __global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASSONE_MINB)
     yg[r - r_begin] = make_double2(p.y[r], p.g[r]);
   }
   __syncthreads();
-  const int c0 = (p.tile0 + blockIdx.x) * kRowsPerCta + 2 * threadIdx.x;
+  const int c0 = p.row0 + (int)(blockIdx.x * 2 * blockDim.x) + 2 * (int)threadIdx.x;
   const bool two = (c0 + 1 < n);
   const double s0 = (c0 < n) ? p.ps[c0] : 0.0, nu0 = (c0 < n) ? -p.pu[c0] : 0.0;
   const double s1 = two ? p.ps[c0 + 1] : 0.0, nu1 = two ? -p.pu[c0 + 1] : 0.0;
-  double* hp = p.H + (c0 - p.tile0 * kRowsPerCta);
+  double* hp = p.H + (c0 - p.row0);
   double St0 = 0.0, St1 = 0.0, Sw0 = 0.0, Sw1 = 0.0;
   bool first = true;
   for (int b0 = r_begin; b0 < r_end && c0 < n; b0 += rb) {
@@ -1239,14 +1241,14 @@ __global__ void __launch_bounds__(kPassThreads) stream_flush_pending(const Strea
   if (!sc->pending) return;
   const int n = p.n, ld = p.ld;
   const double pc1 = sc->pc1;
-  const int c0 = (p.tile0 + blockIdx.x) * kRowsPerCta + 2 * threadIdx.x;
+  const int c0 = p.row0 + (int)(blockIdx.x * 2 * blockDim.x) + 2 * (int)threadIdx.x;
   if (c0 >= n) return;
   const bool two = (c0 + 1 < n);
   const double s0 = p.ps[c0], nu0 = -p.pu[c0];
   const double s1 = two ? p.ps[c0 + 1] : 0.0, nu1 = two ? -p.pu[c0 + 1] : 0.0;
   const int r_begin = blockIdx.y * p.sbcols, r_end = min(r_begin + p.sbcols, n);
   for (int r = r_begin; r < r_end; ++r) {
-    double2* hp = reinterpret_cast<double2*>(p.H + (c0 - p.tile0 * kRowsPerCta) + (size_t)ld * r);
+    double2* hp = reinterpret_cast<double2*>(p.H + (c0 - p.row0) + (size_t)ld * r);
     const double psr = p.ps[r], wr = pc1 * psr, nur = -p.pu[r];
     double2 h = *hp;
     h.x = fma(wr, s0, h.x); h.y = fma(wr, s1, h.y);
@@ -1265,7 +1267,7 @@ __global__ void __launch_bounds__(256) stream_identity(const StreamParams p) {
   const size_t total = ld2 * p.n; // double2 elements
   double2* H2 = reinterpret_cast<double2*>(p.H);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = i / ld2, c = 2 * (i % ld2) + (size_t)p.tile0 * kRowsPerCta; // global row of the slab's entry
+    const size_t r = i / ld2, c = 2 * (i % ld2) + (size_t)p.row0; // global row of the slab's entry
     H2[i] = make_double2(c == r ? 1.0 : 0.0, c + 1 == r ? 1.0 : 0.0);
   }
 }
@@ -1281,6 +1283,7 @@ struct StreamWork {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   size_t vec_smem = 0;
+  int pass_threads = 256; // threads of a sweep CTA
   int clu_ppt = 0;      // one-pass mode: pairs per thread of the cluster vector kernel (0: single-CTA kernel)
   size_t clu_smem = 0;
 };
@@ -1303,7 +1306,7 @@ int hint_env(const char* name, int dflt, int hi) {
 bool sweep_deep(const qn_context* ctx, const qn::StreamParams& p) {
   const int v = hint_env("QN_SWEEP_DEPTH", 0, 16);
   if (v) return v == 16;
-  return p.ntiles * p.nsb < 2 * ctx->prop.multiProcessorCount;
+  return p.ntiles * p.nsb <= ctx->prop.multiProcessorCount;
 }
 PassKernel pass1_kernel(bool deep = false) {
   if (deep) return qn::stream_pass1<0, 0, 16>;
@@ -1338,23 +1341,23 @@ int enqueue_iteration(qn_context* ctx, const StreamWork& w, cudaStream_t st) {
   const dim3 grid(p.ntiles, p.nsb);
   const bool deep = sweep_deep(ctx, p);
   if (p.onepass) { // two kernels per iteration; the head of iteration 1 ran before the graph
-    pass_one_kernel(deep)<<<grid, qn::kPassThreads, sizeof(double) * 6 * p.sbcols, st>>>(p);
+    pass_one_kernel(deep)<<<grid, w.pass_threads, sizeof(double) * 6 * p.sbcols, st>>>(p);
     if (w.clu_ppt) cluster_kernel(w.clu_ppt, true)<<<qn::kCluCtas, qn::kCluThreads, w.clu_smem, st>>>(p);
     else qn::stream_vec_onepass<<<1, qn::kVecThreads, w.vec_smem, st>>>(p);
     QN_CUDA_TRY(cudaGetLastError());
     return QN_OK;
   }
   if (p.fused2) { // three kernels per iteration; the head of iteration 1 ran before the graph
-    pass1_kernel(deep)<<<grid, qn::kPassThreads, sizeof(double) * p.sbcols + pass1_pad(), st>>>(p);
-    pass2_kernel(deep)<<<grid, qn::kPassThreads, sizeof(double) * 4 * p.sbcols, st>>>(p);
+    pass1_kernel(deep)<<<grid, w.pass_threads, sizeof(double) * p.sbcols + pass1_pad(), st>>>(p);
+    pass2_kernel(deep)<<<grid, w.pass_threads, sizeof(double) * 4 * p.sbcols, st>>>(p);
     cluster_kernel(w.clu_ppt, false)<<<qn::kCluCtas, qn::kCluThreads, w.clu_smem, st>>>(p);
     QN_CUDA_TRY(cudaGetLastError());
     return QN_OK;
   }
   qn::stream_vec_begin<<<1, qn::kVecThreads, w.vec_smem, st>>>(p);
-  pass1_kernel(deep)<<<grid, qn::kPassThreads, sizeof(double) * p.sbcols, st>>>(p);
+  pass1_kernel(deep)<<<grid, w.pass_threads, sizeof(double) * p.sbcols, st>>>(p);
   qn::stream_vec_mid<<<1, qn::kVecThreads, w.vec_smem, st>>>(p);
-  pass2_kernel(deep)<<<grid, qn::kPassThreads, sizeof(double) * 4 * p.sbcols, st>>>(p);
+  pass2_kernel(deep)<<<grid, w.pass_threads, sizeof(double) * 4 * p.sbcols, st>>>(p);
   qn::stream_vec_end<<<1, qn::kVecThreads, w.vec_smem, st>>>(p);
   qn::stream_identity<false><<<ctx->prop.multiProcessorCount * 8, 256, 0, st>>>(p);
   QN_CUDA_TRY(cudaGetLastError());
@@ -1379,7 +1382,7 @@ void stream_release(StreamWork& w) {
   } while (0)
 
 // Allocate and lay out the work space of one GPU (shard `shard` of `nshard`: row tiles
-// [tile0, tile0 + ntiles) of B⁻¹), initialise it and capture one iteration into a graph.
+// [row0, row0 + rows) of B⁻¹), pick the sweep CTA size and initialise the scalars.
 // The caller fills peer_base[] for nshard > 1 BEFORE calling stream_capture.
 int stream_setup(qn_context* ctx, StreamWork& w, int n, const double* theta0, bool theta_on_host,
                  const qn_backtracking* ls, double tol, int max_iter, int ntrace, double* d_trace,
@@ -1397,17 +1400,26 @@ int stream_setup(qn_context* ctx, StreamWork& w, int n, const double* theta0, bo
   p.ntrace = ntrace;
   p.trace = d_trace;
   p.onepass = onepass;
-  const int row_tiles = (n + kRowsPerCta - 1) / kRowsPerCta;
+  const int row_tiles = (n + kShardRows - 1) / kShardRows;
   p.nshard = nshard;
   p.shard = shard;
-  p.tile0 = (int)((long long)row_tiles * shard / nshard);
-  p.ntiles = (int)((long long)row_tiles * (shard + 1) / nshard) - p.tile0;
-  const int rows_local = std::min(n, (p.tile0 + p.ntiles) * kRowsPerCta) - p.tile0 * kRowsPerCta;
-  p.ld = (rows_local + 15) & ~15;
+  {
+    const int t0 = (int)((long long)row_tiles * shard / nshard), t1 = (int)((long long)row_tiles * (shard + 1) / nshard);
+    p.row0 = t0 * kShardRows;
+    p.rows = std::min(n, t1 * kShardRows) - p.row0;
+  }
+  // sweep CTAs: 2 rows per thread; halve the CTA (down to 64 threads) while the grid would leave
+  // SMs idle — a single SM cannot keep enough loads in flight to use its share of the bandwidth
+  w.pass_threads = kPassThreads;
+  while (w.pass_threads > 64 &&
+         ((p.rows + 2 * w.pass_threads - 1) / (2 * w.pass_threads)) * p.nsb < 2 * ctx->prop.multiProcessorCount)
+    w.pass_threads /= 2;
+  p.ntiles = (p.rows + 2 * w.pass_threads - 1) / (2 * w.pass_threads);
+  p.ld = (p.rows + 15) & ~15;
   QN_TRY_REL(cudaMalloc(&p.H, sizeof(double) * (size_t)p.ld * n));
   const size_t nv = ((size_t)n + 31) & ~(size_t)31;
   p.nvstride = (int)nv;
-  const size_t words = nv * 22 + 2 * (size_t)p.nsb * n + 128 + row_tiles;
+  const size_t words = nv * 22 + 2 * (size_t)p.nsb * n + 128 + 4 * (size_t)row_tiles; // + one counter per 128-row CTA tile
   cudaError_t e = cudaMalloc(&w.block, sizeof(double) * words);
   if (e != cudaSuccess)
     return qn_fail(QN_ERR_CUDA, "cudaMalloc failed for the streaming work space: %s", cudaGetErrorString(e));
@@ -1557,7 +1569,7 @@ int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_bac
   const StreamParams& p = w.p;
   ctx->last_path = 2;
   ctx->last_grid = p.ntiles * p.nsb;
-  ctx->last_block = qn::kPassThreads;
+  ctx->last_block = w.pass_threads;
   ctx->last_smem = (int)(sizeof(double) * 4 * p.sbcols);
   {
     const int its = host.it + (host.done ? 1 : 0);
@@ -1572,7 +1584,7 @@ int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_bac
     if (d_g_out) QN_TRY_REL(cudaMemcpyAsync(d_g_out, g_src, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     if (d_h_out && onepass) { // the stored matrix lags one update behind: apply it
       const dim3 grid(p.ntiles, p.nsb);
-      qn::stream_flush_pending<<<grid, qn::kPassThreads, 0, st>>>(p);
+      qn::stream_flush_pending<<<grid, w.pass_threads, 0, st>>>(p);
     }
     if (d_h_out)
       QN_TRY_REL(cudaMemcpy2DAsync(d_h_out, sizeof(double) * ldh_out, p.H, sizeof(double) * p.ld,
@@ -1610,8 +1622,8 @@ extern "C" int32_t qn_bfgs_optimize_rowsharded_f64(
                    "streaming path; only Rosenbrock has one", model->kind);
   if (h_out && ldh < n) return qn_fail(QN_ERR_INVALID_ARGUMENT, "ldh < n");
   const int onepass = (flags & QN_FLAG_ONE_PASS) ? 1 : 0;
-  const int row_tiles = (n + kRowsPerCta - 1) / kRowsPerCta;
-  const int G = std::min((int)nctx, row_tiles); // a shard owns at least one 512-row tile
+  const int row_tiles = (n + kShardRows - 1) / kShardRows;
+  const int G = std::min((int)nctx, row_tiles); // a shard owns at least one 512-row unit
   for (int g = 0; g < G; ++g) if (!ctxs[g]) return qn_fail(QN_ERR_INVALID_ARGUMENT, "NULL context %d", g);
   // peer access between every pair of distinct devices
   for (int a = 0; a < G; ++a)
@@ -1671,10 +1683,9 @@ extern "C" int32_t qn_bfgs_optimize_rowsharded_f64(
         if (host.need_reset) qn::stream_identity<true><<<ctxs[g]->prop.multiProcessorCount * 8, 256, 0, sts[g]>>>(p);
         if (onepass) {
           const dim3 grid(p.ntiles, p.nsb);
-          qn::stream_flush_pending<<<grid, qn::kPassThreads, 0, sts[g]>>>(p);
+          qn::stream_flush_pending<<<grid, ws[g].pass_threads, 0, sts[g]>>>(p);
         }
-        const int row0 = p.tile0 * kRowsPerCta;
-        const int rows = std::min(n, (p.tile0 + p.ntiles) * kRowsPerCta) - row0;
+        const int row0 = p.row0, rows = p.rows;
         QN_TRY_REL(cudaMemcpy2DAsync(h_out + row0, sizeof(double) * ldh, p.H, sizeof(double) * p.ld,
                                      sizeof(double) * rows, n, cudaMemcpyDeviceToHost, sts[g]));
         QN_TRY_REL(cudaStreamSynchronize(sts[g]));
@@ -1686,7 +1697,7 @@ extern "C" int32_t qn_bfgs_optimize_rowsharded_f64(
   for (int g = 0; g < G; ++g) {
     ctxs[g]->last_path = 2;
     ctxs[g]->last_grid = ws[g].p.ntiles * ws[g].p.nsb;
-    ctxs[g]->last_block = kPassThreads;
+    ctxs[g]->last_block = ws[g].pass_threads;
     const int its = host.it + (host.done ? 1 : 0);
     ctxs[g]->last_launches = onepass ? 1 + 2 * its : ws[g].p.fused2 ? 1 + 3 * its : 6 * its;
   }
