@@ -1364,6 +1364,8 @@ int enqueue_iteration(qn_context* ctx, const StreamWork& w, cudaStream_t st) {
   return QN_OK;
 }
 
+constexpr int kItersPerGraph = 8; // iterations per graph replay; also the cadence of the done-flag poll
+
 void stream_release(StreamWork& w) {
   if (w.exec) cudaGraphExecDestroy(w.exec);
   if (w.graph) cudaGraphDestroy(w.graph);
@@ -1484,8 +1486,11 @@ int stream_capture(qn_context* ctx, StreamWork& w, cudaStream_t st) {
       if (!p.onepass) w.p.fused2 = 1;
     }
   }
+  // one graph = kItersPerGraph iterations: with several GPUs driven by one host thread the graph
+  // launches themselves (≈ 6 µs each) would otherwise bound the iteration rate
   QN_TRY_REL(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  const int rc = enqueue_iteration(ctx, w, st);
+  int rc = QN_OK;
+  for (int k = 0; k < kItersPerGraph && rc == QN_OK; ++k) rc = enqueue_iteration(ctx, w, st);
   const cudaError_t ce = cudaStreamEndCapture(st, &w.graph);
   if (rc != QN_OK) return rc;
   if (ce != cudaSuccess) return qn_fail(QN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
@@ -1509,15 +1514,19 @@ int stream_run(qn_context* const* ctxs, StreamWork* ws, cudaStream_t* sts, int G
   };
   int rc;
   if (fixed_iters > 0) {
+    // benchmark mode: one untimed graph (kItersPerGraph iterations), then enough timed graphs to
+    // reach fixed_iters; the iteration count of the timed region is read back from the device
     QN_TRY_REL(cudaSetDevice(ctxs[0]->device));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    const int warm = fixed_iters > 2 ? 2 : 0;
-    for (int k = 0; k < warm; ++k) if ((rc = launch_all())) return rc;
+    qn::StreamScalars warm_sc{};
+    if ((rc = launch_all())) return rc;
     QN_TRY_REL(cudaSetDevice(ctxs[0]->device));
+    QN_TRY_REL(cudaMemcpyAsync(&warm_sc, ws[0].p.sc, sizeof warm_sc, cudaMemcpyDeviceToHost, sts[0]));
     cudaEventRecord(e0, sts[0]);
-    for (int k = warm; k < fixed_iters; ++k) if ((rc = launch_all())) return rc;
+    const int graphs = std::max(1, (fixed_iters - kItersPerGraph + kItersPerGraph - 1) / kItersPerGraph);
+    for (int k = 0; k < graphs; ++k) if ((rc = launch_all())) return rc;
     QN_TRY_REL(cudaSetDevice(ctxs[0]->device));
     cudaEventRecord(e1, sts[0]);
     QN_TRY_REL(cudaMemcpyAsync(&host, ws[0].p.sc, sizeof host, cudaMemcpyDeviceToHost, sts[0]));
@@ -1527,15 +1536,17 @@ int stream_run(qn_context* const* ctxs, StreamWork* ws, cudaStream_t* sts, int G
     }
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    if (ms_per_iter_out) *ms_per_iter_out = ms / (float)(fixed_iters - warm);
+    const int timed = host.it - warm_sc.it;
+    if (ms_per_iter_out) *ms_per_iter_out = timed > 0 ? ms / (float)timed : 0.0f;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return QN_OK;
   }
-  // enqueue 8 iterations at a time, then poll the done flag
+  // replay kItersPerGraph iterations at a time, then poll the done flag
   int launched = 0;
   for (;;) {
-    for (int k = 0; k < 8 && launched < max_iter; ++k, ++launched) if ((rc = launch_all())) return rc;
+    if ((rc = launch_all())) return rc;
+    launched += kItersPerGraph;
     QN_TRY_REL(cudaSetDevice(ctxs[0]->device));
     QN_TRY_REL(cudaMemcpyAsync(&host, ws[0].p.sc, sizeof host, cudaMemcpyDeviceToHost, sts[0]));
     QN_TRY_REL(cudaStreamSynchronize(sts[0]));
