@@ -30,6 +30,9 @@ N_DIM = 60
 BATCH = 1 << 16
 SEED = 20261018
 METRIC = "converged BFGS solves/sec (n=60 Rosenbrock, 2^16 batch per GPU)"
+# DRAM bytes of ONE launch of the headline kernel at this workload (dram__bytes_read.sum +
+# dram__bytes_write.sum, ncu --set full on this command): profiles/r1_tile60_bench_ncu.txt
+TILE_KERNEL_DRAM_BYTES_PER_LAUNCH = 33576192 + 32338944
 UNIT = "solves/s"
 
 
@@ -309,7 +312,10 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": K * launch["kernel_launches"] * world,
             "roofline": {
                 "bound": "fp64", "achieved": ach_tf, "peak": mb["dfma"], "unit": "TFLOP/s",
-                "frac": ach_tf / mb["dfma"], "traffic": None,
+                "frac": ach_tf / mb["dfma"],
+                "traffic": TILE_KERNEL_DRAM_BYTES_PER_LAUNCH if (batch == BATCH and launch["path"] == 0) else None,
+                "traffic_note": "DRAM bytes per launch from profiles/r1_tile60_bench_ncu.txt; the algorithmic I/O of a launch is "
+                                "31.5 MB of starts in, 64.2 MB of results out — B^-1 never touches HBM",
                 "peak_source": "qn_microbench_dfma, measured live on this GPU (MEASURED_PEAKS.json has no fp64 entry)",
                 "algorithmic": "8 n^2 = %d flops per BFGS iteration x iterations, per GPU" % int(flops_alg),
                 "smem_equiv": {"achieved": ach_gbs, "peak": mb["lds"], "unit": "GB/s", "frac": ach_gbs / mb["lds"],

@@ -37,7 +37,11 @@ struct PackedCfg {
   static_assert(N % RB == 0 && RB % 2 == 0, "whole, even rule-C2 blocks");
   static constexpr int kSub = 32 / SG;           // problems per warp
   static constexpr int kWarps = 4;               // warps per CTA (never synchronised)
-  static constexpr int kPerSub = 5 * N;          // doubles: Pass2Col[N] + ys[N]
+  // doubles per sub-group: Pass2Col[N] + ys[N], padded so that consecutive sub-groups start 4
+  // banks apart: the LDS.128 that broadcasts column r to every sub-group of the warp then touches
+  // each bank once (unpadded, n = 8: 8 sub-groups on 2 bank groups, 4-way conflicts; ncu showed
+  // 44 % of the kernel's shared-memory wavefronts were conflicts)
+  static constexpr int kPerSub = 5 * N + ((2 - (5 * N) % 16) + 16) % 16;
   static constexpr int kSmemDoubles = kWarps * kSub * kPerSub;
 };
 
