@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASS1_MINB) s
 // ---- pass 2: H[c,r] ← ((H + (c₁s[r])s[c]) - u[r]s[c]) - u[c]s[r] ; partials of d = H⁺∇
 // Residency matters for these sweeps, and FEWER resident CTAs are better: each CTA walks its own
 // 4 KB-per-column stream, and 2 CTAs per SM (296 concurrent streams, all 128 registers spent on loads
-// in flight) beat 3 or 4 (measured at n = 8192, gpurun_out/minb.txt: pass2 172 µs at 2 CTAs/SM
+// in flight) beat 3 or 4 (measured at n = 8192, profiles/r1_stream_residency.txt: pass2 172 µs at 2 CTAs/SM
 // against 207 µs at 3-4; the one-pass sweep 201 / 245 / 253 µs per iteration at 2 / 3 / 4).
 template <int LDH, int STH, int DEPTH = 8>
 __global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASS2_MINB) stream_pass2(const StreamParams p) {
