@@ -116,17 +116,19 @@ struct TileCfg {
   static_assert(N > 32 && N <= 64, "tile kernel covers 33..64");
   static_assert(NB <= 4 && NG <= 16, "tile grid must fit four half-warps");
   // ---- shared memory (doubles) ----
-  // per-warp PRIVATE region (only the owning warp touches it: __syncwarp is enough)
-  static constexpr int wWN = 0;                      // {c₁s, -u}[2 blocks][16]  (double2)
-  static constexpr int wSG = wWN + 64;               // {s, ∇}[2 blocks][16]     (double2)
-  static constexpr int wYsp = wSG + 64;              // y[2 blocks][16]
-  static constexpr int wS = wYsp + 32;               // s  by element (row operands), in the
-  static constexpr int wNu = wS + 80;                // -u by element           quad layout below
-  static constexpr int wX = wNu + 80;                // x_old, ∇, ∇_old, y parked here while the
-  static constexpr int wG = wX + 64;                 //   passes need the registers
-  static constexpr int wGp = wG + 64;
-  static constexpr int wY = wGp + 64;
-  static constexpr int wSize = wY + 64;
+  // per-warp PRIVATE region (only the owning warp touches it: __syncwarp is enough).  Few distinct
+  // address patterns on purpose — every extra base register is spilled in the hot loop (168
+  // registers, 120 of them B⁻¹): the column operands are ONE array of 48-byte records addressed by
+  // slot, everything element-indexed uses the quad layout below.
+  static constexpr int kRec = 6;                     // doubles per column record {c₁s, -u, s, ∇, y, pad}
+  static constexpr int wRec = 0;                     // records of this warp's two column blocks [2][16]
+  static constexpr int wS = wRec + 32 * kRec;        // s  by element (row operands), quad layout
+  static constexpr int wNu = wS + 80;                // -u by element
+  static constexpr int wX = wNu + 80;                // x_old, ∇, ∇_old, y parked here (quad layout) while
+  static constexpr int wG = wX + 80;                 //   the passes need the registers
+  static constexpr int wGp = wG + 80;
+  static constexpr int wY = wGp + 80;
+  static constexpr int wSize = wY + 80;
   // shared by the two warps: block partials of pass 1 and pass 2, [4 blocks][80] each.
   // Quad layout of a 64-element vector: element e = 4q+i sits at quad(e) = (i>>1)·40 + 2q + (i&1),
   // so a thread's four rows are two consecutive-by-q 16-byte words (conflict-free LDS/STS.128),
@@ -170,9 +172,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
   const int col0 = CT * b;
 
   double* pw = smem + warp * C::wSize;             // this warp's private region
-  double2* WN = reinterpret_cast<double2*>(pw + C::wWN);
-  double2* SG = reinterpret_cast<double2*>(pw + C::wSG);
-  double* ysp = pw + C::wYsp;
+  double* rec = pw + C::wRec;                      // column records
   double* s_arr = pw + C::wS;
   double* nu_arr = pw + C::wNu;
   double* part1 = smem + C::oPart1;
@@ -185,7 +185,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
     return (el < N && blk >= 0 && blk < 2) ? blk * 16 + el % CT : -1;
   };
   const int slot_lo = slot_of(lane), slot_hi = slot_of(lane + 32);
-  const int q_lo = C::quad(lane), q_hi = C::quad(lane + 32); // quad-layout index of this lane's elements
+  const int q_lo = C::quad(lane), q_hi = q_lo + 16; // quad-layout index of elements lane, lane + 32
 
   double h[RT][CT]; // the tile: h[i][k] = B⁻¹[row0 + i, col0 + k]
 
@@ -195,8 +195,8 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
     if (hi_valid) pacc = pacc + a.hi * bb.hi;
     return pacc;
   };
-  auto park = [&](const int off, const Pair& v) { pw[off + lane] = v.lo; pw[off + 32 + lane] = v.hi; };
-  auto unpark = [&](const int off) { Pair v; v.lo = pw[off + lane]; v.hi = pw[off + 32 + lane]; return v; };
+  auto park = [&](const int off, const Pair& v) { pw[off + q_lo] = v.lo; pw[off + q_hi] = v.hi; };
+  auto unpark = [&](const int off) { Pair v; v.lo = pw[off + q_lo]; v.hi = pw[off + q_hi]; return v; };
   // Σ_b part[b][e'] in ascending block order (rule C2), for e' = lane and lane+32
   auto combine = [&](const double* part) {
     Pair T;
@@ -278,8 +278,14 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
       // ---- BFGS_update!  QN.jl:34-69.  Operands go to this warp's private arrays.
       s_arr[q_lo] = s.lo;
       s_arr[q_hi] = s.hi;
-      if (slot_lo >= 0) { ysp[slot_lo] = y.lo; SG[slot_lo] = make_double2(s.lo, g.lo); }
-      if (slot_hi >= 0) { ysp[slot_hi] = y.hi; SG[slot_hi] = make_double2(s.hi, g.hi); }
+      if (slot_lo >= 0) {
+        *reinterpret_cast<double2*>(rec + slot_lo * C::kRec + 2) = make_double2(s.lo, g.lo);
+        rec[slot_lo * C::kRec + 4] = y.lo;
+      }
+      if (slot_hi >= 0) {
+        *reinterpret_cast<double2*>(rec + slot_hi * C::kRec + 2) = make_double2(s.hi, g.hi);
+        rec[slot_hi * C::kRec + 4] = y.hi;
+      }
       park(C::wX, x);
       park(C::wG, g);
       park(C::wY, y);
@@ -291,13 +297,13 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
         double tt[RT];
 #pragma unroll
         for (int i = 0; i < RT; ++i) tt[i] = 0.0;
-        const double2* yb = reinterpret_cast<const double2*>(ysp + hb * 16);
-        double2 yy[(CT + 1) / 2];
+        const double* rb_ = rec + hb * 16 * C::kRec;
+        double yy[CT];
 #pragma unroll
-        for (int k2 = 0; k2 < (CT + 1) / 2; ++k2) yy[k2] = yb[k2];
+        for (int k = 0; k < CT; ++k) yy[k] = rb_[k * C::kRec + 4];
 #pragma unroll
         for (int k = 0; k < CT; ++k) {
-          const double yk = (k & 1) ? yy[k >> 1].y : yy[k >> 1].x;
+          const double yk = yy[k];
           if (C::kFull || col0 + k < N) {
 #pragma unroll
             for (int i = 0; i < RT; ++i) tt[i] = fma(yk, h[i][k], tt[i]);
@@ -318,8 +324,8 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
         nu_arr[q_lo] = nu_lo;
         nu_arr[q_hi] = nu_hi;
         // (c₁ s[r]) rounded once per r (rule C4)
-        if (slot_lo >= 0) WN[slot_lo] = make_double2(c1 * s_arr[q_lo], nu_lo);
-        if (slot_hi >= 0) WN[slot_hi] = make_double2(c1 * s_arr[q_hi], nu_hi);
+        if (slot_lo >= 0) *reinterpret_cast<double2*>(rec + slot_lo * C::kRec) = make_double2(c1 * s_arr[q_lo], nu_lo);
+        if (slot_hi >= 0) *reinterpret_cast<double2*>(rec + slot_hi * C::kRec) = make_double2(c1 * s_arr[q_hi], nu_hi);
       }
       __syncwarp();
       QN_TICK(4);
@@ -334,15 +340,16 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
         nuc[0] = n01.x; nuc[1] = n01.y; nuc[2] = n23.x; nuc[3] = n23.y;
 #pragma unroll
         for (int i = 0; i < RT; ++i) acc[i] = 0.0;
-        const double2* wnb = WN + hb * 16;
-        const double2* sgb = SG + hb * 16;
+        const double* rb_ = rec + hb * 16 * C::kRec;
+        auto ld_wn = [&](const int k) { return *reinterpret_cast<const double2*>(rb_ + k * C::kRec); };
+        auto ld_sg = [&](const int k) { return *reinterpret_cast<const double2*>(rb_ + k * C::kRec + 2); };
         // operand ring: the loads of step k+PF are issued while step k computes
         double2 wnr[PF + 1], sgr[PF + 1];
 #pragma unroll
-        for (int k = 0; k < PF && k < CT; ++k) { wnr[k] = wnb[k]; sgr[k] = sgb[k]; }
+        for (int k = 0; k < PF && k < CT; ++k) { wnr[k] = ld_wn(k); sgr[k] = ld_sg(k); }
 #pragma unroll
         for (int k = 0; k < CT; ++k) {
-          if (k + PF < CT) { wnr[(k + PF) % (PF + 1)] = wnb[k + PF]; sgr[(k + PF) % (PF + 1)] = sgb[k + PF]; }
+          if (k + PF < CT) { wnr[(k + PF) % (PF + 1)] = ld_wn(k + PF); sgr[(k + PF) % (PF + 1)] = ld_sg(k + PF); }
           const double2 wn = wnr[k % (PF + 1)], sg = sgr[k % (PF + 1)];
           if (C::kFull || col0 + k < N) {
 #pragma unroll
