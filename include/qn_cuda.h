@@ -65,11 +65,15 @@ enum {
 #define QN_FLAG_FORCE_SMEM 0x2u   /* use the shared-memory-resident kernel even where the
                                      register-resident one exists (testing/ablation) */
 #define QN_FLAG_FORCE_STREAM 0x4u /* use the HBM streaming path regardless of n */
-#define QN_FLAG_ONE_PASS 0x8u     /* streaming path only: one-pass deferred-update variant (16 n²
-                                     instead of 24 n² bytes per iteration).  Same mathematics as
-                                     QN.jl:34-69 but NOT the reference's rounding: iterates agree
-                                     with the default mode to ~1e-14 relative over the first
-                                     iterations, optima to a few 1e-8 */
+#define QN_FLAG_ONE_PASS 0x8u     /* permission to use the one-pass deferred-update order (16 n²
+                                     instead of 24 n² bytes of B⁻¹ traffic per iteration).  Same
+                                     mathematics as QN.jl:34-69 but NOT the reference's rounding:
+                                     iterates agree with the default mode to ~1e-14 relative over
+                                     the first iterations, optima to a few 1e-8.
+                                     Honoured by the streaming path and by the shared-memory /
+                                     register-pair resident kernels (48 <= n <= 160 outside the
+                                     register-tile sizes); the other kernels keep the reference
+                                     order, which a caller who sets the flag accepts either way */
 
 /* BackTracking{O}(c₁, ρₕ, ρₗ, iterations): QN.jl:72-80.  order = O ∈ {2,3}. */
 typedef struct {

@@ -59,7 +59,10 @@ unsigned long long* qn_next_counter(qn_context* ctx, cudaStream_t st) {
 namespace {
 
 // ---- kernel launchers ------------------------------------------------------
-template <class Obj, int NREG, int BLOCK, int MINB, int PAIRN = 0>
+// ONEPASS: the deferred-update order (QN_FLAG_ONE_PASS) — shared-memory and register-pair policies
+// with more threads than elements only; a request that cannot be honoured (too small an n, or no
+// room for the second partial-sum array) silently runs the reference order.
+template <class Obj, int NREG, int BLOCK, int MINB, int PAIRN = 0, bool ONEPASS = false>
 int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Params& op,
                     cudaStream_t st) {
   const int n = p.n;
@@ -76,20 +79,22 @@ int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Par
     for (int G = std::min(nblocks, BLOCK / half); G >= 2; --G) {
       const int cand = ((G * half + 31) / 32) * 32;
       if (cand <= B) break;
-      const size_t need = sizeof(double) * (size_t)qn::resident_smem_layout<Obj>(n, true, cand, op).total;
+      const size_t need = sizeof(double) * (size_t)qn::resident_smem_layout<Obj>(n, true, cand, op, ONEPASS).total;
       if (cand <= BLOCK && need <= (size_t)ctx->prop.sharedMemPerBlockOptin) { nthreads = cand; break; }
     }
   }
+  if (ONEPASS && PAIRN == 0 && nthreads <= B) // no pair policy possible: the reference order
+    return launch_resident<Obj, NREG, BLOCK, MINB, PAIRN, false>(ctx, p, op, st);
   if (NREG == 0 && PAIRN == 0 && BLOCK > 512 && nthreads <= 512) // the 512-thread build may use 128 registers
-    return launch_resident<Obj, 0, 512, 1>(ctx, p, op, st);
-  const qn::ResidentSmem L = qn::resident_smem_layout<Obj>(n, NREG == 0 && PAIRN == 0, nthreads, op);
+    return launch_resident<Obj, 0, 512, 1, 0, ONEPASS>(ctx, p, op, st);
+  const qn::ResidentSmem L = qn::resident_smem_layout<Obj>(n, NREG == 0 && PAIRN == 0, nthreads, op, ONEPASS);
   const size_t smem = sizeof(double) * (size_t)L.total;
   if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin)
     return fail(QN_ERR_UNSUPPORTED_SIZE,
                 "n=%d needs %zu bytes of shared memory per problem; the device allows %zu "
                 "(use the streaming path)",
                 n, smem, (size_t)ctx->prop.sharedMemPerBlockOptin);
-  auto kern = qn::qn_resident_kernel<Obj, NREG, BLOCK, MINB, PAIRN>;
+  auto kern = qn::qn_resident_kernel<Obj, NREG, BLOCK, MINB, PAIRN, ONEPASS>;
   QN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int block = nthreads;
   int occ = 0;
@@ -194,10 +199,15 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
     }
   }
   // n = 128 (BASELINE.json configs[2], [3]): B⁻¹ as 2×16 register tiles of 512 threads, any objective
+  const bool onepass = (flags & QN_FLAG_ONE_PASS) != 0; // honoured by these two policies (and the streaming path)
   if constexpr (Obj::kPairRegister) {
-    if (n == 128 && !(flags & QN_FLAG_FORCE_SMEM)) return launch_resident<Obj, 0, 512, 1, 128>(ctx, p, op, st);
+    if (n == 128 && !(flags & QN_FLAG_FORCE_SMEM))
+      return onepass ? launch_resident<Obj, 0, 512, 1, 128, true>(ctx, p, op, st)
+                     : launch_resident<Obj, 0, 512, 1, 128>(ctx, p, op, st);
   }
-  if (n <= 256) return launch_resident<Obj, 0, 1024, 1>(ctx, p, op, st);
+  if (n <= 256)
+    return onepass ? launch_resident<Obj, 0, 1024, 1, 0, true>(ctx, p, op, st)
+                   : launch_resident<Obj, 0, 1024, 1>(ctx, p, op, st);
   return fail(QN_ERR_UNSUPPORTED_SIZE, "n=%d does not fit the resident path", n);
 }
 

@@ -173,6 +173,33 @@ struct Team {
     return T;
   }
 
+  // Three independent canonical sums at once (one barrier, interleaved butterflies).  Its two
+  // alternating staging regions (3 × stride doubles each) lie BEHIND the two of csum/stage, so the
+  // two kinds of reduction never reuse each other's buffer (resident_smem_layout with onepass).
+  int phase3 = 0;
+  __device__ __forceinline__ void csum3(double v0, double v1, double v2, int count, double& r0, double& r1, double& r2) {
+    double* base = red + 2 * stride + phase3 * 3 * stride;
+    if (c < stride) { base[c] = v0; base[stride + c] = v1; base[2 * stride + c] = v2; }
+    __syncthreads();
+    phase3 ^= 1;
+    double p0 = (lane < count) ? base[lane] : 0.0;
+    double p1 = (lane < count) ? base[stride + lane] : 0.0;
+    double p2 = (lane < count) ? base[2 * stride + lane] : 0.0;
+    for (int i = lane + 32; i < count; i += 32) {
+      p0 = p0 + base[i];
+      p1 = p1 + base[stride + i];
+      p2 = p2 + base[2 * stride + i];
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const double t0 = __shfl_xor_sync(0xffffffffu, p0, off);
+      const double t1 = __shfl_xor_sync(0xffffffffu, p1, off);
+      const double t2 = __shfl_xor_sync(0xffffffffu, p2, off);
+      p0 = p0 + t0; p1 = p1 + t1; p2 = p2 + t2;
+    }
+    r0 = p0; r1 = p1; r2 = p2;
+  }
+
   // Thread c contributes v when c < count.  Result is identical in every thread.
   // Two staging buffers alternate, so the barrier inside the NEXT csum is what
   // protects this one's buffer from being overwritten while a slow warp reads.

@@ -37,12 +37,12 @@ __host__ __device__ inline int resident_block_threads(int n) { return (n + 31) &
 // 16-byte access; with nthreads > B the rule-C2 blocks of the rows are dealt out to thread
 // groups whose block partials meet in `part` ([blocks][B]).
 struct ResidentSmem {
-  int red, xs, ys, cols, scratch, part, h, total;
+  int red, xs, ys, cols, scratch, part, part2, rowp, h, total;
 };
 __host__ __device__ inline int resident_ldh(int n) { return (n + 1) & ~1; }
 template <class Obj>
 __host__ __device__ inline ResidentSmem resident_smem_layout(int n, bool h_in_smem, int nthreads,
-                                                             const typename Obj::Params& op) {
+                                                             const typename Obj::Params& op, bool onepass = false) {
   const int B = resident_block_threads(n);
   const int nblocks = (n + chain_block(n) - 1) / chain_block(n);
   ResidentSmem L;
@@ -50,9 +50,11 @@ __host__ __device__ inline ResidentSmem resident_smem_layout(int n, bool h_in_sm
   L.cols = o; o += 4 * B;   // Pass2Col[B], 16-byte aligned at offset 0
   L.ys = o;   o += B;
   L.xs = o;   o += B;
-  L.red = o;  o += 2 * B;
+  L.red = o;  o += onepass ? 8 * B : 2 * B; // two alternating staging buffers (+ two of three values each for csum3)
   L.scratch = o; o += Obj::scratch_doubles(n, op);
   L.part = o; o += (nthreads > B) ? nblocks * B : 0;
+  L.part2 = o; o += onepass ? nblocks * B : 0; // one-pass mode: partials of the second GEMV (w = B⁻¹∇)
+  L.rowp = o;  o += onepass ? 2 * B : 0;       //   and the pending s / -u by element (row operands)
   L.h = o;    o += h_in_smem ? resident_ldh(n) * n : 0;
   L.total = o + 2; // + problem index broadcast slot
   return L;
@@ -130,11 +132,16 @@ __device__ __forceinline__ void write_problem_scalars(const BatchParams& p, long
 // PAIRN > 0 (with NREG == 0): the "pair" policy with n = PAIRN at compile time and every
 // thread's 2 × rb tile of B⁻¹ (two rows, one rule-C2 block) in REGISTERS; needs
 // blockDim = (B/2) · #blocks so that a thread owns exactly one block.
-template <class Obj, int NREG, int PAIRN = 0>
+// ONEPASS (shared-memory and register-pair policies only): the deferred-update order of
+// oracle/qn_oracle.c qo_bfgs_update_onepass — ONE sweep applies the previous
+// iteration's rank-2 update and accumulates both GEMVs, t = B⁻¹y and w = B⁻¹∇; 16 n² instead of
+// 24 n² bytes of B⁻¹ traffic per iteration.  Not the reference's rounding (QN_FLAG_ONE_PASS).
+template <class Obj, int NREG, int PAIRN = 0, bool ONEPASS = false>
 __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
                                                    const typename Obj::Params& op,
                                                    const long long j, Team& tm, double* ys,
-                                                   Pass2Col* cols, double* hs, double* part) {
+                                                   Pass2Col* cols, double* hs, double* part,
+                                                   double* part2 = nullptr, double* rowp = nullptr) {
   const int n = (NREG > 0) ? NREG : (PAIRN > 0 ? PAIRN : p.n);
   const int c = tm.c;          // thread index: the owner of element c when c < n
   const bool active = c < n;
@@ -161,6 +168,69 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
 
   double x = active ? p.theta0[j * p.theta_stride + c] : 0.0; // copyto!(x_old, x), QN.jl:248
   double g = 0.0, g_prev = 0.0, s = 0.0;
+  double ps = 0.0, pu = 0.0, pc1 = 0.0; // one-pass mode: the pending update (s, u of this element; c₁)
+  bool pending = false;
+  (void)ps; (void)pu; (void)pc1; (void)pending; (void)part2; (void)rowp;
+  // one sweep over this thread's part of B⁻¹ (pair policies): applies the pending update when
+  // APPLY, accumulates t and w when GEMV, block partials to part / part2
+  auto onepass_sweep = [&](const bool apply, const bool gemv) {
+    if (!(bgrp < G && row0 < n)) return;
+    const double2 sAB = *reinterpret_cast<const double2*>(rowp + row0);
+    const double2 nAB = *reinterpret_cast<const double2*>(rowp + B + row0);
+    if (PAIRN > 0) {
+      double t0 = 0.0, t1 = 0.0, w0 = 0.0, w1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < PRB; ++k) {
+        if (k < pcols) {
+          const double2 wn = *reinterpret_cast<const double2*>(&cols[pcol0 + k].w);
+          const double2 sg = *reinterpret_cast<const double2*>(&cols[pcol0 + k].s);
+          double ha = hp[0][k], hb = hp[1][k];
+          if (apply) {
+            ha = fma(wn.x, sAB.x, ha);  hb = fma(wn.x, sAB.y, hb);
+            ha = fma(wn.y, sAB.x, ha);  hb = fma(wn.y, sAB.y, hb);
+            ha = fma(nAB.x, sg.x, ha);  hb = fma(nAB.y, sg.x, hb);
+            hp[0][k] = ha; hp[1][k] = hb;
+          }
+          if (gemv) {
+            const double yr = ys[pcol0 + k];
+            t0 = fma(yr, ha, t0);   t1 = fma(yr, hb, t1);
+            w0 = fma(ha, sg.y, w0); w1 = fma(hb, sg.y, w1);
+          }
+        }
+      }
+      if (gemv) {
+        *reinterpret_cast<double2*>(part + bgrp * B + row0) = make_double2(t0, t1);
+        *reinterpret_cast<double2*>(part2 + bgrp * B + row0) = make_double2(w0, w1);
+      }
+    } else {
+      double* hrow = hs + row0;
+      for (int r0 = bgrp * rb, blk = bgrp; r0 < n; r0 += G * rb, blk += G) {
+        const int r1 = min(r0 + rb, n);
+        double t0 = 0.0, t1 = 0.0, w0 = 0.0, w1 = 0.0;
+#pragma unroll 4
+        for (int r = r0; r < r1; ++r) {
+          const double2 wn = *reinterpret_cast<const double2*>(&cols[r].w);
+          const double2 sg = *reinterpret_cast<const double2*>(&cols[r].s);
+          double2 hh = *reinterpret_cast<const double2*>(hrow + ldh * r);
+          if (apply) {
+            hh.x = fma(wn.x, sAB.x, hh.x);  hh.y = fma(wn.x, sAB.y, hh.y);
+            hh.x = fma(wn.y, sAB.x, hh.x);  hh.y = fma(wn.y, sAB.y, hh.y);
+            hh.x = fma(nAB.x, sg.x, hh.x);  hh.y = fma(nAB.y, sg.x, hh.y);
+            *reinterpret_cast<double2*>(hrow + ldh * r) = hh;
+          }
+          if (gemv) {
+            const double yr = ys[r];
+            t0 = fma(yr, hh.x, t0);   t1 = fma(yr, hh.y, t1);
+            w0 = fma(hh.x, sg.y, w0); w1 = fma(hh.y, sg.y, w1);
+          }
+        }
+        if (gemv) {
+          *reinterpret_cast<double2*>(part + blk * B + row0) = make_double2(t0, t1);
+          *reinterpret_cast<double2*>(part2 + blk * B + row0) = make_double2(w0, w1);
+        }
+      }
+    }
+  };
   double result = __longlong_as_double(0x7ff8000000000000LL); // NaN, QN.jl:291
   int iters = 0, fevals = 0, status = QN_MAX_ITER;
 
@@ -189,6 +259,38 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
     if (it == 1) {
       tm.phase ^= 1; // staged value unused
       m = -1.0;      // QN.jl:263-264
+    } else if (ONEPASS) {
+      // ---- deferred-update BFGS step (qo_bfgs_update_onepass): same mathematics as QN.jl:34-69
+      const double sy = tm.finish(n);  // sᵀy, QN.jl:39
+      const double rho = 1.0 / sy;     // QN.jl:42 (no guard)
+      if (c < B) { // column operands of the PENDING update and of the two GEMVs; y is already in ys
+        cols[c].w = pc1 * ps;   // (c₁ s[r]) of the pending update, rounded once per r (rule C4)
+        cols[c].nu = -pu;
+        cols[c].s = ps;
+        cols[c].g = g;
+        rowp[c] = ps;
+        rowp[B + c] = -pu;
+      }
+      __syncthreads();
+      onepass_sweep(pending, true);
+      __syncthreads();
+      double T = 0.0, W = 0.0;
+      if (active) { // block partials in ascending order (rule C2)
+        T = part[c];
+        W = part2[c];
+        for (int r0 = rb, blk = 1; r0 < n; r0 += rb, ++blk) { T = T + part[blk * B + c]; W = W + part2[blk * B + c]; }
+      }
+      const double u = T * rho;                       // B⁻¹y[c] = t ρ, QN.jl:50
+      double yHy, sg, ug;                             // yᵀB⁻¹y (QN.jl:51), sᵀ∇, uᵀ∇ on one barrier
+      tm.csum3(T * y, s * g, u * g, n, yHy, sg, ug);
+      const double c1 = fma(yHy, rho, 1.0) * rho;     // QN.jl:54
+      // d = H⁺∇ = ((w + (c₁ s)(sᵀ∇)) - u (sᵀ∇)) - s (uᵀ∇); this update becomes the pending one
+      double d = fma(c1 * s, sg, W);
+      d = fma(-u, sg, d);
+      d = fma(-s, ug, d);
+      ps = s; pu = u; pc1 = c1; pending = true;
+      m = tm.csum(d * g, n); // m = dᵀ∇_new, QN.jl:66-68
+      s = d;                 // the new direction; `s, y = y, s`, QN.jl:65,268
     } else {
       // ---- BFGS_update!  QN.jl:34-69
       const double sy = tm.finish(n);  // sᵀy, QN.jl:39
@@ -380,6 +482,7 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
       }
       s = g;
       m = tm.csum(g * g, n);
+      pending = false; // one-pass mode: the reset discards the pending update too
     }
 
     const double alpha = team_linesearch<Obj>(tm, op, p.ls, x, s, l0, m, fevals); // QN.jl:283
@@ -398,6 +501,16 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
   // The reference swaps its two gradient buffers every iteration (QN.jl:286) and only
   // copies into the canonical slot on convergence (QN.jl:258-259): after a failure in an
   // even iteration `gradient(state)` still shows the previous iteration's ∇ (selected above).
+  if (ONEPASS && p.h_out && pending) { // the stored matrix lags one update behind: apply it (qo_flush_pending)
+    __syncthreads();
+    if (c < B) {
+      cols[c].w = pc1 * ps; cols[c].nu = -pu; cols[c].s = ps; cols[c].g = 0.0;
+      rowp[c] = ps; rowp[B + c] = -pu;
+    }
+    __syncthreads();
+    onepass_sweep(true, false);
+    __syncthreads();
+  }
   if (PAIRN > 0 && p.h_out && row0 < n) {
     double* ho = p.h_out + j * p.h_stride;
 #pragma unroll
@@ -424,14 +537,14 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
   write_problem_scalars(p, j, c, result, iters, fevals, status);
 }
 
-template <class Obj, int NREG, int BLOCK, int MINB, int PAIRN = 0>
+template <class Obj, int NREG, int BLOCK, int MINB, int PAIRN = 0, bool ONEPASS = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
 qn_resident_kernel(const BatchParams p, const typename Obj::Params op) {
   // launch: blockDim >= resident_block_threads(n); see launch_resident for the policy
   extern __shared__ __align__(16) double smem[];
   const int n = (NREG > 0) ? NREG : (PAIRN > 0 ? PAIRN : p.n);
   const int B = resident_block_threads(n);
-  const ResidentSmem L = resident_smem_layout<Obj>(n, NREG == 0 && PAIRN == 0, (int)blockDim.x, op);
+  const ResidentSmem L = resident_smem_layout<Obj>(n, NREG == 0 && PAIRN == 0, (int)blockDim.x, op, ONEPASS);
 
   Team tm;
   tm.n = n;
@@ -462,7 +575,8 @@ qn_resident_kernel(const BatchParams p, const typename Obj::Params op) {
     __syncthreads();
     const long long j = *next;
     if (j >= p.batch) break;
-    resident_solve_one<Obj, NREG, PAIRN>(p, op, j, tm, ys, cols, hs, smem + L.part);
+    resident_solve_one<Obj, NREG, PAIRN, ONEPASS>(p, op, j, tm, ys, cols, hs, smem + L.part, smem + L.part2,
+                                                  smem + L.rowp);
   }
 }
 

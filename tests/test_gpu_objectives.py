@@ -104,3 +104,50 @@ def test_single_process_multi_gpu_entry(qn, ob):
         assert np.array_equal(it, ref["iters"]) and np.array_equal(st, ref["status"])
         for e in engines:
             e.close()
+
+
+@pytest.mark.parametrize("n,flags_extra", [(60, "smem"), (61, "smem"), (100, ""), (128, ""), (128, "smem"), (144, "")])
+def test_resident_one_pass_mode(eng, qn, ob, n, flags_extra):
+    """QN_FLAG_ONE_PASS on the resident shared-memory / register-pair kernels:
+    bit for bit equal to the oracle's deferred-update variant (rblock = ONEPASS), within the
+    north-star tolerances of the reference order, and the final B⁻¹ includes the last update."""
+    flags = qn._lib.FLAG_ONE_PASS | (qn._lib.FLAG_FORCE_SMEM if flags_extra == "smem" else 0)
+    batch = 6
+    Theta = starts(n, batch, key=31 * n)
+    sb = qn.BFGSStateBatch(n, batch)
+    got = eng.optimize_batched(qn.Rosenbrock(), Theta, ntrace=5, flags=flags | qn._lib.FLAG_WRITE_H, states=sb)
+    own = ob.optimize_batch(ob.rosenbrock(), Theta, ntrace=5, rblock=ob.ONEPASS)
+    for k in ("x", "g", "ell", "trace"):
+        assert np.array_equal(got[k], own[k], equal_nan=True), k
+    assert np.array_equal(got["iters"], own["iters"]) and np.array_equal(got["fevals"], own["fevals"])
+    assert (got["status"] == qn.CONVERGED).all()
+    ref = ob.optimize_batch(ob.rosenbrock(), Theta, ntrace=5)
+    scale = np.abs(ref["trace"]).max(axis=2, keepdims=True)
+    assert (np.abs(got["trace"] - ref["trace"]) / scale).max() <= 1e-12
+    assert np.abs(got["g"]).max() < 1e-8 and np.abs(got["x"] - ref["x"]).max() <= 5e-8
+    L = sb.L
+    for j in range(2):
+        o = ob.optimize(ob.rosenbrock(), Theta[:, j], L=L, rblock=ob.ONEPASS)
+        assert np.array_equal(sb.data[j, 7 * L:].reshape(n, L)[:, :n], o["state"][7 * L:].reshape(n, L)[:, :n])
+
+
+def test_one_pass_flag_is_a_permission(eng, qn, ob):
+    """Where the deferred-update order has no kernel (register-tile sizes) or no room (n = 159: no
+    shared memory left for the second partial-sum array) the flag leaves the reference order in place."""
+    for n in (60, 159):
+        Theta = starts(n, 4, key=n)
+        got = eng.optimize_batched(qn.Rosenbrock(), Theta, ntrace=5, flags=qn._lib.FLAG_ONE_PASS)
+        ref = ob.optimize_batch(ob.rosenbrock(), Theta, ntrace=5)
+        for k in ("x", "g", "ell", "trace"):
+            assert np.array_equal(got[k], ref[k], equal_nan=True), k
+
+
+def test_resident_one_pass_gaussian(eng, qn, ob):
+    n = 128
+    mu, lam = gaussian_problem(n)
+    Theta = starts(n, 12, key=777)
+    got = eng.optimize_batched(qn.DenseGaussian(mu, lam), Theta, ntrace=5, flags=qn._lib.FLAG_ONE_PASS)
+    own = ob.optimize_batch(ob.OracleModel(ob.DENSE_GAUSSIAN, mu=mu, lam=lam), Theta, ntrace=5, rblock=ob.ONEPASS)
+    for k in ("x", "g", "ell", "trace"):
+        assert np.array_equal(got[k], own[k], equal_nan=True), k
+    assert np.array_equal(got["iters"], own["iters"]) and (got["status"] == qn.CONVERGED).all()
