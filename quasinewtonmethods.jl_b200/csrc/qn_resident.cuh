@@ -133,7 +133,7 @@ __device__ __forceinline__ void write_problem_scalars(const BatchParams& p, long
 // thread's 2 × rb tile of B⁻¹ (two rows, one rule-C2 block) in REGISTERS; needs
 // blockDim = (B/2) · #blocks so that a thread owns exactly one block.
 // ONEPASS (shared-memory and register-pair policies only): the deferred-update order of
-// oracle/qn_oracle.c qo_bfgs_update_onepass — ONE sweep applies the previous
+// streaming path — ONE sweep applies the previous
 // iteration's rank-2 update and accumulates both GEMVs, t = B⁻¹y and w = B⁻¹∇; 16 n² instead of
 // 24 n² bytes of B⁻¹ traffic per iteration.  Not the reference's rounding (QN_FLAG_ONE_PASS).
 template <class Obj, int NREG, int PAIRN = 0, bool ONEPASS = false>
