@@ -97,6 +97,21 @@ function model_handle(ctx::Context, m::LogisticRegression)
                 ctx.ptr, size(m.X, 1), size(m.X, 2), m.X, m.y, m.λ, r))
     r[]
 end
+"""
+The build's plug-in objective (include/qn_objective.cuh, kind QN_OBJ_USER = 100): `params` is the
+opaque blob the objective's `make` interprets; needs a library built with QN_USER_OBJECTIVE
+(point LIBQN_CUDA at it).  The stock library answers QN_ERR_UNREGISTERED_OBJECTIVE.
+"""
+struct UserObjective <: DeviceObjective
+    params::Vector{Float64}
+    n::Int
+end
+function model_handle(ctx::Context, m::UserObjective)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:qn_model_user, libqn), Int32, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}),
+                ctx.ptr, m.n, m.params, sizeof(m.params), r))
+    r[]
+end
 # Any other objective type: an error, like the reference's MethodError at QuasiNewtonMethods.jl:254.
 model_handle(::Context, obj) =
     throw(QNError(QN_ERR_UNREGISTERED_OBJECTIVE,
@@ -153,6 +168,37 @@ function optimize!(states::AbstractVector{<:BFGSState{P,Float64,L}}, obj, Θ::Ab
         end
     end
     (ℓ = ell, iterations = iters, evaluations = fevals, status = status)
+end
+
+# ---- one LARGE problem on several GPUs (row-sharded B⁻¹, include/qn_cuda.h) --------------------
+# optimize!(state, obj, x) for n in the thousands: context g holds the rows of its 512-row tiles of
+# B⁻¹; same result as one GPU, bit for bit.  `one_pass = true` permits the deferred-update order
+# (QN_FLAG_ONE_PASS).  Returns ℓ (or NaN) like optimize!; θ* and ∇ land in the state block.
+const QN_FLAG_ONE_PASS = UInt32(0x8)
+function optimize_rowsharded!(state::AbstractBFGSState{P,Float64,L}, obj, x::AbstractVector{Float64},
+                              ctxs::Vector{Context}, ls::BackTracking=BackTracking(), tol=1e-8;
+                              one_pass::Bool=false) where {P,L}
+    length(x) == P || throw(DimensionMismatch("x has length $(length(x)), state is BFGSState{$P}"))
+    h = model_handle(ctxs[1], obj)
+    cls = Ref(CBackTracking(ls))
+    ptrs = Ptr{Cvoid}[c.ptr for c in ctxs]
+    xo = Vector{Float64}(undef, P); go = Vector{Float64}(undef, P)
+    ell = Ref{Float64}(NaN); iters = Ref{Int32}(0); fevals = Ref{Int32}(0); status = Ref{Int32}(0)
+    ms = Ref{Float64}(0.0)
+    GC.@preserve state obj x ptrs xo go begin
+        check(ccall((:qn_bfgs_optimize_rowsharded_f64, libqn), Int32,
+                    (Ptr{Ptr{Cvoid}}, Int32, Ptr{Cvoid}, Int32, Ptr{Float64}, Ref{CBackTracking}, Float64, Int32,
+                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Ref{Float64}, Ref{Int32}, Ref{Int32}, Ref{Int32},
+                     Int32, Ptr{Float64}, UInt32, Int32, Ref{Float64}),
+                    ptrs, length(ptrs), h, P, pointer(x), cls, tol, 10_000,
+                    xo, go, C_NULL, 0, ell, iters, fevals, status, 0, C_NULL,
+                    one_pass ? QN_FLAG_ONE_PASS : UInt32(0), 0, ms))
+        p = pointer(state)
+        unsafe_copyto!(p, pointer(xo), P)                          # ref_x_old, offset 0
+        unsafe_copyto!(p + L * sizeof(Float64), pointer(go), P)    # ref_∇_new, offset L
+    end
+    free_model(h)
+    ell[]
 end
 
 end # module
