@@ -184,10 +184,7 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
 #define QN_TILE_CASE(N, MINB) \
   case N:                      \
     if constexpr (std::is_same<Obj, qn::Rosenbrock>::value) {                                        \
-      const char* v = getenv("QN_TILE_VARIANT"); /* tuning knob, see DESIGN.md §5 */                 \
-      if (v && v[0] == '7') return launch_tile<N, 7, 1>(ctx, p, st);                                 \
-      if (v && v[0] == '5') return launch_tile<N, 5, 2>(ctx, p, st);                                 \
-      if (v && v[0] == '4') return launch_tile<N, 4, 3>(ctx, p, st);                                 \
+      /* 6 CTAs per SM (168 registers); 4, 5 and 7 were measured slower */            \
       return launch_tile<N, MINB, 1>(ctx, p, st);                                                    \
     }                                                                                                \
     break;

@@ -98,6 +98,17 @@ def test_packed_small_n(eng, qn, ob, n, variant, order, monkeypatch):
         _check(got2, ref)
 
 
+@pytest.mark.parametrize("n", [36, 40, 44, 48, 50, 52, 56, 60, 64])
+def test_tile_kernel_sizes(eng, qn, ob, n):
+    """Every size with a 4×CT register-tile instantiation (qn_reg_sizes.inc), both line-search orders."""
+    Theta = starts(n, 20, key=7000 + n)
+    for order in (2, 3):
+        got = eng.optimize_batched(qn.Rosenbrock(), Theta, ls=qn.BackTracking[order](), ntrace=5)
+        assert eng.last_launch()["path"] == qn._lib.PATH_REGISTER and eng.last_launch()["block"] == 64
+        ref = ob.optimize_batch(ob.rosenbrock(), Theta, ls=ob.backtracking(order), ntrace=5)
+        _check(got, ref)
+
+
 def test_n128_both_resident_policies(eng, qn, ob):
     """n = 128 runs with B⁻¹ as 2x16 register tiles of 512 threads by default and in shared memory
     (row pairs, column blocks dealt out to thread groups) under QN_FLAG_FORCE_SMEM: same bits."""
