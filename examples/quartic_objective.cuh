@@ -19,6 +19,7 @@ struct UserObjective {
   static constexpr int kKind = QN_OBJ_USER;
   static constexpr bool kRegisterPaths = false;
   static constexpr bool kPairRegister = false;
+  static constexpr bool kMemoizeTrials = false; // true: skip a line-search evaluation whose point repeats the previous one
   __host__ __device__ static int scratch_doubles(int, const Params&) { return 0; }
   __device__ static void prologue(Team&, const Params&) {}
 

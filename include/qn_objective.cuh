@@ -21,6 +21,8 @@
 //     static constexpr int kKind = QN_OBJ_USER;
 //     static constexpr bool kRegisterPaths = false; // true: also instantiate the thread-per-row kernels (n = 8, 16, 32)
 //     static constexpr bool kPairRegister = false;  // true: n = 128 keeps B⁻¹ in register tiles
+//     static constexpr bool kMemoizeTrials = false; // true (expensive objectives): a line-search trial whose point is bit for
+//                                                   // bit the previous trial's re-uses its value instead of evaluating again
 //     // doubles of shared scratch (Team::scratch) the objective needs for dimension n
 //     __host__ __device__ static int scratch_doubles(int n, const Params&);
 //     // once per CTA before its first problem (e.g. stage parameters in shared memory)

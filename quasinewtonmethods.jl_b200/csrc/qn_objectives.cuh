@@ -25,6 +25,7 @@ struct Rosenbrock {
   static constexpr int kKind = QN_OBJ_ROSENBROCK;
   static constexpr bool kRegisterPaths = true; // instantiate the register-resident kernels
   static constexpr bool kPairRegister = true;  // n = 128: B⁻¹ in 2×16 register tiles
+  static constexpr bool kMemoizeTrials = false; // an evaluation is O(n): cheaper than the vote
   __host__ __device__ static int scratch_doubles(int, const Params&) { return 0; }
   __device__ static void prologue(Team&, const Params&) {}
 
@@ -69,6 +70,7 @@ struct DenseGaussian {
   static constexpr int kKind = QN_OBJ_DENSE_GAUSSIAN;
   static constexpr bool kRegisterPaths = false; // no thread-per-row / 4×15-tile instantiations
   static constexpr bool kPairRegister = true;   // n = 128: B⁻¹ in 2×16 register tiles
+  static constexpr bool kMemoizeTrials = true;  // an evaluation is an n×n GEMV
   // θ-μ (B doubles), then Λ itself when B⁻¹ lives in registers and the 227 KB of shared memory
   // are free: every CTA solves many problems against the same Λ, so it is fetched from L2 once
   // per CTA instead of once per objective evaluation (128 KB at n = 128).
@@ -132,6 +134,7 @@ struct Logistic {
   // the two GEMVs with X want the registers for loads in flight (measured: 132 ms with B⁻¹ in
   // shared memory against 170 ms with the register tiles, 1024 problems at n = 128)
   static constexpr bool kPairRegister = false;
+  static constexpr bool kMemoizeTrials = true;  // an evaluation is an m×n GEMV against X in L2
   // yᵢzᵢ - softplus(zᵢ) and yᵢ - σ(zᵢ) (m each), then the super-block partials of Xᵀr ([nsb][B])
   __host__ __device__ static int nsb(int m) {
     const int rb = chain_block(m);

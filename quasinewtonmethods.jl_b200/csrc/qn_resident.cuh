@@ -70,21 +70,36 @@ __device__ __forceinline__ double team_linesearch(Team& tm, const typename Obj::
                                                   const double m, int& fevals) {
   double lx0 = l0, lx1 = l0;
   double a1 = 1.0, a2 = 1.0;
-  double dummy;
-  // step!: x_new = x_old + α s (one fma, rule C3), then logdensity. QN.jl:157-162
-  if (tm.c < tm.nvec) tm.xs[tm.c] = fma(a1, s, x);
-  __syncthreads();
-  lx1 = Obj::template eval<false>(tm, op, dummy);
-  ++fevals;
+  // step! (QN.jl:157-162): x_new = x_old + α s (one fma, rule C3), then logdensity.
+  // Objectives with kMemoizeTrials (an evaluation is a GEMV against parameters in L2): when the
+  // trial point is BIT FOR BIT the previous trial point, the previous value is the value and the
+  // evaluation is skipped.  That is the fate of a search that is going to fail: after a step too
+  // small to move x, y = 0 makes ρ = 1/sᵀy infinite (QN.jl:42 has no guard), the direction is NaN,
+  // and all 1052 trials (QN.jl:178-193) evaluate the same all-NaN point.  Same results, same
+  // evaluation count reported.
+  long long xt_prev = 0x7ff8dead00000001LL; // no trial point has these bits
+  double l_prev = 0.0;
+  auto trial = [&](const double a) {
+    ++fevals;
+    const double xt = fma(a, s, x);
+    if (Obj::kMemoizeTrials) {
+      const long long bits = __double_as_longlong(xt);
+      if (__syncthreads_and(tm.c >= tm.nvec || bits == xt_prev)) return l_prev;
+      xt_prev = bits;
+    }
+    double dummy;
+    if (tm.c < tm.nvec) tm.xs[tm.c] = xt;
+    __syncthreads();
+    l_prev = Obj::template eval<false>(tm, op, dummy);
+    return l_prev;
+  };
+  lx1 = trial(a1);
   int iterfinite = 0;
   while (!isfinite(lx1) && iterfinite < 52) { // QN.jl:178-184
     ++iterfinite;
     a1 = a2;
     a2 = 0.5 * a2;
-    if (tm.c < tm.nvec) tm.xs[tm.c] = fma(a2, s, x);
-    __syncthreads();
-    lx1 = Obj::template eval<false>(tm, op, dummy);
-    ++fevals;
+    lx1 = trial(a2);
   }
   long long iteration = 0;
   while (!(lx1 >= fma(a2 * ls.c1, m, l0))) { // QN.jl:187
@@ -110,10 +125,7 @@ __device__ __forceinline__ double team_linesearch(Team& tm, const typename Obj::
     at = nanmin(at, a2 * ls.rho_hi);   // QN.jl:224
     a2 = nanmax(at, a2 * ls.rho_lo);   // QN.jl:225
     lx0 = lx1;                         // QN.jl:228
-    if (tm.c < tm.nvec) tm.xs[tm.c] = fma(a2, s, x);
-    __syncthreads();
-    lx1 = Obj::template eval<false>(tm, op, dummy);
-    ++fevals;
+    lx1 = trial(a2);
   }
   return a2;
 }
