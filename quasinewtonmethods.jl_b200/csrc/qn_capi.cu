@@ -62,7 +62,7 @@ namespace {
 // ONEPASS: the deferred-update order (QN_FLAG_ONE_PASS) — shared-memory and register-pair policies
 // with more threads than elements only; a request that cannot be honoured (too small an n, or no
 // room for the second partial-sum array) silently runs the reference order.
-template <class Obj, int NREG, int BLOCK, int MINB, int PAIRN = 0, bool ONEPASS = false>
+template <class Obj, int NREG, int BLOCK, int MINB, int PAIRN = 0, bool ONEPASS = false, int PROWS = 2>
 int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Params& op,
                     cudaStream_t st) {
   const int n = p.n;
@@ -71,8 +71,8 @@ int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Par
   // the CTA's thread limit and the partial-sum array beside B⁻¹ allow
   const int B = qn::resident_block_threads(n);
   int nthreads = (NREG > 0) ? BLOCK : B;
-  if (PAIRN > 0) { // pair-register policy: one rule-C2 block per thread
-    nthreads = (B / 2) * ((n + qn::chain_block(n) - 1) / qn::chain_block(n));
+  if (PAIRN > 0) { // register-tile policy: PROWS rows × one rule-C2 block per thread
+    nthreads = (B / PROWS) * ((n + qn::chain_block(n) - 1) / qn::chain_block(n));
   } else if (NREG == 0 && n >= 48) {
     const int half = B / 2;
     const int nblocks = (n + qn::chain_block(n) - 1) / qn::chain_block(n);
@@ -94,7 +94,7 @@ int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Par
                 "n=%d needs %zu bytes of shared memory per problem; the device allows %zu "
                 "(use the streaming path)",
                 n, smem, (size_t)ctx->prop.sharedMemPerBlockOptin);
-  auto kern = qn::qn_resident_kernel<Obj, NREG, BLOCK, MINB, PAIRN, ONEPASS>;
+  auto kern = qn::qn_resident_kernel<Obj, NREG, BLOCK, MINB, PAIRN, ONEPASS, PROWS>;
   QN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int block = nthreads;
   int occ = 0;
@@ -195,12 +195,19 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
       }
     }
   }
-  // n = 128 (BASELINE.json configs[2], [3]): B⁻¹ as 2×16 register tiles of 512 threads, any objective
+  // n = 128 (BASELINE.json configs[2], [3]): B⁻¹ as 4×16 register tiles of 256 threads
   const bool onepass = (flags & QN_FLAG_ONE_PASS) != 0; // honoured by these two policies (and the streaming path)
   if constexpr (Obj::kPairRegister) {
-    if (n == 128 && !(flags & QN_FLAG_FORCE_SMEM))
-      return onepass ? launch_resident<Obj, 0, 512, 1, 128, true>(ctx, p, op, st)
-                     : launch_resident<Obj, 0, 512, 1, 128>(ctx, p, op, st);
+    if (n == 128 && !(flags & QN_FLAG_FORCE_SMEM)) {
+      // rows of B⁻¹ per thread: 4 (256 threads × 128 registers of B⁻¹; measured 5.4e7 iterations/s on
+      // Rosenbrock) or, with QN_PAIR_ROWS=2, 2 (512 threads × 64 registers; 4.9e7)
+      const char* v = getenv("QN_PAIR_ROWS");
+      if (v && v[0] == '2')
+        return onepass ? launch_resident<Obj, 0, 512, 1, 128, true>(ctx, p, op, st)
+                       : launch_resident<Obj, 0, 512, 1, 128>(ctx, p, op, st);
+      return onepass ? launch_resident<Obj, 0, 256, 1, 128, true, 4>(ctx, p, op, st)
+                     : launch_resident<Obj, 0, 256, 1, 128, false, 4>(ctx, p, op, st);
+    }
   }
   if (n <= 256)
     return onepass ? launch_resident<Obj, 0, 1024, 1, 0, true>(ctx, p, op, st)

@@ -148,7 +148,7 @@ __device__ __forceinline__ void write_problem_scalars(const BatchParams& p, long
 // streaming path — ONE sweep applies the previous
 // iteration's rank-2 update and accumulates both GEMVs, t = B⁻¹y and w = B⁻¹∇; 16 n² instead of
 // 24 n² bytes of B⁻¹ traffic per iteration.  Not the reference's rounding (QN_FLAG_ONE_PASS).
-template <class Obj, int NREG, int PAIRN = 0, bool ONEPASS = false>
+template <class Obj, int NREG, int PAIRN = 0, bool ONEPASS = false, int PROWS = 2>
 __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
                                                    const typename Obj::Params& op,
                                                    const long long j, Team& tm, double* ys,
@@ -161,9 +161,11 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
   // two rows 2·(c mod B/2), +1 and on the rule-C2 blocks bgrp, bgrp + G, ... of them
   const int B = resident_block_threads(n);
   const bool multi = (NREG == 0) && ((int)blockDim.x > B || PAIRN > 0);
-  const int half = B >> 1;
+  constexpr int PR = (PAIRN > 0) ? PROWS : 2; // rows per thread: 2 in shared memory, 2 or 4 in registers
+  static_assert(PR == 2 || PR == 4, "rows per thread");
+  const int half = B / PR;                    // threads per column-block group
   const int G = (NREG > 0) ? 1 : (int)blockDim.x / half;
-  const int row0 = (NREG > 0) ? c : 2 * (c % half);
+  const int row0 = (NREG > 0) ? c : PR * (c % half);
   const int bgrp = (NREG > 0) ? 0 : c / half;
   const int ldh = (NREG > 0) ? 0 : resident_ldh(n);
   (void)part; (void)multi; (void)G; (void)row0; (void)bgrp; (void)ldh;
@@ -172,7 +174,7 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
   double h[HR]; // row c of B⁻¹ (register policy)
   (void)h; (void)hs;
   constexpr int PRB = (PAIRN > 0) ? chain_block(PAIRN) : 1;
-  double hp[2][PRB]; // rows row0, row0+1 × the columns of block bgrp (pair-register policy)
+  double hp[PR][PRB]; // rows row0 … row0+PR-1 × the columns of block bgrp (register-tile policy)
   (void)hp;
   const int pcol0 = bgrp * PRB;                       // first column of this thread's block
   const int pcols = (PAIRN > 0) ? min(PRB, n - pcol0) : 0; // ... and how many it has
@@ -189,30 +191,39 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
     if (!(bgrp < G && row0 < n)) return;
     const double2 sAB = *reinterpret_cast<const double2*>(rowp + row0);
     const double2 nAB = *reinterpret_cast<const double2*>(rowp + B + row0);
+    (void)sAB; (void)nAB;
     if (PAIRN > 0) {
-      double t0 = 0.0, t1 = 0.0, w0 = 0.0, w1 = 0.0;
+      double sR[PR], nR[PR], tt[PR], ww[PR];
+#pragma unroll
+      for (int i = 0; i < PR; ++i) { sR[i] = rowp[row0 + i]; nR[i] = rowp[B + row0 + i]; tt[i] = 0.0; ww[i] = 0.0; }
 #pragma unroll
       for (int k = 0; k < PRB; ++k) {
         if (k < pcols) {
           const double2 wn = *reinterpret_cast<const double2*>(&cols[pcol0 + k].w);
           const double2 sg = *reinterpret_cast<const double2*>(&cols[pcol0 + k].s);
-          double ha = hp[0][k], hb = hp[1][k];
-          if (apply) {
-            ha = fma(wn.x, sAB.x, ha);  hb = fma(wn.x, sAB.y, hb);
-            ha = fma(wn.y, sAB.x, ha);  hb = fma(wn.y, sAB.y, hb);
-            ha = fma(nAB.x, sg.x, ha);  hb = fma(nAB.y, sg.x, hb);
-            hp[0][k] = ha; hp[1][k] = hb;
-          }
-          if (gemv) {
-            const double yr = ys[pcol0 + k];
-            t0 = fma(yr, ha, t0);   t1 = fma(yr, hb, t1);
-            w0 = fma(ha, sg.y, w0); w1 = fma(hb, sg.y, w1);
+          const double yr = ys[pcol0 + k];
+#pragma unroll
+          for (int i = 0; i < PR; ++i) {
+            double hh = hp[i][k];
+            if (apply) {
+              hh = fma(wn.x, sR[i], hh);
+              hh = fma(wn.y, sR[i], hh);
+              hh = fma(nR[i], sg.x, hh);
+              hp[i][k] = hh;
+            }
+            if (gemv) {
+              tt[i] = fma(yr, hh, tt[i]);
+              ww[i] = fma(hh, sg.y, ww[i]);
+            }
           }
         }
       }
       if (gemv) {
-        *reinterpret_cast<double2*>(part + bgrp * B + row0) = make_double2(t0, t1);
-        *reinterpret_cast<double2*>(part2 + bgrp * B + row0) = make_double2(w0, w1);
+#pragma unroll
+        for (int i = 0; i < PR; i += 2) {
+          *reinterpret_cast<double2*>(part + bgrp * B + row0 + i) = make_double2(tt[i], tt[i + 1]);
+          *reinterpret_cast<double2*>(part2 + bgrp * B + row0 + i) = make_double2(ww[i], ww[i + 1]);
+        }
       }
     } else {
       double* hrow = hs + row0;
@@ -320,16 +331,20 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
         }
       } else if (PAIRN > 0) {
         if (row0 < n) {
-          double t0 = 0.0, t1 = 0.0;
+          double tt[PR];
+#pragma unroll
+          for (int i = 0; i < PR; ++i) tt[i] = 0.0;
 #pragma unroll
           for (int k = 0; k < PRB; ++k) {
             if (k < pcols) {
               const double yr = ys[pcol0 + k];
-              t0 = fma(yr, hp[0][k], t0);
-              t1 = fma(yr, hp[1][k], t1);
+#pragma unroll
+              for (int i = 0; i < PR; ++i) tt[i] = fma(yr, hp[i][k], tt[i]);
             }
           }
-          *reinterpret_cast<double2*>(part + bgrp * B + row0) = make_double2(t0, t1);
+#pragma unroll
+          for (int i = 0; i < PR; i += 2)
+            *reinterpret_cast<double2*>(part + bgrp * B + row0 + i) = make_double2(tt[i], tt[i + 1]);
         }
         __syncthreads();
         if (active) { // block partials in ascending order (rule C2)
@@ -401,24 +416,33 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
         }
       } else if (PAIRN > 0) {
         if (row0 < n) {
-          const double2 sAB = *reinterpret_cast<const double2*>(ys + row0);  // s of the pair (see below)
-          const double2 nAB = *reinterpret_cast<const double2*>(tm.xs + row0); // -u of the pair
-          double accA = 0.0, accB = 0.0;
+          double sR[PR], nR[PR], acc[PR]; // s and -u of this thread's rows (see below), chain accumulators
+#pragma unroll
+          for (int i = 0; i < PR; i += 2) {
+            const double2 s2 = *reinterpret_cast<const double2*>(ys + row0 + i);
+            const double2 n2 = *reinterpret_cast<const double2*>(tm.xs + row0 + i);
+            sR[i] = s2.x; sR[i + 1] = s2.y; nR[i] = n2.x; nR[i + 1] = n2.y;
+            acc[i] = 0.0; acc[i + 1] = 0.0;
+          }
 #pragma unroll
           for (int k = 0; k < PRB; ++k) {
             if (k < pcols) {
               const double2 wn = *reinterpret_cast<const double2*>(&cols[pcol0 + k].w);
               const double2 sg = *reinterpret_cast<const double2*>(&cols[pcol0 + k].s);
-              double ha = hp[0][k], hb = hp[1][k];
-              ha = fma(wn.x, sAB.x, ha);  hb = fma(wn.x, sAB.y, hb);   // + (c₁ s[r]) s[c]
-              ha = fma(wn.y, sAB.x, ha);  hb = fma(wn.y, sAB.y, hb);   // - u[r] s[c]
-              ha = fma(nAB.x, sg.x, ha);  hb = fma(nAB.y, sg.x, hb);   // - u[c] s[r]
-              hp[0][k] = ha; hp[1][k] = hb;
-              accA = fma(ha, sg.y, accA);
-              accB = fma(hb, sg.y, accB);
+#pragma unroll
+              for (int i = 0; i < PR; ++i) {
+                double hh = hp[i][k];
+                hh = fma(wn.x, sR[i], hh);   // + (c₁ s[r]) s[c]
+                hh = fma(wn.y, sR[i], hh);   // - u[r] s[c]
+                hh = fma(nR[i], sg.x, hh);   // - u[c] s[r]
+                hp[i][k] = hh;
+                acc[i] = fma(hh, sg.y, acc[i]);
+              }
             }
           }
-          *reinterpret_cast<double2*>(part + bgrp * B + row0) = make_double2(accA, accB);
+#pragma unroll
+          for (int i = 0; i < PR; i += 2)
+            *reinterpret_cast<double2*>(part + bgrp * B + row0 + i) = make_double2(acc[i], acc[i + 1]);
         }
         __syncthreads();
         if (active) {
@@ -485,10 +509,9 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
         for (int r = 0; r < HR; ++r) h[r] = (r == c) ? 1.0 : 0.0;
       } else if (PAIRN > 0) {
 #pragma unroll
-        for (int k = 0; k < PRB; ++k) {
-          hp[0][k] = (row0 == pcol0 + k) ? 1.0 : 0.0;
-          hp[1][k] = (row0 + 1 == pcol0 + k) ? 1.0 : 0.0;
-        }
+        for (int k = 0; k < PRB; ++k)
+#pragma unroll
+          for (int i = 0; i < PR; ++i) hp[i][k] = (row0 + i == pcol0 + k) ? 1.0 : 0.0;
       } else if (active) {
         for (int r = 0; r < n; ++r) hs[c + ldh * r] = (r == c) ? 1.0 : 0.0;
       }
@@ -528,8 +551,9 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
 #pragma unroll
     for (int k = 0; k < PRB; ++k) {
       if (k < pcols) {
-        ho[row0 + (long long)p.ldh * (pcol0 + k)] = hp[0][k];
-        if (row0 + 1 < n) ho[row0 + 1 + (long long)p.ldh * (pcol0 + k)] = hp[1][k];
+#pragma unroll
+        for (int i = 0; i < PR; ++i)
+          if (row0 + i < n) ho[row0 + i + (long long)p.ldh * (pcol0 + k)] = hp[i][k];
       }
     }
   }
@@ -549,7 +573,7 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
   write_problem_scalars(p, j, c, result, iters, fevals, status);
 }
 
-template <class Obj, int NREG, int BLOCK, int MINB, int PAIRN = 0, bool ONEPASS = false>
+template <class Obj, int NREG, int BLOCK, int MINB, int PAIRN = 0, bool ONEPASS = false, int PROWS = 2>
 __global__ void __launch_bounds__(BLOCK, MINB)
 qn_resident_kernel(const BatchParams p, const typename Obj::Params op) {
   // launch: blockDim >= resident_block_threads(n); see launch_resident for the policy
@@ -587,7 +611,7 @@ qn_resident_kernel(const BatchParams p, const typename Obj::Params op) {
     __syncthreads();
     const long long j = *next;
     if (j >= p.batch) break;
-    resident_solve_one<Obj, NREG, PAIRN, ONEPASS>(p, op, j, tm, ys, cols, hs, smem + L.part, smem + L.part2,
+    resident_solve_one<Obj, NREG, PAIRN, ONEPASS, PROWS>(p, op, j, tm, ys, cols, hs, smem + L.part, smem + L.part2,
                                                   smem + L.rowp);
   }
 }

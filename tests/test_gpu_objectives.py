@@ -33,7 +33,7 @@ def test_gaussian_objective_and_solve(eng, qn, ob, n):
     Theta = starts(n, batch, key=3 * n)
     got = eng.optimize_batched(model, Theta, ntrace=5)
     ref = ob.optimize_batch(omodel, Theta, ntrace=5)
-    # n = 128: B⁻¹ in 2x16 register tiles; other sizes: shared memory
+    # n = 128: B⁻¹ in 4x16 register tiles; other sizes: shared memory
     assert eng.last_launch()["path"] == (qn._lib.PATH_REGISTER if n == 128 else qn._lib.PATH_SMEM)
     for k in ("x", "g", "ell", "trace"):
         assert np.array_equal(got[k], ref[k], equal_nan=True), k

@@ -110,7 +110,7 @@ def test_tile_kernel_sizes(eng, qn, ob, n):
 
 
 def test_n128_both_resident_policies(eng, qn, ob):
-    """n = 128 runs with B⁻¹ as 2x16 register tiles of 512 threads by default and in shared memory
+    """n = 128 runs with B⁻¹ as 4x16 register tiles of 256 threads by default and in shared memory
     (row pairs, column blocks dealt out to thread groups) under QN_FLAG_FORCE_SMEM: same bits."""
     Theta = starts(128, 8, key=1280)
     ref = ob.optimize_batch(ob.rosenbrock(), Theta, ntrace=5)
