@@ -64,7 +64,8 @@ namespace {
 // room for the second partial-sum array) silently runs the reference order.
 template <class Obj, int NREG, int BLOCK, int MINB, int PAIRN = 0, bool ONEPASS = false, int PROWS = 2>
 int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Params& op,
-                    cudaStream_t st) {
+                    cudaStream_t st, int* probe_occ = nullptr) {
+  // probe_occ != nullptr: do not launch, report how many CTAs (= problems) would be resident per SM
   const int n = p.n;
   // shared-memory policy: a thread owns a PAIR of rows of B⁻¹ (one 16-byte access per column)
   // and the rule-C2 column blocks are dealt out to G thread groups of B/2 threads, as many as
@@ -74,20 +75,22 @@ int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Par
   if (PAIRN > 0) { // register-tile policy: PROWS rows × one rule-C2 block per thread
     nthreads = (B / PROWS) * ((n + qn::chain_block(n) - 1) / qn::chain_block(n));
   } else if (NREG == 0 && n >= 48) {
-    const int half = B / 2;
+    const int half = B / PROWS;
     const int nblocks = (n + qn::chain_block(n) - 1) / qn::chain_block(n);
     for (int G = std::min(nblocks, BLOCK / half); G >= 2; --G) {
       const int cand = ((G * half + 31) / 32) * 32;
       if (cand <= B) break;
-      const size_t need = sizeof(double) * (size_t)qn::resident_smem_layout<Obj>(n, true, cand, op, ONEPASS).total;
+      const size_t need = sizeof(double) * (size_t)qn::resident_smem_layout<Obj>(n, true, cand, op, ONEPASS, PROWS).total;
       if (cand <= BLOCK && need <= (size_t)ctx->prop.sharedMemPerBlockOptin) { nthreads = cand; break; }
     }
   }
-  if (ONEPASS && PAIRN == 0 && nthreads <= B) // no pair policy possible: the reference order
-    return launch_resident<Obj, NREG, BLOCK, MINB, PAIRN, false>(ctx, p, op, st);
+  if (ONEPASS && PAIRN == 0 && nthreads <= B) // no row-tile policy possible: the reference order
+    return launch_resident<Obj, NREG, BLOCK, MINB, PAIRN, false, PROWS>(ctx, p, op, st, probe_occ);
+  if (NREG == 0 && PAIRN == 0 && PROWS == 4 && nthreads <= B) // 4-row groups need more threads than elements
+    return launch_resident<Obj, 0, 1024, 1, 0, ONEPASS, 2>(ctx, p, op, st, probe_occ);
   if (NREG == 0 && PAIRN == 0 && BLOCK > 512 && nthreads <= 512) // the 512-thread build may use 128 registers
-    return launch_resident<Obj, 0, 512, 1, 0, ONEPASS>(ctx, p, op, st);
-  const qn::ResidentSmem L = qn::resident_smem_layout<Obj>(n, NREG == 0 && PAIRN == 0, nthreads, op, ONEPASS);
+    return launch_resident<Obj, 0, 512, 1, 0, ONEPASS, PROWS>(ctx, p, op, st, probe_occ);
+  const qn::ResidentSmem L = qn::resident_smem_layout<Obj>(n, NREG == 0 && PAIRN == 0, nthreads, op, ONEPASS, PROWS);
   const size_t smem = sizeof(double) * (size_t)L.total;
   if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin)
     return fail(QN_ERR_UNSUPPORTED_SIZE,
@@ -99,6 +102,7 @@ int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Par
   const int block = nthreads;
   int occ = 0;
   QN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
+  if (probe_occ) { *probe_occ = occ; return QN_OK; }
   if (occ < 1) return fail(QN_ERR_UNSUPPORTED_SIZE, "resident kernel does not fit on an SM (n=%d)", n);
   long long grid = (long long)occ * ctx->prop.multiProcessorCount;
   if (grid > p.batch) grid = p.batch;
@@ -209,9 +213,31 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
                      : launch_resident<Obj, 0, 256, 1, 128, false, 4>(ctx, p, op, st);
     }
   }
-  if (n <= 256)
+  if (n <= 256) {
+    // shared-memory policy: 2 or 4 rows of B⁻¹ per thread.  Four rows halve the threads (and so the
+    // registers) of a CTA: worth it exactly when that lets MORE problems be resident per SM (measured:
+    // n = 96, 100: 2 instead of 1, +23-25 %; with equal residency two rows are 10-15 % faster).  Cheap
+    // objectives only — the GEMVs of the others want the threads.  QN_SMEM_ROWS=2|4 forces a choice.
+    bool four = false;
+    if (n >= 64) {
+      const char* v = getenv("QN_SMEM_ROWS");
+      if (v) {
+        four = (v[0] == '4');
+      } else if (Obj::kRegisterPaths) {
+        int occ2 = 0, occ4 = 0;
+        const int r2 = onepass ? launch_resident<Obj, 0, 1024, 1, 0, true, 2>(ctx, p, op, st, &occ2)
+                               : launch_resident<Obj, 0, 1024, 1, 0, false, 2>(ctx, p, op, st, &occ2);
+        const int r4 = onepass ? launch_resident<Obj, 0, 1024, 1, 0, true, 4>(ctx, p, op, st, &occ4)
+                               : launch_resident<Obj, 0, 1024, 1, 0, false, 4>(ctx, p, op, st, &occ4);
+        four = (r2 == QN_OK && r4 == QN_OK && occ4 > occ2);
+      }
+    }
+    if (four)
+      return onepass ? launch_resident<Obj, 0, 1024, 1, 0, true, 4>(ctx, p, op, st)
+                     : launch_resident<Obj, 0, 1024, 1, 0, false, 4>(ctx, p, op, st);
     return onepass ? launch_resident<Obj, 0, 1024, 1, 0, true>(ctx, p, op, st)
                    : launch_resident<Obj, 0, 1024, 1>(ctx, p, op, st);
+  }
   return fail(QN_ERR_UNSUPPORTED_SIZE, "n=%d does not fit the resident path", n);
 }
 

@@ -39,10 +39,11 @@ __host__ __device__ inline int resident_block_threads(int n) { return (n + 31) &
 struct ResidentSmem {
   int red, xs, ys, cols, scratch, part, part2, rowp, h, total;
 };
-__host__ __device__ inline int resident_ldh(int n) { return (n + 1) & ~1; }
+__host__ __device__ inline int resident_ldh(int n, int pr = 2) { return (n + pr - 1) & ~(pr - 1); }
 template <class Obj>
 __host__ __device__ inline ResidentSmem resident_smem_layout(int n, bool h_in_smem, int nthreads,
-                                                             const typename Obj::Params& op, bool onepass = false) {
+                                                             const typename Obj::Params& op, bool onepass = false,
+                                                             int pr = 2) {
   const int B = resident_block_threads(n);
   const int nblocks = (n + chain_block(n) - 1) / chain_block(n);
   ResidentSmem L;
@@ -55,7 +56,7 @@ __host__ __device__ inline ResidentSmem resident_smem_layout(int n, bool h_in_sm
   L.part = o; o += (nthreads > B) ? nblocks * B : 0;
   L.part2 = o; o += onepass ? nblocks * B : 0; // one-pass mode: partials of the second GEMV (w = B⁻¹∇)
   L.rowp = o;  o += onepass ? 2 * B : 0;       //   and the pending s / -u by element (row operands)
-  L.h = o;    o += h_in_smem ? resident_ldh(n) * n : 0;
+  L.h = o;    o += h_in_smem ? resident_ldh(n, pr) * n : 0;
   L.total = o + 2; // + problem index broadcast slot
   return L;
 }
@@ -161,13 +162,13 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
   // two rows 2·(c mod B/2), +1 and on the rule-C2 blocks bgrp, bgrp + G, ... of them
   const int B = resident_block_threads(n);
   const bool multi = (NREG == 0) && ((int)blockDim.x > B || PAIRN > 0);
-  constexpr int PR = (PAIRN > 0) ? PROWS : 2; // rows per thread: 2 in shared memory, 2 or 4 in registers
+  constexpr int PR = PROWS; // rows of B⁻¹ per thread (shared-memory and register-tile policies): 2 or 4
   static_assert(PR == 2 || PR == 4, "rows per thread");
   const int half = B / PR;                    // threads per column-block group
   const int G = (NREG > 0) ? 1 : (int)blockDim.x / half;
   const int row0 = (NREG > 0) ? c : PR * (c % half);
   const int bgrp = (NREG > 0) ? 0 : c / half;
-  const int ldh = (NREG > 0) ? 0 : resident_ldh(n);
+  const int ldh = (NREG > 0) ? 0 : resident_ldh(n, PR);
   (void)part; (void)multi; (void)G; (void)row0; (void)bgrp; (void)ldh;
   constexpr int HR = (NREG > 0) ? NREG : 1;
   const int rb = chain_block(n); // rule C2 block length
@@ -189,9 +190,6 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
   // APPLY, accumulates t and w when GEMV, block partials to part / part2
   auto onepass_sweep = [&](const bool apply, const bool gemv) {
     if (!(bgrp < G && row0 < n)) return;
-    const double2 sAB = *reinterpret_cast<const double2*>(rowp + row0);
-    const double2 nAB = *reinterpret_cast<const double2*>(rowp + B + row0);
-    (void)sAB; (void)nAB;
     if (PAIRN > 0) {
       double sR[PR], nR[PR], tt[PR], ww[PR];
 #pragma unroll
@@ -227,29 +225,49 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
       }
     } else {
       double* hrow = hs + row0;
+      double sR[PR], nR[PR];
+#pragma unroll
+      for (int i = 0; i < PR; ++i) { sR[i] = rowp[row0 + i]; nR[i] = rowp[B + row0 + i]; }
       for (int r0 = bgrp * rb, blk = bgrp; r0 < n; r0 += G * rb, blk += G) {
         const int r1 = min(r0 + rb, n);
-        double t0 = 0.0, t1 = 0.0, w0 = 0.0, w1 = 0.0;
+        double tt[PR], ww[PR];
+#pragma unroll
+        for (int i = 0; i < PR; ++i) { tt[i] = 0.0; ww[i] = 0.0; }
 #pragma unroll 4
         for (int r = r0; r < r1; ++r) {
           const double2 wn = *reinterpret_cast<const double2*>(&cols[r].w);
           const double2 sg = *reinterpret_cast<const double2*>(&cols[r].s);
-          double2 hh = *reinterpret_cast<const double2*>(hrow + ldh * r);
-          if (apply) {
-            hh.x = fma(wn.x, sAB.x, hh.x);  hh.y = fma(wn.x, sAB.y, hh.y);
-            hh.x = fma(wn.y, sAB.x, hh.x);  hh.y = fma(wn.y, sAB.y, hh.y);
-            hh.x = fma(nAB.x, sg.x, hh.x);  hh.y = fma(nAB.y, sg.x, hh.y);
-            *reinterpret_cast<double2*>(hrow + ldh * r) = hh;
+          const double yr = ys[r];
+          double hh[PR];
+#pragma unroll
+          for (int i = 0; i < PR; i += 2) {
+            const double2 h2 = *reinterpret_cast<const double2*>(hrow + ldh * r + i);
+            hh[i] = h2.x; hh[i + 1] = h2.y;
           }
-          if (gemv) {
-            const double yr = ys[r];
-            t0 = fma(yr, hh.x, t0);   t1 = fma(yr, hh.y, t1);
-            w0 = fma(hh.x, sg.y, w0); w1 = fma(hh.y, sg.y, w1);
+#pragma unroll
+          for (int i = 0; i < PR; ++i) {
+            if (apply) {
+              hh[i] = fma(wn.x, sR[i], hh[i]);
+              hh[i] = fma(wn.y, sR[i], hh[i]);
+              hh[i] = fma(nR[i], sg.x, hh[i]);
+            }
+            if (gemv) {
+              tt[i] = fma(yr, hh[i], tt[i]);
+              ww[i] = fma(hh[i], sg.y, ww[i]);
+            }
+          }
+          if (apply) {
+#pragma unroll
+            for (int i = 0; i < PR; i += 2)
+              *reinterpret_cast<double2*>(hrow + ldh * r + i) = make_double2(hh[i], hh[i + 1]);
           }
         }
         if (gemv) {
-          *reinterpret_cast<double2*>(part + blk * B + row0) = make_double2(t0, t1);
-          *reinterpret_cast<double2*>(part2 + blk * B + row0) = make_double2(w0, w1);
+#pragma unroll
+          for (int i = 0; i < PR; i += 2) {
+            *reinterpret_cast<double2*>(part + blk * B + row0 + i) = make_double2(tt[i], tt[i + 1]);
+            *reinterpret_cast<double2*>(part2 + blk * B + row0 + i) = make_double2(ww[i], ww[i + 1]);
+          }
         }
       }
     }
@@ -367,15 +385,22 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
           const double* hrow = hs + row0;
           for (int r0 = bgrp * rb, blk = bgrp; r0 < n; r0 += G * rb, blk += G) {
             const int r1 = min(r0 + rb, n);
-            double t0 = 0.0, t1 = 0.0;
+            double tt[PR];
+#pragma unroll
+            for (int i = 0; i < PR; ++i) tt[i] = 0.0;
 #pragma unroll 8
             for (int r = r0; r < r1; ++r) {
               const double yr = ys[r];
-              const double2 hh = *reinterpret_cast<const double2*>(hrow + ldh * r);
-              t0 = fma(yr, hh.x, t0);
-              t1 = fma(yr, hh.y, t1);
+#pragma unroll
+              for (int i = 0; i < PR; i += 2) {
+                const double2 hh = *reinterpret_cast<const double2*>(hrow + ldh * r + i);
+                tt[i] = fma(yr, hh.x, tt[i]);
+                tt[i + 1] = fma(yr, hh.y, tt[i + 1]);
+              }
             }
-            *reinterpret_cast<double2*>(part + blk * B + row0) = make_double2(t0, t1);
+#pragma unroll
+            for (int i = 0; i < PR; i += 2)
+              *reinterpret_cast<double2*>(part + blk * B + row0 + i) = make_double2(tt[i], tt[i + 1]);
           }
         }
         __syncthreads();
@@ -471,27 +496,38 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
         }
       } else {
         if (bgrp < G && row0 < n) {
-          // row operands of the pair, published by the rows' owners (zero beyond n)
-          const double2 sAB = *reinterpret_cast<const double2*>(ys + row0);
-          const double2 nAB = *reinterpret_cast<const double2*>(tm.xs + row0);
-          const double sA = sAB.x, sB = sAB.y, nuA = nAB.x, nuB = nAB.y;
+          // row operands of this thread's rows, published by the rows' owners (zero beyond n)
+          double sR[PR], nR[PR];
+#pragma unroll
+          for (int i = 0; i < PR; i += 2) {
+            const double2 s2 = *reinterpret_cast<const double2*>(ys + row0 + i);
+            const double2 n2 = *reinterpret_cast<const double2*>(tm.xs + row0 + i);
+            sR[i] = s2.x; sR[i + 1] = s2.y; nR[i] = n2.x; nR[i + 1] = n2.y;
+          }
           double* hrow = hs + row0;
           for (int r0 = bgrp * rb, blk = bgrp; r0 < n; r0 += G * rb, blk += G) {
             const int r1 = min(r0 + rb, n);
-            double accA = 0.0, accB = 0.0;
+            double acc[PR];
+#pragma unroll
+            for (int i = 0; i < PR; ++i) acc[i] = 0.0;
 #pragma unroll 4
             for (int r = r0; r < r1; ++r) {
               const double2 wn = *reinterpret_cast<const double2*>(&cols[r].w);
               const double2 sg = *reinterpret_cast<const double2*>(&cols[r].s);
-              double2 hh = *reinterpret_cast<const double2*>(hrow + ldh * r);
-              hh.x = fma(wn.x, sA, hh.x);  hh.y = fma(wn.x, sB, hh.y);   // + (c₁ s[r]) s[c]
-              hh.x = fma(wn.y, sA, hh.x);  hh.y = fma(wn.y, sB, hh.y);   // - u[r] s[c]
-              hh.x = fma(nuA, sg.x, hh.x); hh.y = fma(nuB, sg.x, hh.y);  // - u[c] s[r]
-              *reinterpret_cast<double2*>(hrow + ldh * r) = hh;
-              accA = fma(hh.x, sg.y, accA);
-              accB = fma(hh.y, sg.y, accB);
+#pragma unroll
+              for (int i = 0; i < PR; i += 2) {
+                double2 hh = *reinterpret_cast<const double2*>(hrow + ldh * r + i);
+                hh.x = fma(wn.x, sR[i], hh.x);  hh.y = fma(wn.x, sR[i + 1], hh.y);   // + (c₁ s[r]) s[c]
+                hh.x = fma(wn.y, sR[i], hh.x);  hh.y = fma(wn.y, sR[i + 1], hh.y);   // - u[r] s[c]
+                hh.x = fma(nR[i], sg.x, hh.x);  hh.y = fma(nR[i + 1], sg.x, hh.y);   // - u[c] s[r]
+                *reinterpret_cast<double2*>(hrow + ldh * r + i) = hh;
+                acc[i] = fma(hh.x, sg.y, acc[i]);
+                acc[i + 1] = fma(hh.y, sg.y, acc[i + 1]);
+              }
             }
-            *reinterpret_cast<double2*>(part + blk * B + row0) = make_double2(accA, accB);
+#pragma unroll
+            for (int i = 0; i < PR; i += 2)
+              *reinterpret_cast<double2*>(part + blk * B + row0 + i) = make_double2(acc[i], acc[i + 1]);
           }
         }
         __syncthreads();
@@ -580,7 +616,7 @@ qn_resident_kernel(const BatchParams p, const typename Obj::Params op) {
   extern __shared__ __align__(16) double smem[];
   const int n = (NREG > 0) ? NREG : (PAIRN > 0 ? PAIRN : p.n);
   const int B = resident_block_threads(n);
-  const ResidentSmem L = resident_smem_layout<Obj>(n, NREG == 0 && PAIRN == 0, (int)blockDim.x, op, ONEPASS);
+  const ResidentSmem L = resident_smem_layout<Obj>(n, NREG == 0 && PAIRN == 0, (int)blockDim.x, op, ONEPASS, PROWS);
 
   Team tm;
   tm.n = n;
@@ -600,9 +636,9 @@ qn_resident_kernel(const BatchParams p, const typename Obj::Params op) {
   volatile long long* next = reinterpret_cast<volatile long long*>(smem + L.total - 2);
   Obj::prologue(tm, op); // once per CTA: e.g. the dense Gaussian's Λ into shared memory
   if (NREG == 0 && PAIRN == 0) { // the padding row of an odd-n B⁻¹ is read and written by its pair: keep it finite
-    const int ldh = resident_ldh(n);
-    if (ldh > n)
-      for (int r = threadIdx.x; r < n; r += blockDim.x) hs[n + ldh * r] = 0.0;
+    const int ldh = resident_ldh(n, PROWS);
+    for (int pad = n; pad < ldh; ++pad)
+      for (int r = threadIdx.x; r < n; r += blockDim.x) hs[pad + ldh * r] = 0.0;
   }
 
   for (;;) {
