@@ -109,6 +109,28 @@ def test_tile_kernel_sizes(eng, qn, ob, n):
         _check(got, ref)
 
 
+ALL_PATH_SIZES = [1, 2, 3, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 36, 40, 47, 48, 49, 56, 60, 63, 64, 65, 66,
+                  80, 95, 96, 104, 105, 112, 127, 128, 129, 144, 159, 160]
+
+
+@pytest.mark.parametrize("flags_name", ["default", "smem"])
+def test_every_dispatch_branch_first_iterations(eng, qn, ob, flags_name):
+    """One sweep over sizes chosen to hit every branch of the resident dispatch (packed, thread-per-row,
+    register tiles of both kinds, shared memory with 1, 2 or 4 rows per thread, odd sizes with their
+    padding rows): 30 iterations with every iterate traced, bit for bit against the oracle, for both
+    line-search orders; and once more with QN_FLAG_FORCE_SMEM."""
+    flags = qn._lib.FLAG_FORCE_SMEM if flags_name == "smem" else 0
+    for n in ALL_PATH_SIZES:
+        Theta = starts(n, 4, key=9000 + n)
+        for order in (2, 3):
+            got = eng.optimize_batched(qn.Rosenbrock(), Theta, ls=qn.BackTracking[order](), max_iter=30, ntrace=30, flags=flags)
+            ref = ob.optimize_batch(ob.rosenbrock(), Theta, ls=ob.backtracking(order), max_iter=30, ntrace=30)
+            for k in ("x", "g", "ell", "trace"):
+                assert np.array_equal(got[k], ref[k], equal_nan=True), (n, order, k)
+            for k in ("iters", "fevals", "status"):
+                assert np.array_equal(got[k], ref[k]), (n, order, k)
+
+
 def test_n128_both_resident_policies(eng, qn, ob):
     """n = 128 runs with B⁻¹ as 4x16 register tiles of 256 threads by default and in shared memory
     (row pairs, column blocks dealt out to thread groups) under QN_FLAG_FORCE_SMEM: same bits."""
