@@ -37,3 +37,33 @@ def test_objectives_repeat_bitwise(eng, qn):
         b = eng.optimize_batched(obj, Theta)
         for k in ("x", "g", "ell", "iters", "fevals", "status"):
             assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+def test_distinct_contexts_are_independent_across_host_threads(qn, ob):
+    """calls on distinct contexts are independent — the analogue of calling the
+    reference from Threads.@threads with distinct states.  Four host threads, four contexts on the
+    same GPU, different problem shapes at once; every result equals the oracle's."""
+    import threading
+    shapes = [(60, 400), (8, 3000), (128, 40), (100, 60)]
+    engines = [qn.Engine(0) for _ in shapes]
+    out = [None] * len(shapes)
+
+    def work(k):
+        n, batch = shapes[k]
+        Theta = starts(n, batch, key=600 + k)
+        for _ in range(3):
+            out[k] = (Theta, engines[k].optimize_batched(qn.Rosenbrock(), Theta))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(shapes))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for k, (n, batch) in enumerate(shapes):
+        Theta, got = out[k]
+        sel = np.linspace(0, batch - 1, 16).astype(int)
+        ref = ob.optimize_batch(ob.rosenbrock(), np.asfortranarray(Theta[:, sel]))
+        for key in ("x", "g", "ell", "iters", "fevals", "status"):
+            assert np.array_equal(got[key][..., sel], ref[key], equal_nan=True), (n, key)
+    for e in engines:
+        e.close()
