@@ -110,6 +110,55 @@ __device__ __forceinline__ double superblock_sum(int K, int sb, F&& term) {
 __device__ __forceinline__ double nanmin(double a, double b) { return a < b ? a : (isnan(b) ? a : b); }
 __device__ __forceinline__ double nanmax(double a, double b) { return a < b ? b : (isnan(a) ? b : a); }
 
+// linesearch!  QN.jl:165-232, the scalar part shared by every kernel: every thread that calls it
+// runs the same code on the same values, so control flow is uniform across the team.
+// trial(a) evaluates ℓ(x + a s) (step!, QN.jl:157-162) and counts the evaluation; if the caller
+// already has the first trial ℓ(x + 1·s) it passes it as `first` with have_first = true.
+// Returns α (0 = failure, QN.jl:193) and leaves the ℓ of the last trial in lx_last.
+template <class Trial>
+__device__ __forceinline__ double backtracking_linesearch(const LsParams& ls, const double l0, const double m,
+                                                          Trial&& trial, double& lx_last,
+                                                          const bool have_first = false, const double first = 0.0) {
+  double lx0 = l0;
+  double a1 = 1.0, a2 = 1.0;
+  double lx1 = have_first ? first : trial(a1); // QN.jl:174
+  int iterfinite = 0;
+  while (!isfinite(lx1) && iterfinite < 52) { // QN.jl:178-184
+    ++iterfinite;
+    a1 = a2;
+    a2 = 0.5 * a2;
+    lx1 = trial(a2);
+  }
+  long long iteration = 0;
+  while (!(lx1 >= fma(a2 * ls.c1, m, l0))) { // QN.jl:187
+    ++iteration;
+    if (iteration > ls.iterations) { lx_last = lx1; return 0.0; } // QN.jl:193
+    double at;
+    if (ls.order == 2 || iteration == 1) {
+      at = -((m * a2) * a2) / (2.0 * fma(-m, a2, lx1 - l0)); // QN.jl:205
+    } else {
+      const double denom = 1.0 / ((((a1 * a1) * a2) * a2) * (a2 - a1)); // QN.jl:207
+      const double r1 = fma(-m, a2, lx1 - l0);
+      const double r0 = fma(-m, a1, lx0 - l0);
+      const double a = ((a1 * a1) * r1 - (a2 * a2) * r0) * denom;                   // QN.jl:208
+      const double b = ((((-a1) * a1) * a1) * r1 + ((a2 * a2) * a2) * r0) * denom;  // QN.jl:209
+      if (fabs(a) <= kEps + kSqrtTol * fabs(a)) {  // QN.jl:211
+        at = m / (2.0 * b);                        // QN.jl:212
+      } else {
+        const double d = nanmax(b * b - (3.0 * a) * m, 0.0); // QN.jl:215
+        at = (sqrt(d) + b) / (-3.0 * a);                     // QN.jl:218
+      }
+    }
+    a1 = a2;                           // QN.jl:222
+    at = nanmin(at, a2 * ls.rho_hi);   // QN.jl:224
+    a2 = nanmax(at, a2 * ls.rho_lo);   // QN.jl:225
+    lx0 = lx1;                         // QN.jl:228
+    lx1 = trial(a2);
+  }
+  lx_last = lx1;
+  return a2;
+}
+
 // Butterfly of the canonical reduction (rule C1): off = 16,8,4,2,1.
 // IEEE addition is commutative, so every lane ends with the same bits.
 __device__ __forceinline__ double warp_butterfly(double p) {

@@ -69,8 +69,6 @@ __device__ __forceinline__ double team_linesearch(Team& tm, const typename Obj::
                                                   const LsParams& ls, const double x,
                                                   const double s, const double l0,
                                                   const double m, int& fevals) {
-  double lx0 = l0, lx1 = l0;
-  double a1 = 1.0, a2 = 1.0;
   // step! (QN.jl:157-162): x_new = x_old + α s (one fma, rule C3), then logdensity.
   // Objectives with kMemoizeTrials (an evaluation is a GEMV against parameters in L2): when the
   // trial point is BIT FOR BIT the previous trial point, the previous value is the value and the
@@ -94,41 +92,8 @@ __device__ __forceinline__ double team_linesearch(Team& tm, const typename Obj::
     l_prev = Obj::template eval<false>(tm, op, dummy);
     return l_prev;
   };
-  lx1 = trial(a1);
-  int iterfinite = 0;
-  while (!isfinite(lx1) && iterfinite < 52) { // QN.jl:178-184
-    ++iterfinite;
-    a1 = a2;
-    a2 = 0.5 * a2;
-    lx1 = trial(a2);
-  }
-  long long iteration = 0;
-  while (!(lx1 >= fma(a2 * ls.c1, m, l0))) { // QN.jl:187
-    ++iteration;
-    if (iteration > ls.iterations) return 0.0; // QN.jl:193
-    double at;
-    if (ls.order == 2 || iteration == 1) {
-      at = -((m * a2) * a2) / (2.0 * fma(-m, a2, lx1 - l0)); // QN.jl:205
-    } else {
-      const double denom = 1.0 / ((((a1 * a1) * a2) * a2) * (a2 - a1)); // QN.jl:207
-      const double r1 = fma(-m, a2, lx1 - l0);
-      const double r0 = fma(-m, a1, lx0 - l0);
-      const double a = ((a1 * a1) * r1 - (a2 * a2) * r0) * denom;                    // QN.jl:208
-      const double b = ((((-a1) * a1) * a1) * r1 + ((a2 * a2) * a2) * r0) * denom;   // QN.jl:209
-      if (fabs(a) <= kEps + kSqrtTol * fabs(a)) {  // QN.jl:211
-        at = m / (2.0 * b);                        // QN.jl:212
-      } else {
-        const double d = nanmax(b * b - (3.0 * a) * m, 0.0); // QN.jl:215
-        at = (sqrt(d) + b) / (-3.0 * a);                     // QN.jl:218
-      }
-    }
-    a1 = a2;                           // QN.jl:222
-    at = nanmin(at, a2 * ls.rho_hi);   // QN.jl:224
-    a2 = nanmax(at, a2 * ls.rho_lo);   // QN.jl:225
-    lx0 = lx1;                         // QN.jl:228
-    lx1 = trial(a2);
-  }
-  return a2;
+  double lx_last;
+  return backtracking_linesearch(ls, l0, m, trial, lx_last);
 }
 
 __device__ __forceinline__ void write_problem_scalars(const BatchParams& p, long long j, int c,

@@ -404,48 +404,8 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
         ++fevals;
         return rosenbrock_finish<N>(tterm, xn);
       };
-      double lx0 = l0;
-      double a1 = 1.0, a2 = 1.0;
-      if (have_trial) ++fevals; // evaluated above, together with m
-      else lx1 = trial(a1);     // QN.jl:174
-      int iterfinite = 0;
-      while (!isfinite(lx1) && iterfinite < 52) { // QN.jl:178-184
-        ++iterfinite;
-        a1 = a2;
-        a2 = 0.5 * a2;
-        lx1 = trial(a2);
-      }
-      long long iteration = 0;
-      bool failed = false;
-      QN_TICK(10);                               // timing build: start of the Armijo loop
-      while (!(lx1 >= fma(a2 * ls.c1, m, l0))) { // QN.jl:187
-        ++iteration;
-        if (iteration > ls.iterations) { failed = true; break; } // QN.jl:193
-        double at;
-        if (ls.order == 2 || iteration == 1) {
-          at = -((m * a2) * a2) / (2.0 * fma(-m, a2, lx1 - l0)); // QN.jl:205
-        } else {
-          const double denom = 1.0 / ((((a1 * a1) * a2) * a2) * (a2 - a1)); // QN.jl:207
-          const double r1 = fma(-m, a2, lx1 - l0);
-          const double r0 = fma(-m, a1, lx0 - l0);
-          const double a = ((a1 * a1) * r1 - (a2 * a2) * r0) * denom;                   // QN.jl:208
-          const double bq = ((((-a1) * a1) * a1) * r1 + ((a2 * a2) * a2) * r0) * denom; // QN.jl:209
-          if (fabs(a) <= kEps + kSqrtTol * fabs(a)) {  // QN.jl:211
-            at = m / (2.0 * bq);                       // QN.jl:212
-          } else {
-            const double dd = nanmax(bq * bq - (3.0 * a) * m, 0.0); // QN.jl:215
-            at = (sqrt(dd) + bq) / (-3.0 * a);                      // QN.jl:218
-          }
-        }
-        a1 = a2;                           // QN.jl:222
-        at = nanmin(at, a2 * ls.rho_hi);   // QN.jl:224
-        a2 = nanmax(at, a2 * ls.rho_lo);   // QN.jl:225
-        lx0 = lx1;                         // QN.jl:228
-        QN_TICK(8);                        // timing build: interpolation of an extra trial
-        lx1 = trial(a2);
-        QN_TICK(9);                        // timing build: evaluation + butterfly of an extra trial
-      }
-      alpha = failed ? 0.0 : a2;
+      if (have_trial) ++fevals; // the first trial was evaluated above, together with m
+      alpha = backtracking_linesearch(ls, l0, m, trial, lx1, have_trial, lx1);
     }
     QN_TICK(7);
     if (alpha == 0.0) { status = QN_LINESEARCH_FAILED; if (!(it & 1)) g = unpark(C::wGp); break; } // QN.jl:284

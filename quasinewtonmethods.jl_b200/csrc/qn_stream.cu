@@ -401,45 +401,8 @@ __device__ __forceinline__ void stream_finish_iteration(const StreamParams& p, S
     ++fevals;
     return cta_rosenbrock(n, [&](int i) { return fma(a, sv[i], xv[i]); }, nullptr, stage, &red);
   };
-  const LsParams& ls = p.ls;
-  double lx0 = l0, lx1;
-  double a1 = 1.0, a2 = 1.0;
-  lx1 = trial(a1);
-  int iterfinite = 0;
-  while (!isfinite(lx1) && iterfinite < 52) { // QN.jl:178-184
-    ++iterfinite;
-    a1 = a2;
-    a2 = 0.5 * a2;
-    lx1 = trial(a2);
-  }
-  long long iteration = 0;
-  bool failed = false;
-  while (!(lx1 >= fma(a2 * ls.c1, m, l0))) { // QN.jl:187
-    ++iteration;
-    if (iteration > ls.iterations) { failed = true; break; }
-    double at;
-    if (ls.order == 2 || iteration == 1) {
-      at = -((m * a2) * a2) / (2.0 * fma(-m, a2, lx1 - l0));
-    } else {
-      const double denom = 1.0 / ((((a1 * a1) * a2) * a2) * (a2 - a1));
-      const double r1 = fma(-m, a2, lx1 - l0);
-      const double r0 = fma(-m, a1, lx0 - l0);
-      const double a = ((a1 * a1) * r1 - (a2 * a2) * r0) * denom;
-      const double b = ((((-a1) * a1) * a1) * r1 + ((a2 * a2) * a2) * r0) * denom;
-      if (fabs(a) <= kEps + kSqrtTol * fabs(a)) {
-        at = m / (2.0 * b);
-      } else {
-        const double d = nanmax(b * b - (3.0 * a) * m, 0.0);
-        at = (sqrt(d) + b) / (-3.0 * a);
-      }
-    }
-    a1 = a2;
-    at = nanmin(at, a2 * ls.rho_hi);
-    a2 = nanmax(at, a2 * ls.rho_lo);
-    lx0 = lx1;
-    lx1 = trial(a2);
-  }
-  const double alpha = failed ? 0.0 : a2;
+  double lx_last;
+  const double alpha = backtracking_linesearch(p.ls, l0, m, trial, lx_last);
   if (alpha == 0.0) { // QN.jl:284
     if (threadIdx.x == 0) { sc->status = QN_LINESEARCH_FAILED; sc->done = 1; sc->fevals += fevals; sc->need_reset = need_reset; sc->exit_it = it; }
     return;
@@ -1115,44 +1078,8 @@ stream_vec_cluster(const StreamParams p) {
     ncache = nc;
     return cv[0];
   };
-  double lx0 = l0, lx1;
-  double a1 = 1.0, a2 = 1.0;
-  lx1 = trial(a1);
-  int iterfinite = 0;
-  while (!isfinite(lx1) && iterfinite < 52) { // QN.jl:178-184
-    ++iterfinite;
-    a1 = a2;
-    a2 = 0.5 * a2;
-    lx1 = trial(a2);
-  }
-  long long iteration = 0;
-  bool failed = false;
-  while (!(lx1 >= fma(a2 * ls.c1, m, l0))) { // QN.jl:187
-    ++iteration;
-    if (iteration > ls.iterations) { failed = true; break; }
-    double at;
-    if (ls.order == 2 || iteration == 1) {
-      at = -((m * a2) * a2) / (2.0 * fma(-m, a2, lx1 - l0));
-    } else {
-      const double denom = 1.0 / ((((a1 * a1) * a2) * a2) * (a2 - a1));
-      const double q1 = fma(-m, a2, lx1 - l0);
-      const double q0 = fma(-m, a1, lx0 - l0);
-      const double a = ((a1 * a1) * q1 - (a2 * a2) * q0) * denom;
-      const double b = ((((-a1) * a1) * a1) * q1 + ((a2 * a2) * a2) * q0) * denom;
-      if (fabs(a) <= kEps + kSqrtTol * fabs(a)) {
-        at = m / (2.0 * b);
-      } else {
-        const double d = nanmax(b * b - (3.0 * a) * m, 0.0);
-        at = (sqrt(d) + b) / (-3.0 * a);
-      }
-    }
-    a1 = a2;
-    at = nanmin(at, a2 * ls.rho_hi);
-    a2 = nanmax(at, a2 * ls.rho_lo);
-    lx0 = lx1;
-    lx1 = trial(a2);
-  }
-  const double alpha = failed ? 0.0 : a2;
+  double lx_last;
+  const double alpha = backtracking_linesearch(ls, l0, m, trial, lx_last);
   if (alpha == 0.0) { // QN.jl:284
     if (leader) { sc->status = QN_LINESEARCH_FAILED; sc->done = 1; sc->fevals += fevals; sc->need_reset = need_reset; sc->exit_it = it; }
 #pragma unroll
