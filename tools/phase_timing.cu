@@ -32,11 +32,10 @@ int main(int argc, char** argv) {
   std::vector<int> it(nprob);
   cudaMemcpy(it.data(), d_it, nprob * 4, cudaMemcpyDeviceToHost);
   // block 0 solved whichever problems it pulled; with grid == batch it solved about one
-  const char* names[11] = {"loop top/trace", "conv check", "publish", "rho + pass 1 + barrier b",
-                           "combine + yHy + c1 + publish", "pass 2 + barrier d", "combine + m & trial butterfly", "tail of line search",
-                           "  extra trial: interpolation", "  extra trial: evaluation + butterfly", "  (reset/first-trial block before the Armijo loop)"};
-  unsigned long long tot = 0; for (int k = 0; k < 11; ++k) tot += clk[k];
+  const char* names[8] = {"loop top/trace", "conv check", "publish", "rho + pass 1 + barrier b",
+                          "combine + yHy + c1 + publish", "pass 2 + barrier d", "combine + m & trial butterfly", "rest of line search"};
+  unsigned long long tot = 0; for (int k = 0; k < 8; ++k) tot += clk[k];
   printf("CTAs=%d  iterations of problem 0: %d  total cycles %llu  -> %.0f cycles/iteration\n", nprob, it[0], tot, (double)tot / it[0]);
-  for (int k = 0; k < 11; ++k) printf("  %-50s %9llu  %6.1f cyc/iter  %5.1f%%\n", names[k], clk[k], (double)clk[k] / it[0], 100.0 * clk[k] / tot);
+  for (int k = 0; k < 8; ++k) printf("  %-50s %9llu  %6.1f cyc/iter  %5.1f%%\n", names[k], clk[k], (double)clk[k] / it[0], 100.0 * clk[k] / tot);
   return 0;
 }
