@@ -62,7 +62,8 @@ namespace {
 // ONEPASS: the deferred-update order (QN_FLAG_ONE_PASS) — shared-memory and register-pair policies
 // with more threads than elements only; a request that cannot be honoured (too small an n, or no
 // room for the second partial-sum array) silently runs the reference order.
-template <class Obj, int NREG, int BLOCK, int MINB, int PAIRN = 0, bool ONEPASS = false, int PROWS = 2>
+template <class Obj, int NREG, int BLOCK, int MINB, int PAIRN = 0, bool ONEPASS = false, int PROWS = 2,
+          int PREG = PROWS>
 int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Params& op,
                     cudaStream_t st, int* probe_occ = nullptr) {
   // probe_occ != nullptr: do not launch, report how many CTAs (= problems) would be resident per SM
@@ -90,14 +91,15 @@ int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Par
     return launch_resident<Obj, 0, 1024, 1, 0, ONEPASS, 2>(ctx, p, op, st, probe_occ);
   if (NREG == 0 && PAIRN == 0 && BLOCK > 512 && nthreads <= 512) // the 512-thread build may use 128 registers
     return launch_resident<Obj, 0, 512, 1, 0, ONEPASS, PROWS>(ctx, p, op, st, probe_occ);
-  const qn::ResidentSmem L = qn::resident_smem_layout<Obj>(n, NREG == 0 && PAIRN == 0, nthreads, op, ONEPASS, PROWS);
+  const qn::ResidentSmem L = qn::resident_smem_layout<Obj>(n, NREG == 0 && PAIRN == 0, nthreads, op, ONEPASS, PROWS,
+                                                           PAIRN > 0 ? PROWS - PREG : 0);
   const size_t smem = sizeof(double) * (size_t)L.total;
   if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin)
     return fail(QN_ERR_UNSUPPORTED_SIZE,
                 "n=%d needs %zu bytes of shared memory per problem; the device allows %zu "
                 "(use the streaming path)",
                 n, smem, (size_t)ctx->prop.sharedMemPerBlockOptin);
-  auto kern = qn::qn_resident_kernel<Obj, NREG, BLOCK, MINB, PAIRN, ONEPASS, PROWS>;
+  auto kern = qn::qn_resident_kernel<Obj, NREG, BLOCK, MINB, PAIRN, ONEPASS, PROWS, PREG>;
   QN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int block = nthreads;
   int occ = 0;
@@ -203,10 +205,18 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
   const bool onepass = (flags & QN_FLAG_ONE_PASS) != 0; // honoured by these two policies (and the streaming path)
   if constexpr (Obj::kPairRegister) {
     if (n == 128 && !(flags & QN_FLAG_FORCE_SMEM)) {
-      // rows of B⁻¹ per thread: 4 (256 threads × 128 registers of B⁻¹; measured 5.4e7 iterations/s on
-      // Rosenbrock) or, with QN_PAIR_ROWS=2, 2 (512 threads × 64 registers; 4.9e7)
+      // 4×16 tiles of 256 threads.  QN_PAIR_ROWS selects the variant: '4' all four rows in registers
+      // (128 registers of B⁻¹, one problem per SM; 5.4e7 iterations/s on Rosenbrock), 'h' hybrid —
+      // two rows in registers, two in shared memory, TWO problems per SM (6.1e7) —, '2' the 2×16
+      // tiles of 512 threads (4.9e7).  Default: hybrid for cheap objectives; for the others the
+      // second resident problem buys nothing (dense Gaussian 2.21e7 against 2.19e7) and all-register
+      // tiles leave the shared memory to the objective (Λ).
       const char* v = getenv("QN_PAIR_ROWS");
-      if (v && v[0] == '2')
+      const char variant = v ? v[0] : (Obj::kRegisterPaths ? 'h' : '4');
+      if (variant == 'h')
+        return onepass ? launch_resident<Obj, 0, 256, 2, 128, true, 4, 2>(ctx, p, op, st)
+                       : launch_resident<Obj, 0, 256, 2, 128, false, 4, 2>(ctx, p, op, st);
+      if (variant == '2')
         return onepass ? launch_resident<Obj, 0, 512, 1, 128, true>(ctx, p, op, st)
                        : launch_resident<Obj, 0, 512, 1, 128>(ctx, p, op, st);
       return onepass ? launch_resident<Obj, 0, 256, 1, 128, true, 4>(ctx, p, op, st)

@@ -43,7 +43,7 @@ __host__ __device__ inline int resident_ldh(int n, int pr = 2) { return (n + pr 
 template <class Obj>
 __host__ __device__ inline ResidentSmem resident_smem_layout(int n, bool h_in_smem, int nthreads,
                                                              const typename Obj::Params& op, bool onepass = false,
-                                                             int pr = 2) {
+                                                             int pr = 2, int hybrid_rows = 0) {
   const int B = resident_block_threads(n);
   const int nblocks = (n + chain_block(n) - 1) / chain_block(n);
   ResidentSmem L;
@@ -56,7 +56,9 @@ __host__ __device__ inline ResidentSmem resident_smem_layout(int n, bool h_in_sm
   L.part = o; o += (nthreads > B) ? nblocks * B : 0;
   L.part2 = o; o += onepass ? nblocks * B : 0; // one-pass mode: partials of the second GEMV (w = B⁻¹∇)
   L.rowp = o;  o += onepass ? 2 * B : 0;       //   and the pending s / -u by element (row operands)
-  L.h = o;    o += h_in_smem ? resident_ldh(n, pr) * n : 0;
+  // B⁻¹ itself (shared-memory policy), or — register-tile policy with hybrid_rows of every thread's
+  // pr rows kept here — those rows, packed: [(B/pr)·hybrid_rows] × n
+  L.h = o;    o += h_in_smem ? resident_ldh(n, pr) * n : (B / pr) * hybrid_rows * n;
   L.total = o + 2; // + problem index broadcast slot
   return L;
 }
@@ -114,7 +116,10 @@ __device__ __forceinline__ void write_problem_scalars(const BatchParams& p, long
 // streaming path — ONE sweep applies the previous
 // iteration's rank-2 update and accumulates both GEMVs, t = B⁻¹y and w = B⁻¹∇; 16 n² instead of
 // 24 n² bytes of B⁻¹ traffic per iteration.  Not the reference's rounding (QN_FLAG_ONE_PASS).
-template <class Obj, int NREG, int PAIRN = 0, bool ONEPASS = false, int PROWS = 2>
+// PREG (register-tile policy): how many of a thread's PROWS rows live in registers; the others
+// (0 or 2) live in shared memory, which halves the registers of a CTA so that TWO problems are
+// resident per SM at n = 128.
+template <class Obj, int NREG, int PAIRN = 0, bool ONEPASS = false, int PROWS = 2, int PREG = PROWS>
 __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
                                                    const typename Obj::Params& op,
                                                    const long long j, Team& tm, double* ys,
@@ -140,11 +145,29 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
   double h[HR]; // row c of B⁻¹ (register policy)
   (void)h; (void)hs;
   constexpr int PRB = (PAIRN > 0) ? chain_block(PAIRN) : 1;
-  double hp[PR][PRB]; // rows row0 … row0+PR-1 × the columns of block bgrp (register-tile policy)
-  (void)hp;
   const int pcol0 = bgrp * PRB;                       // first column of this thread's block
   const int pcols = (PAIRN > 0) ? min(PRB, n - pcol0) : 0; // ... and how many it has
   (void)pcol0; (void)pcols;
+  constexpr int PX = (PAIRN > 0) ? PR - PREG : 0; // rows of the tile kept in shared memory
+  static_assert(PX == 0 || PX == 2, "hybrid tiles keep 0 or 2 rows in shared memory");
+  double hp[PREG > 0 ? PREG : 1][PRB]; // rows row0 … row0+PREG-1 × the columns of block bgrp (register-tile policy)
+  (void)hp;
+  double* hx = hs + PX * (c % half);  // this thread's shared-memory rows of column 0; column stride ldx
+  const int ldx = half * PX;
+  (void)hx; (void)ldx;
+  auto load_tile_col = [&](const int k, double (&hh)[PR]) {
+#pragma unroll
+    for (int i = 0; i < PREG; ++i) hh[i] = hp[i][k];
+    if (PX) {
+      const double2 v = *reinterpret_cast<const double2*>(hx + ldx * (pcol0 + k));
+      hh[PR - 2] = v.x; hh[PR - 1] = v.y;
+    }
+  };
+  auto store_tile_col = [&](const int k, const double (&hh)[PR]) {
+#pragma unroll
+    for (int i = 0; i < PREG; ++i) hp[i][k] = hh[i];
+    if (PX) *reinterpret_cast<double2*>(hx + ldx * (pcol0 + k)) = make_double2(hh[PR - 2], hh[PR - 1]);
+  };
 
   double x = active ? p.theta0[j * p.theta_stride + c] : 0.0; // copyto!(x_old, x), QN.jl:248
   double g = 0.0, g_prev = 0.0, s = 0.0;
@@ -165,20 +188,21 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
           const double2 wn = *reinterpret_cast<const double2*>(&cols[pcol0 + k].w);
           const double2 sg = *reinterpret_cast<const double2*>(&cols[pcol0 + k].s);
           const double yr = ys[pcol0 + k];
+          double hh[PR];
+          load_tile_col(k, hh);
 #pragma unroll
           for (int i = 0; i < PR; ++i) {
-            double hh = hp[i][k];
             if (apply) {
-              hh = fma(wn.x, sR[i], hh);
-              hh = fma(wn.y, sR[i], hh);
-              hh = fma(nR[i], sg.x, hh);
-              hp[i][k] = hh;
+              hh[i] = fma(wn.x, sR[i], hh[i]);
+              hh[i] = fma(wn.y, sR[i], hh[i]);
+              hh[i] = fma(nR[i], sg.x, hh[i]);
             }
             if (gemv) {
-              tt[i] = fma(yr, hh, tt[i]);
-              ww[i] = fma(hh, sg.y, ww[i]);
+              tt[i] = fma(yr, hh[i], tt[i]);
+              ww[i] = fma(hh[i], sg.y, ww[i]);
             }
           }
+          if (apply) store_tile_col(k, hh);
         }
       }
       if (gemv) {
@@ -321,8 +345,10 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
           for (int k = 0; k < PRB; ++k) {
             if (k < pcols) {
               const double yr = ys[pcol0 + k];
+              double hh[PR];
+              load_tile_col(k, hh);
 #pragma unroll
-              for (int i = 0; i < PR; ++i) tt[i] = fma(yr, hp[i][k], tt[i]);
+              for (int i = 0; i < PR; ++i) tt[i] = fma(yr, hh[i], tt[i]);
             }
           }
 #pragma unroll
@@ -419,15 +445,16 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
             if (k < pcols) {
               const double2 wn = *reinterpret_cast<const double2*>(&cols[pcol0 + k].w);
               const double2 sg = *reinterpret_cast<const double2*>(&cols[pcol0 + k].s);
+              double hh[PR];
+              load_tile_col(k, hh);
 #pragma unroll
               for (int i = 0; i < PR; ++i) {
-                double hh = hp[i][k];
-                hh = fma(wn.x, sR[i], hh);   // + (c₁ s[r]) s[c]
-                hh = fma(wn.y, sR[i], hh);   // - u[r] s[c]
-                hh = fma(nR[i], sg.x, hh);   // - u[c] s[r]
-                hp[i][k] = hh;
-                acc[i] = fma(hh, sg.y, acc[i]);
+                hh[i] = fma(wn.x, sR[i], hh[i]);   // + (c₁ s[r]) s[c]
+                hh[i] = fma(wn.y, sR[i], hh[i]);   // - u[r] s[c]
+                hh[i] = fma(nR[i], sg.x, hh[i]);   // - u[c] s[r]
+                acc[i] = fma(hh[i], sg.y, acc[i]);
               }
+              store_tile_col(k, hh);
             }
           }
 #pragma unroll
@@ -510,9 +537,14 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
         for (int r = 0; r < HR; ++r) h[r] = (r == c) ? 1.0 : 0.0;
       } else if (PAIRN > 0) {
 #pragma unroll
-        for (int k = 0; k < PRB; ++k)
+        for (int k = 0; k < PRB; ++k) {
+          if (k < pcols || PX == 0) {
+            double hh[PR];
 #pragma unroll
-          for (int i = 0; i < PR; ++i) hp[i][k] = (row0 + i == pcol0 + k) ? 1.0 : 0.0;
+            for (int i = 0; i < PR; ++i) hh[i] = (row0 + i == pcol0 + k) ? 1.0 : 0.0;
+            store_tile_col(k, hh);
+          }
+        }
       } else if (active) {
         for (int r = 0; r < n; ++r) hs[c + ldh * r] = (r == c) ? 1.0 : 0.0;
       }
@@ -552,9 +584,11 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
 #pragma unroll
     for (int k = 0; k < PRB; ++k) {
       if (k < pcols) {
+        double hh[PR];
+        load_tile_col(k, hh);
 #pragma unroll
         for (int i = 0; i < PR; ++i)
-          if (row0 + i < n) ho[row0 + i + (long long)p.ldh * (pcol0 + k)] = hp[i][k];
+          if (row0 + i < n) ho[row0 + i + (long long)p.ldh * (pcol0 + k)] = hh[i];
       }
     }
   }
@@ -574,14 +608,16 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
   write_problem_scalars(p, j, c, result, iters, fevals, status);
 }
 
-template <class Obj, int NREG, int BLOCK, int MINB, int PAIRN = 0, bool ONEPASS = false, int PROWS = 2>
+template <class Obj, int NREG, int BLOCK, int MINB, int PAIRN = 0, bool ONEPASS = false, int PROWS = 2,
+          int PREG = PROWS>
 __global__ void __launch_bounds__(BLOCK, MINB)
 qn_resident_kernel(const BatchParams p, const typename Obj::Params op) {
   // launch: blockDim >= resident_block_threads(n); see launch_resident for the policy
   extern __shared__ __align__(16) double smem[];
   const int n = (NREG > 0) ? NREG : (PAIRN > 0 ? PAIRN : p.n);
   const int B = resident_block_threads(n);
-  const ResidentSmem L = resident_smem_layout<Obj>(n, NREG == 0 && PAIRN == 0, (int)blockDim.x, op, ONEPASS, PROWS);
+  const ResidentSmem L = resident_smem_layout<Obj>(n, NREG == 0 && PAIRN == 0, (int)blockDim.x, op, ONEPASS, PROWS,
+                                                   PAIRN > 0 ? PROWS - PREG : 0);
 
   Team tm;
   tm.n = n;
@@ -612,7 +648,7 @@ qn_resident_kernel(const BatchParams p, const typename Obj::Params op) {
     __syncthreads();
     const long long j = *next;
     if (j >= p.batch) break;
-    resident_solve_one<Obj, NREG, PAIRN, ONEPASS, PROWS>(p, op, j, tm, ys, cols, hs, smem + L.part, smem + L.part2,
+    resident_solve_one<Obj, NREG, PAIRN, ONEPASS, PROWS, PREG>(p, op, j, tm, ys, cols, hs, smem + L.part, smem + L.part2,
                                                   smem + L.rowp);
   }
 }
