@@ -75,6 +75,7 @@ int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Par
   int nthreads = (NREG > 0) ? BLOCK : B;
   if (PAIRN > 0) { // register-tile policy: PROWS rows × one rule-C2 block per thread
     nthreads = (B / PROWS) * ((n + qn::chain_block(n) - 1) / qn::chain_block(n));
+    nthreads = (nthreads + 31) & ~31; // whole warps (the reductions shuffle with a full mask)
   } else if (NREG == 0 && n >= 48) {
     const int half = B / PROWS;
     const int nblocks = (n + qn::chain_block(n) - 1) / qn::chain_block(n);
@@ -201,26 +202,34 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
       }
     }
   }
-  // n = 128 (BASELINE.json configs[2], [3]): B⁻¹ as 4×16 register tiles of 256 threads
-  const bool onepass = (flags & QN_FLAG_ONE_PASS) != 0; // honoured by these two policies (and the streaming path)
+  // Register tiles beyond the 4×15-tile sizes (qn_resident.cuh, PAIRN): a thread owns 4 rows × one
+  // rule-C2 block.  QN_PAIR_ROWS selects the variant: 'h' hybrid — two of the four rows in registers,
+  // two in shared memory, which fits every n <= 160 and makes TWO problems resident per SM up to
+  // n = 128 (Rosenbrock: n = 128 6.3e7 iterations/s, n = 160 3.1e7 against 1.8e7 with B⁻¹ in shared
+  // memory) —, '4' all four rows in registers (n = 128 only: 5.4e7), '2' 2×16 tiles of 512 threads
+  // (n = 128 only: 4.9e7).  Default: hybrid for cheap objectives at every 64 < n <= 160; for the
+  // others the second resident problem buys nothing (dense Gaussian 2.21e7 against 2.19e7) and
+  // all-register tiles at n = 128 leave the shared memory to the objective (Λ).
+  const bool onepass = (flags & QN_FLAG_ONE_PASS) != 0; // honoured by these policies (and the streaming path)
   if constexpr (Obj::kPairRegister) {
-    if (n == 128 && !(flags & QN_FLAG_FORCE_SMEM)) {
-      // 4×16 tiles of 256 threads.  QN_PAIR_ROWS selects the variant: '4' all four rows in registers
-      // (128 registers of B⁻¹, one problem per SM; 5.4e7 iterations/s on Rosenbrock), 'h' hybrid —
-      // two rows in registers, two in shared memory, TWO problems per SM (6.1e7) —, '2' the 2×16
-      // tiles of 512 threads (4.9e7).  Default: hybrid for cheap objectives; for the others the
-      // second resident problem buys nothing (dense Gaussian 2.21e7 against 2.19e7) and all-register
-      // tiles leave the shared memory to the objective (Λ).
+    if (!(flags & QN_FLAG_FORCE_SMEM)) {
       const char* v = getenv("QN_PAIR_ROWS");
       const char variant = v ? v[0] : (Obj::kRegisterPaths ? 'h' : '4');
-      if (variant == 'h')
-        return onepass ? launch_resident<Obj, 0, 256, 2, 128, true, 4, 2>(ctx, p, op, st)
-                       : launch_resident<Obj, 0, 256, 2, 128, false, 4, 2>(ctx, p, op, st);
-      if (variant == '2')
-        return onepass ? launch_resident<Obj, 0, 512, 1, 128, true>(ctx, p, op, st)
-                       : launch_resident<Obj, 0, 512, 1, 128>(ctx, p, op, st);
-      return onepass ? launch_resident<Obj, 0, 256, 1, 128, true, 4>(ctx, p, op, st)
-                     : launch_resident<Obj, 0, 256, 1, 128, false, 4>(ctx, p, op, st);
+      if (variant == 'h' && n > 64 && n <= 160) {
+        const int B = qn::resident_block_threads(n);
+        const int threads = ((B / 4) * ((n + qn::chain_block(n) - 1) / qn::chain_block(n)) + 31) & ~31;
+        if (threads <= 256)
+          return onepass ? launch_resident<Obj, 0, 256, 2, 1, true, 4, 2>(ctx, p, op, st)
+                         : launch_resident<Obj, 0, 256, 2, 1, false, 4, 2>(ctx, p, op, st);
+        return onepass ? launch_resident<Obj, 0, 512, 1, 1, true, 4, 2>(ctx, p, op, st)
+                       : launch_resident<Obj, 0, 512, 1, 1, false, 4, 2>(ctx, p, op, st);
+      }
+      if (n == 128 && variant == '2')
+        return onepass ? launch_resident<Obj, 0, 512, 1, 1, true>(ctx, p, op, st)
+                       : launch_resident<Obj, 0, 512, 1, 1>(ctx, p, op, st);
+      if (n == 128 && variant != 's')
+        return onepass ? launch_resident<Obj, 0, 256, 1, 1, true, 4>(ctx, p, op, st)
+                       : launch_resident<Obj, 0, 256, 1, 1, false, 4>(ctx, p, op, st);
     }
   }
   if (n <= 256) {

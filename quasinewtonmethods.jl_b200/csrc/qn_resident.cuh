@@ -109,9 +109,9 @@ __device__ __forceinline__ void write_problem_scalars(const BatchParams& p, long
   }
 }
 
-// PAIRN > 0 (with NREG == 0): the "pair" policy with n = PAIRN at compile time and every
-// thread's 2 × rb tile of B⁻¹ (two rows, one rule-C2 block) in REGISTERS; needs
-// blockDim = (B/2) · #blocks so that a thread owns exactly one block.
+// PAIRN > 0 (with NREG == 0): the register-tile policy — every thread's PROWS × rb tile of B⁻¹
+// (PROWS rows, one rule-C2 block of rb <= 16 columns) lives in REGISTERS (or, PREG < PROWS, partly
+// in shared memory); needs blockDim >= (B/PROWS) · #blocks so that a thread owns exactly one block.
 // ONEPASS (shared-memory and register-pair policies only): the deferred-update order of
 // streaming path — ONE sweep applies the previous
 // iteration's rank-2 update and accumulates both GEMVs, t = B⁻¹y and w = B⁻¹∇; 16 n² instead of
@@ -125,7 +125,7 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
                                                    const long long j, Team& tm, double* ys,
                                                    Pass2Col* cols, double* hs, double* part,
                                                    double* part2 = nullptr, double* rowp = nullptr) {
-  const int n = (NREG > 0) ? NREG : (PAIRN > 0 ? PAIRN : p.n);
+  const int n = (NREG > 0) ? NREG : p.n;
   const int c = tm.c;          // thread index: the owner of element c when c < n
   const bool active = c < n;
   // shared-memory policy with more threads than elements ("pair" policy): thread c works on the
@@ -144,9 +144,9 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
   const int rb = chain_block(n); // rule C2 block length
   double h[HR]; // row c of B⁻¹ (register policy)
   (void)h; (void)hs;
-  constexpr int PRB = (PAIRN > 0) ? chain_block(PAIRN) : 1;
-  const int pcol0 = bgrp * PRB;                       // first column of this thread's block
-  const int pcols = (PAIRN > 0) ? min(PRB, n - pcol0) : 0; // ... and how many it has
+  constexpr int PRB = (PAIRN > 0) ? 16 : 1; // a rule-C2 block has at most 16 columns
+  const int pcol0 = bgrp * rb;                        // first column of this thread's block
+  const int pcols = (PAIRN > 0) ? min(rb, n - pcol0) : 0;  // ... and how many it has (<= 0: none)
   (void)pcol0; (void)pcols;
   constexpr int PX = (PAIRN > 0) ? PR - PREG : 0; // rows of the tile kept in shared memory
   static_assert(PX == 0 || PX == 2, "hybrid tiles keep 0 or 2 rows in shared memory");
@@ -178,6 +178,7 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
   // APPLY, accumulates t and w when GEMV, block partials to part / part2
   auto onepass_sweep = [&](const bool apply, const bool gemv) {
     if (!(bgrp < G && row0 < n)) return;
+    if (PAIRN > 0 && pcols <= 0) return;
     if (PAIRN > 0) {
       double sR[PR], nR[PR], tt[PR], ww[PR];
 #pragma unroll
@@ -337,7 +338,7 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
           T = (r0 == 0) ? t : T + t;
         }
       } else if (PAIRN > 0) {
-        if (row0 < n) {
+        if (row0 < n && pcols > 0) { // (threads beyond the last column block: the rounding of the CTA to whole warps)
           double tt[PR];
 #pragma unroll
           for (int i = 0; i < PR; ++i) tt[i] = 0.0;
@@ -431,7 +432,7 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
           D = (r0 == 0) ? acc : D + acc;
         }
       } else if (PAIRN > 0) {
-        if (row0 < n) {
+        if (row0 < n && pcols > 0) { // (threads beyond the last column block: the rounding of the CTA to whole warps)
           double sR[PR], nR[PR], acc[PR]; // s and -u of this thread's rows (see below), chain accumulators
 #pragma unroll
           for (int i = 0; i < PR; i += 2) {
@@ -579,7 +580,7 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
     onepass_sweep(true, false);
     __syncthreads();
   }
-  if (PAIRN > 0 && p.h_out && row0 < n) {
+  if (PAIRN > 0 && p.h_out && row0 < n && pcols > 0) {
     double* ho = p.h_out + j * p.h_stride;
 #pragma unroll
     for (int k = 0; k < PRB; ++k) {
@@ -614,7 +615,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 qn_resident_kernel(const BatchParams p, const typename Obj::Params op) {
   // launch: blockDim >= resident_block_threads(n); see launch_resident for the policy
   extern __shared__ __align__(16) double smem[];
-  const int n = (NREG > 0) ? NREG : (PAIRN > 0 ? PAIRN : p.n);
+  const int n = (NREG > 0) ? NREG : p.n;
   const int B = resident_block_threads(n);
   const ResidentSmem L = resident_smem_layout<Obj>(n, NREG == 0 && PAIRN == 0, (int)blockDim.x, op, ONEPASS, PROWS,
                                                    PAIRN > 0 ? PROWS - PREG : 0);
