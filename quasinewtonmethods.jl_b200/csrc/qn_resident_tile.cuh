@@ -47,17 +47,6 @@ struct Pair {
   double lo, hi;
 };
 
-// butterfly of rule C1 for two independent sums at once (same latency as one)
-__device__ __forceinline__ void warp_butterfly2(double& a, double& b) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const double ta = __shfl_xor_sync(0xffffffffu, a, off);
-    const double tb = __shfl_xor_sync(0xffffffffu, b, off);
-    a = a + ta;
-    b = b + tb;
-  }
-}
-
 // Warp-level Rosenbrock (test/runtests.jl:4-33) on a replicated vector.  Lane i < N
 // evaluates pair i: θ1 = x[i] is its own `lo`; θ2 = x[i+N] comes from the lane that
 // holds it, by one 64-bit shuffle (each lane is asked for at most one of lo/hi
@@ -120,9 +109,10 @@ struct TileCfg {
   // address patterns on purpose — every extra base register is spilled in the hot loop (168
   // registers, 120 of them B⁻¹): the column operands are ONE array of 48-byte records addressed by
   // slot, everything element-indexed uses the quad layout below.
-  static constexpr int kRec = 6;                     // doubles per column record {c₁s, -u, s, ∇, y, pad}
+  static constexpr int kRec = 6;                     // doubles per column record {c₁s, -u, s, ∇, pad, pad}
   static constexpr int wRec = 0;                     // records of this warp's two column blocks [2][16]
-  static constexpr int wS = wRec + 32 * kRec;        // s  by element (row operands), quad layout
+  static constexpr int wYb = wRec + 32 * kRec;       // y by slot [2][16]: pass 1 reads it two columns at a time
+  static constexpr int wS = wYb + 32;                // s  by element (row operands), quad layout
   static constexpr int wNu = wS + 80;                // -u by element
   static constexpr int wX = wNu + 80;                // x_old, ∇, ∇_old, y parked here (quad layout) while
   static constexpr int wG = wX + 80;                 //   the passes need the registers
@@ -143,16 +133,27 @@ struct TileCfg {
 template <int N>
 __host__ __device__ constexpr int tile_smem_doubles() { return TileCfg<N>::oEnd + 2; }
 
-__device__ __forceinline__ void warp_butterfly3(double& a, double& b, double& c) {
+// Three rule-C1 butterflies on shared shuffles.  A butterfly leaves the same tree sum in every
+// lane, so only one lane per sum has to finish it: at offset 16 the sums a and b trade halves
+// (lanes with bit 4 clear carry on with a, the others with b — one exchange instead of two), at
+// offset 8 that register and c do the same (bit 3 clear: a or b; set: c), offsets 4, 2, 1 are
+// ordinary levels, and three broadcasts hand the finished sums (lanes 0, 16 and 8) to everyone.
+// Every partial is formed from the same two operands as in warp_butterfly (IEEE addition is
+// commutative): the same bits with 9 exchanges and 6 additions instead of 15 and 15 — and with a
+// dependent chain of 6 where the register-starved schedule of three interleaved butterflies had 15.
+__device__ __forceinline__ void warp_butterfly3(double& a, double& b, double& c, const int lane) {
+  const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+  const double r16 = __shfl_xor_sync(0xffffffffu, up16 ? a : b, 16);
+  const double c16 = __shfl_xor_sync(0xffffffffu, c, 16);
+  const double ab = (up16 ? b : a) + r16;
+  c = c + c16;
+  const double r8 = __shfl_xor_sync(0xffffffffu, up8 ? ab : c, 8);
+  double v = (up8 ? c : ab) + r8;
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const double ta = __shfl_xor_sync(0xffffffffu, a, off);
-    const double tb = __shfl_xor_sync(0xffffffffu, b, off);
-    const double tc = __shfl_xor_sync(0xffffffffu, c, off);
-    a = a + ta;
-    b = b + tb;
-    c = c + tc;
-  }
+  for (int off = 4; off >= 1; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
+  a = __shfl_sync(0xffffffffu, v, 0);
+  b = __shfl_sync(0xffffffffu, v, 16);
+  c = __shfl_sync(0xffffffffu, v, 8);
 }
 
 template <int N, int PF>
@@ -173,6 +174,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
 
   double* pw = smem + warp * C::wSize;             // this warp's private region
   double* rec = pw + C::wRec;                      // column records
+  double* yb_arr = pw + C::wYb;
   double* s_arr = pw + C::wS;
   double* nu_arr = pw + C::wNu;
   double* part1 = smem + C::oPart1;
@@ -280,11 +282,11 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
       s_arr[q_hi] = s.hi;
       if (slot_lo >= 0) {
         *reinterpret_cast<double2*>(rec + slot_lo * C::kRec + 2) = make_double2(s.lo, g.lo);
-        rec[slot_lo * C::kRec + 4] = y.lo;
+        yb_arr[slot_lo] = y.lo;
       }
       if (slot_hi >= 0) {
         *reinterpret_cast<double2*>(rec + slot_hi * C::kRec + 2) = make_double2(s.hi, g.hi);
-        rec[slot_hi * C::kRec + 4] = y.hi;
+        yb_arr[slot_hi] = y.hi;
       }
       park(C::wX, x);
       park(C::wG, g);
@@ -297,13 +299,17 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
         double tt[RT];
 #pragma unroll
         for (int i = 0; i < RT; ++i) tt[i] = 0.0;
-        const double* rb_ = rec + hb * 16 * C::kRec;
-        double yy[CT];
+        // y's block, two columns per LDS.128: eight loads issued back to back ahead of the fmas (the
+        // warp barrier keeps ptxas from sinking each load to its first use), so their latency is
+        // paid once and not per column
+        const double2* yb2 = reinterpret_cast<const double2*>(yb_arr + hb * 16);
+        double2 yy[(CT + 1) / 2];
 #pragma unroll
-        for (int k = 0; k < CT; ++k) yy[k] = rb_[k * C::kRec + 4];
+        for (int k = 0; k < (CT + 1) / 2; ++k) yy[k] = yb2[k];
+        __syncwarp(); // keeps the loads above it
 #pragma unroll
         for (int k = 0; k < CT; ++k) {
-          const double yk = yy[k];
+          const double yk = (k & 1) ? yy[k >> 1].y : yy[k >> 1].x;
           if (C::kFull || col0 + k < N) {
 #pragma unroll
             for (int i = 0; i < RT; ++i) tt[i] = fma(yk, h[i][k], tt[i]);
@@ -377,7 +383,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
       double tterm;
       spec_eval(1.0, d, sp, xn, tterm);
       m = dot(d, g);
-      warp_butterfly3(m, tterm, sp.sy);
+      warp_butterfly3(m, tterm, sp.sy, lane);
       sp.term_next = tterm;
       lx1 = rosenbrock_finish<N>(tterm, xn);
       have_trial = true;
@@ -400,7 +406,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
       auto trial = [&](const double a) {
         double tterm;
         spec_eval(a, d, sp, xn, tterm);
-        warp_butterfly3(tterm, sp.term_next, sp.sy);
+        warp_butterfly3(tterm, sp.term_next, sp.sy, lane);
         ++fevals;
         return rosenbrock_finish<N>(tterm, xn);
       };
@@ -443,7 +449,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
 // registers per thread: 168 lets 6 CTAs stay resident; MINB = 7 asks for 144 (experiment)
 template <int N, int MINB, int PF>
 __global__ void __launch_bounds__(64) __maxnreg__(MINB >= 7 ? 144 : (MINB == 6 ? 168 : (MINB == 5 ? 200 : 255)))
-qn_resident_tile_kernel(const BatchParams p) {
+qn_resident_tile_kernel(const __grid_constant__ BatchParams p) {
   extern __shared__ __align__(16) double smem[];
   volatile long long* next = reinterpret_cast<volatile long long*>(smem + tile_smem_doubles<N>() - 2);
   for (;;) {
