@@ -230,7 +230,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
     park(C::wGp, zero);
   }
   double result = __longlong_as_double(0x7ff8000000000000LL); // NaN, QN.jl:291
-  int iters = 0, fevals = 0, status = QN_MAX_ITER;
+  int iters = 0, fevals = 0, status = QN_MAX_ITER; // iters (completed iterations) is set where the loop is left
 
   // A line-search trial at step a along d (QN.jl:157-162), evaluated TOGETHER with what the
   // next iteration needs if the trial is accepted: update_state! (QN.jl:21-27) gives
@@ -262,10 +262,16 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
   for (int it = 1; it <= p.max_iter; ++it) { // QN.jl:250,253
     QN_TICK(0);
     ++fevals; // the ∂logdensity! of this iteration (QN.jl:254), evaluated by the accepted trial
-    if (!isfinite(l0)) { status = QN_NONFINITE; if (!(it & 1)) g = unpark(C::wGp); break; } // QN.jl:255
-    // maximum(abs, ∇_new) < tol, QN.jl:257 (a NaN entry makes it false)
+    // QN.jl:255 (ℓ₀ not finite) and QN.jl:257-261 (maximum(abs, ∇_new) < tol; a NaN entry makes it
+    // false) leave the loop through ONE branch: the vote is taken before either is looked at
     const bool small = fabs(g.lo) < p.tol && (!hi_valid || fabs(g.hi) < p.tol);
-    if (__all_sync(0xffffffffu, small)) { status = QN_CONVERGED; result = l0; break; } // QN.jl:258-261
+    const bool all_small = __all_sync(0xffffffffu, small);
+    if (!isfinite(l0) || all_small) {
+      iters = it - 1;
+      if (!isfinite(l0)) { status = QN_NONFINITE; if (!(it & 1)) g = unpark(C::wGp); }
+      else { status = QN_CONVERGED; result = l0; }
+      break;
+    }
     QN_TICK(1);
 
     double m;
@@ -324,14 +330,15 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
       {
         const Pair T = combine(part1);
         const Pair yv = unpark(C::wY);
+        const double s_lo = s_arr[q_lo], s_hi = s_arr[q_hi]; // fetched ahead of the butterfly that c₁ waits for
         const double yHy = warp_butterfly(dot(T, yv)); // Σ_c t[c] y[c], QN.jl:51
         const double c1 = fma(yHy, rho, 1.0) * rho;    // QN.jl:54
         const double nu_lo = -(T.lo * rho), nu_hi = -(T.hi * rho); // -B⁻¹y[c] = -(t ρ), QN.jl:50
         nu_arr[q_lo] = nu_lo;
         nu_arr[q_hi] = nu_hi;
         // (c₁ s[r]) rounded once per r (rule C4)
-        if (slot_lo >= 0) *reinterpret_cast<double2*>(rec + slot_lo * C::kRec) = make_double2(c1 * s_arr[q_lo], nu_lo);
-        if (slot_hi >= 0) *reinterpret_cast<double2*>(rec + slot_hi * C::kRec) = make_double2(c1 * s_arr[q_hi], nu_hi);
+        if (slot_lo >= 0) *reinterpret_cast<double2*>(rec + slot_lo * C::kRec) = make_double2(c1 * s_lo, nu_lo);
+        if (slot_hi >= 0) *reinterpret_cast<double2*>(rec + slot_hi * C::kRec) = make_double2(c1 * s_hi, nu_hi);
       }
       __syncwarp();
       QN_TICK(4);
@@ -414,16 +421,15 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
       alpha = backtracking_linesearch(ls, l0, m, trial, lx1, have_trial, lx1);
     }
     QN_TICK(7);
-    if (alpha == 0.0) { status = QN_LINESEARCH_FAILED; if (!(it & 1)) g = unpark(C::wGp); break; } // QN.jl:284
+    if (alpha == 0.0) { status = QN_LINESEARCH_FAILED; iters = it - 1; if (!(it & 1)) g = unpark(C::wGp); break; } // QN.jl:284
     // ---- accept: update_state! (QN.jl:21-27) and the buffer swap (QN.jl:286) were already
     // applied to the candidate; its ∂logdensity! becomes the next iteration's (QN.jl:254).
     s.lo = alpha * d.lo; s.hi = alpha * d.hi; // s ← αs      QN.jl:23-24
     x.lo = x.lo + s.lo;  x.hi = x.hi + s.hi;  // x_old += s  QN.jl:25
-    ++iters;
     if (p.trace != nullptr && it <= p.ntrace && owner)
       p.trace[(j * p.ntrace + (it - 1)) * (long long)N + e] = mine(x);
     // N iterations exhausted (QN.jl:250,291); which ∇ the canonical slot shows: see qn_resident.cuh
-    if (it == p.max_iter) { if (!(it & 1)) g = unpark(C::wGp); break; }
+    if (it == p.max_iter) { iters = it; if (!(it & 1)) g = unpark(C::wGp); break; }
     park(C::wGp, g);
     y.lo = g.lo - sp.g.lo; y.hi = g.hi - sp.g.hi; // y = ∇_old - ∇_new, QN.jl:38
     sy = sp.sy;

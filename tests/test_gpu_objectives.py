@@ -132,14 +132,20 @@ def test_resident_one_pass_mode(eng, qn, ob, n, flags_extra):
 
 
 def test_one_pass_flag_is_a_permission(eng, qn, ob):
-    """Where the deferred-update order has no kernel (register-tile sizes) or no room (n = 159: no
-    shared memory left for the second partial-sum array) the flag leaves the reference order in place."""
-    for n in (60, 159):
+    """Where the deferred-update order has no kernel (register-tile sizes) or no room (n = 159 with B⁻¹
+    wholly in shared memory: nothing left for the second partial-sum array) the flag leaves the
+    reference order in place; the hybrid register/shared-memory tiles (the default at n = 159) have
+    the room and follow the deferred-update order, bit for bit with its oracle variant."""
+    F = qn._lib
+    for n, flags, rblock in ((60, F.FLAG_ONE_PASS, None), (159, F.FLAG_ONE_PASS | F.FLAG_FORCE_SMEM, None),
+                             (159, F.FLAG_ONE_PASS, ob.ONEPASS), (100, F.FLAG_ONE_PASS, ob.ONEPASS)):
         Theta = starts(n, 4, key=n)
-        got = eng.optimize_batched(qn.Rosenbrock(), Theta, ntrace=5, flags=qn._lib.FLAG_ONE_PASS)
-        ref = ob.optimize_batch(ob.rosenbrock(), Theta, ntrace=5)
+        got = eng.optimize_batched(qn.Rosenbrock(), Theta, ntrace=5, flags=flags)
+        kw = {} if rblock is None else dict(rblock=rblock)
+        ref = ob.optimize_batch(ob.rosenbrock(), Theta, ntrace=5, **kw)
         for k in ("x", "g", "ell", "trace"):
-            assert np.array_equal(got[k], ref[k], equal_nan=True), k
+            assert np.array_equal(got[k], ref[k], equal_nan=True), (n, flags, k)
+        assert np.array_equal(got["iters"], ref["iters"]), (n, flags)
 
 
 def test_resident_one_pass_gaussian(eng, qn, ob):
