@@ -143,6 +143,42 @@ int launch_tile(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
   return QN_OK;
 }
 
+// The same kernel with the tile in tensor memory (qn_resident_tile.cuh, TM): CTAs of 128 threads =
+// two problems, 128 columns of tensor memory each, 4 CTAs = 8 problems per SM where the register
+// file holds 6.  cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for a kernel that calls
+// tcgen05.alloc (it cannot know the column count); the grid is sized for the 4 CTAs per SM that
+// registers (128 × 128 × 4 = the file), shared memory and 4 × 128 columns allow — measured: the
+// throughput grows 1.6e8 → 2.5e8 → 3.0e8 → 3.7e8 iterations/s from 1 to 4 CTAs per SM (n = 60).
+template <int N, int PF>
+int launch_tile_tmem(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
+  const size_t smem = 2 * sizeof(double) * (size_t)qn::tile_smem_doubles<N>();
+  auto kern = qn::qn_resident_tile_tmem_kernel<N, PF>;
+  QN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  long long grid = 4LL * ctx->prop.multiProcessorCount;
+  if (grid > (p.batch + 1) / 2) grid = (p.batch + 1) / 2;
+  p.counter = qn_next_counter(ctx, st);
+  kern<<<(unsigned)grid, 128, smem, st>>>(p);
+  QN_CUDA_TRY(cudaGetLastError());
+  ctx->last_path = 0;
+  ctx->last_grid = (int)grid;
+  ctx->last_block = 128;
+  ctx->last_smem = (int)smem;
+  ctx->last_launches = 1;
+  return QN_OK;
+}
+
+// Where the tile lives: tensor memory when it is the faster home (measured per size on B200,
+// 2^15-2^16 problems: n = 44 +1 %, 48 +6 %, 50 +8 %, 56 +1 %, 60 +3 %, 64 +8 %; n = 36, 40, 52 are
+// 1-3 % faster from registers) and the batch fills 8 problems per SM; QN_TILE_TMEM=0 / 1 forces
+// the register file / tensor memory.
+inline bool tile_in_tensor_memory(const qn_context* ctx, const int n, const long long batch) {
+  const char* v = getenv("QN_TILE_TMEM");
+  if (v && v[0] == '0') return false;
+  if (v && v[0] == '1') return true;
+  const bool faster = n == 44 || n == 48 || n == 50 || n == 56 || n == 60 || n == 64;
+  return faster && batch >= 8LL * ctx->prop.multiProcessorCount;
+}
+
 // n = 8, 16, 32 (Rosenbrock): several problems per warp (qn_resident_packed.cuh)
 template <int N, int RPT, int MINB>
 int launch_packed(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
@@ -191,6 +227,7 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
 #define QN_TILE_CASE(N, MINB) \
   case N:                      \
     if constexpr (std::is_same<Obj, qn::Rosenbrock>::value) {                                        \
+      if (tile_in_tensor_memory(ctx, N, p.batch)) return launch_tile_tmem<N, 1>(ctx, p, st);          \
       /* 6 CTAs per SM (168 registers); 4, 5 and 7 were measured slower */            \
       return launch_tile<N, MINB, 1>(ctx, p, st);                                                    \
     }                                                                                                \

@@ -156,14 +156,92 @@ __device__ __forceinline__ void warp_butterfly3(double& a, double& b, double& c,
   c = __shfl_sync(0xffffffffu, v, 8);
 }
 
-template <int N, int PF>
-__device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long long j, double* smem) {
+
+// ---- tensor memory as the home of the tile (TM = true) -------------------------------------------
+// The register file caps the all-register kernel at 6 problems per SM (120 of 168 registers are
+// B⁻¹).  Tensor memory is as large as the register file (256 KB per SM), has its own data path
+// (measured on B200, tools/tmem_bench.cu: 475 B/clk/SM of tcgen05.ld, 890 B/clk/SM of tcgen05.st,
+// 30 cycles for a dependent 4 KB load — the shared-memory pipe moves 128 B/clk), and a thread may
+// use its own lane as plain storage: no MMA is involved.  With the tile there, a thread needs
+// < 128 registers, so 8 problems are resident per SM (4 warps per scheduler instead of 3).
+// A warp reaches only the lanes 32·(warp mod 4)…+31, so a CTA is 4 warps = TWO problems
+// (threads 0-63 and 64-127, each pair with its own named barrier and its own pulls from the work
+// queue) and owns 128 columns: a thread's 4×CT tile as chunks of 4 columns × 4 rows = 16 doubles
+// = 32 columns in the first version; as built, chunks of half a column (see TmChunk) — one
+// tcgen05.ld/st .32x32b per chunk, a few chunks in flight ahead of the one being used.
+// one chunk = EPC consecutive elements of the thread's tile in the order e = 4k + i (column k, row i):
+// EPC = 2 (half a column, tcgen05.ld/st .32x32b.x4 — a register quadruple like that of an LDS.128)
+// or 4 (one column, .x8).  The 32-bit words of tcgen05.ld/st are paired into fp64 registers inside
+// the asm block (mov.b64 of an aligned register pair is a renaming, not an instruction).
+#ifndef QN_TM_EPC
+#define QN_TM_EPC 4 // measured: one column per chunk 77.2 ms, half a column 80.5 ms per 2^16 problems (n = 60)
+#endif
+#ifndef QN_TM_PARK
+#define QN_TM_PARK 0 // 1: x, ∇, y wait in shared memory during the passes, as in the all-register kernel
+#endif
+#ifndef QN_TM_DEPTH
+#define QN_TM_DEPTH (QN_TM_EPC == 2 ? 4 : 2) // chunks in flight ahead of the one being used
+#endif
+template <int EPC>
+struct TmChunk { double d[EPC]; };
+// tcgen05.wait::ld emits no instruction: ptxas guards the destination registers of LDTM with a
+// scoreboard like those of any load, so a value is never read before it has arrived; the statement
+// only marks, for the PTX memory model, where the loaded values may be used.
+__device__ __forceinline__ void tm_wait_load() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+template <int EPC>
+__device__ __forceinline__ void tm_load(TmChunk<EPC>& c, const uint32_t addr) {
+  static_assert(EPC == 2 || EPC == 4, "chunk of 2 or 4 elements");
+  if constexpr (EPC == 2) {
+    asm volatile("{\n.reg .b32 t0a, t0b, t1a, t1b;\n"
+                 "tcgen05.ld.sync.aligned.32x32b.x4.b32 {t0a, t0b, t1a, t1b}, [%2];\n"
+                 "mov.b64 %0, {t0a, t0b};\nmov.b64 %1, {t1a, t1b};\n}\n"
+                 : "=d"(c.d[0]), "=d"(c.d[1]) : "r"(addr));
+  } else {
+    asm volatile("{\n.reg .b32 t0a, t0b, t1a, t1b, t2a, t2b, t3a, t3b;\n"
+                 "tcgen05.ld.sync.aligned.32x32b.x8.b32 {t0a, t0b, t1a, t1b, t2a, t2b, t3a, t3b}, [%4];\n"
+                 "mov.b64 %0, {t0a, t0b};\nmov.b64 %1, {t1a, t1b};\nmov.b64 %2, {t2a, t2b};\nmov.b64 %3, {t3a, t3b};\n}\n"
+                 : "=d"(c.d[0]), "=d"(c.d[1]), "=d"(c.d[2]), "=d"(c.d[3]) : "r"(addr));
+  }
+}
+template <int EPC>
+__device__ __forceinline__ void tm_store(const uint32_t addr, const TmChunk<EPC>& c) {
+  if constexpr (EPC == 2) {
+    asm volatile("{\n.reg .b32 t0a, t0b, t1a, t1b;\n"
+                 "mov.b64 {t0a, t0b}, %1;\nmov.b64 {t1a, t1b}, %2;\n"
+                 "tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {t0a, t0b, t1a, t1b};\n}\n"
+                 :: "r"(addr), "d"(c.d[0]), "d"(c.d[1]) : "memory");
+  } else {
+    asm volatile("{\n.reg .b32 t0a, t0b, t1a, t1b, t2a, t2b, t3a, t3b;\n"
+                 "mov.b64 {t0a, t0b}, %1;\nmov.b64 {t1a, t1b}, %2;\nmov.b64 {t2a, t2b}, %3;\nmov.b64 {t3a, t3b}, %4;\n"
+                 "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {t0a, t0b, t1a, t1b, t2a, t2b, t3a, t3b};\n}\n"
+                 :: "r"(addr), "d"(c.d[0]), "d"(c.d[1]), "d"(c.d[2]), "d"(c.d[3]) : "memory");
+  }
+}
+__device__ __forceinline__ void tm_wait_store() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+// barrier of one problem's 64 threads (barrier 0 stays the CTA's)
+// (immediate ids: with the id in a register ptxas reserves all 16 barriers and one CTA fills the SM)
+__device__ __forceinline__ void pair_barrier(const int pair) {
+  if (pair == 0) asm volatile("bar.sync 1, 64;\n" ::: "memory");
+  else asm volatile("bar.sync 2, 64;\n" ::: "memory");
+}
+
+template <int N, int PF, bool TM = false>
+__device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long long j, double* smem, const uint32_t tmem = 0) {
   using C = TileCfg<N>;
   constexpr int RT = C::RT, CT = C::CT, NB = C::NB;
-  const int t = threadIdx.x;
+  const int t = TM ? (threadIdx.x & 63) : threadIdx.x; // thread of this problem
   const int lane = t & 31;
   const int warp = t >> 5;
   const int e = t;                    // the element this thread writes out at the end
+  constexpr int EPC = QN_TM_EPC;                        // elements per chunk of the tile in tensor memory (TM)
+  constexpr int SPC = 4 / EPC;                          // chunks per column
+  constexpr int NCH = TileCfg<N>::CT * SPC;             // chunks
+  constexpr int WPC = 2 * EPC;                          // 32-bit columns per chunk
+  constexpr int TD = QN_TM_DEPTH;                       // prefetch distance in chunks
+  static_assert(!TM || NCH * WPC <= 128, "the tile must fit the CTA's 128 columns");
+  auto cta_sync = [&]() {
+    if constexpr (TM) pair_barrier((int)(threadIdx.x >> 6)); else __syncthreads();
+  };
   const bool owner = e < N;
   const bool hi_valid = lane + 32 < N;
   const int b = t >> 4;               // column block of this thread's tile (one per half-warp)
@@ -189,7 +267,8 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
   const int slot_lo = slot_of(lane), slot_hi = slot_of(lane + 32);
   const int q_lo = C::quad(lane), q_hi = q_lo + 16; // quad-layout index of elements lane, lane + 32
 
-  double h[RT][CT]; // the tile: h[i][k] = B⁻¹[row0 + i, col0 + k]
+  double h[TM ? 1 : RT][TM ? 1 : CT]; // the tile: h[i][k] = B⁻¹[row0 + i, col0 + k] (TM: in tensor memory)
+  (void)h;
 
   auto mine = [&](const Pair& v) { return warp ? v.hi : v.lo; }; // element e of a replicated vector
   auto dot = [&](const Pair& a, const Pair& bb) {                // lane accumulator of rule C1
@@ -226,9 +305,14 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
     s.lo = s.hi = y.lo = y.hi = 0.0;
     const double term = rosenbrock_warp_terms<N, true>(lane, x, g); // QN.jl:254 of iteration 1
     l0 = rosenbrock_finish<N>(warp_butterfly(term), x);
-    Pair zero; zero.lo = zero.hi = 0.0;
-    park(C::wGp, zero);
   }
+  // ∇ of the previous iteration (what the canonical slot shows after a failure in an even
+  // iteration): parked in shared memory, or kept in registers when the tile is in tensor memory
+  constexpr bool kParkGp = !TM || QN_TM_PARK;
+  Pair gp; gp.lo = gp.hi = 0.0;
+  auto save_gp = [&](const Pair& v) { if (kParkGp) park(C::wGp, v); else gp = v; };
+  auto load_gp = [&]() { return kParkGp ? unpark(C::wGp) : gp; };
+  save_gp(gp);
   double result = __longlong_as_double(0x7ff8000000000000LL); // NaN, QN.jl:291
   int iters = 0, fevals = 0, status = QN_MAX_ITER; // iters (completed iterations) is set where the loop is left
 
@@ -268,7 +352,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
     const bool all_small = __all_sync(0xffffffffu, small);
     if (!isfinite(l0) || all_small) {
       iters = it - 1;
-      if (!isfinite(l0)) { status = QN_NONFINITE; if (!(it & 1)) g = unpark(C::wGp); }
+      if (!isfinite(l0)) { status = QN_NONFINITE; if (!(it & 1)) g = load_gp(); }
       else { status = QN_CONVERGED; result = l0; }
       break;
     }
@@ -294,9 +378,13 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
         *reinterpret_cast<double2*>(rec + slot_hi * C::kRec + 2) = make_double2(s.hi, g.hi);
         yb_arr[slot_hi] = y.hi;
       }
-      park(C::wX, x);
-      park(C::wG, g);
-      park(C::wY, y);
+      // (with the tile in tensor memory the registers can keep x, ∇ and y through the passes)
+      constexpr bool kPark = !TM || QN_TM_PARK;
+      if (kPark) {
+        park(C::wX, x);
+        park(C::wG, g);
+        park(C::wY, y);
+      }
       __syncwarp();
       QN_TICK(2);
       const double rho = 1.0 / sy; // QN.jl:42 (no guard)
@@ -313,23 +401,43 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
 #pragma unroll
         for (int k = 0; k < (CT + 1) / 2; ++k) yy[k] = yb2[k];
         __syncwarp(); // keeps the loads above it
+        if constexpr (TM) {
+          TmChunk<EPC> ring[TD + 1];
 #pragma unroll
-        for (int k = 0; k < CT; ++k) {
-          const double yk = (k & 1) ? yy[k >> 1].y : yy[k >> 1].x;
-          if (C::kFull || col0 + k < N) {
+          for (int c = 0; c < TD && c < NCH; ++c) tm_load(ring[c], tmem + WPC * c);
 #pragma unroll
-            for (int i = 0; i < RT; ++i) tt[i] = fma(yk, h[i][k], tt[i]);
+          for (int k = 0; k < CT; ++k) {
+            const double yk = (k & 1) ? yy[k >> 1].y : yy[k >> 1].x;
+#pragma unroll
+            for (int sc = 0; sc < SPC; ++sc) {
+              const int c = k * SPC + sc;
+              tm_wait_load();
+              if (c + TD < NCH) tm_load(ring[(c + TD) % (TD + 1)], tmem + WPC * (c + TD));
+              if (C::kFull || col0 + k < N) {
+#pragma unroll
+                for (int r = 0; r < EPC; ++r) tt[sc * EPC + r] = fma(yk, ring[c % (TD + 1)].d[r], tt[sc * EPC + r]);
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < CT; ++k) {
+            const double yk = (k & 1) ? yy[k >> 1].y : yy[k >> 1].x;
+            if (C::kFull || col0 + k < N) {
+#pragma unroll
+              for (int i = 0; i < RT; ++i) tt[i] = fma(yk, h[i][k], tt[i]);
+            }
           }
         }
         double* pp = part1 + b * C::kQuad + 2 * q;
         *reinterpret_cast<double2*>(pp) = make_double2(tt[0], tt[1]);
         *reinterpret_cast<double2*>(pp + 40) = make_double2(tt[2], tt[3]);
       }
-      __syncthreads(); // pass-1 partials of both warps visible
+      cta_sync(); // pass-1 partials of both warps visible
       QN_TICK(3);
       {
         const Pair T = combine(part1);
-        const Pair yv = unpark(C::wY);
+        const Pair yv = kPark ? unpark(C::wY) : y;
         const double s_lo = s_arr[q_lo], s_hi = s_arr[q_hi]; // fetched ahead of the butterfly that c₁ waits for
         const double yHy = warp_butterfly(dot(T, yv)); // Σ_c t[c] y[c], QN.jl:51
         const double c1 = fma(yHy, rho, 1.0) * rho;    // QN.jl:54
@@ -344,35 +452,66 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
       QN_TICK(4);
       // pass 2 on the tile: H ← H + c₁ssᵀ - usᵀ - suᵀ fused with d = H⁺∇_new   QN.jl:56-67
       {
-        double sc[RT], nuc[RT], acc[RT];
+        double sc_[RT], nuc[RT], acc[RT];
         const double2 s01 = *reinterpret_cast<const double2*>(s_arr + 2 * q);
         const double2 s23 = *reinterpret_cast<const double2*>(s_arr + 40 + 2 * q);
         const double2 n01 = *reinterpret_cast<const double2*>(nu_arr + 2 * q);
         const double2 n23 = *reinterpret_cast<const double2*>(nu_arr + 40 + 2 * q);
-        sc[0] = s01.x; sc[1] = s01.y; sc[2] = s23.x; sc[3] = s23.y;
+        sc_[0] = s01.x; sc_[1] = s01.y; sc_[2] = s23.x; sc_[3] = s23.y;
         nuc[0] = n01.x; nuc[1] = n01.y; nuc[2] = n23.x; nuc[3] = n23.y;
 #pragma unroll
         for (int i = 0; i < RT; ++i) acc[i] = 0.0;
         const double* rb_ = rec + hb * 16 * C::kRec;
         auto ld_wn = [&](const int k) { return *reinterpret_cast<const double2*>(rb_ + k * C::kRec); };
         auto ld_sg = [&](const int k) { return *reinterpret_cast<const double2*>(rb_ + k * C::kRec + 2); };
-        // operand ring: the loads of step k+PF are issued while step k computes
-        double2 wnr[PF + 1], sgr[PF + 1];
+        if constexpr (TM) {
+          TmChunk<EPC> ring[TD + 1];
 #pragma unroll
-        for (int k = 0; k < PF && k < CT; ++k) { wnr[k] = ld_wn(k); sgr[k] = ld_sg(k); }
+          for (int c = 0; c < TD && c < NCH; ++c) tm_load(ring[c], tmem + WPC * c);
 #pragma unroll
-        for (int k = 0; k < CT; ++k) {
-          if (k + PF < CT) { wnr[(k + PF) % (PF + 1)] = ld_wn(k + PF); sgr[(k + PF) % (PF + 1)] = ld_sg(k + PF); }
-          const double2 wn = wnr[k % (PF + 1)], sg = sgr[k % (PF + 1)];
-          if (C::kFull || col0 + k < N) {
+          for (int k = 0; k < CT; ++k) {
+            const double2 wn = ld_wn(k), sg = ld_sg(k);
 #pragma unroll
-            for (int i = 0; i < RT; ++i) {
-              double hh = h[i][k];
-              hh = fma(wn.x, sc[i], hh);   // + (c₁ s[r]) s[c]
-              hh = fma(wn.y, sc[i], hh);   // - u[r] s[c]
-              hh = fma(nuc[i], sg.x, hh);  // - u[c] s[r]
-              h[i][k] = hh;
-              acc[i] = fma(hh, sg.y, acc[i]);
+            for (int sc = 0; sc < SPC; ++sc) {
+              const int c = k * SPC + sc;
+              TmChunk<EPC>& cur = ring[c % (TD + 1)];
+              tm_wait_load();
+              if (c + TD < NCH) tm_load(ring[(c + TD) % (TD + 1)], tmem + WPC * (c + TD));
+              if (C::kFull || col0 + k < N) {
+#pragma unroll
+                for (int r = 0; r < EPC; ++r) {
+                  const int i = sc * EPC + r;
+                  double hh = cur.d[r];
+                  hh = fma(wn.x, sc_[i], hh);  // + (c₁ s[r]) s[c]
+                  hh = fma(wn.y, sc_[i], hh);  // - u[r] s[c]
+                  hh = fma(nuc[i], sg.x, hh);  // - u[c] s[r]
+                  cur.d[r] = hh;
+                  acc[i] = fma(hh, sg.y, acc[i]);
+                }
+              }
+              tm_store(tmem + WPC * c, cur); // by the whole warp (.sync.aligned), also where a half-warp has no column k
+            }
+          }
+          tm_wait_store();
+        } else {
+          // operand ring: the loads of step k+PF are issued while step k computes
+          double2 wnr[PF + 1], sgr[PF + 1];
+  #pragma unroll
+          for (int k = 0; k < PF && k < CT; ++k) { wnr[k] = ld_wn(k); sgr[k] = ld_sg(k); }
+  #pragma unroll
+          for (int k = 0; k < CT; ++k) {
+            if (k + PF < CT) { wnr[(k + PF) % (PF + 1)] = ld_wn(k + PF); sgr[(k + PF) % (PF + 1)] = ld_sg(k + PF); }
+            const double2 wn = wnr[k % (PF + 1)], sg = sgr[k % (PF + 1)];
+            if (C::kFull || col0 + k < N) {
+  #pragma unroll
+              for (int i = 0; i < RT; ++i) {
+                double hh = h[i][k];
+                hh = fma(wn.x, sc_[i], hh);   // + (c₁ s[r]) s[c]
+                hh = fma(wn.y, sc_[i], hh);   // - u[r] s[c]
+                hh = fma(nuc[i], sg.x, hh);  // - u[c] s[r]
+                h[i][k] = hh;
+                acc[i] = fma(hh, sg.y, acc[i]);
+              }
             }
           }
         }
@@ -380,11 +519,13 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
         *reinterpret_cast<double2*>(pp) = make_double2(acc[0], acc[1]);
         *reinterpret_cast<double2*>(pp + 40) = make_double2(acc[2], acc[3]);
       }
-      __syncthreads(); // pass-2 partials of both warps visible
+      cta_sync(); // pass-2 partials of both warps visible
       QN_TICK(5);
       d = combine(part2); // the new direction d = H⁺∇_new; `s, y = y, s`, QN.jl:65,268
-      x = unpark(C::wX);
-      g = unpark(C::wG);
+      if (kPark) {
+        x = unpark(C::wX);
+        g = unpark(C::wG);
+      }
       // m = dᵀ∇_new (QN.jl:66-68) shares its butterfly with the first line-search trial
       // ℓ(x + 1·d) (QN.jl:174) and with s'ᵀy' of the iteration that follows if it is accepted.
       double tterm;
@@ -397,10 +538,21 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
       QN_TICK(6);
     }
     if (m <= 0.0) { // QN.jl:272-280: H ← I, s ← ∇_new, m ← ∇ᵀ∇
+      if constexpr (TM) {
 #pragma unroll
-      for (int i = 0; i < RT; ++i)
+        for (int c = 0; c < NCH; ++c) {
+          TmChunk<EPC> hc;
 #pragma unroll
-        for (int k = 0; k < CT; ++k) h[i][k] = (row0 + i == col0 + k) ? 1.0 : 0.0;
+          for (int r = 0; r < EPC; ++r) hc.d[r] = (row0 + (c % SPC) * EPC + r == col0 + c / SPC) ? 1.0 : 0.0;
+          tm_store(tmem + WPC * c, hc);
+        }
+        tm_wait_store();
+      } else {
+#pragma unroll
+        for (int i = 0; i < RT; ++i)
+#pragma unroll
+          for (int k = 0; k < CT; ++k) h[i][k] = (row0 + i == col0 + k) ? 1.0 : 0.0;
+      }
       d = g;
       m = warp_butterfly(dot(g, g));
       have_trial = false;
@@ -421,7 +573,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
       alpha = backtracking_linesearch(ls, l0, m, trial, lx1, have_trial, lx1);
     }
     QN_TICK(7);
-    if (alpha == 0.0) { status = QN_LINESEARCH_FAILED; iters = it - 1; if (!(it & 1)) g = unpark(C::wGp); break; } // QN.jl:284
+    if (alpha == 0.0) { status = QN_LINESEARCH_FAILED; iters = it - 1; if (!(it & 1)) g = load_gp(); break; } // QN.jl:284
     // ---- accept: update_state! (QN.jl:21-27) and the buffer swap (QN.jl:286) were already
     // applied to the candidate; its ∂logdensity! becomes the next iteration's (QN.jl:254).
     s.lo = alpha * d.lo; s.hi = alpha * d.hi; // s ← αs      QN.jl:23-24
@@ -429,8 +581,8 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
     if (p.trace != nullptr && it <= p.ntrace && owner)
       p.trace[(j * p.ntrace + (it - 1)) * (long long)N + e] = mine(x);
     // N iterations exhausted (QN.jl:250,291); which ∇ the canonical slot shows: see qn_resident.cuh
-    if (it == p.max_iter) { iters = it; if (!(it & 1)) g = unpark(C::wGp); break; }
-    park(C::wGp, g);
+    if (it == p.max_iter) { iters = it; if (!(it & 1)) g = load_gp(); break; }
+    save_gp(g);
     y.lo = g.lo - sp.g.lo; y.hi = g.hi - sp.g.hi; // y = ∇_old - ∇_new, QN.jl:38
     sy = sp.sy;
     g = sp.g;
@@ -441,13 +593,28 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
     if (p.x_out) p.x_out[j * p.x_stride + e] = mine(x);
     if (p.g_out) p.g_out[j * p.g_stride + e] = mine(g);
   }
-  if (p.h_out && b < NB) {
+  // (TM: every thread of the warp takes part in the .sync.aligned loads, also a half-warp without a column block)
+  if (p.h_out && (TM || b < NB)) {
     double* ho = p.h_out + j * p.h_stride;
+    if constexpr (TM) {
 #pragma unroll
-    for (int i = 0; i < RT; ++i)
+      for (int c = 0; c < NCH; ++c) {
+        TmChunk<EPC> hc;
+        tm_load(hc, tmem + WPC * c);
+        tm_wait_load();
 #pragma unroll
-      for (int k = 0; k < CT; ++k)
-        if (row0 + i < N && col0 + k < N) ho[(row0 + i) + (long long)p.ldh * (col0 + k)] = h[i][k];
+        for (int r = 0; r < EPC; ++r) {
+          const int k = c / SPC, i = (c % SPC) * EPC + r;
+          if (row0 + i < N && col0 + k < N) ho[(row0 + i) + (long long)p.ldh * (col0 + k)] = hc.d[r];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < RT; ++i)
+#pragma unroll
+        for (int k = 0; k < CT; ++k)
+          if (row0 + i < N && col0 + k < N) ho[(row0 + i) + (long long)p.ldh * (col0 + k)] = h[i][k];
+    }
   }
   write_problem_scalars(p, j, t, result, iters, fevals, status);
 }
@@ -466,6 +633,39 @@ qn_resident_tile_kernel(const __grid_constant__ BatchParams p) {
     if (j >= p.batch) break;
     tile_solve_one<N, PF>(p, j, smem);
   }
+}
+
+// The tensor-memory variant: 4 warps = two problems per CTA, 128 columns of tensor memory per CTA,
+// 4 CTAs = 8 problems per SM.  Each pair of warps runs its own persistent loop.
+template <int N, int PF>
+__global__ void __launch_bounds__(128, 4)
+qn_resident_tile_tmem_kernel(const __grid_constant__ BatchParams p) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ uint32_t tmem_base;
+  constexpr int kPairDoubles = tile_smem_doubles<N>();
+  const int pair = (int)(threadIdx.x >> 6);
+  double* sm = smem + pair * kPairDoubles;
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;\n"
+                 :: "l"((unsigned long long)__cvta_generic_to_shared(&tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = tmem_base + (((threadIdx.x >> 5) * 32u) << 16); // this warp's 32 lanes
+  volatile long long* next = reinterpret_cast<volatile long long*>(sm + kPairDoubles - 2);
+  for (;;) {
+    pair_barrier(pair); // the previous problem's shared-memory traffic is finished
+    if ((threadIdx.x & 63) == 0) *next = (long long)atomicAdd(p.counter, 1ULL);
+    pair_barrier(pair);
+    const long long j = *next;
+    if (j >= p.batch) break;
+    tile_solve_one<N, PF, true>(p, j, sm, tmem);
+  }
+  __syncthreads(); // both problems are done with the tensor memory
+  if (threadIdx.x < 32)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;\n" :: "r"(tmem_base) : "memory");
 }
 
 }  // namespace qn

@@ -109,6 +109,55 @@ def test_tile_kernel_sizes(eng, qn, ob, n):
         _check(got, ref)
 
 
+@pytest.mark.parametrize("n", [36, 40, 44, 48, 50, 52, 56, 60, 64])
+def test_tile_kernel_in_tensor_memory(eng, qn, ob, n, monkeypatch):
+    """The same kernel with B⁻¹ tiles in tensor memory (tcgen05.ld/st; CTAs of 128 threads = two
+    problems, 8 problems per SM): the default for large batches of n = 44, 48, 50, 56, 60, 64, forced
+    here for every tile size (QN_TILE_TMEM=1) and for batches that leave a pair of warps idle.  Same
+    bits as the oracle — traces, counts, both line-search orders, the final B⁻¹, iteration caps
+    (which ∇ the canonical slot shows), a non-finite start — and as the all-register kernel."""
+    monkeypatch.setenv("QN_TILE_TMEM", "1")
+    R = qn.Rosenbrock()
+    for batch in (1, 21):
+        Theta = starts(n, batch, key=8000 + n)
+        for order in (2, 3):
+            got = eng.optimize_batched(R, Theta, ls=qn.BackTracking[order](), ntrace=5)
+            assert eng.last_launch()["path"] == qn._lib.PATH_REGISTER and eng.last_launch()["block"] == 128
+            ref = ob.optimize_batch(ob.rosenbrock(), Theta, ls=ob.backtracking(order), ntrace=5)
+            _check(got, ref)
+    # final B⁻¹ (read back from tensor memory) and the BFGSState layout
+    batch = 5
+    Theta = starts(n, batch, key=8100 + n)
+    sb = qn.BFGSStateBatch(n, batch)
+    sb.data[:] = np.nan
+    r = eng.optimize_batched(R, Theta, states=sb, flags=qn._lib.FLAG_WRITE_H)
+    assert eng.last_launch()["block"] == 128
+    L = sb.L
+    for j in range(batch):
+        o = ob.optimize(ob.rosenbrock(), Theta[:, j], L=L)
+        assert np.array_equal(sb.data[j, 7 * L:].reshape(n, L)[:, :n], o["state"][7 * L:].reshape(n, L)[:, :n])
+        assert np.array_equal(sb.data[j, :n], o["x"]) and np.array_equal(sb.data[j, L:L + n], o["g"])
+    # iteration caps (odd: latest ∇, even: previous ∇ — kept in registers on this path) and a NaN start
+    for cap in (1, 2, 5, 6):
+        Th = starts(n, 4, key=cap)
+        if cap == 5:
+            Th[3, 2] = np.nan
+        got = eng.optimize_batched(R, Th, max_iter=cap, ntrace=cap)
+        ref = ob.optimize_batch(ob.rosenbrock(), Th, max_iter=cap, ntrace=cap)
+        for k in ("x", "g", "trace", "ell"):
+            assert np.array_equal(got[k], ref[k], equal_nan=True), (n, cap, k)
+        for k in ("iters", "fevals", "status"):
+            assert np.array_equal(got[k], ref[k]), (n, cap, k)
+    # and the all-register kernel gives the same bits on a batch large enough for either
+    Theta = starts(n, 300, key=8200 + n)
+    a = eng.optimize_batched(R, Theta)
+    monkeypatch.setenv("QN_TILE_TMEM", "0")
+    b_ = eng.optimize_batched(R, Theta)
+    assert eng.last_launch()["block"] == 64
+    for k in ("x", "g", "ell", "iters", "fevals", "status"):
+        assert np.array_equal(a[k], b_[k], equal_nan=True), k
+
+
 ALL_PATH_SIZES = [1, 2, 3, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 36, 40, 47, 48, 49, 56, 60, 63, 64, 65, 66,
                   80, 95, 96, 104, 105, 112, 127, 128, 129, 144, 159, 160]
 
@@ -171,6 +220,7 @@ def test_full_size_batch(eng, qn, ob):
     n, batch = 60, 1 << 16
     Theta = starts(n, batch)
     got = eng.optimize_batched(qn.Rosenbrock(), Theta)
+    assert eng.last_launch()["block"] == 128  # at this size the tiles live in tensor memory (8 problems per SM)
     assert (got["status"] == qn.CONVERGED).all()
     assert np.abs(got["g"]).max() < TOL_G
     assert np.abs(got["x"] - 1).max() < 2e-7

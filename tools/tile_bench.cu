@@ -3,7 +3,7 @@
 // AND for identical bits in one gpurun call.  The header is found through -I (point it at the
 // variant's directory):
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -std=c++17 --expt-relaxed-constexpr \
-//        -I quasinewtonmethods.jl_b200/csrc [-DTB_MINB=6 -DTB_PF=1 -DTB_GC=1] -o tile_bench tools/tile_bench.cu
+//        -I quasinewtonmethods.jl_b200/csrc [-DTB_MINB=6 -DTB_PF=1 -DTB_TMEM -DQN_TM_KC=2] -o tile_bench tools/tile_bench.cu
 //   ./tile_bench [problems = 65536] [timed launches = 3]
 #include <cstdio>
 #include <cstdlib>
@@ -47,20 +47,29 @@ int main(int argc, char** argv) {
   p.ls = qn::LsParams{1e-4, 0.5, 0.1, 1000, 2};
   p.x_out = d_x; p.x_stride = n; p.g_out = d_g; p.g_stride = n; p.ell_out = d_ell;
   p.iters_out = d_it; p.fevals_out = d_fe; p.status_out = d_st; p.counter = d_cnt;
+#ifdef TB_TMEM // the tensor-memory variant: two problems per CTA of 128 threads
+  const size_t smem = 2 * sizeof(double) * qn::tile_smem_doubles<n>();
+  auto kern = qn::qn_resident_tile_tmem_kernel<n, TB_PF>;
+  const int block = 128;
+#else
   const size_t smem = sizeof(double) * qn::tile_smem_doubles<n>();
   auto kern = qn::qn_resident_tile_kernel<n, TB_MINB, TB_PF>;
+  const int block = 64;
+#endif
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int perSM = 0, sms = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, 64, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, block, smem);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  const int grid = (int)std::min<long long>(nprob, (long long)perSM * sms);
+  const int occ_api = perSM;
+  if (getenv("TB_PERSM")) perSM = atoi(getenv("TB_PERSM")); // resident CTAs per SM the grid is sized for
+  const int grid = (int)std::min<long long>((nprob + block / 64 - 1) / (block / 64), (long long)perSM * sms);
   cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   std::vector<float> ms;
   for (int r = 0; r < reps + 1; ++r) {
     cudaMemset(d_cnt, 0, 8);
     cudaEventRecord(e0);
-    kern<<<grid, 64, smem>>>(p);
+    kern<<<grid, block, smem>>>(p);
     cudaEventRecord(e1);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
@@ -81,7 +90,7 @@ int main(int argc, char** argv) {
   long long iters = 0, conv = 0; for (long long j = 0; j < nprob; ++j) { iters += it[j]; conv += st[j] == 0; }
   std::sort(ms.begin(), ms.end());
   const double med = ms[ms.size() / 2];
-  printf("n=%d problems=%lld grid=%d (%d/SM) regs=%d smem=%zu: median %.3f ms (min %.3f)  %.4g iterations/s  %.4g solves/s  converged %lld  hash %016llx\n",
-         n, nprob, grid, perSM, fa.numRegs, smem, med, ms[0], iters / (med * 1e-3), nprob / (med * 1e-3), conv, h);
+  printf("n=%d problems=%lld grid=%d (%d/SM, occupancy API %d) regs=%d smem=%zu: median %.3f ms (min %.3f)  %.4g iterations/s  %.4g solves/s  converged %lld  hash %016llx\n",
+         n, nprob, grid, perSM, occ_api, fa.numRegs, smem, med, ms[0], iters / (med * 1e-3), nprob / (med * 1e-3), conv, h);
   return 0;
 }
