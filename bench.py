@@ -31,8 +31,10 @@ BATCH = 1 << 16
 SEED = 20261018
 METRIC = "converged BFGS solves/sec (n=60 Rosenbrock, 2^16 batch per GPU)"
 # DRAM bytes of ONE launch of the headline kernel at this workload (dram__bytes_read.sum +
-# dram__bytes_write.sum, ncu --set full on this command): profiles/r1_tile60_bench_ncu.txt
-TILE_KERNEL_DRAM_BYTES_PER_LAUNCH = 33576192 + 32338944
+# dram__bytes_write.sum, ncu --set full on this command): profiles/r1_tile60_tmem_bench_ncu.txt for
+# the kernel with the tiles in tensor memory (CTAs of 128 threads), profiles/r1_tile60_bench_ncu.txt
+# for the all-register kernel (CTAs of 64 threads)
+TILE_KERNEL_DRAM_BYTES_PER_LAUNCH = {128: 32798464 + 14649600, 64: 33576192 + 32338944}
 UNIT = "solves/s"
 
 
@@ -296,6 +298,8 @@ def run_ours(args, rank, world, local_rank):
                                    "tol 1e-8 (BASELINE.json configs[1])",
                        "n": n, "per_gpu_batch": batch, "global_batch": batch * world,
                        "path": ["register-resident", "smem-resident", "stream"][launch["path"]],
+                       "tile_home": ("tensor memory (tcgen05.ld/st), 8 problems per SM" if launch["block"] == 128
+                                     else "register file, 6 problems per SM") if launch["path"] == 0 else None,
                        "grid": launch["grid"], "block": launch["block"], "smem_bytes": launch["smem_bytes"],
                        "l2": "256 MB buffer written between timed steps (L2 flush, outside the events)",
                        "parallelism": "independent problems sharded over %d GPU(s), no collective" % world},
@@ -313,9 +317,12 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {
                 "bound": "fp64", "achieved": ach_tf, "peak": mb["dfma"], "unit": "TFLOP/s",
                 "frac": ach_tf / mb["dfma"],
-                "traffic": TILE_KERNEL_DRAM_BYTES_PER_LAUNCH if (batch == BATCH and launch["path"] == 0) else None,
-                "traffic_note": "DRAM bytes per launch from profiles/r1_tile60_bench_ncu.txt; the algorithmic I/O of a launch is "
-                                "31.5 MB of starts in, 64.2 MB of results out — B^-1 never touches HBM",
+                "traffic": TILE_KERNEL_DRAM_BYTES_PER_LAUNCH.get(launch["block"]) if (batch == BATCH and launch["path"] == 0) else None,
+                "traffic_note": "DRAM bytes per launch from profiles/r1_tile60_tmem_bench_ncu.txt (r1_tile60_bench_ncu.txt for the "
+                                "all-register kernel); the algorithmic I/O of a launch is 31.5 MB of starts in, 64.2 MB of results "
+                                "out (part of which is still in L2 when the kernel ends) — B^-1 never touches HBM",
+                "pipes": "ncu on this launch: FP64 pipe 51 % busy, LSU data pipe 56 %, issue slots 61 %, 4 warps per scheduler "
+                         "(profiles/r1_tile60_tmem_bench_ncu.txt) — no single pipe is the bound; see DESIGN.md 5.1",
                 "peak_source": "qn_microbench_dfma, measured live on this GPU (MEASURED_PEAKS.json has no fp64 entry)",
                 "algorithmic": "8 n^2 = %d flops per BFGS iteration x iterations, per GPU" % int(flops_alg),
                 "smem_equiv": {"achieved": ach_gbs, "peak": mb["lds"], "unit": "GB/s", "frac": ach_gbs / mb["lds"],

@@ -653,7 +653,10 @@ qn_resident_tile_tmem_kernel(const __grid_constant__ BatchParams p) {
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  const uint32_t tmem = tmem_base + (((threadIdx.x >> 5) * 32u) << 16); // this warp's 32 lanes
+  // this warp's 32 lanes; the warp-wide reduction (of 32 equal values) tells the compiler that the
+  // address is warp-uniform, so it stays in a uniform register instead of being moved there
+  // (R2UR) in front of every tcgen05.ld/st
+  const uint32_t tmem = __reduce_max_sync(0xffffffffu, tmem_base + (((threadIdx.x >> 5) * 32u) << 16));
   volatile long long* next = reinterpret_cast<volatile long long*>(sm + kPairDoubles - 2);
   for (;;) {
     pair_barrier(pair); // the previous problem's shared-memory traffic is finished
