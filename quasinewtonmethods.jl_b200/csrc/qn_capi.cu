@@ -242,8 +242,8 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
   // Register tiles beyond the 4×15-tile sizes (qn_resident.cuh, PAIRN): a thread owns 4 rows × one
   // rule-C2 block.  QN_PAIR_ROWS selects the variant: 'h' hybrid — two of the four rows in registers,
   // two in shared memory, which fits every n <= 160 and makes TWO problems resident per SM up to
-  // n = 128 (Rosenbrock: n = 128 6.3e7 iterations/s, n = 160 3.1e7 against 1.8e7 with B⁻¹ in shared
-  // memory) —, '4' all four rows in registers (n = 128 only: 5.4e7), '2' 2×16 tiles of 512 threads
+  // n = 128 (Rosenbrock: n = 128 6.1e7 iterations/s, n = 96 7.0e7 against 4.1e7 and n = 160 2.2e7
+  // against 1.8e7 with B⁻¹ in shared memory) —, '4' all four rows in registers (n = 128 only: 5.4e7), '2' 2×16 tiles of 512 threads
   // (n = 128 only: 4.9e7).  Default: hybrid for cheap objectives at every 64 < n <= 160; for the
   // others the second resident problem buys nothing (dense Gaussian 2.21e7 against 2.19e7) and
   // all-register tiles at n = 128 leave the shared memory to the objective (Λ).
@@ -252,6 +252,12 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
     if (!(flags & QN_FLAG_FORCE_SMEM)) {
       const char* v = getenv("QN_PAIR_ROWS");
       const char variant = v ? v[0] : (Obj::kRegisterPaths ? 'h' : '4');
+      // n = 128 (BASELINE.json configs[2], [3]) has its own instantiations with n at compile time
+      // (hybrid 6.3e7 against 4.7e7 iterations/s with n at run time; dense Gaussian 1.04e6 against
+      // 0.68e6 solves/s); the other sizes share the run-time-n build
+      if (variant == 'h' && n == 128)
+        return onepass ? launch_resident<Obj, 0, 256, 2, 128, true, 4, 2>(ctx, p, op, st)
+                       : launch_resident<Obj, 0, 256, 2, 128, false, 4, 2>(ctx, p, op, st);
       if (variant == 'h' && n > 64 && n <= 160) {
         const int B = qn::resident_block_threads(n);
         const int threads = ((B / 4) * ((n + qn::chain_block(n) - 1) / qn::chain_block(n)) + 31) & ~31;
@@ -262,11 +268,11 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
                        : launch_resident<Obj, 0, 512, 1, 1, false, 4, 2>(ctx, p, op, st);
       }
       if (n == 128 && variant == '2')
-        return onepass ? launch_resident<Obj, 0, 512, 1, 1, true>(ctx, p, op, st)
-                       : launch_resident<Obj, 0, 512, 1, 1>(ctx, p, op, st);
+        return onepass ? launch_resident<Obj, 0, 512, 1, 128, true>(ctx, p, op, st)
+                       : launch_resident<Obj, 0, 512, 1, 128>(ctx, p, op, st);
       if (n == 128 && variant != 's')
-        return onepass ? launch_resident<Obj, 0, 256, 1, 1, true, 4>(ctx, p, op, st)
-                       : launch_resident<Obj, 0, 256, 1, 1, false, 4>(ctx, p, op, st);
+        return onepass ? launch_resident<Obj, 0, 256, 1, 128, true, 4>(ctx, p, op, st)
+                       : launch_resident<Obj, 0, 256, 1, 128, false, 4>(ctx, p, op, st);
     }
   }
   if (n <= 256) {

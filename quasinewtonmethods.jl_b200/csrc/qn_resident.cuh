@@ -109,7 +109,7 @@ __device__ __forceinline__ void write_problem_scalars(const BatchParams& p, long
   }
 }
 
-// PAIRN > 0 (with NREG == 0): the register-tile policy — every thread's PROWS × rb tile of B⁻¹
+// PAIRN > 0 (with NREG == 0; PAIRN = n at compile time, or 1 for n at run time): the register-tile policy — every thread's PROWS × rb tile of B⁻¹
 // (PROWS rows, one rule-C2 block of rb <= 16 columns) lives in REGISTERS (or, PREG < PROWS, partly
 // in shared memory); needs blockDim >= (B/PROWS) · #blocks so that a thread owns exactly one block.
 // ONEPASS (shared-memory and register-pair policies only): the deferred-update order of
@@ -125,7 +125,7 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
                                                    const long long j, Team& tm, double* ys,
                                                    Pass2Col* cols, double* hs, double* part,
                                                    double* part2 = nullptr, double* rowp = nullptr) {
-  const int n = (NREG > 0) ? NREG : p.n;
+  const int n = (NREG > 0) ? NREG : (PAIRN > 1 ? PAIRN : p.n); // PAIRN = 1: tiles with n at run time
   const int c = tm.c;          // thread index: the owner of element c when c < n
   const bool active = c < n;
   // shared-memory policy with more threads than elements ("pair" policy): thread c works on the
@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 qn_resident_kernel(const BatchParams p, const typename Obj::Params op) {
   // launch: blockDim >= resident_block_threads(n); see launch_resident for the policy
   extern __shared__ __align__(16) double smem[];
-  const int n = (NREG > 0) ? NREG : p.n;
+  const int n = (NREG > 0) ? NREG : (PAIRN > 1 ? PAIRN : p.n); // PAIRN = 1: tiles with n at run time
   const int B = resident_block_threads(n);
   const ResidentSmem L = resident_smem_layout<Obj>(n, NREG == 0 && PAIRN == 0, (int)blockDim.x, op, ONEPASS, PROWS,
                                                    PAIRN > 0 ? PROWS - PREG : 0);
