@@ -163,16 +163,16 @@ __device__ __forceinline__ void warp_butterfly3(double& a, double& b, double& c,
 // (measured on B200, tools/tmem_bench.cu: 475 B/clk/SM of tcgen05.ld, 890 B/clk/SM of tcgen05.st,
 // 30 cycles for a dependent 4 KB load — the shared-memory pipe moves 128 B/clk), and a thread may
 // use its own lane as plain storage: no MMA is involved.  With the tile there, a thread needs
-// < 128 registers, so 8 problems are resident per SM (4 warps per scheduler instead of 3).
+// < 128 registers, so 8 problems are resident per SM (4 warps per scheduler instead of 3), x, ∇
+// and y stay in registers through the passes, and nothing spills.
 // A warp reaches only the lanes 32·(warp mod 4)…+31, so a CTA is 4 warps = TWO problems
 // (threads 0-63 and 64-127, each pair with its own named barrier and its own pulls from the work
-// queue) and owns 128 columns: a thread's 4×CT tile as chunks of 4 columns × 4 rows = 16 doubles
-// = 32 columns in the first version; as built, chunks of half a column (see TmChunk) — one
-// tcgen05.ld/st .32x32b per chunk, a few chunks in flight ahead of the one being used.
-// one chunk = EPC consecutive elements of the thread's tile in the order e = 4k + i (column k, row i):
-// EPC = 2 (half a column, tcgen05.ld/st .32x32b.x4 — a register quadruple like that of an LDS.128)
-// or 4 (one column, .x8).  The 32-bit words of tcgen05.ld/st are paired into fp64 registers inside
-// the asm block (mov.b64 of an aligned register pair is a renaming, not an instruction).
+// queue) and owns 128 columns.  A thread's 4×CT tile is stored in the order e = 4k + i (column k,
+// row i), two 32-bit columns per element, and moved in chunks of EPC consecutive elements: EPC = 4
+// (one column, tcgen05.ld/st .32x32b.x8; the default) or 2 (half a column, .x4), QN_TM_DEPTH
+// chunks in flight ahead of the one being used.  The 32-bit words of tcgen05.ld/st are paired into
+// fp64 registers inside the asm block.  Every tcgen05 instruction is .sync.aligned: it must be
+// reached by the whole warp, also by a half-warp whose column block lies beyond n.
 #ifndef QN_TM_EPC
 #define QN_TM_EPC 4 // measured: one column per chunk 77.2 ms, half a column 80.5 ms per 2^16 problems (n = 60)
 #endif
