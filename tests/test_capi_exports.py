@@ -64,3 +64,19 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".inc", ".jl")):
                 text = open(os.path.join(dirpath, f), encoding="utf-8").read()
                 assert "qn_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_headline_kernel_uses_tensor_memory(qn):
+    """The sm_100a SASS of the n = 60 kernel that large batches run moves its B⁻¹ tiles with tensor-memory
+    loads and stores (LDTM / STTM — what tcgen05.ld / tcgen05.st compile to) and computes in fp64 FMAs."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    name = "_ZN2qn28qn_resident_tile_tmem_kernelILi60ELi1EEEvNS_11BatchParamsE"
+    out = subprocess.run([cuobjdump, "-sass", "-fun", name, qn._lib.SO_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out or "sm_100" in out
+    assert out.count("LDTM") >= 30 and out.count("STTM") >= 15, (out.count("LDTM"), out.count("STTM"))
+    assert out.count("DFMA") >= 300
+    assert "UTCATOMSWS" in out  # tcgen05.alloc
