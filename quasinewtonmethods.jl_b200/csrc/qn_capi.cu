@@ -63,7 +63,7 @@ namespace {
 // with more threads than elements only; a request that cannot be honoured (too small an n, or no
 // room for the second partial-sum array) silently runs the reference order.
 template <class Obj, int NREG, int BLOCK, int MINB, int PAIRN = 0, bool ONEPASS = false, int PROWS = 2,
-          int PREG = PROWS>
+          int PREG = PROWS, bool PTM = false>
 int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Params& op,
                     cudaStream_t st, int* probe_occ = nullptr) {
   // probe_occ != nullptr: do not launch, report how many CTAs (= problems) would be resident per SM
@@ -93,18 +93,19 @@ int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Par
   if (NREG == 0 && PAIRN == 0 && BLOCK > 512 && nthreads <= 512) // the 512-thread build may use 128 registers
     return launch_resident<Obj, 0, 512, 1, 0, ONEPASS, PROWS>(ctx, p, op, st, probe_occ);
   const qn::ResidentSmem L = qn::resident_smem_layout<Obj>(n, NREG == 0 && PAIRN == 0, nthreads, op, ONEPASS, PROWS,
-                                                           PAIRN > 0 ? PROWS - PREG : 0);
+                                                           (PAIRN > 0 && !PTM) ? PROWS - PREG : 0);
   const size_t smem = sizeof(double) * (size_t)L.total;
   if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin)
     return fail(QN_ERR_UNSUPPORTED_SIZE,
                 "n=%d needs %zu bytes of shared memory per problem; the device allows %zu "
                 "(use the streaming path)",
                 n, smem, (size_t)ctx->prop.sharedMemPerBlockOptin);
-  auto kern = qn::qn_resident_kernel<Obj, NREG, BLOCK, MINB, PAIRN, ONEPASS, PROWS, PREG>;
+  auto kern = qn::qn_resident_kernel<Obj, NREG, BLOCK, MINB, PAIRN, ONEPASS, PROWS, PREG, PTM>;
   QN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int block = nthreads;
   int occ = 0;
   QN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
+  if (PTM) occ = 2; // the occupancy query answers 1 for a kernel that allocates tensor memory (see launch_tile_tmem)
   if (probe_occ) { *probe_occ = occ; return QN_OK; }
   if (occ < 1) return fail(QN_ERR_UNSUPPORTED_SIZE, "resident kernel does not fit on an SM (n=%d)", n);
   long long grid = (long long)occ * ctx->prop.multiProcessorCount;
@@ -246,16 +247,21 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
   // against 1.8e7 with B⁻¹ in shared memory) —, '4' all four rows in registers (n = 128 only: 5.4e7), '2' 2×16 tiles of 512 threads
   // (n = 128 only: 4.9e7).  Default: hybrid for cheap objectives at every 64 < n <= 160; for the
   // others the second resident problem buys nothing (dense Gaussian 2.21e7 against 2.19e7) and
-  // all-register tiles at n = 128 leave the shared memory to the objective (Λ).
+  // all-register tiles at n = 128 leave the shared memory to the objective (Λ).  't' (n = 128, the
+  // default for cheap objectives): the hybrid tiles with their two other rows in TENSOR MEMORY instead
+  // of shared memory (tcgen05.ld/st .x4 per tile column, the next column in flight): 6.95e7 against
+  // 6.05e7 iterations/s, 16 KB instead of 82 KB of shared memory per problem.
   const bool onepass = (flags & QN_FLAG_ONE_PASS) != 0; // honoured by these policies (and the streaming path)
   if constexpr (Obj::kPairRegister) {
     if (!(flags & QN_FLAG_FORCE_SMEM)) {
       const char* v = getenv("QN_PAIR_ROWS");
-      const char variant = v ? v[0] : (Obj::kRegisterPaths ? 'h' : '4');
+      const char variant = v ? v[0] : (Obj::kRegisterPaths ? (n == 128 && !onepass ? 't' : 'h') : '4');
       // n = 128 (BASELINE.json configs[2], [3]) has its own instantiations with n at compile time
       // (hybrid 6.3e7 against 4.7e7 iterations/s with n at run time; dense Gaussian 1.04e6 against
       // 0.68e6 solves/s); the other sizes share the run-time-n build
-      if (variant == 'h' && n == 128)
+      if (variant == 't' && n == 128 && !onepass) // hybrid tiles, the other two rows in tensor memory
+        return launch_resident<Obj, 0, 256, 2, 128, false, 4, 2, true>(ctx, p, op, st);
+      if ((variant == 'h' || variant == 't') && n == 128)
         return onepass ? launch_resident<Obj, 0, 256, 2, 128, true, 4, 2>(ctx, p, op, st)
                        : launch_resident<Obj, 0, 256, 2, 128, false, 4, 2>(ctx, p, op, st);
       if (variant == 'h' && n > 64 && n <= 160) {

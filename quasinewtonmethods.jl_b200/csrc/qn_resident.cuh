@@ -109,6 +109,23 @@ __device__ __forceinline__ void write_problem_scalars(const BatchParams& p, long
   }
 }
 
+// Two fp64 values of the calling thread's own tensor-memory lane (tcgen05.ld/st .32x32b.x4: four
+// 32-bit columns); see qn_resident_tile.cuh for what was measured about this home.
+__device__ __forceinline__ void tm2_load(double (&v)[2], const uint32_t addr) {
+  asm volatile("{\n.reg .b32 t0a, t0b, t1a, t1b;\n"
+               "tcgen05.ld.sync.aligned.32x32b.x4.b32 {t0a, t0b, t1a, t1b}, [%2];\n"
+               "mov.b64 %0, {t0a, t0b};\nmov.b64 %1, {t1a, t1b};\n}\n"
+               : "=d"(v[0]), "=d"(v[1]) : "r"(addr));
+}
+__device__ __forceinline__ void tm2_store(const uint32_t addr, const double a, const double b) {
+  asm volatile("{\n.reg .b32 t0a, t0b, t1a, t1b;\n"
+               "mov.b64 {t0a, t0b}, %1;\nmov.b64 {t1a, t1b}, %2;\n"
+               "tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {t0a, t0b, t1a, t1b};\n}\n"
+               :: "r"(addr), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void tm2_wait_load() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tm2_wait_store() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
 // PAIRN > 0 (with NREG == 0; PAIRN = n at compile time, or 1 for n at run time): the register-tile policy — every thread's PROWS × rb tile of B⁻¹
 // (PROWS rows, one rule-C2 block of rb <= 16 columns) lives in REGISTERS (or, PREG < PROWS, partly
 // in shared memory); needs blockDim >= (B/PROWS) · #blocks so that a thread owns exactly one block.
@@ -119,12 +136,18 @@ __device__ __forceinline__ void write_problem_scalars(const BatchParams& p, long
 // PREG (register-tile policy): how many of a thread's PROWS rows live in registers; the others
 // (0 or 2) live in shared memory, which halves the registers of a CTA so that TWO problems are
 // resident per SM at n = 128.
-template <class Obj, int NREG, int PAIRN = 0, bool ONEPASS = false, int PROWS = 2, int PREG = PROWS>
+// PTM (hybrid tiles of a full-size CTA only: every thread owns a complete tile, so the .sync.aligned
+// tensor-memory instructions are reached by whole warps): the rows that are not in registers live
+// in the thread's tensor-memory lane (`tmem`: lane and first column of this warp) instead of
+// shared memory; column k of the two rows at columns 4k … 4k+3, the next column in flight while
+// this one is used.
+template <class Obj, int NREG, int PAIRN = 0, bool ONEPASS = false, int PROWS = 2, int PREG = PROWS, bool PTM = false>
 __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
                                                    const typename Obj::Params& op,
                                                    const long long j, Team& tm, double* ys,
                                                    Pass2Col* cols, double* hs, double* part,
-                                                   double* part2 = nullptr, double* rowp = nullptr) {
+                                                   double* part2 = nullptr, double* rowp = nullptr,
+                                                   const uint32_t tmem = 0) {
   const int n = (NREG > 0) ? NREG : (PAIRN > 1 ? PAIRN : p.n); // PAIRN = 1: tiles with n at run time
   const int c = tm.c;          // thread index: the owner of element c when c < n
   const bool active = c < n;
@@ -155,18 +178,36 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
   double* hx = hs + PX * (c % half);  // this thread's shared-memory rows of column 0; column stride ldx
   const int ldx = half * PX;
   (void)hx; (void)ldx;
+  static_assert(!PTM || (PX == 2 && !ONEPASS), "tensor-memory rows: hybrid tiles in the reference order");
+  double tmv[2][2]; // PTM: the tensor-memory rows of this column and of the next one
+  (void)tmv;
+  auto tile_begin = [&]() { // before a sweep over the columns k = 0, 1, …: column 0 on its way
+    if constexpr (PTM) tm2_load(tmv[0], tmem);
+  };
   auto load_tile_col = [&](const int k, double (&hh)[PR]) {
 #pragma unroll
     for (int i = 0; i < PREG; ++i) hh[i] = hp[i][k];
     if (PX) {
-      const double2 v = *reinterpret_cast<const double2*>(hx + ldx * (pcol0 + k));
-      hh[PR - 2] = v.x; hh[PR - 1] = v.y;
+      if constexpr (PTM) {
+        tm2_wait_load();
+        if (k + 1 < PRB) tm2_load(tmv[(k + 1) & 1], tmem + 4 * (k + 1));
+        hh[PR - 2] = tmv[k & 1][0]; hh[PR - 1] = tmv[k & 1][1];
+      } else {
+        const double2 v = *reinterpret_cast<const double2*>(hx + ldx * (pcol0 + k));
+        hh[PR - 2] = v.x; hh[PR - 1] = v.y;
+      }
     }
   };
   auto store_tile_col = [&](const int k, const double (&hh)[PR]) {
 #pragma unroll
     for (int i = 0; i < PREG; ++i) hp[i][k] = hh[i];
-    if (PX) *reinterpret_cast<double2*>(hx + ldx * (pcol0 + k)) = make_double2(hh[PR - 2], hh[PR - 1]);
+    if (PX) {
+      if constexpr (PTM) tm2_store(tmem + 4 * k, hh[PR - 2], hh[PR - 1]);
+      else *reinterpret_cast<double2*>(hx + ldx * (pcol0 + k)) = make_double2(hh[PR - 2], hh[PR - 1]);
+    }
+  };
+  auto tile_end = [&]() { // after a sweep that stored
+    if constexpr (PTM) tm2_wait_store();
   };
 
   double x = active ? p.theta0[j * p.theta_stride + c] : 0.0; // copyto!(x_old, x), QN.jl:248
@@ -342,6 +383,7 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
           double tt[PR];
 #pragma unroll
           for (int i = 0; i < PR; ++i) tt[i] = 0.0;
+          tile_begin();
 #pragma unroll
           for (int k = 0; k < PRB; ++k) {
             if (k < pcols) {
@@ -441,6 +483,7 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
             sR[i] = s2.x; sR[i + 1] = s2.y; nR[i] = n2.x; nR[i + 1] = n2.y;
             acc[i] = 0.0; acc[i + 1] = 0.0;
           }
+          tile_begin();
 #pragma unroll
           for (int k = 0; k < PRB; ++k) {
             if (k < pcols) {
@@ -458,6 +501,7 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
               store_tile_col(k, hh);
             }
           }
+          tile_end();
 #pragma unroll
           for (int i = 0; i < PR; i += 2)
             *reinterpret_cast<double2*>(part + bgrp * B + row0 + i) = make_double2(acc[i], acc[i + 1]);
@@ -546,6 +590,7 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
             store_tile_col(k, hh);
           }
         }
+        tile_end();
       } else if (active) {
         for (int r = 0; r < n; ++r) hs[c + ldh * r] = (r == c) ? 1.0 : 0.0;
       }
@@ -582,6 +627,7 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
   }
   if (PAIRN > 0 && p.h_out && row0 < n && pcols > 0) {
     double* ho = p.h_out + j * p.h_stride;
+    tile_begin();
 #pragma unroll
     for (int k = 0; k < PRB; ++k) {
       if (k < pcols) {
@@ -610,7 +656,7 @@ __device__ __forceinline__ void resident_solve_one(const BatchParams& p,
 }
 
 template <class Obj, int NREG, int BLOCK, int MINB, int PAIRN = 0, bool ONEPASS = false, int PROWS = 2,
-          int PREG = PROWS>
+          int PREG = PROWS, bool PTM = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
 qn_resident_kernel(const BatchParams p, const typename Obj::Params op) {
   // launch: blockDim >= resident_block_threads(n); see launch_resident for the policy
@@ -618,7 +664,25 @@ qn_resident_kernel(const BatchParams p, const typename Obj::Params op) {
   const int n = (NREG > 0) ? NREG : (PAIRN > 1 ? PAIRN : p.n); // PAIRN = 1: tiles with n at run time
   const int B = resident_block_threads(n);
   const ResidentSmem L = resident_smem_layout<Obj>(n, NREG == 0 && PAIRN == 0, (int)blockDim.x, op, ONEPASS, PROWS,
-                                                   PAIRN > 0 ? PROWS - PREG : 0);
+                                                   (PAIRN > 0 && !PTM) ? PROWS - PREG : 0);
+  // PTM: 4 columns per tile column and thread; warps 4-7 of the CTA sit on the lanes of warps 0-3,
+  // one 64-column band further (n = 128: 256 threads, 16 tile columns, 128 columns per CTA)
+  uint32_t tmem = 0, tmem_base = 0;
+  if constexpr (PTM) {
+    static_assert(BLOCK <= 256, "tensor-memory rows: at most two bands of four warps");
+    __shared__ uint32_t tmem_base_s;
+    if (threadIdx.x < 32) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;\n"
+                   :: "l"((unsigned long long)__cvta_generic_to_shared(&tmem_base_s)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    tmem_base = tmem_base_s;
+    const uint32_t w = threadIdx.x >> 5;
+    tmem = __reduce_max_sync(0xffffffffu, tmem_base + (((w & 3) * 32u) << 16) + (w >> 2) * 64u);
+  }
 
   Team tm;
   tm.n = n;
@@ -649,8 +713,13 @@ qn_resident_kernel(const BatchParams p, const typename Obj::Params op) {
     __syncthreads();
     const long long j = *next;
     if (j >= p.batch) break;
-    resident_solve_one<Obj, NREG, PAIRN, ONEPASS, PROWS, PREG>(p, op, j, tm, ys, cols, hs, smem + L.part, smem + L.part2,
-                                                  smem + L.rowp);
+    resident_solve_one<Obj, NREG, PAIRN, ONEPASS, PROWS, PREG, PTM>(p, op, j, tm, ys, cols, hs, smem + L.part,
+                                                                    smem + L.part2, smem + L.rowp, tmem);
+  }
+  if constexpr (PTM) {
+    __syncthreads(); // every warp is done with the tensor memory
+    if (threadIdx.x < 32)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;\n" :: "r"(tmem_base) : "memory");
   }
 }
 

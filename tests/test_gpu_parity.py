@@ -191,6 +191,40 @@ def test_n128_both_resident_policies(eng, qn, ob):
         _check(got, ref)
 
 
+def test_n128_tiles_with_rows_in_tensor_memory(eng, qn, ob, monkeypatch):
+    """n = 128 hybrid tiles whose two non-register rows live in tensor memory instead of shared memory
+    (QN_PAIR_ROWS=t, the default): same bits as the oracle, including the final B⁻¹ read back from
+    tensor memory, and as the shared-memory hybrid (QN_PAIR_ROWS=h)."""
+    n = 128
+    Theta = starts(n, 40, key=1289)
+    a = eng.optimize_batched(qn.Rosenbrock(), Theta)
+    assert eng.last_launch()["smem_bytes"] < 32768  # no B⁻¹ rows in shared memory
+    monkeypatch.setenv("QN_PAIR_ROWS", "h")
+    b_ = eng.optimize_batched(qn.Rosenbrock(), Theta)
+    assert eng.last_launch()["smem_bytes"] > 65536
+    for k in ("x", "g", "ell", "iters", "fevals", "status"):
+        assert np.array_equal(a[k], b_[k], equal_nan=True), k
+    monkeypatch.setenv("QN_PAIR_ROWS", "t")
+    for batch in (1, 5, 300):
+        Theta = starts(n, batch, key=1290 + batch)
+        nref = min(batch, 6)
+        sb = qn.BFGSStateBatch(n, batch)
+        got = eng.optimize_batched(qn.Rosenbrock(), Theta, ntrace=5, states=sb, flags=qn._lib.FLAG_WRITE_H)
+        assert eng.last_launch()["path"] == qn._lib.PATH_REGISTER and eng.last_launch()["block"] == 256
+        ref = ob.optimize_batch(ob.rosenbrock(), Theta[:, :nref], ntrace=5)
+        sub = {k: (None if got[k] is None else got[k][:nref] if k == "trace" else got[k][..., :nref]) for k in got}
+        _check(sub, ref)
+        L = sb.L
+        o = ob.optimize(ob.rosenbrock(), Theta[:, 0], L=L)
+        assert np.array_equal(sb.data[0, 7 * L:].reshape(n, L)[:, :n], o["state"][7 * L:].reshape(n, L)[:, :n])
+    for cap in (1, 2, 3):
+        Th = starts(n, 3, key=cap)
+        got = eng.optimize_batched(qn.Rosenbrock(), Th, max_iter=cap, ntrace=cap)
+        ref = ob.optimize_batch(ob.rosenbrock(), Th, max_iter=cap, ntrace=cap)
+        for k in ("x", "g", "trace", "fevals", "iters", "status"):
+            assert np.array_equal(got[k], ref[k]), (cap, k)
+
+
 def test_committed_oracle_vectors(eng, qn):
     """Against the committed fixtures (no oracle call): tests/golden/oracle_vectors.npz."""
     v = np.load(os.path.join(GOLDEN, "oracle_vectors.npz"))
