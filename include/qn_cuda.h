@@ -101,6 +101,15 @@ int32_t qn_destroy(qn_context* ctx);
 int32_t qn_device_info(qn_context* ctx, char* name, size_t name_len, int32_t* sm_count,
                        int32_t* smem_per_block, int32_t* clock_khz);
 
+/* Tuning / ablation switches of a context (they replace the QN_* environment variables, which are
+ * now read once, in qn_create, as defaults).  Keys: "tile_tmem" (-1 auto | 0 | 1), "pack" (0 | 1),
+ * "pack_variant" (0 | 1 | 2 | 4), "pair_rows" (0 auto | 'h' | 't' | '4' | '2' | 's'), "smem_rows" (0 | 2 | 4),
+ * "lambda_smem", "stream_cluster", "stream_tma" (-1 auto | 0 | 1), "sweep_depth" (0 | 8 | 16),
+ * "hint_p1_ld", "hint_p2_ld", "hint_p2_st", "hint_one_ld", "p1_pad_kb", "latency" (-1 auto | 0 | 1),
+ * "record_exit" (0 | 1).  None of them changes a result bit.  Unknown key -> QN_ERR_INVALID_ARGUMENT. */
+int32_t qn_set_option(qn_context* ctx, const char* key, int64_t value);
+int32_t qn_get_option(qn_context* ctx, const char* key, int64_t* value);
+
 /* pinned host memory for callers that want full-speed host<->device copies */
 int32_t qn_host_alloc(void** ptr, size_t bytes);
 int32_t qn_host_free(void* ptr);
@@ -219,6 +228,12 @@ int32_t qn_bfgs_optimize_rowsharded_f64(qn_context* const* ctxs, int32_t nctx,
  * path 0 = register-resident, 1 = shared-memory-resident, 2 = HBM streaming. */
 int32_t qn_last_launch_info(qn_context* ctx, int32_t* path, int32_t* grid, int32_t* block,
                             int32_t* smem_bytes, int32_t* kernel_launches);
+
+/* Tail of the last batched launch made with option "record_exit" = 1 (n = 36..64 tile kernels; call
+ * after the results are back): span_ms = first start to last end on the device, idle_fraction =
+ * share of the launch's problem-slot time spent after the work queue ran dry, slots = resident
+ * problem slots.  Names the limiter of strong scaling (bench.py). */
+int32_t qn_last_tail_profile(qn_context* ctx, double* span_ms, double* idle_fraction, int32_t* slots);
 
 /* Streaming (large-n) path benchmark: `iters` BFGS iterations (first two untimed) of an
  * n-dimensional Rosenbrock problem with B⁻¹ in HBM.  gbs = achieved ALGORITHMIC bandwidth,

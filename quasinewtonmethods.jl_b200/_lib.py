@@ -52,6 +52,9 @@ SIGNATURES = {
     "qn_create": (C.c_int32, [C.POINTER(_vp), C.c_int32]),
     "qn_destroy": (C.c_int32, [_vp]),
     "qn_device_info": (C.c_int32, [_vp, C.c_char_p, C.c_size_t, _ip, _ip, _ip]),
+    "qn_set_option": (C.c_int32, [_vp, C.c_char_p, C.c_int64]),
+    "qn_get_option": (C.c_int32, [_vp, C.c_char_p, C.POINTER(C.c_int64)]),
+    "qn_last_tail_profile": (C.c_int32, [_vp, _dp, _dp, _ip]),
     "qn_host_alloc": (C.c_int32, [C.POINTER(_vp), C.c_size_t]),
     "qn_host_free": (C.c_int32, [_vp]),
     "qn_state_ld": (C.c_int32, [C.c_int32, C.c_int32]),

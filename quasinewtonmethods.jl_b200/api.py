@@ -27,7 +27,7 @@ from ._lib import (CONVERGED, LINESEARCH_FAILED, MAX_ITER, NONFINITE, QNError,
 __all__ = [
     "BFGSState", "BFGSStateBatch", "BackTracking", "Rosenbrock", "DenseGaussian",
     "LogisticRegression", "UserObjective", "optimize_", "optimize", "optimum", "gradient", "logdensity",
-    "dlogdensity_", "Engine", "default_engine", "optimize_rowsharded", "QNError", "UnregisteredObjectiveError",
+    "dlogdensity_", "Engine", "default_engine", "optimize_rowsharded", "optimize_batched_multi", "QNError", "UnregisteredObjectiveError",
     "CONVERGED", "NONFINITE", "LINESEARCH_FAILED", "MAX_ITER",
 ]
 
@@ -252,6 +252,24 @@ class Engine:
         _lib.check(self._lib.qn_last_launch_info(self._ctx, *[C.byref(x) for x in v]))
         return dict(zip(("path", "grid", "block", "smem_bytes", "kernel_launches"), [x.value for x in v]))
 
+    def set_option(self, key, value):
+        """qn_set_option: tuning / ablation switch of this context (include/qn_cuda.h lists the keys).
+        A one-character string stands for its character code ("pair_rows": 'h', 't', ...)."""
+        if isinstance(value, str):
+            value = ord(value[0]) if value else 0
+        _lib.check(self._lib.qn_set_option(self._ctx, key.encode(), int(value)))
+
+    def get_option(self, key):
+        v = C.c_int64()
+        _lib.check(self._lib.qn_get_option(self._ctx, key.encode(), C.byref(v)))
+        return v.value
+
+    def tail_profile(self):
+        """Tail of the last tile-kernel launch made with option record_exit = 1."""
+        span, idle, slots = C.c_double(), C.c_double(), C.c_int32()
+        _lib.check(self._lib.qn_last_tail_profile(self._ctx, C.byref(span), C.byref(idle), C.byref(slots)))
+        return dict(span_ms=span.value, idle_fraction=idle.value, slots=slots.value)
+
     def microbench(self):
         out = {}
         for name in ("dfma", "lds", "hbm"):
@@ -313,6 +331,33 @@ class Engine:
         g = np.empty((n, batch), order="F") if grad else None
         _lib.check(self._lib.qn_logdensity_batched_f64(self._ctx, h, n, batch, _ptr(Theta), _ptr(ell), _ptr(g)))
         return (ell, g) if grad else ell
+
+
+def optimize_batched_multi(engines, obj, Theta, ls=None, tol=1e-8, max_iter=MAX_ITER_DEFAULT, flags=0,
+                           out=None):
+    """One batch sharded over several GPUs from ONE process (qn_bfgs_optimize_batched_multi_f64;
+    SURVEY §8(e) row 1): problem j goes to engines[j mod G], no inter-GPU communication, the host
+    scatters the starts and gathers the results.  `out`: optional dict of preallocated (pinned)
+    arrays x, g (n×batch, column-major), ell, iters, fevals, status to write into."""
+    Theta = np.asfortranarray(Theta, dtype=np.float64)
+    n, batch = Theta.shape
+    ls = ls or BackTracking()
+    lsc = ls._c()
+    lib = engines[0]._lib
+    G = len(engines)
+    ctxs = (C.c_void_p * G)(*[e._ctx for e in engines])
+    models = (C.c_void_p * G)(*[e.model_handle(obj) for e in engines])
+    out = out or {}
+    x = out.get("x") if out.get("x") is not None else np.empty((n, batch), order="F")
+    g = out.get("g") if out.get("g") is not None else np.empty((n, batch), order="F")
+    ell = out.get("ell") if out.get("ell") is not None else np.empty(batch)
+    iters = out.get("iters") if out.get("iters") is not None else np.empty(batch, dtype=np.int32)
+    fevals = out.get("fevals") if out.get("fevals") is not None else np.empty(batch, dtype=np.int32)
+    status = out.get("status") if out.get("status") is not None else np.empty(batch, dtype=np.int32)
+    _lib.check(lib.qn_bfgs_optimize_batched_multi_f64(
+        ctxs, G, models, n, batch, _ptr(Theta), C.byref(lsc), tol, max_iter, _ptr(x), _ptr(g), _ptr(ell),
+        _ptr(iters), _ptr(fevals), _ptr(status), flags))
+    return dict(x=x, g=g, ell=ell, iters=iters, fevals=fevals, status=status)
 
 
 def optimize_rowsharded(engines, obj, theta, ls=None, tol=1e-8, max_iter=MAX_ITER_DEFAULT, ntrace=0,

@@ -49,6 +49,16 @@ int qn_ensure_stage(qn_context* ctx, size_t bytes) {
   return QN_OK;
 }
 
+int qn_ensure_hstage(qn_context* ctx, size_t bytes) {
+  if (bytes <= ctx->hstage_bytes) return QN_OK;
+  if (ctx->hstage) cudaFreeHost(ctx->hstage);
+  ctx->hstage = nullptr;
+  ctx->hstage_bytes = 0;
+  QN_CUDA_TRY(cudaMallocHost(&ctx->hstage, bytes));
+  ctx->hstage_bytes = bytes;
+  return QN_OK;
+}
+
 unsigned long long* qn_next_counter(qn_context* ctx, cudaStream_t st) {
   unsigned long long* c = ctx->counter + ctx->counter_slot;
   ctx->counter_slot = (ctx->counter_slot + 1) % qn_context::kCounterSlots;
@@ -57,6 +67,20 @@ unsigned long long* qn_next_counter(qn_context* ctx, cudaStream_t st) {
 }
 
 namespace {
+
+// option "record_exit": arm the exit stamps for a launch with `slots` problem slots
+void arm_exit_stamps(qn_context* ctx, qn::BatchParams& p, long long slots, cudaStream_t st) {
+  p.exit_ns = nullptr;
+  p.exit_cap = 0;
+  ctx->exit_slots_used = 0;
+  if (!ctx->opt.record_exit) return;
+  const int used = (int)std::min<long long>(slots, qn_context::kExitSlots);
+  cudaMemsetAsync(ctx->exit_ns, 0xff, sizeof(unsigned long long), st);                 // earliest start
+  cudaMemsetAsync(ctx->exit_ns + 1, 0, sizeof(unsigned long long) * (used + 1), st);   // latest end, slots
+  p.exit_ns = ctx->exit_ns;
+  p.exit_cap = used;
+  ctx->exit_slots_used = used;
+}
 
 // ---- kernel launchers ------------------------------------------------------
 // ONEPASS: the deferred-update order (QN_FLAG_ONE_PASS) — shared-memory and register-pair policies
@@ -134,6 +158,7 @@ int launch_tile(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
   long long grid = (long long)occ * ctx->prop.multiProcessorCount;
   if (grid > p.batch) grid = p.batch;
   p.counter = qn_next_counter(ctx, st);
+  arm_exit_stamps(ctx, p, grid, st);
   kern<<<(unsigned)grid, 64, smem, st>>>(p);
   QN_CUDA_TRY(cudaGetLastError());
   ctx->last_path = 0;
@@ -158,6 +183,7 @@ int launch_tile_tmem(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
   long long grid = 4LL * ctx->prop.multiProcessorCount;
   if (grid > (p.batch + 1) / 2) grid = (p.batch + 1) / 2;
   p.counter = qn_next_counter(ctx, st);
+  arm_exit_stamps(ctx, p, 2 * grid, st);
   kern<<<(unsigned)grid, 128, smem, st>>>(p);
   QN_CUDA_TRY(cudaGetLastError());
   ctx->last_path = 0;
@@ -170,12 +196,11 @@ int launch_tile_tmem(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
 
 // Where the tile lives: tensor memory when it is the faster home (measured per size on B200,
 // 2^15-2^16 problems: n = 44 +1 %, 48 +6 %, 50 +8 %, 56 +1 %, 60 +3 %, 64 +8 %; n = 36, 40, 52 are
-// 1-3 % faster from registers) and the batch fills 8 problems per SM; QN_TILE_TMEM=0 / 1 forces
+// 1-3 % faster from registers) and the batch fills 8 problems per SM; option "tile_tmem" = 0 / 1 forces
 // the register file / tensor memory.
 inline bool tile_in_tensor_memory(const qn_context* ctx, const int n, const long long batch) {
-  const char* v = getenv("QN_TILE_TMEM");
-  if (v && v[0] == '0') return false;
-  if (v && v[0] == '1') return true;
+  if (ctx->opt.tile_tmem == 0) return false;
+  if (ctx->opt.tile_tmem == 1) return true;
   const bool faster = n == 44 || n == 48 || n == 50 || n == 56 || n == 60 || n == 64;
   return faster && batch >= 8LL * ctx->prop.multiProcessorCount;
 }
@@ -212,9 +237,8 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
   if constexpr (Obj::kRegisterPaths) {
     if (!(flags & QN_FLAG_FORCE_SMEM)) {
       if constexpr (std::is_same<Obj, qn::Rosenbrock>::value) {
-        if (!getenv("QN_NO_PACK")) { // A/B knob: the thread-per-row kernels stay available
-          const char* v = getenv("QN_PACK_VARIANT"); // tuning knob: rows per lane
-          const int rpt = v ? atoi(v) : 0;
+        if (ctx->opt.pack) { // A/B knob: the thread-per-row kernels stay available
+          const int rpt = ctx->opt.pack_variant; // tuning knob: rows per lane
           // defaults measured on B200 (2^18 problems): n = 8: 2 rows per lane 8.2e9 it/s (1: 6.7e9);
           // n = 16: 2 rows 3.7e9 (1: 2.8e9, 4: 3.3e9); n = 32: 2 rows 1.14e9 (thread per row: 0.90e9)
           if (n == 8) return rpt == 1 ? launch_packed<8, 1, 8>(ctx, p, st) : rpt == 4 ? launch_packed<8, 4, 4>(ctx, p, st) : launch_packed<8, 2, 6>(ctx, p, st);
@@ -241,7 +265,7 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
     }
   }
   // Register tiles beyond the 4×15-tile sizes (qn_resident.cuh, PAIRN): a thread owns 4 rows × one
-  // rule-C2 block.  QN_PAIR_ROWS selects the variant: 'h' hybrid — two of the four rows in registers,
+  // rule-C2 block.  option "pair_rows" selects the variant: 'h' hybrid — two of the four rows in registers,
   // two in shared memory, which fits every n <= 160 and makes TWO problems resident per SM up to
   // n = 128 (Rosenbrock: n = 128 6.1e7 iterations/s, n = 96 7.0e7 against 4.1e7 and n = 160 2.2e7
   // against 1.8e7 with B⁻¹ in shared memory) —, '4' all four rows in registers (n = 128 only: 5.4e7), '2' 2×16 tiles of 512 threads
@@ -254,8 +278,7 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
   const bool onepass = (flags & QN_FLAG_ONE_PASS) != 0; // honoured by these policies (and the streaming path)
   if constexpr (Obj::kPairRegister) {
     if (!(flags & QN_FLAG_FORCE_SMEM)) {
-      const char* v = getenv("QN_PAIR_ROWS");
-      const char variant = v ? v[0] : (Obj::kRegisterPaths ? (n == 128 && !onepass ? 't' : 'h') : '4');
+      const char variant = ctx->opt.pair_rows ? (char)ctx->opt.pair_rows : (Obj::kRegisterPaths ? (n == 128 && !onepass ? 't' : 'h') : '4');
       // n = 128 (BASELINE.json configs[2], [3]) has its own instantiations with n at compile time
       // (hybrid 6.3e7 against 4.7e7 iterations/s with n at run time; dense Gaussian 1.04e6 against
       // 0.68e6 solves/s); the other sizes share the run-time-n build
@@ -285,12 +308,11 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
     // shared-memory policy: 2 or 4 rows of B⁻¹ per thread.  Four rows halve the threads (and so the
     // registers) of a CTA: worth it exactly when that lets MORE problems be resident per SM (measured:
     // n = 96, 100: 2 instead of 1, +23-25 %; with equal residency two rows are 10-15 % faster).  Cheap
-    // objectives only — the GEMVs of the others want the threads.  QN_SMEM_ROWS=2|4 forces a choice.
+    // objectives only — the GEMVs of the others want the threads.  option "smem_rows" = 2 | 4 forces a choice.
     bool four = false;
     if (n >= 64) {
-      const char* v = getenv("QN_SMEM_ROWS");
-      if (v) {
-        four = (v[0] == '4');
+      if (ctx->opt.smem_rows) {
+        four = (ctx->opt.smem_rows == 4);
       } else if (Obj::kRegisterPaths) {
         int occ2 = 0, occ4 = 0;
         const int r2 = onepass ? launch_resident<Obj, 0, 1024, 1, 0, true, 2>(ctx, p, op, st, &occ2)
@@ -309,7 +331,18 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
   return fail(QN_ERR_UNSUPPORTED_SIZE, "n=%d does not fit the resident path", n);
 }
 
-// Large n: B⁻¹ in HBM, one problem at a time on the whole GPU (qn_stream.cu).
+// per-problem scalars of a streamed solve, written on the stream the solve ran on
+__global__ void stream_scalars_kernel(double* ell_out, int* iters_out, int* fevals_out, int* status_out,
+                                      long long j, double ell, int it, int fe, int status) {
+  if (ell_out) ell_out[j] = ell;
+  if (iters_out) iters_out[j] = it;
+  if (fevals_out) fevals_out[j] = fe;
+  if (status_out) status_out[j] = status;
+}
+
+// Large n: B⁻¹ in HBM, one problem at a time on the whole GPU (qn_stream.cu).  This path is
+// SYNCHRONOUS (the host polls the convergence flag between graph replays): it waits for the
+// caller's stream, runs on the context's stream and returns when the batch is finished.
 int dispatch_stream(qn_context* ctx, const qn_model* model, qn::BatchParams& p,
                     const qn_backtracking* ls, uint32_t flags, cudaStream_t st) {
   if (model->kind != QN_OBJ_ROSENBROCK)
@@ -333,11 +366,10 @@ int dispatch_stream(qn_context* ctx, const qn_model* model, qn::BatchParams& p,
                              (flags & QN_FLAG_ONE_PASS) ? 1 : 0);
     if (rc) return rc;
     launches += ctx->last_launches;
-    if (p.ell_out) QN_CUDA_TRY(cudaMemcpy(p.ell_out + j, &ell, sizeof ell, cudaMemcpyHostToDevice));
-    if (p.iters_out) QN_CUDA_TRY(cudaMemcpy(p.iters_out + j, &it, sizeof it, cudaMemcpyHostToDevice));
-    if (p.fevals_out) QN_CUDA_TRY(cudaMemcpy(p.fevals_out + j, &fe, sizeof fe, cudaMemcpyHostToDevice));
-    if (p.status_out) QN_CUDA_TRY(cudaMemcpy(p.status_out + j, &status, sizeof status, cudaMemcpyHostToDevice));
+    stream_scalars_kernel<<<1, 1, 0, run>>>(p.ell_out, p.iters_out, p.fevals_out, p.status_out, j, ell, it, fe, status);
+    QN_CUDA_TRY(cudaGetLastError());
   }
+  if (st != run) QN_CUDA_TRY(cudaStreamSynchronize(run)); // results are complete when the call returns
   ctx->last_launches = launches;
   return QN_OK;
 }
@@ -355,7 +387,7 @@ int dispatch_model(qn_context* ctx, const qn_model* model, qn::BatchParams& p,
                     model->n, p.n);
       qn::DenseGaussian::Params op{model->d_a, model->d_b, 0};
       // register-pair policy (n = 128): shared memory is free, keep Λ there (128 KB of the 227 KB)
-      if (p.n == 128 && !(flags & QN_FLAG_FORCE_SMEM) && !getenv("QN_NO_LAMBDA_SMEM")) op.lam_in_smem = 1;
+      if (p.n == 128 && !(flags & QN_FLAG_FORCE_SMEM) && ctx->opt.lambda_smem) op.lam_in_smem = 1;
       return dispatch_size<qn::DenseGaussian>(ctx, p, op, flags, st);
     }
     case QN_OBJ_LOGISTIC: {
@@ -367,11 +399,43 @@ int dispatch_model(qn_context* ctx, const qn_model* model, qn::BatchParams& p,
     }
 #ifdef QN_USER_OBJECTIVE_HEADER
     case QN_OBJ_USER:
+      if (model->n && model->n != p.n)
+        return fail(QN_ERR_INVALID_ARGUMENT, "user objective was registered for n=%d, call has n=%d", model->n, p.n);
       return dispatch_size<qn::UserObjective>(ctx, p, qn::UserObjective::make(model->d_a, model->bytes, p.n), flags, st);
 #endif
     default:
       return fail(QN_ERR_UNREGISTERED_OBJECTIVE,
                   "objective kind %d has no registered device implementation", model->kind);
+  }
+}
+
+// option table: key -> field of qn_options (qn_set_option / qn_get_option; env defaults in qn_create)
+struct OptKey { const char* key; int qn_options::*field; const char* env; int env_mode; }; // env_mode 0: atoi, 1: presence clears, 2: first char
+const OptKey kOptKeys[] = {
+  {"tile_tmem", &qn_options::tile_tmem, "QN_TILE_TMEM", 0},
+  {"pack", &qn_options::pack, "QN_NO_PACK", 1},
+  {"pack_variant", &qn_options::pack_variant, "QN_PACK_VARIANT", 0},
+  {"pair_rows", &qn_options::pair_rows, "QN_PAIR_ROWS", 2},
+  {"smem_rows", &qn_options::smem_rows, "QN_SMEM_ROWS", 0},
+  {"lambda_smem", &qn_options::lambda_smem, "QN_NO_LAMBDA_SMEM", 1},
+  {"stream_cluster", &qn_options::stream_cluster, "QN_STREAM_NO_CLUSTER", 1},
+  {"stream_tma", &qn_options::stream_tma, "QN_STREAM_TMA", 0},
+  {"sweep_depth", &qn_options::sweep_depth, "QN_SWEEP_DEPTH", 0},
+  {"hint_p1_ld", &qn_options::hint_p1_ld, "QN_HINT_P1_LD", 0},
+  {"hint_p2_ld", &qn_options::hint_p2_ld, "QN_HINT_P2_LD", 0},
+  {"hint_p2_st", &qn_options::hint_p2_st, "QN_HINT_P2_ST", 0},
+  {"hint_one_ld", &qn_options::hint_one_ld, "QN_HINT_ONE_LD", 0},
+  {"p1_pad_kb", &qn_options::p1_pad_kb, "QN_P1_PAD_KB", 0},
+  {"latency", &qn_options::latency, "QN_LATENCY", 0},
+  {"record_exit", &qn_options::record_exit, "QN_RECORD_EXIT", 0},
+};
+void options_from_env(qn_options& o) {
+  for (const OptKey& k : kOptKeys) {
+    const char* v = getenv(k.env);
+    if (!v) continue;
+    if (k.env_mode == 1) o.*(k.field) = 0;
+    else if (k.env_mode == 2) o.*(k.field) = (int)(unsigned char)v[0];
+    else o.*(k.field) = atoi(v);
   }
 }
 
@@ -434,10 +498,13 @@ int32_t qn_create(qn_context** out, int32_t device) {
   qn_context* ctx = new (std::nothrow) qn_context;
   if (!ctx) return fail(QN_ERR_CUDA, "out of host memory");
   ctx->device = device;
+  options_from_env(ctx->opt); // the only place the environment is read
   cudaError_t err = cudaGetDeviceProperties(&ctx->prop, device);
   if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (err == cudaSuccess)
     err = cudaMalloc(&ctx->counter, sizeof(unsigned long long) * qn_context::kCounterSlots);
+  if (err == cudaSuccess)
+    err = cudaMalloc(&ctx->exit_ns, sizeof(unsigned long long) * (qn_context::kExitSlots + 2));
   if (err != cudaSuccess) {
     delete ctx;
     return fail(QN_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(err));
@@ -446,6 +513,7 @@ int32_t qn_create(qn_context** out, int32_t device) {
     // The kernels are compiled for sm_100a only; refuse early with a clear message.
     int major = ctx->prop.major, minor = ctx->prop.minor;
     cudaFree(ctx->counter);
+    cudaFree(ctx->exit_ns);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return fail(QN_ERR_NO_DEVICE, "device is sm_%d%d; libqn_cuda is built for sm_100a only", major,
@@ -460,10 +528,33 @@ int32_t qn_destroy(qn_context* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->stage) cudaFree(ctx->stage);
+  if (ctx->hstage) cudaFreeHost(ctx->hstage);
   cudaFree(ctx->counter);
+  cudaFree(ctx->exit_ns);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return QN_OK;
+}
+
+int32_t qn_set_option(qn_context* ctx, const char* key, int64_t value) {
+  if (!ctx || !key) return fail(QN_ERR_INVALID_ARGUMENT, "NULL argument");
+  for (const OptKey& k : kOptKeys)
+    if (!strcmp(k.key, key)) {
+      std::lock_guard<std::mutex> lock(ctx->mu);
+      ctx->opt.*(k.field) = (int)value;
+      return QN_OK;
+    }
+  return fail(QN_ERR_INVALID_ARGUMENT, "unknown option '%s'", key);
+}
+
+int32_t qn_get_option(qn_context* ctx, const char* key, int64_t* value) {
+  if (!ctx || !key || !value) return fail(QN_ERR_INVALID_ARGUMENT, "NULL argument");
+  for (const OptKey& k : kOptKeys)
+    if (!strcmp(k.key, key)) {
+      *value = ctx->opt.*(k.field);
+      return QN_OK;
+    }
+  return fail(QN_ERR_INVALID_ARGUMENT, "unknown option '%s'", key);
 }
 
 int32_t qn_device_info(qn_context* ctx, char* name, size_t name_len, int32_t* sm_count,
@@ -600,16 +691,15 @@ int32_t qn_model_free(qn_model* m) {
   return QN_OK;
 }
 
-// ---- optimize!, device pointers
-int32_t qn_bfgs_optimize_batched_device_f64(qn_context* ctx, const qn_model* model, int32_t n,
-                                            int64_t batch, const double* theta0,
-                                            int64_t theta_stride, const qn_backtracking* ls,
-                                            double tol, int32_t max_iter, double* states,
-                                            int64_t state_stride, int32_t ld, double* x_out,
-                                            double* g_out, double* ell_out, int32_t* iters_out,
-                                            int32_t* fevals_out, int32_t* status_out,
-                                            int32_t ntrace, double* trace_out, uint32_t flags,
-                                            void* stream) {
+}  // extern "C"
+
+// ---- optimize!, device pointers; the caller holds ctx->mu
+int qn_optimize_device_locked(qn_context* ctx, const qn_model* model, int32_t n, int64_t batch,
+                              const double* theta0, int64_t theta_stride, const qn_backtracking* ls,
+                              double tol, int32_t max_iter, double* states, int64_t state_stride,
+                              int32_t ld, double* x_out, double* g_out, double* ell_out,
+                              int32_t* iters_out, int32_t* fevals_out, int32_t* status_out,
+                              int32_t ntrace, double* trace_out, uint32_t flags, cudaStream_t st) {
   int rc = check_common(ctx, model, n, batch, theta0, ls, max_iter);
   if (rc) return rc;
   if (theta_stride < n) return fail(QN_ERR_INVALID_ARGUMENT, "theta_stride < n");
@@ -623,7 +713,6 @@ int32_t qn_bfgs_optimize_batched_device_f64(qn_context* ctx, const qn_model* mod
     return fail(QN_ERR_INVALID_ARGUMENT, "ntrace > 0 needs trace_out");
   if (batch == 0) return QN_OK;
   QN_CUDA_TRY(cudaSetDevice(ctx->device));
-  cudaStream_t st = (cudaStream_t)stream; // used literally: NULL is the CUDA default stream
 
   qn::BatchParams p{};
   p.n = n;
@@ -655,8 +744,26 @@ int32_t qn_bfgs_optimize_batched_device_f64(qn_context* ctx, const qn_model* mod
   p.status_out = status_out;
   p.ntrace = ntrace;
   p.trace = trace_out;
-  std::lock_guard<std::mutex> lock(ctx->mu);
   return dispatch_model(ctx, model, p, ls, flags, st);
+}
+
+extern "C" {
+
+int32_t qn_bfgs_optimize_batched_device_f64(qn_context* ctx, const qn_model* model, int32_t n,
+                                            int64_t batch, const double* theta0,
+                                            int64_t theta_stride, const qn_backtracking* ls,
+                                            double tol, int32_t max_iter, double* states,
+                                            int64_t state_stride, int32_t ld, double* x_out,
+                                            double* g_out, double* ell_out, int32_t* iters_out,
+                                            int32_t* fevals_out, int32_t* status_out,
+                                            int32_t ntrace, double* trace_out, uint32_t flags,
+                                            void* stream) {
+  if (!ctx) return fail(QN_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  // `stream` is used literally: NULL is the CUDA default stream
+  return qn_optimize_device_locked(ctx, model, n, batch, theta0, theta_stride, ls, tol, max_iter, states,
+                                   state_stride, ld, x_out, g_out, ell_out, iters_out, fevals_out,
+                                   status_out, ntrace, trace_out, flags, (cudaStream_t)stream);
 }
 
 // ---- optimize!, host pointers (the call a Julia / Python user makes)
@@ -691,11 +798,13 @@ int32_t qn_bfgs_optimize_batched_f64(qn_context* ctx, const qn_model* model, int
   const size_t o_fe = carve(sizeof(int32_t) * batch);
   const size_t o_st = carve(sizeof(int32_t) * batch);
   const size_t o_tr = carve(sizeof(double) * nb * (size_t)ntrace);
-  const size_t o_h = carve(want_h ? sizeof(double) * (size_t)n * n * batch : 0);
-  {
-    std::lock_guard<std::mutex> lock(ctx->mu);
-    rc = qn_ensure_stage(ctx, off);
-  }
+  // B⁻¹ is staged in the layout of the state blocks (column stride ld), so ONE strided copy returns it
+  const size_t hblk = (size_t)n * ld;
+  const size_t o_h = carve(want_h ? sizeof(double) * hblk * batch : 0);
+  // One lock from staging to the final synchronise: the staging buffer and the stream belong to the
+  // context, so two host calls on one context run one after the other.
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  rc = qn_ensure_stage(ctx, off);
   if (rc) return rc;
   char* base = (char*)ctx->stage;
   cudaStream_t st = ctx->stream;
@@ -720,8 +829,10 @@ int32_t qn_bfgs_optimize_batched_f64(qn_context* ctx, const qn_model* model, int
   p.g_stride = n;
   if (want_h) {
     p.h_out = (double*)(base + o_h);
-    p.h_stride = (long long)n * n;
-    p.ldh = n;
+    p.h_stride = (long long)hblk;
+    p.ldh = ld;
+    if (ld > n) // the padding rows are never written by the kernels: give the copy defined bytes
+      QN_CUDA_TRY(cudaMemsetAsync(base + o_h, 0, sizeof(double) * hblk * batch, st));
   }
   p.ell_out = (double*)(base + o_ell);
   p.iters_out = (int*)(base + o_it);
@@ -729,10 +840,7 @@ int32_t qn_bfgs_optimize_batched_f64(qn_context* ctx, const qn_model* model, int
   p.status_out = (int*)(base + o_st);
   p.ntrace = ntrace;
   p.trace = ntrace ? (double*)(base + o_tr) : nullptr;
-  {
-    std::lock_guard<std::mutex> lock(ctx->mu);
-    rc = dispatch_model(ctx, model, p, ls, flags, st);
-  }
+  rc = dispatch_model(ctx, model, p, ls, flags, st);
   if (rc) return rc;
 
   // results back to the caller's buffers
@@ -744,14 +852,10 @@ int32_t qn_bfgs_optimize_batched_f64(qn_context* ctx, const qn_model* model, int
     QN_CUDA_TRY(cudaMemcpy2DAsync(states + ld, sizeof(double) * state_stride, base + o_g,
                                   sizeof(double) * n, sizeof(double) * n, batch,
                                   cudaMemcpyDeviceToHost, st));
-    if (want_h) {
-      for (int64_t j = 0; j < batch; ++j)
-        QN_CUDA_TRY(cudaMemcpy2DAsync(states + j * state_stride + 7 * (int64_t)ld,
-                                      sizeof(double) * ld,
-                                      base + o_h + sizeof(double) * (size_t)n * n * j,
-                                      sizeof(double) * n, sizeof(double) * n, n,
-                                      cudaMemcpyDeviceToHost, st));
-    }
+    if (want_h) // field 8 of every block (QN.jl:142), n·ld contiguous doubles per problem: one strided copy
+      QN_CUDA_TRY(cudaMemcpy2DAsync(states + 7 * (int64_t)ld, sizeof(double) * state_stride, base + o_h,
+                                    sizeof(double) * hblk, sizeof(double) * hblk, batch,
+                                    cudaMemcpyDeviceToHost, st));
   }
   if (x_out) QN_CUDA_TRY(cudaMemcpyAsync(x_out, base + o_x, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
   if (g_out) QN_CUDA_TRY(cudaMemcpyAsync(g_out, base + o_g, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
@@ -773,6 +877,32 @@ int32_t qn_bfgs_optimize_f64(qn_context* ctx, const qn_model* model, int32_t n, 
   return qn_bfgs_optimize_batched_f64(ctx, model, n, 1, x, ls, tol, 10000, state,
                                       qn_state_len(n, ld), ld, nullptr, nullptr, ell, iters, fevals,
                                       status, 0, nullptr, flags);
+}
+
+// Tail of the last tile-kernel launch made with option "record_exit" = 1 (after the caller has
+// synchronised): span = latest end - earliest start; idle_fraction = Σ_slots (end - exit_slot) /
+// (slots · span), the share of the launch's slot-time spent with the work queue empty.
+int32_t qn_last_tail_profile(qn_context* ctx, double* span_ms, double* idle_fraction, int32_t* slots) {
+  if (!ctx) return fail(QN_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  const int used = ctx->exit_slots_used;
+  if (span_ms) *span_ms = 0.0;
+  if (idle_fraction) *idle_fraction = 0.0;
+  if (slots) *slots = used;
+  if (used <= 0) return QN_OK;
+  QN_CUDA_TRY(cudaSetDevice(ctx->device));
+  std::vector<unsigned long long> h(used + 2);
+  QN_CUDA_TRY(cudaMemcpy(h.data(), ctx->exit_ns, sizeof(unsigned long long) * (used + 2), cudaMemcpyDeviceToHost));
+  const unsigned long long t0 = h[0], t1 = h[1];
+  if (t1 <= t0) return QN_OK;
+  double idle = 0.0;
+  int counted = 0;
+  for (int k = 0; k < used; ++k)
+    if (h[2 + k] >= t0 && h[2 + k] <= t1) { idle += (double)(t1 - h[2 + k]); ++counted; }
+  if (span_ms) *span_ms = (double)(t1 - t0) * 1e-6;
+  if (idle_fraction && counted) *idle_fraction = idle / ((double)counted * (double)(t1 - t0));
+  if (slots) *slots = counted;
+  return QN_OK;
 }
 
 int32_t qn_last_launch_info(qn_context* ctx, int32_t* path, int32_t* grid, int32_t* block,

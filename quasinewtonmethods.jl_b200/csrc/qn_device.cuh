@@ -45,7 +45,27 @@ struct BatchParams {
   int ntrace;
   double* trace;   // [batch][ntrace][n]
   unsigned long long* counter; // persistent-grid work queue
+  // optional (option "record_exit"): [0] earliest start, [1] latest end, [2 + slot] the %globaltimer
+  // stamp at which problem slot `slot` found the work queue empty — the tail of a launch made visible
+  unsigned long long* exit_ns;
+  int exit_cap;
 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void stamp_start(const BatchParams& p) {
+  if (p.exit_ns) atomicMin(p.exit_ns, global_ns());
+}
+__device__ __forceinline__ void stamp_exit(const BatchParams& p, const int slot) {
+  if (p.exit_ns) {
+    const unsigned long long t = global_ns();
+    if (slot < p.exit_cap) p.exit_ns[2 + slot] = t;
+    atomicMax(p.exit_ns + 1, t);
+  }
+}
 
 // Rule C2: a row sum over K terms is cut into balanced blocks of
 // ceil(K / ceil(K/16)) <= 16 consecutive terms; one sequential FMA chain per block,

@@ -18,8 +18,27 @@ int qn_fail(int code, const char* fmt, ...);
                      __FILE__, __LINE__);                                                 \
   } while (0)
 
+// Tuning / ablation switches of one context (qn_set_option; the QN_* environment variables of the
+// same names are read ONCE, in qn_create, as defaults — dispatch never calls getenv).
+struct qn_options {
+  int tile_tmem = -1;     // "tile_tmem":  -1 auto, 0 tile in registers, 1 tile in tensor memory   (QN_TILE_TMEM)
+  int pack = 1;           // "pack":        several small problems per warp (n = 8, 16, 32)        (QN_NO_PACK clears)
+  int pack_variant = 0;   // "pack_variant": rows per lane 1 | 2 | 4, 0 = measured default         (QN_PACK_VARIANT)
+  int pair_rows = 0;      // "pair_rows":   0 auto, else 'h' | 't' | '4' | '2' | 's'                 (QN_PAIR_ROWS)
+  int smem_rows = 0;      // "smem_rows":   0 auto, 2 or 4 rows per thread                          (QN_SMEM_ROWS)
+  int lambda_smem = 1;    // "lambda_smem": dense Gaussian n = 128 keeps Λ in shared memory         (QN_NO_LAMBDA_SMEM clears)
+  int stream_cluster = 1; // "stream_cluster": cluster vector kernel of the streaming path          (QN_STREAM_NO_CLUSTER clears)
+  int stream_tma = -1;    // "stream_tma":  -1 auto, 0 LDG sweeps, 1 cp.async.bulk-staged sweeps    (QN_STREAM_TMA)
+  int sweep_depth = 0;    // "sweep_depth": 0 auto, 8 or 16 loads in flight                         (QN_SWEEP_DEPTH)
+  int hint_p1_ld = 0, hint_p2_ld = 2, hint_p2_st = 1, hint_one_ld = 4; // cache hints, QN_HINT_*
+  int p1_pad_kb = 0;      // "p1_pad_kb"                                                            (QN_P1_PAD_KB)
+  int latency = -1;       // "latency":     -1 auto, 0/1 the single-problem latency kernel          (QN_LATENCY)
+  int record_exit = 0;    // "record_exit": tile kernels stamp %globaltimer when a problem slot runs dry
+};
+
 struct qn_context {
   int device = 0;
+  qn_options opt;
   cudaStream_t stream = nullptr;
   cudaDeviceProp prop{};
   unsigned long long* counter = nullptr; // ring of work-queue counters
@@ -27,6 +46,11 @@ struct qn_context {
   static constexpr int kCounterSlots = 64;
   void* stage = nullptr; // grow-only device staging for the host-pointer entry points
   size_t stage_bytes = 0;
+  void* hstage = nullptr; // grow-only PINNED host staging (multi-GPU gather of the per-problem scalars)
+  size_t hstage_bytes = 0;
+  unsigned long long* exit_ns = nullptr; // [kExitSlots + 2] start, end and per-slot exit stamps (record_exit)
+  static constexpr int kExitSlots = 4096;
+  int exit_slots_used = 0;
   int last_path = -1, last_grid = 0, last_block = 0, last_smem = 0, last_launches = 0;
   std::mutex mu;
 };
@@ -43,8 +67,16 @@ struct qn_model {
   size_t bytes = 0;      // user objective: size of the parameter blob at d_a
 };
 
-// grow the context's device staging buffer (caller holds ctx->mu or is single-threaded)
+// grow the context's device / pinned-host staging buffer (caller holds ctx->mu)
 int qn_ensure_stage(qn_context* ctx, size_t bytes);
+int qn_ensure_hstage(qn_context* ctx, size_t bytes);
+// qn_bfgs_optimize_batched_device_f64 for a caller that already holds ctx->mu
+int qn_optimize_device_locked(qn_context* ctx, const qn_model* model, int32_t n, int64_t batch,
+                              const double* theta0, int64_t theta_stride, const qn_backtracking* ls,
+                              double tol, int32_t max_iter, double* states, int64_t state_stride,
+                              int32_t ld, double* x_out, double* g_out, double* ell_out,
+                              int32_t* iters_out, int32_t* fevals_out, int32_t* status_out,
+                              int32_t ntrace, double* trace_out, uint32_t flags, cudaStream_t st);
 // next zeroed work-queue counter, zeroing enqueued on `st`
 unsigned long long* qn_next_counter(qn_context* ctx, cudaStream_t st);
 

@@ -180,7 +180,15 @@ __device__ __forceinline__ void warp_butterfly3(double& a, double& b, double& c,
 #define QN_TM_PARK 0 // 1: x, ∇, y wait in shared memory during the passes, as in the all-register kernel
 #endif
 #ifndef QN_TM_DEPTH
-#define QN_TM_DEPTH (QN_TM_EPC == 2 ? 4 : 2) // chunks in flight ahead of the one being used
+#define QN_TM_DEPTH (QN_TM_EPC == 2 ? 4 : (QN_TM_STW == 1 ? 1 : 2)) // chunks in flight ahead of the one being used
+#endif
+#ifndef QN_TM_STW
+// elements per tcgen05.st of pass 2: 4 = the chunk (.x8), 2 (.x4), 1 (.x2).  Measured on B200 (n = 60, 2^16
+// problems, tools/tile_bench.cu, same output hash): 76.2 / 74.7 / 73.3 ms, and 71.3 ms for .x2 with a
+// prefetch distance of ONE chunk (the registers the staging block needed now hide nothing worth having).
+// ptxas copies every element into an aligned 8-register block in front of an .x8 store (120 of pass
+// 2's 480 instructions per thread); a .x2 store takes the DFMA's own register pair.
+#define QN_TM_STW 1
 #endif
 template <int EPC>
 struct TmChunk { double d[EPC]; };
@@ -216,6 +224,17 @@ __device__ __forceinline__ void tm_store(const uint32_t addr, const TmChunk<EPC>
                  "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {t0a, t0b, t1a, t1b, t2a, t2b, t3a, t3b};\n}\n"
                  :: "r"(addr), "d"(c.d[0]), "d"(c.d[1]), "d"(c.d[2]), "d"(c.d[3]) : "memory");
   }
+}
+// One fp64 element per store (tcgen05.st .x2): its two 32-bit words are the register pair the DFMA
+// wrote, so ptxas needs no staging block in front of the store (the .x8 form costs 8 register moves
+// per column: 120 of pass 2's 480 instructions per thread).
+__device__ __forceinline__ void tm_store1(const uint32_t addr, const double v) {
+  asm volatile("{\n.reg .b32 ta, tb;\nmov.b64 {ta, tb}, %1;\n"
+               "tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {ta, tb};\n}\n" :: "r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void tm_store2(const uint32_t addr, const double v0, const double v1) {
+  asm volatile("{\n.reg .b32 t0a, t0b, t1a, t1b;\nmov.b64 {t0a, t0b}, %1;\nmov.b64 {t1a, t1b}, %2;\n"
+               "tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {t0a, t0b, t1a, t1b};\n}\n" :: "r"(addr), "d"(v0), "d"(v1) : "memory");
 }
 __device__ __forceinline__ void tm_wait_store() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 // barrier of one problem's 64 threads (barrier 0 stays the CTA's)
@@ -489,7 +508,16 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
                   acc[i] = fma(hh, sg.y, acc[i]);
                 }
               }
-              tm_store(tmem + WPC * c, cur); // by the whole warp (.sync.aligned), also where a half-warp has no column k
+              // by the whole warp (.sync.aligned), also where a half-warp has no column k
+              if constexpr (QN_TM_STW == 1) {
+#pragma unroll
+                for (int r = 0; r < EPC; ++r) tm_store1(tmem + WPC * c + 2 * r, cur.d[r]);
+              } else if constexpr (QN_TM_STW == 2) {
+#pragma unroll
+                for (int r = 0; r < EPC; r += 2) tm_store2(tmem + WPC * c + 2 * r, cur.d[r], cur.d[r + 1]);
+              } else {
+                tm_store(tmem + WPC * c, cur);
+              }
             }
           }
           tm_wait_store();
@@ -625,6 +653,7 @@ __global__ void __launch_bounds__(64) __maxnreg__(MINB >= 7 ? 144 : (MINB == 6 ?
 qn_resident_tile_kernel(const __grid_constant__ BatchParams p) {
   extern __shared__ __align__(16) double smem[];
   volatile long long* next = reinterpret_cast<volatile long long*>(smem + tile_smem_doubles<N>() - 2);
+  if (threadIdx.x == 0) stamp_start(p);
   for (;;) {
     __syncthreads(); // the previous problem's shared-memory traffic is finished
     if (threadIdx.x == 0) *next = (long long)atomicAdd(p.counter, 1ULL);
@@ -633,6 +662,7 @@ qn_resident_tile_kernel(const __grid_constant__ BatchParams p) {
     if (j >= p.batch) break;
     tile_solve_one<N, PF>(p, j, smem);
   }
+  if (threadIdx.x == 0) stamp_exit(p, (int)blockIdx.x);
 }
 
 // The tensor-memory variant: 4 warps = two problems per CTA, 128 columns of tensor memory per CTA,
@@ -658,6 +688,7 @@ qn_resident_tile_tmem_kernel(const __grid_constant__ BatchParams p) {
   // (R2UR) in front of every tcgen05.ld/st
   const uint32_t tmem = __reduce_max_sync(0xffffffffu, tmem_base + (((threadIdx.x >> 5) * 32u) << 16));
   volatile long long* next = reinterpret_cast<volatile long long*>(sm + kPairDoubles - 2);
+  if (threadIdx.x == 0) stamp_start(p);
   for (;;) {
     pair_barrier(pair); // the previous problem's shared-memory traffic is finished
     if ((threadIdx.x & 63) == 0) *next = (long long)atomicAdd(p.counter, 1ULL);
@@ -666,6 +697,7 @@ qn_resident_tile_tmem_kernel(const __grid_constant__ BatchParams p) {
     if (j >= p.batch) break;
     tile_solve_one<N, PF, true>(p, j, sm, tmem);
   }
+  if ((threadIdx.x & 63) == 0) stamp_exit(p, 2 * (int)blockIdx.x + pair);
   __syncthreads(); // both problems are done with the tensor memory
   if (threadIdx.x < 32)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;\n" :: "r"(tmem_base) : "memory");

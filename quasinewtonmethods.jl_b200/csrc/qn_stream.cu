@@ -60,27 +60,26 @@ using PassKernel = void (*)(const qn::StreamParams);
 // n = 8192: pass2 .lu loads + .cs stores 356 -> 316 µs per iteration; one-pass sweep .cg loads
 // 216 -> 206 µs).  The full 5×4 sweep of hints was run once (scripts/exp_stream_hints.sh, git
 // history); the combinations worth keeping are instantiated and selectable for A/B runs.
-int hint_env(const char* name, int dflt, int hi) {
-  const char* v = getenv(name);
-  if (!v) return dflt;
-  const int k = atoi(v);
-  return (k < 0 || k > hi) ? dflt : k;
-}
+// The hints are options of the context (qn_set_option "hint_p1_ld" ...; the QN_HINT_* environment
+// variables are read once, in qn_create).  t_opt: the options of the context this thread is serving.
+thread_local const qn_options* t_opt = nullptr;
+const qn_options& opts() { static const qn_options dflt; return t_opt ? *t_opt : dflt; }
+int hint_opt(int k, int dflt, int hi) { return (k < 0 || k > hi) ? dflt : k; }
 // deep = 16 instead of 8 loads in flight per thread (a whole rule-C2 block): for grids that leave
 // most SMs with at most one CTA — the shards of the row-sharded mode — where each thread's walk
 // over its 256 columns is a chain of exposed memory latencies
 bool sweep_deep(const qn_context* ctx, const qn::StreamParams& p) {
-  const int v = hint_env("QN_SWEEP_DEPTH", 0, 16);
+  const int v = hint_opt(ctx->opt.sweep_depth, 0, 16);
   if (v) return v == 16;
   return p.ntiles * p.nsb <= ctx->prop.multiProcessorCount;
 }
 PassKernel pass1_kernel(bool deep = false) {
   if (deep) return qn::stream_pass1<0, 0, 16>;
-  return hint_env("QN_HINT_P1_LD", 0, 4) == 4 ? qn::stream_pass1<4, 0> : qn::stream_pass1<0, 0>;
+  return hint_opt(opts().hint_p1_ld, 0, 4) == 4 ? qn::stream_pass1<4, 0> : qn::stream_pass1<0, 0>;
 }
 PassKernel pass2_kernel(bool deep = false) {
   if (deep) return qn::stream_pass2<2, 1, 16>;
-  const int ld = hint_env("QN_HINT_P2_LD", 2, 4), st = hint_env("QN_HINT_P2_ST", 1, 3);
+  const int ld = hint_opt(opts().hint_p2_ld, 2, 4), st = hint_opt(opts().hint_p2_st, 1, 3);
   if (ld == 0 && st == 0) return qn::stream_pass2<0, 0>; // no hints
   if (ld == 0) return qn::stream_pass2<0, 1>;            // .cs stores only
   if (st == 0) return qn::stream_pass2<2, 0>;            // .lu loads only
@@ -88,14 +87,14 @@ PassKernel pass2_kernel(bool deep = false) {
 }
 PassKernel pass_one_kernel(bool deep = false) {
   if (deep) return qn::stream_pass_one<4, 0, 16>;
-  const int ld = hint_env("QN_HINT_ONE_LD", 4, 4);
+  const int ld = hint_opt(opts().hint_one_ld, 4, 4);
   if (ld == 0) return qn::stream_pass_one<0, 0>;         // no hints
   if (ld == 1) return qn::stream_pass_one<1, 0>;         // .cs loads
   return qn::stream_pass_one<4, 0>;                      // default: .cg loads
 }
 
 // extra dynamic shared memory for pass1, a residency knob (bytes): QN_P1_PAD_KB
-size_t pass1_pad() { return (size_t)hint_env("QN_P1_PAD_KB", 0, 200) * 1024; }
+size_t pass1_pad() { return (size_t)hint_opt(opts().p1_pad_kb, 0, 200) * 1024; }
 using VecKernel = void (*)(const qn::StreamParams);
 VecKernel cluster_kernel(int ppt, bool onepass) {
   if (onepass) return ppt == 1 ? qn::stream_vec_cluster<1, true> : ppt == 2 ? qn::stream_vec_cluster<2, true> : qn::stream_vec_cluster<3, true>;
@@ -103,6 +102,7 @@ VecKernel cluster_kernel(int ppt, bool onepass) {
 }
 
 int enqueue_iteration(qn_context* ctx, const StreamWork& w, cudaStream_t st) {
+  t_opt = &ctx->opt;
   const qn::StreamParams& p = w.p;
   const dim3 grid(p.ntiles, p.nsb);
   const bool deep = sweep_deep(ctx, p);
@@ -225,6 +225,7 @@ int stream_setup(qn_context* ctx, StreamWork& w, int n, const double* theta0, bo
 }
 
 int stream_capture(qn_context* ctx, StreamWork& w, cudaStream_t st) {
+  t_opt = &ctx->opt;
   const qn::StreamParams& p = w.p;
   const int n = p.n;
   QN_TRY_REL(cudaSetDevice(ctx->device));
@@ -240,7 +241,7 @@ int stream_capture(qn_context* ctx, StreamWork& w, cudaStream_t st) {
     QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_end, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
     QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_onepass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
   }
-  if (!getenv("QN_STREAM_NO_CLUSTER")) {
+  if (ctx->opt.stream_cluster) {
     // the cluster vector kernel: a thread owns up to 3 Rosenbrock pairs; a rank stages n doubles
     const int pairs = n >> 1, cap = qn::kCluCtas * qn::kCluThreads;
     const int ppt = pairs <= cap ? 1 : (pairs + cap - 1) / cap;

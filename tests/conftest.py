@@ -40,3 +40,18 @@ def qn():
 def eng(qn):
     """The product engine on cuda:0.  Fails loudly when the CUDA path is unavailable."""
     return qn.default_engine(0)
+
+
+@pytest.fixture
+def option(eng):
+    """Set options of the session's context for one test (qn_set_option) and restore them after."""
+    saved = {}
+
+    def set_(key, value):
+        if key not in saved:
+            saved[key] = eng.get_option(key)
+        eng.set_option(key, value)
+
+    yield set_
+    for k, v in saved.items():
+        eng.set_option(k, v)

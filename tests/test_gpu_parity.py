@@ -80,11 +80,11 @@ def test_ragged_sizes_smem_path(eng, qn, ob, n):
 
 @pytest.mark.parametrize("n,variant", [(8, "1"), (8, "2"), (8, "4"), (16, "1"), (16, "2"), (16, "4"), (32, "2")])
 @pytest.mark.parametrize("order", [2, 3])
-def test_packed_small_n(eng, qn, ob, n, variant, order, monkeypatch):
+def test_packed_small_n(eng, qn, ob, n, variant, order, option):
     """n = 8, 16: several problems per warp (qn_resident_packed.cuh), ragged batch sizes so that
     sub-groups run dry at different times, iteration caps, traces; and the thread-per-row kernel
-    (QN_NO_PACK) gives the same bits."""
-    monkeypatch.setenv("QN_PACK_VARIANT", variant)  # rows per lane (qn_capi.cu dispatch_size)
+    (option pack = 0) gives the same bits."""
+    option("pack_variant", int(variant))  # rows per lane (qn_capi.cu dispatch_size)
     ls = qn.BackTracking[order]()
     ols = ob.backtracking(order)
     for batch, kw in ((1, {}), (7, {}), (133, {}), (64, dict(max_iter=3)), (64, dict(max_iter=4))):
@@ -92,9 +92,9 @@ def test_packed_small_n(eng, qn, ob, n, variant, order, monkeypatch):
         ref = ob.optimize_batch(ob.rosenbrock(), Theta, ls=ols, ntrace=5, **kw)
         got = eng.optimize_batched(qn.Rosenbrock(), Theta, ls=ls, ntrace=5, **kw)
         _check(got, ref)
-        monkeypatch.setenv("QN_NO_PACK", "1")
+        option("pack", 0)
         got2 = eng.optimize_batched(qn.Rosenbrock(), Theta, ls=ls, ntrace=5, **kw)
-        monkeypatch.delenv("QN_NO_PACK")
+        option("pack", 1)
         _check(got2, ref)
 
 
@@ -110,13 +110,13 @@ def test_tile_kernel_sizes(eng, qn, ob, n):
 
 
 @pytest.mark.parametrize("n", [36, 40, 44, 48, 50, 52, 56, 60, 64])
-def test_tile_kernel_in_tensor_memory(eng, qn, ob, n, monkeypatch):
+def test_tile_kernel_in_tensor_memory(eng, qn, ob, n, option):
     """The same kernel with B⁻¹ tiles in tensor memory (tcgen05.ld/st; CTAs of 128 threads = two
     problems, 8 problems per SM): the default for large batches of n = 44, 48, 50, 56, 60, 64, forced
-    here for every tile size (QN_TILE_TMEM=1) and for batches that leave a pair of warps idle.  Same
+    here for every tile size (option tile_tmem = 1) and for batches that leave a pair of warps idle.  Same
     bits as the oracle — traces, counts, both line-search orders, the final B⁻¹, iteration caps
     (which ∇ the canonical slot shows), a non-finite start — and as the all-register kernel."""
-    monkeypatch.setenv("QN_TILE_TMEM", "1")
+    option("tile_tmem", 1)
     R = qn.Rosenbrock()
     for batch in (1, 21):
         Theta = starts(n, batch, key=8000 + n)
@@ -151,7 +151,7 @@ def test_tile_kernel_in_tensor_memory(eng, qn, ob, n, monkeypatch):
     # and the all-register kernel gives the same bits on a batch large enough for either
     Theta = starts(n, 300, key=8200 + n)
     a = eng.optimize_batched(R, Theta)
-    monkeypatch.setenv("QN_TILE_TMEM", "0")
+    option("tile_tmem", 0)
     b_ = eng.optimize_batched(R, Theta)
     assert eng.last_launch()["block"] == 64
     for k in ("x", "g", "ell", "iters", "fevals", "status"):
@@ -191,20 +191,20 @@ def test_n128_both_resident_policies(eng, qn, ob):
         _check(got, ref)
 
 
-def test_n128_tiles_with_rows_in_tensor_memory(eng, qn, ob, monkeypatch):
+def test_n128_tiles_with_rows_in_tensor_memory(eng, qn, ob, option):
     """n = 128 hybrid tiles whose two non-register rows live in tensor memory instead of shared memory
-    (QN_PAIR_ROWS=t, the default): same bits as the oracle, including the final B⁻¹ read back from
-    tensor memory, and as the shared-memory hybrid (QN_PAIR_ROWS=h)."""
+    (option pair_rows = 't', the default): same bits as the oracle, including the final B⁻¹ read back from
+    tensor memory, and as the shared-memory hybrid (pair_rows = 'h')."""
     n = 128
     Theta = starts(n, 40, key=1289)
     a = eng.optimize_batched(qn.Rosenbrock(), Theta)
     assert eng.last_launch()["smem_bytes"] < 32768  # no B⁻¹ rows in shared memory
-    monkeypatch.setenv("QN_PAIR_ROWS", "h")
+    option("pair_rows", "h")
     b_ = eng.optimize_batched(qn.Rosenbrock(), Theta)
     assert eng.last_launch()["smem_bytes"] > 65536
     for k in ("x", "g", "ell", "iters", "fevals", "status"):
         assert np.array_equal(a[k], b_[k], equal_nan=True), k
-    monkeypatch.setenv("QN_PAIR_ROWS", "t")
+    option("pair_rows", "t")
     for batch in (1, 5, 300):
         Theta = starts(n, batch, key=1290 + batch)
         nref = min(batch, 6)

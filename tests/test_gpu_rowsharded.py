@@ -56,3 +56,30 @@ def test_rowsharded_full_solve_small(qn, ob):
     got = qn.optimize_rowsharded(engs, qn.Rosenbrock(), Theta[:, 0], ntrace=5, max_iter=400)
     ref = ob.optimize_batch(ob.rosenbrock(), Theta, ntrace=5, max_iter=400)
     _same(got, ref)
+
+
+def test_rowsharded_on_distinct_gpus(qn, ob, eng):
+    """The peer-store exchange over NVLink proper: needs >= 2 GPUs (skipped on a 1-GPU box; the log of a
+    2-GPU run is committed as profiles/r2_rowsharded_2gpu_pytest.txt).  Config 5's size, two-pass
+    (the reference's order): first iterations bit for bit against the oracle AND the one-GPU path."""
+    ndev = qn._lib.load().qn_device_count()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs (has %d)" % ndev)
+    G = min(ndev, 8)
+    engs = [qn.Engine(g) for g in range(G)]
+    assert len({e.device for e in engs}) == G
+    n, iters = 8192, 6
+    Theta = starts(n, 1, key=8192)
+    got = qn.optimize_rowsharded(engs, qn.Rosenbrock(), Theta[:, 0], max_iter=iters, ntrace=iters)
+    ref = ob.optimize_batch(ob.rosenbrock(), Theta, max_iter=iters, ntrace=iters)
+    _same(got, ref)
+    one = eng.optimize_batched(qn.Rosenbrock(), Theta, max_iter=iters, ntrace=iters)
+    _same(got, one)
+    # one-pass mode and a full solve on a smaller size, all shards on their own GPU
+    n = 2100
+    Theta = starts(n, 1, key=2100)
+    got = qn.optimize_rowsharded(engs, qn.Rosenbrock(), Theta[:, 0], ntrace=5, max_iter=600)
+    ref = ob.optimize_batch(ob.rosenbrock(), Theta, ntrace=5, max_iter=600)
+    _same(got, ref)
+    for e in engs:
+        e.close()

@@ -84,9 +84,9 @@ def test_one_pass_mode(eng, qn, ob, n, iters):
 
 
 @pytest.mark.parametrize("n,iters", [(61, 0), (200, 60)])
-def test_one_pass_mode_single_cta_fallback(eng, qn, ob, n, iters, monkeypatch):
+def test_one_pass_mode_single_cta_fallback(eng, qn, ob, n, iters, option):
     """The single-CTA vector kernel (used when n is beyond the cluster kernel's reach) gives the same bits."""
-    monkeypatch.setenv("QN_STREAM_NO_CLUSTER", "1")
+    option("stream_cluster", 0)
     flags = qn._lib.FLAG_FORCE_STREAM | qn._lib.FLAG_ONE_PASS
     Theta = starts(n, 2, key=70 + n)
     kw = dict(max_iter=iters) if iters else {}

@@ -1,5 +1,5 @@
 // phase_timing.cu — per-phase SM-cycle accounting of the register-tile kernel for ONE CTA
-// (QN_PHASE_TIMING build of qn_resident_tile.cuh).  Usage: ./phase_timing [nCTAs]
+// (QN_PHASE_TIMING build of qn_resident_tile.cuh).  Usage: ./phase_timing [problems = resident CTAs / pairs]
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -DQN_PHASE_TIMING -std=c++17 \
 //        --expt-relaxed-constexpr -o phase_timing phase_timing.cu
 #include <cstdio>
@@ -23,8 +23,14 @@ int main(int argc, char** argv) {
   p.n = n; p.max_iter = 10000; p.batch = nprob; p.theta0 = d_th; p.theta_stride = n; p.tol = 1e-8;
   p.ls = qn::LsParams{1e-4, 0.5, 0.1, 1000, 2};
   p.x_out = d_x; p.x_stride = n; p.iters_out = d_it; p.counter = d_cnt;
+#ifdef PT_TMEM // the tensor-memory kernel: CTAs of 128 threads = two problems (build with -DPT_TMEM)
+  const size_t smem = 2 * sizeof(double) * qn::tile_smem_doubles<60>();
+  cudaFuncSetAttribute(qn::qn_resident_tile_tmem_kernel<60, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  qn::qn_resident_tile_tmem_kernel<60, 1><<<(nprob + 1) / 2, 128, smem>>>(p);
+#else
   const size_t smem = sizeof(double) * qn::tile_smem_doubles<60>();
   qn::qn_resident_tile_kernel<60, 6, 1><<<nprob, 64, smem>>>(p);
+#endif
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
   unsigned long long clk[16];

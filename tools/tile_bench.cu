@@ -29,6 +29,15 @@ static unsigned long long fnv(const void* p, size_t bytes, unsigned long long h 
   return h;
 }
 
+// One thread on its own stream: SM cycles and nanoseconds while the benchmark kernel runs -> the
+// SM clock the kernel actually ran at (nvidia-smi samples every 100 ms; this is exact).
+__global__ void clock_probe(volatile int* stop, unsigned long long* out) {
+  unsigned long long t0, t1; long long c0 = clock64(), c1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do { c1 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); __nanosleep(2000); } while (!*stop);
+  out[0] = (unsigned long long)(c1 - c0); out[1] = t1 - t0;
+}
+
 int main(int argc, char** argv) {
   constexpr int n = TB_N;
   const long long nprob = argc > 1 ? atoll(argv[1]) : 65536;
@@ -61,17 +70,29 @@ int main(int argc, char** argv) {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, block, smem);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int occ_api = perSM;
+#ifdef TB_TMEM
+  perSM = 4; // the occupancy API answers 1 for a kernel that allocates tensor memory; 4 x 128 columns fit
+#endif
   if (getenv("TB_PERSM")) perSM = atoi(getenv("TB_PERSM")); // resident CTAs per SM the grid is sized for
   const int grid = (int)std::min<long long>((nprob + block / 64 - 1) / (block / 64), (long long)perSM * sms);
   cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   std::vector<float> ms;
+  int* h_stop; unsigned long long* h_probe; cudaHostAlloc(&h_stop, 4, cudaHostAllocMapped); cudaHostAlloc(&h_probe, 16, cudaHostAllocMapped);
+  cudaStream_t ps; cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking);
+  double mhz = 0;
   for (int r = 0; r < reps + 1; ++r) {
     cudaMemset(d_cnt, 0, 8);
+    cudaDeviceSynchronize();
+    *h_stop = 0;
+    clock_probe<<<1, 1, 0, ps>>>(h_stop, h_probe);
     cudaEventRecord(e0);
     kern<<<grid, block, smem>>>(p);
     cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    *h_stop = 1;
     cudaError_t e = cudaDeviceSynchronize();
+    if (r) mhz = h_probe[1] ? 1e3 * (double)h_probe[0] / (double)h_probe[1] : 0;
     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
     float t; cudaEventElapsedTime(&t, e0, e1);
     if (r) ms.push_back(t);
@@ -90,7 +111,7 @@ int main(int argc, char** argv) {
   long long iters = 0, conv = 0; for (long long j = 0; j < nprob; ++j) { iters += it[j]; conv += st[j] == 0; }
   std::sort(ms.begin(), ms.end());
   const double med = ms[ms.size() / 2];
-  printf("n=%d problems=%lld grid=%d (%d/SM, occupancy API %d) regs=%d smem=%zu: median %.3f ms (min %.3f)  %.4g iterations/s  %.4g solves/s  converged %lld  hash %016llx\n",
-         n, nprob, grid, perSM, occ_api, fa.numRegs, smem, med, ms[0], iters / (med * 1e-3), nprob / (med * 1e-3), conv, h);
+  printf("n=%d problems=%lld grid=%d (%d/SM, occupancy API %d) regs=%d smem=%zu: median %.3f ms (min %.3f)  %.4g iterations/s  %.4g solves/s  converged %lld  SM clock under load %.0f MHz  hash %016llx\n",
+         n, nprob, grid, perSM, occ_api, fa.numRegs, smem, med, ms[0], iters / (med * 1e-3), nprob / (med * 1e-3), conv, mhz, h);
   return 0;
 }
