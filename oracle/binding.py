@@ -42,11 +42,19 @@ class Info(C.Structure):
                 ("status", C.c_int32), ("_pad", C.c_int32)]
 
 
+_FAST_SO = os.path.join(_HERE, "libqn_fastport.so")
+
+
+def _stale(so, deps):
+    return not os.path.exists(so) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(so) for f in deps)
+
+
 def build(force=False):
-    if force or not os.path.exists(_SO) or any(
-            os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_SO)
-            for f in ("qn_oracle.c", "qn_oracle.h", "Makefile")):
+    if force or _stale(_SO, ("qn_oracle.c", "qn_oracle.h", "Makefile")):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libqn_oracle.so"])
+    if force or _stale(_FAST_SO, ("qn_fastport.c", "qn_oracle.h", "Makefile")):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libqn_fastport.so"])
     return _SO
 
 
@@ -188,3 +196,58 @@ def optimize_batch(model, theta0, ls=None, tol=1e-8, max_iter=10000, ntrace=0, n
 
 def num_cores():
     return lib().qo_num_cores()
+
+
+# ---------------------------------------------------------------------------- the fast port
+# oracle/qn_fastport.c: the same algorithm with the freedoms @turbo / @fastmath take (free summation
+# order, contraction).  CPU BASELINE ONLY — never the parity checker (tests hold it to the
+# north-star tolerances against the strict oracle above).
+_fast = None
+
+
+def fast_lib():
+    global _fast
+    if _fast is None:
+        if not os.path.exists(_FAST_SO):
+            build()
+        L = C.CDLL(_FAST_SO)
+        dp = C.POINTER(C.c_double)
+        L.qf_optimize.restype = C.c_double
+        L.qf_optimize.argtypes = [C.c_int, dp, C.POINTER(Backtracking), C.c_double, C.c_int64, dp, dp,
+                                  C.c_int, dp, C.POINTER(Info)]
+        L.qf_time_single.restype = None
+        L.qf_time_single.argtypes = [C.c_int, dp, C.POINTER(Backtracking), C.c_double, C.c_int, dp]
+        L.qf_optimize_batch.restype = C.c_int64
+        L.qf_optimize_batch.argtypes = [C.c_int, C.c_int64, dp, C.POINTER(Backtracking), C.c_double,
+                                        C.c_int64, dp, dp, dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                        C.POINTER(C.c_int32), C.c_int, dp, C.c_int]
+        _fast = L
+    return _fast
+
+
+def fast_optimize_batch(theta0, ls=None, tol=1e-8, max_iter=10000, ntrace=0, nthreads=0, want_xg=True):
+    """Rosenbrock batch through the fast port; same result dict as optimize_batch."""
+    theta0 = np.asfortranarray(theta0, dtype=np.float64)
+    n, batch = theta0.shape
+    ls = ls or backtracking()
+    x = np.empty((n, batch), order="F") if want_xg else None
+    g = np.empty((n, batch), order="F") if want_xg else None
+    ell = np.empty(batch)
+    iters = np.empty(batch, dtype=np.int64)
+    fevals = np.empty(batch, dtype=np.int64)
+    status = np.empty(batch, dtype=np.int32)
+    trace = np.full((batch, ntrace, n), np.nan) if ntrace else None
+    nconv = fast_lib().qf_optimize_batch(
+        n, batch, _dp(theta0), C.byref(ls), tol, max_iter, _dp(x), _dp(g), _dp(ell),
+        iters.ctypes.data_as(C.POINTER(C.c_int64)), fevals.ctypes.data_as(C.POINTER(C.c_int64)),
+        status.ctypes.data_as(C.POINTER(C.c_int32)), ntrace, _dp(trace), nthreads)
+    return dict(x=x, g=g, ell=ell, iters=iters, fevals=fevals, status=status, trace=trace, converged=int(nconv))
+
+
+def fast_time_single(x0, reps=200, ls=None, tol=1e-8):
+    """Per-call seconds of `reps` solves of one problem, timed inside C (BenchmarkTools-style)."""
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    ls = ls or backtracking()
+    sec = np.empty(reps)
+    fast_lib().qf_time_single(x0.size, _dp(x0), C.byref(ls), tol, reps, _dp(sec))
+    return sec
