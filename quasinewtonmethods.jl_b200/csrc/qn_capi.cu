@@ -345,10 +345,14 @@ __global__ void stream_scalars_kernel(double* ell_out, int* iters_out, int* feva
 // caller's stream, runs on the context's stream and returns when the batch is finished.
 int dispatch_stream(qn_context* ctx, const qn_model* model, qn::BatchParams& p,
                     const qn_backtracking* ls, uint32_t flags, cudaStream_t st) {
-  if (model->kind != QN_OBJ_ROSENBROCK)
+  // the objective registry of this path: Rosenbrock (cluster vector kernel, one-pass mode) and the
+  // dense Gaussian (CTA-cooperative objective in the single-CTA vector kernels)
+  if (model->kind != QN_OBJ_ROSENBROCK && model->kind != QN_OBJ_DENSE_GAUSSIAN)
     return fail(QN_ERR_UNREGISTERED_OBJECTIVE,
                 "objective kind %d has no registered device implementation on the streaming path "
-                "(n=%d); only Rosenbrock has one", model->kind, p.n);
+                "(n=%d); Rosenbrock and the dense Gaussian have one", model->kind, p.n);
+  if (model->kind == QN_OBJ_DENSE_GAUSSIAN && model->n != p.n)
+    return fail(QN_ERR_INVALID_ARGUMENT, "dense Gaussian model has n=%d, call has n=%d", model->n, p.n);
   // the graph cannot be captured on the legacy default stream: run on the context's stream,
   // ordered after whatever the caller enqueued on `st`
   cudaStream_t run = ctx->stream;
@@ -363,7 +367,7 @@ int dispatch_stream(qn_context* ctx, const qn_model* model, qn::BatchParams& p,
                              p.h_out ? p.h_out + j * p.h_stride : nullptr, p.ldh, &ell, &it, &fe,
                              &status, p.ntrace,
                              p.trace ? p.trace + (size_t)j * p.ntrace * p.n : nullptr, run, nullptr, 0,
-                             (flags & QN_FLAG_ONE_PASS) ? 1 : 0);
+                             (flags & QN_FLAG_ONE_PASS) ? 1 : 0, model->kind, model->d_a, model->d_b);
     if (rc) return rc;
     launches += ctx->last_launches;
     stream_scalars_kernel<<<1, 1, 0, run>>>(p.ell_out, p.iters_out, p.fevals_out, p.status_out, j, ell, it, fe, status);
@@ -420,6 +424,8 @@ const OptKey kOptKeys[] = {
   {"lambda_smem", &qn_options::lambda_smem, "QN_NO_LAMBDA_SMEM", 1},
   {"stream_cluster", &qn_options::stream_cluster, "QN_STREAM_NO_CLUSTER", 1},
   {"stream_tma", &qn_options::stream_tma, "QN_STREAM_TMA", 0},
+  {"l2_persist_mb", &qn_options::l2_persist_mb, "QN_L2_PERSIST_MB", 0},
+  {"sweep_order", &qn_options::sweep_order, "QN_SWEEP_ORDER", 0},
   {"sweep_depth", &qn_options::sweep_depth, "QN_SWEEP_DEPTH", 0},
   {"hint_p1_ld", &qn_options::hint_p1_ld, "QN_HINT_P1_LD", 0},
   {"hint_p2_ld", &qn_options::hint_p2_ld, "QN_HINT_P2_LD", 0},
@@ -549,6 +555,11 @@ int32_t qn_set_option(qn_context* ctx, const char* key, int64_t value) {
 
 int32_t qn_get_option(qn_context* ctx, const char* key, int64_t* value) {
   if (!ctx || !key || !value) return fail(QN_ERR_INVALID_ARGUMENT, "NULL argument");
+  // read-only facts of the device / the last solve
+  if (!strcmp(key, "device_l2_mb")) { *value = ctx->prop.l2CacheSize >> 20; return QN_OK; }
+  if (!strcmp(key, "device_l2_persist_max_mb")) { *value = ctx->prop.persistingL2CacheMaxSize >> 20; return QN_OK; }
+  if (!strcmp(key, "device_access_window_max_mb")) { *value = ctx->prop.accessPolicyMaxWindowSize >> 20; return QN_OK; }
+  if (!strcmp(key, "last_l2_persist_mb")) { *value = ctx->last_l2_persist_bytes >> 20; return QN_OK; }
   for (const OptKey& k : kOptKeys)
     if (!strcmp(k.key, key)) {
       *value = ctx->opt.*(k.field);

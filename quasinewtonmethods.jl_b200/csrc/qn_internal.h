@@ -29,6 +29,8 @@ struct qn_options {
   int lambda_smem = 1;    // "lambda_smem": dense Gaussian n = 128 keeps Λ in shared memory         (QN_NO_LAMBDA_SMEM clears)
   int stream_cluster = 1; // "stream_cluster": cluster vector kernel of the streaming path          (QN_STREAM_NO_CLUSTER clears)
   int stream_tma = -1;    // "stream_tma":  -1 auto, 0 LDG sweeps, 1 cp.async.bulk-staged sweeps    (QN_STREAM_TMA)
+  int l2_persist_mb = 0;  // "l2_persist_mb": leading part of B⁻¹ kept resident in L2 by the streaming path; -1 device maximum, 0 off = default: measured SLOWER beyond 16 MB (QN_L2_PERSIST_MB)
+  int sweep_order = -1;   // "sweep_order": -1 default, 0 ascending, 1 pass1 descending, 2 pass2 descending (QN_SWEEP_ORDER)
   int sweep_depth = 0;    // "sweep_depth": 0 auto, 8 or 16 loads in flight                         (QN_SWEEP_DEPTH)
   int hint_p1_ld = 0, hint_p2_ld = 2, hint_p2_st = 1, hint_one_ld = 4; // cache hints, QN_HINT_*
   int p1_pad_kb = 0;      // "p1_pad_kb"                                                            (QN_P1_PAD_KB)
@@ -52,6 +54,7 @@ struct qn_context {
   static constexpr int kExitSlots = 4096;
   int exit_slots_used = 0;
   int last_path = -1, last_grid = 0, last_block = 0, last_smem = 0, last_launches = 0;
+  long long last_l2_persist_bytes = 0; // streaming path: size of the L2-persisting window of the last solve
   std::mutex mu;
 };
 
@@ -92,4 +95,5 @@ int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_bac
                     double tol, int max_iter, double* d_x_out, double* d_g_out, double* d_h_out,
                     int ldh_out, double* ell, int* iters, int* fevals, int* status, int ntrace,
                     double* d_trace, cudaStream_t st, float* ms_per_iter_out, int fixed_iters,
-                    int onepass);
+                    int onepass, int obj_kind = QN_OBJ_ROSENBROCK, const double* obj_a = nullptr,
+                    const double* obj_b = nullptr);

@@ -33,11 +33,17 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <vector>
 
 #include "qn_device.cuh"
 #include "qn_internal.h"
 
 #include "qn_stream_kernels.cuh"
+
+#ifndef QN_SWEEP_ORDER_DEFAULT
+#define QN_SWEEP_ORDER_DEFAULT 0
+#endif
 
 
 // -------------------------------------------------------------------------- host side
@@ -52,7 +58,77 @@ struct StreamWork {
   int pass_threads = 256; // threads of a sweep CTA
   int clu_ppt = 0;      // one-pass mode: pairs per thread of the cluster vector kernel (0: single-CTA kernel)
   size_t clu_smem = 0;
+  size_t persist_bytes = 0; // leading bytes of H inside the L2-persisting access-policy window
+  cudaStream_t window_stream = nullptr; // the stream that carries the window attribute
 };
+
+// The L2-persisting window of one work space: the leading `persist_sb` super-blocks of B⁻¹ (a
+// contiguous run of columns) get the persisting access property on every sweep launch, so they are
+// read from and written to the 126 MB L2 instead of HBM in every iteration after the first
+// (B200_PROFILING: "keep tensors resident instead of re-reading them").  Option "l2_persist_mb":
+// -1 = as much as the device allows (cudaDevAttrMaxPersistingL2CacheSize), 0 = off.
+void window_value(const StreamWork& w, cudaLaunchAttributeValue& v) {
+  memset(&v, 0, sizeof v);
+  v.accessPolicyWindow.base_ptr = w.p.H;
+  v.accessPolicyWindow.num_bytes = w.persist_bytes;
+  v.accessPolicyWindow.hitRatio = 1.0f;
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+}
+int persist_setup(qn_context* ctx, StreamWork& w) {
+  qn::StreamParams& p = w.p;
+  p.persist_sb = 0;
+  w.persist_bytes = 0;
+  const long long want_mb = ctx->opt.l2_persist_mb;
+  if (want_mb == 0) return QN_OK;
+  const size_t cap = (size_t)ctx->prop.persistingL2CacheMaxSize;
+  const size_t maxwin = (size_t)ctx->prop.accessPolicyMaxWindowSize;
+  if (cap == 0 || maxwin == 0) return QN_OK;
+  size_t want = want_mb < 0 ? cap : std::min(cap, (size_t)want_mb << 20);
+  want = std::min(want, maxwin);
+  const size_t sb_bytes = sizeof(double) * (size_t)p.ld * p.sbcols;
+  const size_t h_bytes = sizeof(double) * (size_t)p.ld * p.n;
+  int k = (int)std::min<size_t>((size_t)p.nsb, want / sb_bytes);
+  if (k == 0) return QN_OK;
+  p.persist_sb = k;
+  w.persist_bytes = std::min(h_bytes, (size_t)k * sb_bytes);
+  // set aside exactly what the window needs: the set-aside is taken from the L2 of every other access
+  QN_CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(cap, w.persist_bytes)));
+  ctx->last_l2_persist_bytes = (long long)w.persist_bytes;
+  return QN_OK;
+}
+int persist_apply_stream(StreamWork& w, cudaStream_t st) {
+  if (!w.persist_bytes) return QN_OK;
+  w.window_stream = st;
+  cudaLaunchAttributeValue v;
+  window_value(w, v);
+  QN_CUDA_TRY(cudaStreamSetAttribute(st, cudaLaunchAttributeAccessPolicyWindow, &v));
+  return QN_OK;
+}
+int persist_apply_graph(const StreamWork& w) { // every kernel node of the captured graph
+  if (!w.persist_bytes) return QN_OK;
+  size_t nn = 0;
+  QN_CUDA_TRY(cudaGraphGetNodes(w.graph, nullptr, &nn));
+  std::vector<cudaGraphNode_t> nodes(nn);
+  QN_CUDA_TRY(cudaGraphGetNodes(w.graph, nodes.data(), &nn));
+  cudaLaunchAttributeValue v;
+  window_value(w, v);
+  for (size_t i = 0; i < nn; ++i) {
+    cudaGraphNodeType t;
+    QN_CUDA_TRY(cudaGraphNodeGetType(nodes[i], &t));
+    if (t == cudaGraphNodeTypeKernel)
+      QN_CUDA_TRY(cudaGraphKernelNodeSetAttribute(nodes[i], cudaLaunchAttributeAccessPolicyWindow, &v));
+  }
+  return QN_OK;
+}
+void persist_release(const StreamWork& w) { // the device of the work space is current
+  if (!w.persist_bytes) return;
+  cudaLaunchAttributeValue v;
+  memset(&v, 0, sizeof v);
+  if (w.window_stream) cudaStreamSetAttribute(w.window_stream, cudaLaunchAttributeAccessPolicyWindow, &v); // no window
+  cudaCtxResetPersistingL2Cache();
+  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0); // give the set-aside back
+}
 
 using PassKernel = void (*)(const qn::StreamParams);
 
@@ -73,13 +149,19 @@ bool sweep_deep(const qn_context* ctx, const qn::StreamParams& p) {
   if (v) return v == 16;
   return p.ntiles * p.nsb <= ctx->prop.multiProcessorCount;
 }
+// option "sweep_order": 0 both sweeps walk their column blocks in ascending order (round 1), 1 pass1
+// descending, 2 pass2 descending — a descending sweep starts where the ascending one before it ended,
+// on what that one left in L2 (single-GPU, 8-deep sweeps only)
+int sweep_order() { return hint_opt(opts().sweep_order, QN_SWEEP_ORDER_DEFAULT, 2); }
 PassKernel pass1_kernel(bool deep = false) {
   if (deep) return qn::stream_pass1<0, 0, 16>;
+  if (sweep_order() == 1) return qn::stream_pass1<0, 0, 8, true>;
   return hint_opt(opts().hint_p1_ld, 0, 4) == 4 ? qn::stream_pass1<4, 0> : qn::stream_pass1<0, 0>;
 }
 PassKernel pass2_kernel(bool deep = false) {
   if (deep) return qn::stream_pass2<2, 1, 16>;
   const int ld = hint_opt(opts().hint_p2_ld, 2, 4), st = hint_opt(opts().hint_p2_st, 1, 3);
+  if (sweep_order() == 2) return qn::stream_pass2<2, 1, 8, true>;
   if (ld == 0 && st == 0) return qn::stream_pass2<0, 0>; // no hints
   if (ld == 0) return qn::stream_pass2<0, 1>;            // .cs stores only
   if (st == 0) return qn::stream_pass2<2, 0>;            // .lu loads only
@@ -93,9 +175,25 @@ PassKernel pass_one_kernel(bool deep = false) {
   return qn::stream_pass_one<4, 0>;                      // default: .cg loads
 }
 
+// option "stream_tma": the two-pass sweeps staged through shared memory by the bulk-copy engine
+// (stream_pass1_tma / stream_pass2_tma); -1 = the measured default
+#ifndef QN_STREAM_TMA_DEFAULT
+#define QN_STREAM_TMA_DEFAULT 0
+#endif
+bool sweep_tma(const qn_context* ctx, const qn::StreamParams& p) {
+  const int v = ctx->opt.stream_tma;
+  return !p.onepass && (v < 0 ? QN_STREAM_TMA_DEFAULT != 0 : v != 0);
+}
 // extra dynamic shared memory for pass1, a residency knob (bytes): QN_P1_PAD_KB
 size_t pass1_pad() { return (size_t)hint_opt(opts().p1_pad_kb, 0, 200) * 1024; }
 using VecKernel = void (*)(const qn::StreamParams);
+// the single-CTA vector kernels of the registered objective (the objective registry of this path)
+VecKernel vec_begin_kernel(int kind) {
+  return kind == QN_OBJ_DENSE_GAUSSIAN ? qn::stream_vec_begin<qn::SGaussian> : qn::stream_vec_begin<qn::SRosenbrock>;
+}
+VecKernel vec_end_kernel(int kind) {
+  return kind == QN_OBJ_DENSE_GAUSSIAN ? qn::stream_vec_end<qn::SGaussian> : qn::stream_vec_end<qn::SRosenbrock>;
+}
 VecKernel cluster_kernel(int ppt, bool onepass) {
   if (onepass) return ppt == 1 ? qn::stream_vec_cluster<1, true> : ppt == 2 ? qn::stream_vec_cluster<2, true> : qn::stream_vec_cluster<3, true>;
   return ppt == 1 ? qn::stream_vec_cluster<1, false> : ppt == 2 ? qn::stream_vec_cluster<2, false> : qn::stream_vec_cluster<3, false>;
@@ -114,17 +212,22 @@ int enqueue_iteration(qn_context* ctx, const StreamWork& w, cudaStream_t st) {
     return QN_OK;
   }
   if (p.fused2) { // three kernels per iteration; the head of iteration 1 ran before the graph
-    pass1_kernel(deep)<<<grid, w.pass_threads, sizeof(double) * p.sbcols + pass1_pad(), st>>>(p);
-    pass2_kernel(deep)<<<grid, w.pass_threads, sizeof(double) * 4 * p.sbcols, st>>>(p);
+    if (sweep_tma(ctx, p)) {
+      qn::stream_pass1_tma<<<grid, w.pass_threads, qn::tma_smem_bytes(p.sbcols, 1, 2 * w.pass_threads), st>>>(p);
+      qn::stream_pass2_tma<<<grid, w.pass_threads, qn::tma_smem_bytes(p.sbcols, 4, 2 * w.pass_threads), st>>>(p);
+    } else {
+      pass1_kernel(deep)<<<grid, w.pass_threads, sizeof(double) * p.sbcols + pass1_pad(), st>>>(p);
+      pass2_kernel(deep)<<<grid, w.pass_threads, sizeof(double) * 4 * p.sbcols, st>>>(p);
+    }
     cluster_kernel(w.clu_ppt, false)<<<qn::kCluCtas, qn::kCluThreads, w.clu_smem, st>>>(p);
     QN_CUDA_TRY(cudaGetLastError());
     return QN_OK;
   }
-  qn::stream_vec_begin<<<1, qn::kVecThreads, w.vec_smem, st>>>(p);
+  vec_begin_kernel(p.obj_kind)<<<1, qn::kVecThreads, w.vec_smem, st>>>(p);
   pass1_kernel(deep)<<<grid, w.pass_threads, sizeof(double) * p.sbcols, st>>>(p);
   qn::stream_vec_mid<<<1, qn::kVecThreads, w.vec_smem, st>>>(p);
   pass2_kernel(deep)<<<grid, w.pass_threads, sizeof(double) * 4 * p.sbcols, st>>>(p);
-  qn::stream_vec_end<<<1, qn::kVecThreads, w.vec_smem, st>>>(p);
+  vec_end_kernel(p.obj_kind)<<<1, qn::kVecThreads, w.vec_smem, st>>>(p);
   qn::stream_identity<false><<<ctx->prop.multiProcessorCount * 8, 256, 0, st>>>(p);
   QN_CUDA_TRY(cudaGetLastError());
   return QN_OK;
@@ -133,6 +236,7 @@ int enqueue_iteration(qn_context* ctx, const StreamWork& w, cudaStream_t st) {
 constexpr int kItersPerGraph = 8; // iterations per graph replay; also the cadence of the done-flag poll
 
 void stream_release(StreamWork& w) {
+  persist_release(w);
   if (w.exec) cudaGraphExecDestroy(w.exec);
   if (w.graph) cudaGraphDestroy(w.graph);
   if (w.block) cudaFree(w.block);
@@ -154,9 +258,14 @@ void stream_release(StreamWork& w) {
 // The caller fills peer_base[] for nshard > 1 BEFORE calling stream_capture.
 int stream_setup(qn_context* ctx, StreamWork& w, int n, const double* theta0, bool theta_on_host,
                  const qn_backtracking* ls, double tol, int max_iter, int ntrace, double* d_trace,
-                 int onepass, int shard, int nshard, cudaStream_t st) {
+                 int onepass, int shard, int nshard, cudaStream_t st, int obj_kind = QN_OBJ_ROSENBROCK,
+                 const double* obj_a = nullptr, const double* obj_b = nullptr) {
   using namespace qn;
   StreamParams& p = w.p;
+  p.obj_kind = obj_kind;
+  p.obj_a = obj_a;
+  p.obj_b = obj_b;
+  if (obj_kind != QN_OBJ_ROSENBROCK) onepass = 0; // the deferred-update order is a permission; only Rosenbrock has its kernels
   QN_TRY_REL(cudaSetDevice(ctx->device));
   p.n = n;
   p.rb = chain_block(n);
@@ -185,6 +294,7 @@ int stream_setup(qn_context* ctx, StreamWork& w, int n, const double* theta0, bo
   p.ntiles = (p.rows + 2 * w.pass_threads - 1) / (2 * w.pass_threads);
   p.ld = (p.rows + 15) & ~15;
   QN_TRY_REL(cudaMalloc(&p.H, sizeof(double) * (size_t)p.ld * n));
+  { const int prc = persist_setup(ctx, w); if (prc) return prc; }
   const size_t nv = ((size_t)n + 31) & ~(size_t)31;
   p.nvstride = (int)nv;
   const size_t words = nv * 22 + 2 * (size_t)p.nsb * n + 128 + 4 * (size_t)row_tiles; // + one counter per 128-row CTA tile
@@ -235,13 +345,21 @@ int stream_capture(qn_context* ctx, StreamWork& w, cudaStream_t st) {
   if (pass1_pad())
     QN_TRY_REL(cudaFuncSetAttribute(pass1_kernel(deep), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(sizeof(double) * p.sbcols + pass1_pad())));
+  if (sweep_tma(ctx, p)) {
+    QN_TRY_REL(cudaFuncSetAttribute(qn::stream_pass1_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)qn::tma_smem_bytes(p.sbcols, 1, 2 * w.pass_threads)));
+    QN_TRY_REL(cudaFuncSetAttribute(qn::stream_pass2_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)qn::tma_smem_bytes(p.sbcols, 4, 2 * w.pass_threads)));
+  }
   if (w.vec_smem) {
-    QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_begin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
+    QN_TRY_REL(cudaFuncSetAttribute(vec_begin_kernel(p.obj_kind), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
+    if (p.obj_kind != QN_OBJ_ROSENBROCK)
+      QN_TRY_REL(cudaFuncSetAttribute(vec_begin_kernel(QN_OBJ_ROSENBROCK), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
     QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
-    QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_end, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
+    QN_TRY_REL(cudaFuncSetAttribute(vec_end_kernel(p.obj_kind), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
     QN_TRY_REL(cudaFuncSetAttribute(qn::stream_vec_onepass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));
   }
-  if (ctx->opt.stream_cluster) {
+  if (ctx->opt.stream_cluster && p.obj_kind == QN_OBJ_ROSENBROCK) {
     // the cluster vector kernel: a thread owns up to 3 Rosenbrock pairs; a rank stages n doubles
     const int pairs = n >> 1, cap = qn::kCluCtas * qn::kCluThreads;
     const int ppt = pairs <= cap ? 1 : (pairs + cap - 1) / cap;
@@ -255,14 +373,16 @@ int stream_capture(qn_context* ctx, StreamWork& w, cudaStream_t st) {
   }
   // one graph = kItersPerGraph iterations: with several GPUs driven by one host thread the graph
   // launches themselves (≈ 6 µs each) would otherwise bound the iteration rate
+  { const int prc = persist_apply_stream(w, st); if (prc) return prc; }
   QN_TRY_REL(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
   int rc = QN_OK;
   for (int k = 0; k < kItersPerGraph && rc == QN_OK; ++k) rc = enqueue_iteration(ctx, w, st);
   const cudaError_t ce = cudaStreamEndCapture(st, &w.graph);
   if (rc != QN_OK) return rc;
   if (ce != cudaSuccess) return qn_fail(QN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+  { const int prc = persist_apply_graph(w); if (prc) return prc; }
   QN_TRY_REL(cudaGraphInstantiate(&w.exec, w.graph, 0));
-  if (p.onepass || p.fused2) qn::stream_vec_begin<<<1, qn::kVecThreads, w.vec_smem, st>>>(p); // head of iteration 1
+  if (p.onepass || p.fused2) vec_begin_kernel(p.obj_kind)<<<1, qn::kVecThreads, w.vec_smem, st>>>(p); // head of iteration 1
   QN_TRY_REL(cudaGetLastError());
   return QN_OK;
 }
@@ -334,13 +454,15 @@ int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_bac
                     double tol, int max_iter, double* d_x_out, double* d_g_out, double* d_h_out,
                     int ldh_out, double* ell, int* iters, int* fevals, int* status, int ntrace,
                     double* d_trace, cudaStream_t st, float* ms_per_iter_out, int fixed_iters,
-                    int onepass) {
+                    int onepass, int obj_kind, const double* obj_a, const double* obj_b) {
   using namespace qn;
+  if (obj_kind != QN_OBJ_ROSENBROCK) onepass = 0;
   StreamWork w;
   StreamScalars host{};
   host.result = NAN;
   host.status = QN_MAX_ITER;
-  int rc = stream_setup(ctx, w, n, d_theta0, false, ls, tol, max_iter, ntrace, d_trace, onepass, 0, 1, st);
+  int rc = stream_setup(ctx, w, n, d_theta0, false, ls, tol, max_iter, ntrace, d_trace, onepass, 0, 1, st,
+                        obj_kind, obj_a, obj_b);
   if (rc == QN_OK && max_iter > 0) rc = stream_capture(ctx, w, st);
   if (rc == QN_OK && max_iter > 0) rc = stream_run(&ctx, &w, &st, 1, max_iter, fixed_iters, ms_per_iter_out, host);
   if (rc != QN_OK) { stream_release(w); return rc; }

@@ -34,6 +34,18 @@ __device__ __forceinline__ void st_h(double* ptr, const double2 v) {
   else *reinterpret_cast<double2*>(ptr) = v;
 }
 
+// The leading `persist_sb` super-blocks of B⁻¹ (a contiguous run of columns) are kept RESIDENT IN L2
+// across iterations (an access-policy window with the persisting property, qn_stream.cu): their
+// accesses carry no eviction hint, the rest of the matrix streams with the kernel's hints.
+template <int HINT>
+__device__ __forceinline__ double2 ld_hk(const double* ptr, const bool keep) {
+  return keep ? *reinterpret_cast<const double2*>(ptr) : ld_h<HINT>(ptr);
+}
+template <int HINT>
+__device__ __forceinline__ void st_hk(double* ptr, const double2 v, const bool keep) {
+  if (keep) *reinterpret_cast<double2*>(ptr) = v; else st_h<HINT>(ptr, v);
+}
+
 struct StreamScalars {
   double l0, sy, rho, c1, m, result;
   int it;          // completed outer iterations
@@ -72,6 +84,13 @@ struct StreamParams {
   int nshard, shard;
   int row0, rows;   // this GPU's slab: rows [row0, row0 + rows) of B⁻¹ (all of them when nshard = 1)
   int ntiles;       // CTA row tiles of a sweep on this GPU: 2·blockDim rows each
+  // the objective (QN.jl:8-9): kind + device parameters.  Rosenbrock needs none; dense Gaussian:
+  // obj_a = μ (n), obj_b = Λ (n×n column-major).  The cluster vector kernel and the one-pass mode
+  // are Rosenbrock's; any other registered objective runs the single-CTA vector kernels.
+  int obj_kind;
+  const double* obj_a;
+  const double* obj_b;
+  int persist_sb; // leading super-blocks of B⁻¹ inside the L2-persisting window (0: none)
   int fused2; // two-pass mode in three kernels: pass1 (+ yᵀB⁻¹y, c₁), pass2 (c₁s on the fly), cluster kernel
   double* base;
   double* peer_base[8];
@@ -260,6 +279,40 @@ __device__ __forceinline__ double cta_rosenbrock(int n, XF&& X, double* g, doubl
   return s;
 }
 
+// The objective protocol for the single-CTA vector kernels: eval(p, X, g, stage, red) returns ℓ at
+// the point X(i) and writes ∇ to g when g != nullptr (logdensity / ∂logdensity!, QN.jl:8-9).
+struct SRosenbrock {
+  template <class XF>
+  __device__ __forceinline__ static double eval(const StreamParams& p, XF&& X, double* g, double* stage, double* red) {
+    return cta_rosenbrock(p.n, X, g, stage, red);
+  }
+};
+// Dense Gaussian ℓ = -½ (θ-μ)ᵀΛ(θ-μ), ∇ = -Λ(θ-μ), CTA-cooperative: d = θ-μ to
+// p.xs, z = Λd by rule-C2 row chains (thread c: rows c, c + T, …; a column of Λ is read by
+// consecutive threads) to p.w — dead between pass2 and the next vec_mid, which is when the
+// objective runs —, ℓ = -½ csum(d·z).  Same order as the oracle's gauss_eval: the same bits.
+struct SGaussian {
+  template <class XF>
+  __device__ __forceinline__ static double eval(const StreamParams& p, XF&& X, double* g, double* stage, double* red) {
+    const int n = p.n, T = blockDim.x;
+    const double* mu = p.obj_a;
+    const double* lam = p.obj_b;
+    double* d = p.xs;
+    double* z = p.w;
+    for (int i = threadIdx.x; i < n; i += T) d[i] = X(i) - mu[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < n; c += T) {
+      const double zc = chain_rowsum(n, [&](int r, double& a, double& b) { a = lam[c + (size_t)n * r]; b = d[r]; });
+      z[c] = zc;
+      if (g) g[c] = -zc;
+    }
+    __syncthreads();
+    const double q = cta_csum(n, stage, red, [&](int i) { return d[i] * z[i]; });
+    return -0.5 * q;
+  }
+};
+
+template <class SObj>
 __global__ void __launch_bounds__(kVecThreads) stream_vec_begin(const StreamParams p) {
   extern __shared__ __align__(16) double vsm[];
   __shared__ double red;
@@ -270,7 +323,7 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_begin(const StreamPara
   const int it = sc->it + 1;
   double* stage = p.stage_in_smem ? vsm : p.tmp;
   const double* xv = p.x;
-  const double l0 = cta_rosenbrock(n, [&](int i) { return xv[i]; }, p.g, stage, &red); // QN.jl:254
+  const double l0 = SObj::eval(p, [&](int i) { return xv[i]; }, p.g, stage, &red); // QN.jl:254
   __syncthreads();
   if (threadIdx.x == 0) { sc->l0 = l0; sc->fevals += 1; flag = 1; }
   if (!isfinite(l0)) { // QN.jl:255
@@ -354,6 +407,7 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_mid(const StreamParams
 // Second half of an iteration, shared by the two-pass and the one-pass mode: the reset
 // decision (QN.jl:272-280), the whole line search (QN.jl:165-232), update_state! (QN.jl:21-27)
 // and the bookkeeping.  Runs in one CTA; s holds the direction, m = dᵀ∇.
+template <class SObj = SRosenbrock>
 __device__ __forceinline__ void stream_finish_iteration(const StreamParams& p, StreamScalars* sc, const int it,
                                                         const double l0, double m, double* stage, double* redp) {
   const int n = p.n;
@@ -375,7 +429,7 @@ __device__ __forceinline__ void stream_finish_iteration(const StreamParams& p, S
   const double* sv = p.s;
   auto trial = [&](double a) { // step! (QN.jl:157-162): x_new[i] = x_old[i] + a s[i] as one fma
     ++fevals;
-    return cta_rosenbrock(n, [&](int i) { return fma(a, sv[i], xv[i]); }, nullptr, stage, &red);
+    return SObj::eval(p, [&](int i) { return fma(a, sv[i], xv[i]); }, nullptr, stage, &red);
   };
   double lx_last;
   const double alpha = backtracking_linesearch(p.ls, l0, m, trial, lx_last);
@@ -401,6 +455,7 @@ __device__ __forceinline__ void stream_finish_iteration(const StreamParams& p, S
 }
 
 
+template <class SObj>
 __global__ void __launch_bounds__(kVecThreads) stream_vec_end(const StreamParams p) {
   extern __shared__ __align__(16) double vsm[];
   __shared__ double red;
@@ -424,18 +479,26 @@ __global__ void __launch_bounds__(kVecThreads) stream_vec_end(const StreamParams
   } else {
     m = sc->m;
   }
-  stream_finish_iteration(p, sc, it, l0, m, stage, &red);
+  stream_finish_iteration<SObj>(p, sc, it, l0, m, stage, &red);
 }
 
 #ifndef QN_PASS2_MINB
 #define QN_PASS2_MINB 2
 #endif
+__device__ __forceinline__ void pass1_finish(const StreamParams& p, const StreamScalars* sc, const int sb,
+                                             const int c0, const bool two, const double S0, const double S1);
+__device__ __forceinline__ void pass2_finish(const StreamParams& p, const StreamScalars* sc, const int sb,
+                                             const int c0, const bool two, const double S0, const double S1);
 #ifndef QN_PASS1_MINB
 #define QN_PASS1_MINB 4
 #endif
 // ---- pass 1: partial[sb][c] = Σ_{blocks of sb} chain_b(c),  chain_b(c) = Σ_{r in b} y[r] H[c,r]
-template <int LDH, int STH, int DEPTH = 8>
-__global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASS1_MINB) stream_pass1(const StreamParams p) {
+// DESC: the rule-C2 blocks of the super-block are walked from the LAST to the first (the chain inside a
+// block still runs in ascending column order, and the block partials are still added in ascending
+// order — they wait in registers), so that the sweep starts where the previous sweep over B⁻¹ ended:
+// what that sweep left in the 126 MB L2 is read before it is evicted.
+template <int LDH, int STH, int DEPTH = 8, bool DESC = false>
+__global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : (DESC ? 2 : QN_PASS1_MINB)) stream_pass1(const StreamParams p) {
   const StreamScalars* sc = p.sc;
   if (sc->done || sc->skip_update) return;
   extern __shared__ __align__(16) double sm[];
@@ -447,21 +510,21 @@ __global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASS1_MINB) s
   for (int r = r_begin + threadIdx.x; r < r_end; r += blockDim.x) ys[r - r_begin] = p.y[r];
   __syncthreads();
   const bool reset = p.fused2 && sc->need_reset != 0; // B⁻¹ ← I (QN.jl:144-148) folded into the sweeps
+  const bool keep = sb < p.persist_sb;                 // this super-block stays in L2
   const int c0 = p.row0 + (int)(blockIdx.x * 2 * blockDim.x) + 2 * (int)threadIdx.x;
   const bool two = (c0 + 1 < n);
   const double* hp = p.H + (c0 - p.row0);
   double S0 = 0.0, S1 = 0.0;
-  bool first = true;
-  for (int b0 = r_begin; b0 < r_end && c0 < n; b0 += rb) {
+  auto block_chain2 = [&](const int b0, double& t0, double& t1) { // one rule-C2 block: ascending fma chains of both rows
     const int b1 = min(b0 + rb, r_end);
-    double t0 = 0.0, t1 = 0.0;
+    t0 = 0.0; t1 = 0.0;
     int r = b0;
     for (; r + DEPTH <= b1; r += DEPTH) { // 8 independent 128-bit loads in flight
       double2 h[DEPTH];
 #pragma unroll
       for (int k = 0; k < DEPTH; ++k)
         h[k] = reset ? make_double2(c0 == r + k ? 1.0 : 0.0, c0 + 1 == r + k ? 1.0 : 0.0)
-                     : ld_h<LDH>(hp + (size_t)ld * (r + k));
+                     : ld_hk<LDH>(hp + (size_t)ld * (r + k), keep);
 #pragma unroll
       for (int k = 0; k < DEPTH; ++k) {
         const double yr = ys[r + k - r_begin];
@@ -471,15 +534,40 @@ __global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASS1_MINB) s
     }
     for (; r < b1; ++r) {
       const double2 h = reset ? make_double2(c0 == r ? 1.0 : 0.0, c0 + 1 == r ? 1.0 : 0.0)
-                              : ld_h<LDH>(hp + (size_t)ld * r);
+                              : ld_hk<LDH>(hp + (size_t)ld * r, keep);
       const double yr = ys[r - r_begin];
       t0 = fma(yr, h.x, t0);
       t1 = fma(yr, h.y, t1);
     }
-    S0 = first ? t0 : S0 + t0;
-    S1 = first ? t1 : S1 + t1;
-    first = false;
+  };
+  if constexpr (DESC) {
+    double T0[16], T1[16]; // a super-block has at most 16 blocks (sbcols = 16 rb)
+#pragma unroll
+    for (int bi = 15; bi >= 0; --bi) {
+      T0[bi] = 0.0; T1[bi] = 0.0;
+      if (r_begin + bi * rb < r_end && c0 < n) block_chain2(r_begin + bi * rb, T0[bi], T1[bi]);
+    }
+    S0 = T0[0]; S1 = T1[0];
+#pragma unroll
+    for (int bi = 1; bi < 16; ++bi)
+      if (r_begin + bi * rb < r_end) { S0 = S0 + T0[bi]; S1 = S1 + T1[bi]; }
+  } else {
+    bool first = true;
+    for (int b0 = r_begin; b0 < r_end && c0 < n; b0 += rb) {
+      double t0, t1;
+      block_chain2(b0, t0, t1);
+      S0 = first ? t0 : S0 + t0;
+      S1 = first ? t1 : S1 + t1;
+      first = false;
+    }
   }
+  pass1_finish(p, sc, sb, c0, two, S0, S1);
+}
+
+// End of pass 1 for one CTA: its super-block partials, then (last CTA of the row tile) the row sums.
+__device__ __forceinline__ void pass1_finish(const StreamParams& p, const StreamScalars* sc, const int sb,
+                                             const int c0, const bool two, const double S0, const double S1) {
+  const int n = p.n;
   if (c0 < n) {
     double* out = p.partial + (size_t)sb * n + c0;
     out[0] = S0;
@@ -518,7 +606,7 @@ __global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASS1_MINB) s
 // 4 KB-per-column stream, and 2 CTAs per SM (296 concurrent streams, all 128 registers spent on loads
 // in flight) beat 3 or 4 (measured at n = 8192, profiles/r1_stream_residency.txt: pass2 172 µs at 2 CTAs/SM
 // against 207 µs at 3-4; the one-pass sweep 201 / 245 / 253 µs per iteration at 2 / 3 / 4).
-template <int LDH, int STH, int DEPTH = 8>
+template <int LDH, int STH, int DEPTH = 8, bool DESC = false>
 __global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASS2_MINB) stream_pass2(const StreamParams p) {
   const StreamScalars* sc = p.sc;
   if (sc->done || sc->skip_update) return;
@@ -529,6 +617,7 @@ __global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASS2_MINB) s
   const int r_begin = sb * p.sbcols;
   const int r_end = min(r_begin + p.sbcols, n);
   const bool reset = p.fused2 && sc->need_reset != 0;
+  const bool keep = sb < p.persist_sb; // this super-block stays in L2
   const double c1 = sc->c1;
   for (int r = r_begin + threadIdx.x; r < r_end; r += blockDim.x) {
     const double sr = p.s[r];
@@ -541,17 +630,16 @@ __global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASS2_MINB) s
   const double s1 = two ? p.s[c0 + 1] : 0.0, nu1 = two ? p.nu[c0 + 1] : 0.0;
   double* hp = p.H + (c0 - p.row0);
   double S0 = 0.0, S1 = 0.0;
-  bool first = true;
-  for (int b0 = r_begin; b0 < r_end && c0 < n; b0 += rb) {
+  auto block_update2 = [&](const int b0, double& a0, double& a1) { // one rule-C2 block, ascending columns
     const int b1 = min(b0 + rb, r_end);
-    double a0 = 0.0, a1 = 0.0;
+    a0 = 0.0; a1 = 0.0;
     int r = b0;
     for (; r + DEPTH <= b1; r += DEPTH) {
       double2 h[DEPTH];
 #pragma unroll
       for (int k = 0; k < DEPTH; ++k)
         h[k] = reset ? make_double2(c0 == r + k ? 1.0 : 0.0, c0 + 1 == r + k ? 1.0 : 0.0)
-                     : ld_h<LDH>(hp + (size_t)ld * (r + k));
+                     : ld_hk<LDH>(hp + (size_t)ld * (r + k), keep);
 #pragma unroll
       for (int k = 0; k < DEPTH; ++k) {
         const double4 o = ops[r + k - r_begin];
@@ -559,27 +647,51 @@ __global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASS2_MINB) s
         h0 = fma(o.x, s0, h0); h1 = fma(o.x, s1, h1);     // + (c₁ s[r]) s[c]
         h0 = fma(o.y, s0, h0); h1 = fma(o.y, s1, h1);     // - u[r] s[c]
         h0 = fma(nu0, o.z, h0); h1 = fma(nu1, o.z, h1);   // - u[c] s[r]
-        st_h<STH>(hp + (size_t)ld * (r + k), make_double2(h0, h1));
+        st_hk<STH>(hp + (size_t)ld * (r + k), make_double2(h0, h1), keep);
         a0 = fma(h0, o.w, a0);
         a1 = fma(h1, o.w, a1);
       }
     }
     for (; r < b1; ++r) {
       const double2 h = reset ? make_double2(c0 == r ? 1.0 : 0.0, c0 + 1 == r ? 1.0 : 0.0)
-                              : ld_h<LDH>(hp + (size_t)ld * r);
+                              : ld_hk<LDH>(hp + (size_t)ld * r, keep);
       const double4 o = ops[r - r_begin];
       double h0 = h.x, h1 = h.y;
       h0 = fma(o.x, s0, h0); h1 = fma(o.x, s1, h1);
       h0 = fma(o.y, s0, h0); h1 = fma(o.y, s1, h1);
       h0 = fma(nu0, o.z, h0); h1 = fma(nu1, o.z, h1);
-      st_h<STH>(hp + (size_t)ld * r, make_double2(h0, h1));
+      st_hk<STH>(hp + (size_t)ld * r, make_double2(h0, h1), keep);
       a0 = fma(h0, o.w, a0);
       a1 = fma(h1, o.w, a1);
     }
-    S0 = first ? a0 : S0 + a0;
-    S1 = first ? a1 : S1 + a1;
-    first = false;
+  };
+  if constexpr (DESC) { // last block first (see stream_pass1): the partials wait in registers
+    double A0[16], A1[16];
+#pragma unroll
+    for (int bi = 15; bi >= 0; --bi) {
+      A0[bi] = 0.0; A1[bi] = 0.0;
+      if (r_begin + bi * rb < r_end && c0 < n) block_update2(r_begin + bi * rb, A0[bi], A1[bi]);
+    }
+    S0 = A0[0]; S1 = A1[0];
+#pragma unroll
+    for (int bi = 1; bi < 16; ++bi)
+      if (r_begin + bi * rb < r_end) { S0 = S0 + A0[bi]; S1 = S1 + A1[bi]; }
+  } else {
+    bool first = true;
+    for (int b0 = r_begin; b0 < r_end && c0 < n; b0 += rb) {
+      double a0, a1;
+      block_update2(b0, a0, a1);
+      S0 = first ? a0 : S0 + a0;
+      S1 = first ? a1 : S1 + a1;
+      first = false;
+    }
   }
+  pass2_finish(p, sc, sb, c0, two, S0, S1);
+}
+
+__device__ __forceinline__ void pass2_finish(const StreamParams& p, const StreamScalars* sc, const int sb,
+                                             const int c0, const bool two, const double S0, const double S1) {
+  const int n = p.n;
   if (c0 < n) {
     double* out = p.partial + (size_t)sb * n + c0;
     out[0] = S0;
@@ -589,6 +701,227 @@ __global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASS2_MINB) s
     bstore(p, p.tmp2 + c, d * p.g[c]); // term of m = dᵀ∇_new, QN.jl:66
     bstore(p, p.dvec + c, d);          // the new direction (other CTAs of this launch still read s)
   });
+}
+
+// =====================================================================================================
+// TMA-staged sweeps (option "stream_tma").  B⁻¹ is column-major, so the 512 rows of a CTA's tile are
+// ONE contiguous 4 KB run per column: the bulk-copy engine (cp.async.bulk, the 1-D form of TMA) moves
+// whole columns of the tile between HBM and a shared-memory ring — kTmaCols columns per stage,
+// kTmaStages stages, completion through mbarriers (expect_tx / complete_tx) — while the threads do
+// nothing but LDS.128 + fma on landed data.  No thread holds a global address or a load in flight:
+// the registers the LDG version spends on 8-16 loads in flight are free, and the DMA keeps
+// kTmaStages·kTmaCols·4 KB per CTA on their way.  pass 2 writes its updated columns back into the
+// stage and the same engine stores them (cp.async.bulk.global.shared::cta + bulk groups); a stage is
+// refilled once its stores have READ the shared memory (cp.async.bulk.wait_group.read).
+// Same arithmetic, same order (rule C2) as stream_pass1 / stream_pass2: the same bits.
+constexpr int kTmaCols = 8;    // columns per stage
+constexpr int kTmaStages = 3;  // 3 × 8 × 4 KB = 96 KB of ring per CTA, two CTAs per SM
+
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, const unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, const unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, const unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred P1;\nWAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra.uni WAIT_DONE;\nbra.uni WAIT_LOOP;\nWAIT_DONE:\n}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, const unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               :: "r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global, tracked by the executing thread's bulk groups
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, const unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+               :: "l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" :: "n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;\n" :: "n"(N) : "memory"); }
+// generic-proxy writes (st.shared, mbarrier.init) become visible to the async proxy
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// shared memory of a TMA sweep: [operands of the super-block | mbarriers | ring]
+__host__ __device__ constexpr size_t tma_ring_offset(const int sbcols, const int ops_per_col) {
+  return (((size_t)sbcols * ops_per_col * sizeof(double) + kTmaStages * sizeof(uint64_t)) + 127) & ~(size_t)127;
+}
+__host__ __device__ constexpr size_t tma_smem_bytes(const int sbcols, const int ops_per_col, const int tile_rows) {
+  return tma_ring_offset(sbcols, ops_per_col) + (size_t)kTmaStages * kTmaCols * tile_rows * sizeof(double);
+}
+
+// ---- pass 1, TMA-staged
+__global__ void __launch_bounds__(kPassThreads, 2) stream_pass1_tma(const StreamParams p) {
+  const StreamScalars* sc = p.sc;
+  if (sc->done || sc->skip_update) return;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int n = p.n, ld = p.ld, rb = p.rb;
+  double* ys = reinterpret_cast<double*>(smraw); // y of this super-block's columns
+  uint64_t* full = reinterpret_cast<uint64_t*>(smraw + (size_t)p.sbcols * sizeof(double));
+  const int tile_rows = 2 * (int)blockDim.x;
+  unsigned char* ring = smraw + tma_ring_offset(p.sbcols, 1);
+  const int sb = blockIdx.y;
+  const int r_begin = sb * p.sbcols;
+  const int r_end = min(r_begin + p.sbcols, n);
+  const int ncols = r_end - r_begin;
+  const int nstg = (ncols + kTmaCols - 1) / kTmaCols;
+  const bool reset = p.fused2 && sc->need_reset != 0; // B⁻¹ ← I: nothing to fetch
+  const int tile0 = (int)blockIdx.x * tile_rows;       // first row of this tile inside the slab
+  const int rows_here = min(tile_rows, ld - tile0);    // ld is a multiple of 16 rows = 128 bytes
+  const unsigned col_bytes = (unsigned)rows_here * sizeof(double);
+  const double* gsrc = p.H + tile0;                    // column r of the tile at gsrc + ld·r
+  auto issue = [&](const int stg) { // one elected thread: the bulk copies of stage `stg`
+    const int slot = stg % kTmaStages;
+    const int cfirst = stg * kTmaCols, cn = min(kTmaCols, ncols - cfirst);
+    mbar_expect_tx(full + slot, col_bytes * (unsigned)cn);
+    for (int k = 0; k < cn; ++k)
+      bulk_g2s(ring + ((size_t)slot * kTmaCols + k) * tile_rows * sizeof(double),
+               gsrc + (size_t)ld * (r_begin + cfirst + k), col_bytes, full + slot);
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTmaStages; ++s) mbar_init(full + s, 1);
+    fence_async_smem();
+  }
+  for (int r = r_begin + threadIdx.x; r < r_end; r += blockDim.x) ys[r - r_begin] = p.y[r];
+  __syncthreads();
+  if (threadIdx.x == 0 && !reset)
+    for (int s = 0; s < kTmaStages && s < nstg; ++s) issue(s);
+  const int c0 = p.row0 + tile0 + 2 * (int)threadIdx.x;
+  const bool two = (c0 + 1 < n);
+  const bool rowok = c0 < n;
+  double S0 = 0.0, S1 = 0.0, t0 = 0.0, t1 = 0.0;
+  bool first = true;
+  int inblk = 0; // columns of the current rule-C2 block already folded into t0, t1
+  for (int stg = 0; stg < nstg; ++stg) {
+    const int slot = stg % kTmaStages;
+    if (!reset) mbar_wait(full + slot, (unsigned)(stg / kTmaStages) & 1u);
+    const double2* src = reinterpret_cast<const double2*>(ring + (size_t)slot * kTmaCols * tile_rows * sizeof(double)) + threadIdx.x;
+    double2 h[kTmaCols];
+#pragma unroll
+    for (int k = 0; k < kTmaCols; ++k) {
+      const int r = r_begin + stg * kTmaCols + k;
+      h[k] = reset ? make_double2(c0 == r ? 1.0 : 0.0, c0 + 1 == r ? 1.0 : 0.0) : src[(size_t)k * blockDim.x];
+    }
+#pragma unroll
+    for (int k = 0; k < kTmaCols; ++k) {
+      const int cc = stg * kTmaCols + k;
+      if (cc < ncols && rowok) {
+        const double yr = ys[cc];
+        t0 = fma(yr, h[k].x, t0);
+        t1 = fma(yr, h[k].y, t1);
+        if (++inblk == rb || cc == ncols - 1) { // the block's chain is complete: add its partial in order
+          S0 = first ? t0 : S0 + t0;
+          S1 = first ? t1 : S1 + t1;
+          first = false; t0 = 0.0; t1 = 0.0; inblk = 0;
+        }
+      }
+    }
+    __syncthreads(); // every thread has read the stage: it can be refilled
+    if (threadIdx.x == 0 && !reset && stg + kTmaStages < nstg) issue(stg + kTmaStages);
+  }
+  pass1_finish(p, sc, sb, c0, two, S0, S1);
+}
+
+// ---- pass 2, TMA-staged: columns land in the ring, are updated in place and stored by the engine
+__global__ void __launch_bounds__(kPassThreads, 2) stream_pass2_tma(const StreamParams p) {
+  const StreamScalars* sc = p.sc;
+  if (sc->done || sc->skip_update) return;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int n = p.n, ld = p.ld, rb = p.rb;
+  double4* ops = reinterpret_cast<double4*>(smraw); // {c₁s[r], -u[r], s[r], ∇[r]} per column
+  uint64_t* full = reinterpret_cast<uint64_t*>(smraw + (size_t)p.sbcols * 4 * sizeof(double));
+  const int tile_rows = 2 * (int)blockDim.x;
+  unsigned char* ring = smraw + tma_ring_offset(p.sbcols, 4);
+  const int sb = blockIdx.y;
+  const int r_begin = sb * p.sbcols;
+  const int r_end = min(r_begin + p.sbcols, n);
+  const int ncols = r_end - r_begin;
+  const int nstg = (ncols + kTmaCols - 1) / kTmaCols;
+  const bool reset = p.fused2 && sc->need_reset != 0;
+  const double c1 = sc->c1;
+  const int tile0 = (int)blockIdx.x * tile_rows;
+  const int rows_here = min(tile_rows, ld - tile0);
+  const unsigned col_bytes = (unsigned)rows_here * sizeof(double);
+  double* gsrc = p.H + tile0;
+  auto stage_ptr = [&](const int slot, const int k) { return ring + ((size_t)slot * kTmaCols + k) * tile_rows * sizeof(double); };
+  auto issue = [&](const int stg) {
+    const int slot = stg % kTmaStages;
+    const int cfirst = stg * kTmaCols, cn = min(kTmaCols, ncols - cfirst);
+    mbar_expect_tx(full + slot, col_bytes * (unsigned)cn);
+    for (int k = 0; k < cn; ++k)
+      bulk_g2s(stage_ptr(slot, k), gsrc + (size_t)ld * (r_begin + cfirst + k), col_bytes, full + slot);
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTmaStages; ++s) mbar_init(full + s, 1);
+    fence_async_smem();
+  }
+  for (int r = r_begin + threadIdx.x; r < r_end; r += blockDim.x) {
+    const double sr = p.s[r];
+    ops[r - r_begin] = make_double4(p.fused2 ? c1 * sr : p.w[r], p.nu[r], sr, p.g[r]); // (c₁ s[r]) once per r (rule C4)
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && !reset)
+    for (int s = 0; s < kTmaStages && s < nstg; ++s) issue(s);
+  const int c0 = p.row0 + tile0 + 2 * (int)threadIdx.x;
+  const bool two = (c0 + 1 < n);
+  const bool rowok = c0 < n;
+  const double s0 = rowok ? p.s[c0] : 0.0, nu0 = rowok ? p.nu[c0] : 0.0;
+  const double s1 = two ? p.s[c0 + 1] : 0.0, nu1 = two ? p.nu[c0 + 1] : 0.0;
+  double S0 = 0.0, S1 = 0.0, a0 = 0.0, a1 = 0.0;
+  bool first = true;
+  int inblk = 0;
+  for (int stg = 0; stg < nstg; ++stg) {
+    const int slot = stg % kTmaStages;
+    if (!reset) mbar_wait(full + slot, (unsigned)(stg / kTmaStages) & 1u);
+    double2* buf = reinterpret_cast<double2*>(stage_ptr(slot, 0)) + threadIdx.x;
+    double2 h[kTmaCols];
+#pragma unroll
+    for (int k = 0; k < kTmaCols; ++k) {
+      const int r = r_begin + stg * kTmaCols + k;
+      h[k] = reset ? make_double2(c0 == r ? 1.0 : 0.0, c0 + 1 == r ? 1.0 : 0.0) : buf[(size_t)k * blockDim.x];
+    }
+#pragma unroll
+    for (int k = 0; k < kTmaCols; ++k) {
+      const int cc = stg * kTmaCols + k;
+      if (cc < ncols && rowok) {
+        const double4 o = ops[cc];
+        double h0 = h[k].x, h1 = h[k].y;
+        h0 = fma(o.x, s0, h0); h1 = fma(o.x, s1, h1);     // + (c₁ s[r]) s[c]
+        h0 = fma(o.y, s0, h0); h1 = fma(o.y, s1, h1);     // - u[r] s[c]
+        h0 = fma(nu0, o.z, h0); h1 = fma(nu1, o.z, h1);   // - u[c] s[r]
+        buf[(size_t)k * blockDim.x] = make_double2(h0, h1);
+        a0 = fma(h0, o.w, a0);
+        a1 = fma(h1, o.w, a1);
+        if (++inblk == rb || cc == ncols - 1) {
+          S0 = first ? a0 : S0 + a0;
+          S1 = first ? a1 : S1 + a1;
+          first = false; a0 = 0.0; a1 = 0.0; inblk = 0;
+        }
+      }
+    }
+    fence_async_smem(); // this thread's updated elements are visible to the bulk-copy engine
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int cfirst = stg * kTmaCols, cn = min(kTmaCols, ncols - cfirst);
+      for (int k = 0; k < cn; ++k)
+        bulk_s2g(gsrc + (size_t)ld * (r_begin + cfirst + k), stage_ptr(slot, k), col_bytes);
+      bulk_commit();
+      // all but the newest group have READ their shared memory: the stage used one step ago is free
+      // (in reset mode, where nothing is fetched, this is what lets the threads overwrite it two
+      // steps from now); refill it with the stage that comes kTmaStages - 1 steps after this one
+      bulk_wait_read<1>();
+      if (!reset && stg >= 1 && stg - 1 + kTmaStages < nstg) issue(stg - 1 + kTmaStages);
+    }
+  }
+  if (threadIdx.x == 0) bulk_wait_all<0>(); // the stores are complete (and visible) before this CTA signs off
+  __syncthreads();
+  pass2_finish(p, sc, sb, c0, two, S0, S1);
 }
 
 // ---- one-pass mode: ONE sweep applies the pending update of the previous
@@ -610,6 +943,7 @@ __global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASSONE_MINB)
   const int r_end = min(r_begin + p.sbcols, n);
   const bool pending = sc->pending != 0;
   const bool reset = sc->need_reset != 0; // B⁻¹ ← I (QN.jl:144-148) is folded into this sweep
+  const bool keep = sb < p.persist_sb;    // this super-block stays in L2
   const double pc1 = sc->pc1;
   for (int r = r_begin + threadIdx.x; r < r_end; r += blockDim.x) {
     const double psr = p.ps[r];
@@ -633,17 +967,17 @@ __global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASSONE_MINB)
 #pragma unroll
       for (int k = 0; k < DEPTH; ++k)
         h[k] = reset ? make_double2(c0 == r + k ? 1.0 : 0.0, c0 + 1 == r + k ? 1.0 : 0.0)
-                     : ld_h<LDH>(hp + (size_t)ld * (r + k));
+                     : ld_hk<LDH>(hp + (size_t)ld * (r + k), keep);
 #pragma unroll
       for (int k = 0; k < DEPTH; ++k) {
         double h0 = h[k].x, h1 = h[k].y;
-        if (reset) st_h<STH>(hp + (size_t)ld * (r + k), h[k]);
+        if (reset) st_hk<STH>(hp + (size_t)ld * (r + k), h[k], keep);
         if (pending) {
           const double4 o = ops[r + k - r_begin];
           h0 = fma(o.x, s0, h0); h1 = fma(o.x, s1, h1);
           h0 = fma(o.y, s0, h0); h1 = fma(o.y, s1, h1);
           h0 = fma(nu0, o.z, h0); h1 = fma(nu1, o.z, h1);
-          st_h<STH>(hp + (size_t)ld * (r + k), make_double2(h0, h1));
+          st_hk<STH>(hp + (size_t)ld * (r + k), make_double2(h0, h1), keep);
         }
         const double2 q = yg[r + k - r_begin];
         t0 = fma(q.x, h0, t0); t1 = fma(q.x, h1, t1);
@@ -652,15 +986,15 @@ __global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASSONE_MINB)
     }
     for (; r < b1; ++r) {
       const double2 h = reset ? make_double2(c0 == r ? 1.0 : 0.0, c0 + 1 == r ? 1.0 : 0.0)
-                              : ld_h<LDH>(hp + (size_t)ld * r);
+                              : ld_hk<LDH>(hp + (size_t)ld * r, keep);
       double h0 = h.x, h1 = h.y;
-      if (reset) st_h<STH>(hp + (size_t)ld * r, h);
+      if (reset) st_hk<STH>(hp + (size_t)ld * r, h, keep);
       if (pending) {
         const double4 o = ops[r - r_begin];
         h0 = fma(o.x, s0, h0); h1 = fma(o.x, s1, h1);
         h0 = fma(o.y, s0, h0); h1 = fma(o.y, s1, h1);
         h0 = fma(nu0, o.z, h0); h1 = fma(nu1, o.z, h1);
-        st_h<STH>(hp + (size_t)ld * r, make_double2(h0, h1));
+        st_hk<STH>(hp + (size_t)ld * r, make_double2(h0, h1), keep);
       }
       const double2 q = yg[r - r_begin];
       t0 = fma(q.x, h0, t0); t1 = fma(q.x, h1, t1);

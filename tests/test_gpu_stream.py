@@ -54,10 +54,37 @@ def test_large_n_full_solve_and_h_writeback(eng, qn, ob):
 
 
 def test_stream_rejects_unregistered_objective(eng, qn):
-    from problems import gaussian_problem
-    mu, lam = gaussian_problem(200)
+    """An objective without a device implementation on this path is an error, never a CPU fallback
+    (the MethodError analogue, QN.jl:254): logistic regression has none beyond the resident sizes."""
+    from problems import logistic_problem
+    X, y, lam = logistic_problem(64, 200)
     with pytest.raises(qn.UnregisteredObjectiveError):
-        eng.optimize_batched(qn.DenseGaussian(mu, lam), starts(200, 1))
+        eng.optimize_batched(qn.LogisticRegression(X, y, lam), starts(200, 1))
+
+
+@pytest.mark.parametrize("n,iters", [(60, 0), (200, 0), (333, 0), (700, 40)])
+def test_stream_dense_gaussian(eng, qn, ob, n, iters):
+    """The reference's optimize! takes any objective at any P (QN.jl:254); here the dense Gaussian runs
+    beyond the resident sizes through a CTA-cooperative objective in the streaming path's vector
+    kernels (rule-C2 row chains for Λ(θ-μ)): bit for bit its oracle, full solves to θ* = μ."""
+    from problems import gaussian_problem
+    mu, lam = gaussian_problem(n)
+    model = qn.DenseGaussian(mu, lam)
+    omodel = ob.OracleModel(ob.DENSE_GAUSSIAN, mu=mu, lam=lam)
+    Theta = starts(n, 2, key=5200 + n)
+    kw = dict(max_iter=iters) if iters else {}
+    nt = iters if iters else 5
+    flags = qn._lib.FLAG_FORCE_STREAM if n <= 160 else 0
+    got = eng.optimize_batched(model, Theta, ntrace=nt, flags=flags, **kw)
+    assert eng.last_launch()["path"] == qn._lib.PATH_STREAM
+    ref = ob.optimize_batch(omodel, Theta, ntrace=nt, **kw)
+    _same(got, ref)
+    if not iters:
+        assert (got["status"] == qn.CONVERGED).all()
+        assert np.abs(got["x"] - mu[:, None]).max() < 1e-7
+    # QN_FLAG_ONE_PASS is a permission: this objective keeps the reference order
+    got1 = eng.optimize_batched(model, Theta[:, :1], ntrace=nt, flags=flags | qn._lib.FLAG_ONE_PASS, **kw)
+    assert np.array_equal(got1["x"][:, 0], got["x"][:, 0]) and got1["iters"][0] == got["iters"][0]
 
 
 @pytest.mark.parametrize("n,iters", [(60, 0), (61, 0), (200, 60), (1024, 20), (8193, 6), (9001, 6), (16500, 4)])
@@ -105,3 +132,25 @@ def test_one_pass_h_writeback(eng, qn, ob):
     o = ob.optimize(ob.rosenbrock(), Theta[:, 0], L=sb.L, rblock=ob.ONEPASS)
     L = sb.L
     assert np.array_equal(sb.data[0, 7 * L:].reshape(n, L)[:, :n], o["state"][7 * L:].reshape(n, L)[:, :n])
+
+
+@pytest.mark.parametrize("n,iters", [(17, 0), (61, 0), (192, 0), (161, 40), (777, 25), (2049, 12), (8192, 5)])
+def test_tma_staged_sweeps_same_bits(eng, qn, ob, n, iters, option):
+    """Option stream_tma = 1: the two sweeps of the reference-order mode staged through a
+    shared-memory ring by the bulk-copy engine (cp.async.bulk + mbarrier; stream_pass1_tma /
+    stream_pass2_tma).  Same arithmetic in the same order: bit for bit the oracle — full solves
+    (with their resets of B⁻¹), ragged sizes, the final B⁻¹ the engine stored, and config 5's size."""
+    option("stream_tma", 1)
+    Theta = starts(n, 1, key=4400 + n)
+    kw = dict(max_iter=iters) if iters else {}
+    nt = iters if iters else 5
+    sb = qn.BFGSStateBatch(n, 1) if n <= 800 else None
+    flags = qn._lib.FLAG_FORCE_STREAM | (qn._lib.FLAG_WRITE_H if sb is not None else 0)
+    got = eng.optimize_batched(qn.Rosenbrock(), Theta, ntrace=nt, flags=flags, states=sb, **kw)
+    assert eng.last_launch()["path"] == qn._lib.PATH_STREAM
+    ref = ob.optimize_batch(ob.rosenbrock(), Theta, ntrace=nt, **kw)
+    _same(got, ref)
+    if sb is not None:
+        L = sb.L
+        o = ob.optimize(ob.rosenbrock(), Theta[:, 0], L=L, **kw)
+        assert np.array_equal(sb.data[0, 7 * L:].reshape(n, L)[:, :n], o["state"][7 * L:].reshape(n, L)[:, :n])
