@@ -150,8 +150,9 @@ int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Par
 // that form (qn_resident_tile.cuh).
 template <int N, int MINB, int PF>
 int launch_tile(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
-  const size_t smem = sizeof(double) * (size_t)qn::tile_smem_doubles<N>();
+  const size_t smem = sizeof(double) * (size_t)qn::tile_problem_smem_doubles<N>();
   auto kern = qn::qn_resident_tile_kernel<N, MINB, PF>;
+  p.sm_count = ctx->prop.multiProcessorCount;
   int occ = 0;
   QN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 64, smem));
   if (occ < 1) return fail(QN_ERR_UNSUPPORTED_SIZE, "tile kernel does not fit on an SM (n=%d)", N);
@@ -177,8 +178,9 @@ int launch_tile(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
 // throughput grows 1.6e8 → 2.5e8 → 3.0e8 → 3.7e8 iterations/s from 1 to 4 CTAs per SM (n = 60).
 template <int N, int PF>
 int launch_tile_tmem(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
-  const size_t smem = 2 * sizeof(double) * (size_t)qn::tile_smem_doubles<N>();
+  const size_t smem = 2 * sizeof(double) * (size_t)qn::tile_problem_smem_doubles<N>();
   auto kern = qn::qn_resident_tile_tmem_kernel<N, PF>;
+  p.sm_count = ctx->prop.multiProcessorCount;
   QN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   long long grid = 4LL * ctx->prop.multiProcessorCount;
   if (grid > (p.batch + 1) / 2) grid = (p.batch + 1) / 2;

@@ -49,6 +49,7 @@ struct BatchParams {
   // stamp at which problem slot `slot` found the work queue empty — the tail of a launch made visible
   unsigned long long* exit_ns;
   int exit_cap;
+  int sm_count; // SMs of the device (tile kernels: which warp of a pair leads alternates per residency slot)
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {

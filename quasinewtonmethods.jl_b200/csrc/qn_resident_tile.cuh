@@ -34,12 +34,19 @@ namespace qn {
 
 // Optional per-phase cycle accounting (build with -DQN_PHASE_TIMING; tools/phase_timing.py).
 #ifdef QN_PHASE_TIMING
+// Accumulated in SHARED memory (a global read-modify-write per tick would put an L2 round trip, several
+// hundred cycles under load, into every phase) and flushed once per problem; a tick costs ~40 cycles.
 __device__ unsigned long long g_phase_clk[16];
-#define QN_TICK(k) do { const long long _t = clock64(); if (threadIdx.x == 0 && blockIdx.x == 0) g_phase_clk[k] += (unsigned long long)(_t - _tprev); _tprev = _t; } while (0)
-#define QN_TICK_INIT long long _tprev = clock64()
+#define QN_TICK_ON ((threadIdx.x & 31) == 0 && threadIdx.x < 64 && blockIdx.x == 0)
+#define QN_TICK(k) do { const long long _t = clock64(); if (QN_TICK_ON) _shclk[k] += (unsigned long long)(_t - _tprev); _tprev = clock64(); } while (0)
+#define QN_COUNT(k) do { if (QN_TICK_ON) _shclk[k] += 1ULL; } while (0)
+#define QN_TICK_INIT __shared__ unsigned long long _shclk[16]; if (QN_TICK_ON) { for (int _k = 0; _k < 16; ++_k) _shclk[_k] = 0; } long long _tprev = clock64()
+#define QN_TICK_FLUSH do { if (QN_TICK_ON) { for (int _k = 0; _k < 16; ++_k) g_phase_clk[_k] += _shclk[_k]; } } while (0)
 #else
 #define QN_TICK(k) do { } while (0)
+#define QN_COUNT(k) do { } while (0)
 #define QN_TICK_INIT do { } while (0)
+#define QN_TICK_FLUSH do { } while (0)
 #endif
 
 // two elements of a length-n vector per lane: lo = v[lane], hi = v[lane + 32]
@@ -617,6 +624,7 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
     l0 = (alpha == 1.0) ? lx1 : rosenbrock_finish<N>(sp.term_next, x);
   }
 
+  QN_TICK_FLUSH;
   if (owner) {
     if (p.x_out) p.x_out[j * p.x_stride + e] = mine(x);
     if (p.g_out) p.g_out[j * p.g_stride + e] = mine(g);
@@ -647,12 +655,513 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
   write_problem_scalars(p, j, t, result, iters, fevals, status);
 }
 
+// =====================================================================================================
+// Leader / helper form of the same solve (QN_TILE_LH, the default).
+//
+// In tile_solve_one BOTH warps of a problem run the whole O(n) part — objective, line search, dot
+// products, butterflies — on replicated vectors: 370 of a warp's 810 instructions per iteration, and
+// twice the shuffles and FP64 adds the problem needs.  Here one warp, the LEADER, owns the vectors
+// and runs that part alone; the HELPER only sweeps its half of the tile (pass 1, pass 2) and waits.
+// Its issue slots, FP64 pipe time and shuffle traffic go to the other problems resident on the SM.
+// The leader's arithmetic is the replicated warp's, operation for operation: the same bits.
+//
+// Hand-shakes: four mbarriers per problem in shared memory (arrive = release, wait = acquire; the
+// SM's 16 named barriers do not stretch to 4 CTAs x 2 problems x 4 hand-shakes):
+//   CMD   leader -> helper   a command word: PASS (operands of pass 1 are published) or EXIT, each
+//                            with an optional RESET (B⁻¹ <- I in the helper's half of the tile first)
+//   P1    helper -> leader   the helper's pass-1 partials are in shared memory
+//   OPS2  leader -> helper   c₁s, -u (column records) and -u by row are published
+//   P2    helper -> leader   the helper's pass-2 partials are in shared memory
+// Exactly one command per iteration and the leader waits for P2 before the next one, so a hand-shake
+// never overtakes the previous one.  Which warp of a pair leads alternates with the CTA's residency
+// slot, so that every scheduler of the SM hosts two leaders and two helpers.
+#ifndef QN_TILE_LH
+#define QN_TILE_LH 1
+#endif
+#ifndef QN_LH_HOIST
+#define QN_LH_HOIST 1
+#endif
+template <int N>
+struct TileLhCfg {
+  static constexpr int kRec = 6;                 // doubles per column record {c₁s, -u, s, ∇, pad, pad}
+  static constexpr int oRec = 0;                 // [4 blocks][16 slots] records
+  static constexpr int oYb = oRec + 64 * kRec;   // y by slot [4][16]
+  static constexpr int oS = oYb + 64;            // s by element, quad layout (row operands)
+  static constexpr int oNu = oS + 80;            // -u by element
+  static constexpr int oX = oNu + 80;            // x_old, ∇, ∇_old, y parked here while the passes need the
+  static constexpr int oG = oX + 80;             //   registers (tile in the register file only)
+  static constexpr int oGp = oG + 80;
+  static constexpr int oY = oGp + 80;
+  static constexpr int oPart1 = oY + 80;         // block partials of pass 1 and pass 2, [4 blocks][80]
+  static constexpr int oPart2 = oPart1 + 4 * 80;
+  static constexpr int oBar = oPart2 + 4 * 80;   // four mbarriers
+  static constexpr int oCmd = oBar + 4;          // the command word
+  static constexpr int oEnd = oCmd + 2;          // (+ 2 doubles for the kernel's work-queue slot)
+};
+template <int N>
+__host__ __device__ constexpr int tile_lh_smem_doubles() { return TileLhCfg<N>::oEnd + 2; }
+// shared memory (doubles) of one problem in the tile kernels as they are built
+template <int N>
+__host__ __device__ constexpr int tile_problem_smem_doubles() {
+  return QN_TILE_LH ? tile_lh_smem_doubles<N>() : tile_smem_doubles<N>();
+}
+
+constexpr int kLhPass = 1, kLhExit = 2, kLhReset = 4;
+__device__ __forceinline__ void lh_bar_init(uint64_t* bar, const unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void lh_arrive(uint64_t* bar) { // every lane of the warp: count 32, release
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];\n" :: "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void lh_wait(uint64_t* bar, const unsigned parity) { // acquire
+  asm volatile(
+      "{\n.reg .pred P1;\nLH_WAIT:\n"
+      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra.uni LH_DONE;\nbra.uni LH_WAIT;\nLH_DONE:\n}\n"
+      :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+// `ph`: this warp's parity bits of the four hand-shakes (bit k = barrier k), carried across problems.
+template <int N, int PF, bool TM>
+__device__ __forceinline__ void tile_solve_lh(const BatchParams& p, const long long j, double* smem,
+                                              const uint32_t tmem, const bool leader, unsigned& ph) {
+  using C = TileCfg<N>;
+  using L = TileLhCfg<N>;
+  constexpr int RT = C::RT, CT = C::CT, NB = C::NB;
+  const int t = TM ? (threadIdx.x & 63) : threadIdx.x; // thread of this problem
+  const int lane = t & 31;
+  constexpr int EPC = QN_TM_EPC, SPC = 4 / EPC, NCH = CT * SPC, WPC = 2 * EPC, TD = QN_TM_DEPTH;
+  static_assert(!TM || NCH * WPC <= 128, "the tile must fit the CTA's 128 columns");
+  const bool hi_valid = lane + 32 < N;
+  const int b = t >> 4;               // column block of this thread's tile (one per half-warp)
+  const int q = t & 15;               // row group
+  const int row0 = RT * q;
+  const int col0 = CT * b;
+  double* rec = smem + L::oRec;
+  double* yb_arr = smem + L::oYb;
+  double* s_arr = smem + L::oS;
+  double* nu_arr = smem + L::oNu;
+  double* part1 = smem + L::oPart1;
+  double* part2 = smem + L::oPart2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::oBar); // 0 CMD, 1 P1, 2 OPS2, 3 P2
+  volatile int* cmd = reinterpret_cast<volatile int*>(smem + L::oCmd);
+
+  double h[TM ? 1 : RT][TM ? 1 : CT]; // the tile: h[i][k] = B⁻¹[row0 + i, col0 + k] (TM: in tensor memory)
+  (void)h;
+
+  // ---- the two sweeps over this thread's tile, and the tile's reset and write-out: BOTH roles
+  auto pass1 = [&]() { // t[i] = Σ_k y[col0+k] H[row0+i, col0+k], QN.jl:44-49 -> part1
+    double tt[RT];
+#pragma unroll
+    for (int i = 0; i < RT; ++i) tt[i] = 0.0;
+    const double2* yb2 = reinterpret_cast<const double2*>(yb_arr + b * 16);
+    double2 yy[(CT + 1) / 2];
+#pragma unroll
+    for (int k = 0; k < (CT + 1) / 2; ++k) yy[k] = yb2[k];
+    __syncwarp(); // keeps the loads above it
+    if constexpr (TM) {
+      TmChunk<EPC> ring[TD + 1];
+#pragma unroll
+      for (int c = 0; c < TD && c < NCH; ++c) tm_load(ring[c], tmem + WPC * c);
+#pragma unroll
+      for (int k = 0; k < CT; ++k) {
+        const double yk = (k & 1) ? yy[k >> 1].y : yy[k >> 1].x;
+#pragma unroll
+        for (int sc = 0; sc < SPC; ++sc) {
+          const int c = k * SPC + sc;
+          tm_wait_load();
+          if (c + TD < NCH) tm_load(ring[(c + TD) % (TD + 1)], tmem + WPC * (c + TD));
+          if (C::kFull || col0 + k < N) {
+#pragma unroll
+            for (int r = 0; r < EPC; ++r) tt[sc * EPC + r] = fma(yk, ring[c % (TD + 1)].d[r], tt[sc * EPC + r]);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < CT; ++k) {
+        const double yk = (k & 1) ? yy[k >> 1].y : yy[k >> 1].x;
+        if (C::kFull || col0 + k < N) {
+#pragma unroll
+          for (int i = 0; i < RT; ++i) tt[i] = fma(yk, h[i][k], tt[i]);
+        }
+      }
+    }
+    double* pp = part1 + b * C::kQuad + 2 * q;
+    *reinterpret_cast<double2*>(pp) = make_double2(tt[0], tt[1]);
+    *reinterpret_cast<double2*>(pp + 40) = make_double2(tt[2], tt[3]);
+  };
+  auto pass2 = [&]() { // H ← H + c₁ssᵀ - usᵀ - suᵀ fused with d = H⁺∇_new, QN.jl:56-67 -> part2
+    double sc_[RT], nuc[RT], acc[RT];
+    const double2 s01 = *reinterpret_cast<const double2*>(s_arr + 2 * q);
+    const double2 s23 = *reinterpret_cast<const double2*>(s_arr + 40 + 2 * q);
+    const double2 n01 = *reinterpret_cast<const double2*>(nu_arr + 2 * q);
+    const double2 n23 = *reinterpret_cast<const double2*>(nu_arr + 40 + 2 * q);
+    sc_[0] = s01.x; sc_[1] = s01.y; sc_[2] = s23.x; sc_[3] = s23.y;
+    nuc[0] = n01.x; nuc[1] = n01.y; nuc[2] = n23.x; nuc[3] = n23.y;
+#pragma unroll
+    for (int i = 0; i < RT; ++i) acc[i] = 0.0;
+    const double* rb_ = rec + b * 16 * L::kRec;
+    auto ld_wn = [&](const int k) { return *reinterpret_cast<const double2*>(rb_ + k * L::kRec); };
+    auto ld_sg = [&](const int k) { return *reinterpret_cast<const double2*>(rb_ + k * L::kRec + 2); };
+    if constexpr (TM) {
+      TmChunk<EPC> ring[TD + 1];
+#pragma unroll
+      for (int c = 0; c < TD && c < NCH; ++c) tm_load(ring[c], tmem + WPC * c);
+#pragma unroll
+      for (int k = 0; k < CT; ++k) {
+        const double2 wn = ld_wn(k), sg = ld_sg(k);
+#pragma unroll
+        for (int sc = 0; sc < SPC; ++sc) {
+          const int c = k * SPC + sc;
+          TmChunk<EPC>& cur = ring[c % (TD + 1)];
+          tm_wait_load();
+          if (c + TD < NCH) tm_load(ring[(c + TD) % (TD + 1)], tmem + WPC * (c + TD));
+          if (C::kFull || col0 + k < N) {
+#pragma unroll
+            for (int r = 0; r < EPC; ++r) {
+              const int i = sc * EPC + r;
+              double hh = cur.d[r];
+              hh = fma(wn.x, sc_[i], hh);  // + (c₁ s[r]) s[c]
+              hh = fma(wn.y, sc_[i], hh);  // - u[r] s[c]
+              hh = fma(nuc[i], sg.x, hh);  // - u[c] s[r]
+              cur.d[r] = hh;
+              acc[i] = fma(hh, sg.y, acc[i]);
+            }
+          }
+          // by the whole warp (.sync.aligned), also where a half-warp has no column k
+          if constexpr (QN_TM_STW == 1) {
+#pragma unroll
+            for (int r = 0; r < EPC; ++r) tm_store1(tmem + WPC * c + 2 * r, cur.d[r]);
+          } else if constexpr (QN_TM_STW == 2) {
+#pragma unroll
+            for (int r = 0; r < EPC; r += 2) tm_store2(tmem + WPC * c + 2 * r, cur.d[r], cur.d[r + 1]);
+          } else {
+            tm_store(tmem + WPC * c, cur);
+          }
+        }
+      }
+      tm_wait_store();
+    } else {
+      double2 wnr[PF + 1], sgr[PF + 1];
+#pragma unroll
+      for (int k = 0; k < PF && k < CT; ++k) { wnr[k] = ld_wn(k); sgr[k] = ld_sg(k); }
+#pragma unroll
+      for (int k = 0; k < CT; ++k) {
+        if (k + PF < CT) { wnr[(k + PF) % (PF + 1)] = ld_wn(k + PF); sgr[(k + PF) % (PF + 1)] = ld_sg(k + PF); }
+        const double2 wn = wnr[k % (PF + 1)], sg = sgr[k % (PF + 1)];
+        if (C::kFull || col0 + k < N) {
+#pragma unroll
+          for (int i = 0; i < RT; ++i) {
+            double hh = h[i][k];
+            hh = fma(wn.x, sc_[i], hh);
+            hh = fma(wn.y, sc_[i], hh);
+            hh = fma(nuc[i], sg.x, hh);
+            h[i][k] = hh;
+            acc[i] = fma(hh, sg.y, acc[i]);
+          }
+        }
+      }
+    }
+    double* pp = part2 + b * C::kQuad + 2 * q;
+    *reinterpret_cast<double2*>(pp) = make_double2(acc[0], acc[1]);
+    *reinterpret_cast<double2*>(pp + 40) = make_double2(acc[2], acc[3]);
+  };
+  auto reset_tile = [&]() { // B⁻¹ ← I, QN.jl:144-148
+    if constexpr (TM) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        TmChunk<EPC> hc;
+#pragma unroll
+        for (int r = 0; r < EPC; ++r) hc.d[r] = (row0 + (c % SPC) * EPC + r == col0 + c / SPC) ? 1.0 : 0.0;
+        tm_store(tmem + WPC * c, hc);
+      }
+      tm_wait_store();
+    } else {
+#pragma unroll
+      for (int i = 0; i < RT; ++i)
+#pragma unroll
+        for (int k = 0; k < CT; ++k) h[i][k] = (row0 + i == col0 + k) ? 1.0 : 0.0;
+    }
+  };
+  auto write_h = [&]() { // final B⁻¹ (QN_FLAG_WRITE_H); TM: whole warps take part in the .sync.aligned loads
+    if (!(p.h_out && (TM || b < NB))) return;
+    double* ho = p.h_out + j * p.h_stride;
+    if constexpr (TM) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        TmChunk<EPC> hc;
+        tm_load(hc, tmem + WPC * c);
+        tm_wait_load();
+#pragma unroll
+        for (int r = 0; r < EPC; ++r) {
+          const int k = c / SPC, i = (c % SPC) * EPC + r;
+          if (row0 + i < N && col0 + k < N) ho[(row0 + i) + (long long)p.ldh * (col0 + k)] = hc.d[r];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < RT; ++i)
+#pragma unroll
+        for (int k = 0; k < CT; ++k)
+          if (row0 + i < N && col0 + k < N) ho[(row0 + i) + (long long)p.ldh * (col0 + k)] = h[i][k];
+    }
+  };
+
+  // ---- helper: nothing but its half of the sweeps
+  if (!leader) {
+    for (;;) {
+      lh_wait(bars + 0, ph & 1u); ph ^= 1u;
+      const int c = *cmd;
+      if (c & kLhReset) reset_tile();
+      if (c & kLhExit) break;
+      pass1();
+      lh_arrive(bars + 1);
+      lh_wait(bars + 2, (ph >> 2) & 1u); ph ^= 4u;
+      pass2();
+      lh_arrive(bars + 3);
+    }
+    write_h();
+    return;
+  }
+
+  // ---- leader: the vectors (element `lane` in lo, `lane + 32` in hi: the accumulator layout of rule C1)
+  // slot of element el in the block-padded column arrays
+  auto slot_of = [&](const int el) { return el < N ? (el / CT) * 16 + el % CT : -1; };
+  const int slot_lo = slot_of(lane), slot_hi = slot_of(lane + 32);
+  const int q_lo = C::quad(lane), q_hi = q_lo + 16; // quad-layout index of elements lane, lane + 32
+  auto dot = [&](const Pair& a, const Pair& bb) {   // lane accumulator of rule C1
+    double pacc = a.lo * bb.lo;
+    if (hi_valid) pacc = pacc + a.hi * bb.hi;
+    return pacc;
+  };
+  auto park = [&](const int off, const Pair& v) { smem[off + q_lo] = v.lo; smem[off + q_hi] = v.hi; };
+  auto unpark = [&](const int off) { Pair v; v.lo = smem[off + q_lo]; v.hi = smem[off + q_hi]; return v; };
+  auto combine = [&](const double* part) { // Σ_b part[b][e'] in ascending block order (rule C2), e' = lane, lane + 32
+    Pair T;
+    T.lo = part[q_lo];
+#pragma unroll
+    for (int bb = 1; bb < NB; ++bb) T.lo = T.lo + part[bb * C::kQuad + q_lo];
+    T.hi = 0.0;
+    if (hi_valid) {
+      T.hi = part[q_hi];
+#pragma unroll
+      for (int bb = 1; bb < NB; ++bb) T.hi = T.hi + part[bb * C::kQuad + q_hi];
+    }
+    return T;
+  };
+  auto command = [&](const int c) { // publish a command (and everything written before it) to the helper
+    if (lane == 0) *cmd = c;
+    __syncwarp();
+    lh_arrive(bars + 0);
+  };
+
+  // The parameters the loop tests on its critical path, read ONCE per problem: a warp-wide reduction
+  // of 32 equal values marks them warp-uniform, so they live in uniform registers instead of being
+  // fetched from the constant bank (LDC + dependent compare + branch, ~40 cycles each) every iteration.
+#if QN_LH_HOIST
+  auto uni32 = [](const int v) { return __reduce_max_sync(0xffffffffu, v); };
+  auto uni64 = [&](const double v) {
+    return __hiloint2double(__reduce_max_sync(0xffffffffu, __double2hiint(v)), (int)__reduce_max_sync(0xffffffffu, (unsigned)__double2loint(v)));
+  };
+  LsParams ls;
+  ls.c1 = uni64(p.ls.c1); ls.rho_hi = uni64(p.ls.rho_hi); ls.rho_lo = uni64(p.ls.rho_lo);
+  ls.iterations = (long long)uni32((int)min(p.ls.iterations, 2000000000LL)); ls.order = uni32(p.ls.order);
+  const double tol = uni64(p.tol);
+  const int max_iter = uni32(p.max_iter);
+  const int ntrace = p.trace != nullptr ? uni32(p.ntrace) : 0;
+#else
+  const LsParams& ls = p.ls;
+  const double tol = p.tol;
+  const int max_iter = p.max_iter;
+  const int ntrace = p.trace != nullptr ? p.ntrace : 0;
+#endif
+  Pair x, g, s, y;
+  double l0, sy = 0.0;
+  {
+    const double* th = p.theta0 + j * p.theta_stride; // copyto!(x_old, x), QN.jl:248
+    x.lo = th[lane];
+    x.hi = hi_valid ? th[lane + 32] : 0.0;
+    s.lo = s.hi = y.lo = y.hi = 0.0;
+    const double term = rosenbrock_warp_terms<N, true>(lane, x, g); // QN.jl:254 of iteration 1
+    l0 = rosenbrock_finish<N>(warp_butterfly(term), x);
+  }
+  constexpr bool kParkGp = !TM || QN_TM_PARK;
+  Pair gp; gp.lo = gp.hi = 0.0;
+  auto save_gp = [&](const Pair& v) { if (kParkGp) park(L::oGp, v); else gp = v; };
+  auto load_gp = [&]() { return kParkGp ? unpark(L::oGp) : gp; };
+  save_gp(gp);
+  double result = __longlong_as_double(0x7ff8000000000000LL); // NaN, QN.jl:291
+  int iters = 0, fevals = 0, status = QN_MAX_ITER;
+  bool helper_reset = false; // the helper's half of the tile still has to be reset (with the next command)
+
+  struct Spec { Pair g; double term_next, sy; };
+  auto spec_eval = [&](const double a, const Pair& d, Spec& sp, Pair& xn, double& term_trial) { // see tile_solve_one
+    Pair sn, xo, yn;
+    sn.lo = a * d.lo;     sn.hi = a * d.hi;
+    xo.lo = x.lo + sn.lo; xo.hi = x.hi + sn.hi;
+    sp.term_next = rosenbrock_warp_terms<N, true>(lane, xo, sp.g);
+    if (a == 1.0) {
+      xn = xo;
+      term_trial = sp.term_next;
+    } else {
+      xn.lo = fma(a, d.lo, x.lo);
+      xn.hi = fma(a, d.hi, x.hi);
+      Pair unused;
+      term_trial = rosenbrock_warp_terms<N, false>(lane, xn, unused);
+    }
+    yn.lo = g.lo - sp.g.lo; yn.hi = g.hi - sp.g.hi;
+    sp.sy = dot(sn, yn);
+  };
+
+  QN_TICK_INIT;
+  for (int it = 1; it <= max_iter; ++it) { // QN.jl:250,253
+    QN_TICK(0);
+    ++fevals;
+    const bool small = fabs(g.lo) < tol && (!hi_valid || fabs(g.hi) < tol);
+    const bool all_small = __all_sync(0xffffffffu, small);
+    if (!isfinite(l0) || all_small) {
+      iters = it - 1;
+      if (!isfinite(l0)) { status = QN_NONFINITE; if (!(it & 1)) g = load_gp(); }
+      else { status = QN_CONVERGED; result = l0; }
+      break;
+    }
+    QN_TICK(1);
+    double m;
+    Pair d;
+    Spec sp;
+    Pair xn;
+    double lx1 = 0.0;
+    bool have_trial = false;
+    if (it == 1) {
+      m = -1.0; // QN.jl:263-264
+    } else {
+      // ---- BFGS_update!  QN.jl:34-69.  Operands for BOTH warps' column blocks.
+      s_arr[q_lo] = s.lo;
+      s_arr[q_hi] = s.hi;
+      *reinterpret_cast<double2*>(rec + slot_lo * L::kRec + 2) = make_double2(s.lo, g.lo);
+      yb_arr[slot_lo] = y.lo;
+      if (slot_hi >= 0) {
+        *reinterpret_cast<double2*>(rec + slot_hi * L::kRec + 2) = make_double2(s.hi, g.hi);
+        yb_arr[slot_hi] = y.hi;
+      }
+      constexpr bool kPark = !TM || QN_TM_PARK;
+      if (kPark) {
+        park(L::oX, x);
+        park(L::oG, g);
+        park(L::oY, y);
+      }
+      command(kLhPass | (helper_reset ? kLhReset : 0));
+      helper_reset = false;
+      QN_TICK(2);
+      const double rho = 1.0 / sy; // QN.jl:42 (no guard)
+      pass1();
+      lh_wait(bars + 1, (ph >> 1) & 1u); ph ^= 2u; // the helper's pass-1 partials
+      QN_TICK(3);
+      {
+        const Pair T = combine(part1);
+        const Pair yv = kPark ? unpark(L::oY) : y;
+        const double s_lo = s_arr[q_lo], s_hi = s_arr[q_hi];
+        const double yHy = warp_butterfly(dot(T, yv)); // Σ_c t[c] y[c], QN.jl:51
+        const double c1 = fma(yHy, rho, 1.0) * rho;    // QN.jl:54
+        const double nu_lo = -(T.lo * rho), nu_hi = -(T.hi * rho); // -B⁻¹y[c] = -(t ρ), QN.jl:50
+        nu_arr[q_lo] = nu_lo;
+        nu_arr[q_hi] = nu_hi;
+        // (c₁ s[r]) rounded once per r (rule C4)
+        *reinterpret_cast<double2*>(rec + slot_lo * L::kRec) = make_double2(c1 * s_lo, nu_lo);
+        if (slot_hi >= 0) *reinterpret_cast<double2*>(rec + slot_hi * L::kRec) = make_double2(c1 * s_hi, nu_hi);
+      }
+      __syncwarp();
+      lh_arrive(bars + 2);
+      QN_TICK(4);
+      pass2();
+      lh_wait(bars + 3, (ph >> 3) & 1u); ph ^= 8u; // the helper's pass-2 partials
+      QN_TICK(5);
+      d = combine(part2); // the new direction d = H⁺∇_new; `s, y = y, s`, QN.jl:65,268
+      if (kPark) {
+        x = unpark(L::oX);
+        g = unpark(L::oG);
+      }
+      double tterm;
+      spec_eval(1.0, d, sp, xn, tterm);
+      m = dot(d, g);
+      warp_butterfly3(m, tterm, sp.sy, lane);
+      sp.term_next = tterm;
+      lx1 = rosenbrock_finish<N>(tterm, xn);
+      have_trial = true;
+      QN_TICK(6);
+    }
+    if (m <= 0.0) { // QN.jl:272-280: H ← I, s ← ∇_new, m ← ∇ᵀ∇
+      reset_tile();
+      helper_reset = true;
+      d = g;
+      m = warp_butterfly(dot(g, g));
+      have_trial = false;
+    }
+    double alpha;
+    {
+      auto trial = [&](const double a) {
+        QN_TICK(7); // the scalar part of the line search up to this trial
+        double tterm;
+        spec_eval(a, d, sp, xn, tterm);
+        warp_butterfly3(tterm, sp.term_next, sp.sy, lane);
+        ++fevals;
+        const double v = rosenbrock_finish<N>(tterm, xn);
+        QN_TICK(8); // one extra trial
+        QN_COUNT(9);
+        return v;
+      };
+      if (have_trial) ++fevals;
+      alpha = backtracking_linesearch(ls, l0, m, trial, lx1, have_trial, lx1);
+    }
+    QN_TICK(7);
+    if (alpha == 0.0) { status = QN_LINESEARCH_FAILED; iters = it - 1; if (!(it & 1)) g = load_gp(); break; } // QN.jl:284
+    s.lo = alpha * d.lo; s.hi = alpha * d.hi; // s ← αs      QN.jl:23-24
+    x.lo = x.lo + s.lo;  x.hi = x.hi + s.hi;  // x_old += s  QN.jl:25
+    if (it <= ntrace) {
+      double* tr = p.trace + (j * p.ntrace + (it - 1)) * (long long)N;
+      tr[lane] = x.lo;
+      if (hi_valid) tr[lane + 32] = x.hi;
+    }
+    if (it == max_iter) { iters = it; if (!(it & 1)) g = load_gp(); break; }
+    save_gp(g);
+    y.lo = g.lo - sp.g.lo; y.hi = g.hi - sp.g.hi; // y = ∇_old - ∇_new, QN.jl:38
+    sy = sp.sy;
+    g = sp.g;
+    l0 = (alpha == 1.0) ? lx1 : rosenbrock_finish<N>(sp.term_next, x);
+  }
+  QN_TICK_FLUSH;
+  command(kLhExit | (helper_reset ? kLhReset : 0));
+  if (p.x_out) {
+    double* xo = p.x_out + j * p.x_stride;
+    xo[lane] = x.lo;
+    if (hi_valid) xo[lane + 32] = x.hi;
+  }
+  if (p.g_out) {
+    double* go = p.g_out + j * p.g_stride;
+    go[lane] = g.lo;
+    if (hi_valid) go[lane + 32] = g.hi;
+  }
+  write_h();
+  write_problem_scalars(p, j, lane, result, iters, fevals, status);
+}
+
 // registers per thread: 168 lets 6 CTAs stay resident; MINB = 7 asks for 144 (experiment)
 template <int N, int MINB, int PF>
 __global__ void __launch_bounds__(64) __maxnreg__(MINB >= 7 ? 144 : (MINB == 6 ? 168 : (MINB == 5 ? 200 : 255)))
 qn_resident_tile_kernel(const __grid_constant__ BatchParams p) {
   extern __shared__ __align__(16) double smem[];
+#if QN_TILE_LH
+  volatile long long* next = reinterpret_cast<volatile long long*>(smem + tile_lh_smem_doubles<N>() - 2);
+  if (threadIdx.x == 0) {
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TileLhCfg<N>::oBar);
+    for (int k = 0; k < 4; ++k) lh_bar_init(bars + k, 32);
+  }
+  const bool leader = (int)(threadIdx.x >> 5) == (int)((blockIdx.x / (p.sm_count > 0 ? p.sm_count : 148)) & 1);
+  unsigned ph = 0;
+#else
   volatile long long* next = reinterpret_cast<volatile long long*>(smem + tile_smem_doubles<N>() - 2);
+#endif
   if (threadIdx.x == 0) stamp_start(p);
   for (;;) {
     __syncthreads(); // the previous problem's shared-memory traffic is finished
@@ -660,7 +1169,11 @@ qn_resident_tile_kernel(const __grid_constant__ BatchParams p) {
     __syncthreads();
     const long long j = *next;
     if (j >= p.batch) break;
+#if QN_TILE_LH
+    tile_solve_lh<N, PF, false>(p, j, smem, 0u, leader, ph);
+#else
     tile_solve_one<N, PF>(p, j, smem);
+#endif
   }
   if (threadIdx.x == 0) stamp_exit(p, (int)blockIdx.x);
 }
@@ -672,9 +1185,22 @@ __global__ void __launch_bounds__(128, 4)
 qn_resident_tile_tmem_kernel(const __grid_constant__ BatchParams p) {
   extern __shared__ __align__(16) double smem[];
   __shared__ uint32_t tmem_base;
+#if QN_TILE_LH
+  constexpr int kPairDoubles = tile_lh_smem_doubles<N>();
+#else
   constexpr int kPairDoubles = tile_smem_doubles<N>();
+#endif
   const int pair = (int)(threadIdx.x >> 6);
   double* sm = smem + pair * kPairDoubles;
+#if QN_TILE_LH
+  if ((threadIdx.x & 63) == 0) {
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + TileLhCfg<N>::oBar);
+    for (int k = 0; k < 4; ++k) lh_bar_init(bars + k, 32);
+  }
+  // which warp of a pair leads alternates with the CTA's residency slot (CTA b, b + #SM, ... share an SM)
+  const bool leader = (int)((threadIdx.x >> 5) & 1) == (int)((blockIdx.x / (p.sm_count > 0 ? p.sm_count : 148)) & 1);
+  unsigned ph = 0;
+#endif
   if (threadIdx.x < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;\n"
                  :: "l"((unsigned long long)__cvta_generic_to_shared(&tmem_base)) : "memory");
@@ -695,7 +1221,11 @@ qn_resident_tile_tmem_kernel(const __grid_constant__ BatchParams p) {
     pair_barrier(pair);
     const long long j = *next;
     if (j >= p.batch) break;
+#if QN_TILE_LH
+    tile_solve_lh<N, PF, true>(p, j, sm, tmem, leader, ph);
+#else
     tile_solve_one<N, PF, true>(p, j, sm, tmem);
+#endif
   }
   if ((threadIdx.x & 63) == 0) stamp_exit(p, 2 * (int)blockIdx.x + pair);
   __syncthreads(); // both problems are done with the tensor memory

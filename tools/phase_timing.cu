@@ -22,13 +22,13 @@ int main(int argc, char** argv) {
   qn::BatchParams p{};
   p.n = n; p.max_iter = 10000; p.batch = nprob; p.theta0 = d_th; p.theta_stride = n; p.tol = 1e-8;
   p.ls = qn::LsParams{1e-4, 0.5, 0.1, 1000, 2};
-  p.x_out = d_x; p.x_stride = n; p.iters_out = d_it; p.counter = d_cnt;
+  p.x_out = d_x; p.x_stride = n; p.iters_out = d_it; p.counter = d_cnt; p.sm_count = 148;
 #ifdef PT_TMEM // the tensor-memory kernel: CTAs of 128 threads = two problems (build with -DPT_TMEM)
-  const size_t smem = 2 * sizeof(double) * qn::tile_smem_doubles<60>();
+  const size_t smem = 2 * sizeof(double) * qn::tile_problem_smem_doubles<60>();
   cudaFuncSetAttribute(qn::qn_resident_tile_tmem_kernel<60, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   qn::qn_resident_tile_tmem_kernel<60, 1><<<(nprob + 1) / 2, 128, smem>>>(p);
 #else
-  const size_t smem = sizeof(double) * qn::tile_smem_doubles<60>();
+  const size_t smem = sizeof(double) * qn::tile_problem_smem_doubles<60>();
   qn::qn_resident_tile_kernel<60, 6, 1><<<nprob, 64, smem>>>(p);
 #endif
   cudaError_t e = cudaDeviceSynchronize();
@@ -38,10 +38,12 @@ int main(int argc, char** argv) {
   std::vector<int> it(nprob);
   cudaMemcpy(it.data(), d_it, nprob * 4, cudaMemcpyDeviceToHost);
   // block 0 solved whichever problems it pulled; with grid == batch it solved about one
-  const char* names[8] = {"loop top/trace", "conv check", "publish", "rho + pass 1 + barrier b",
-                          "combine + yHy + c1 + publish", "pass 2 + barrier d", "combine + m & trial butterfly", "rest of line search"};
-  unsigned long long tot = 0; for (int k = 0; k < 8; ++k) tot += clk[k];
+  const char* names[9] = {"accept -> loop top", "convergence check", "publish + command", "rho + pass 1 + wait for the partials",
+                          "combine + yHy + c1 + publish", "pass 2 + wait for the partials", "combine + first trial + m butterfly",
+                          "line search, scalar part", "line search, extra trials"};
+  unsigned long long tot = 0; for (int k = 0; k < 9; ++k) tot += clk[k];
   printf("CTAs=%d  iterations of problem 0: %d  total cycles %llu  -> %.0f cycles/iteration\n", nprob, it[0], tot, (double)tot / it[0]);
-  for (int k = 0; k < 8; ++k) printf("  %-50s %9llu  %6.1f cyc/iter  %5.1f%%\n", names[k], clk[k], (double)clk[k] / it[0], 100.0 * clk[k] / tot);
+  for (int k = 0; k < 9; ++k) printf("  %-50s %9llu  %6.1f cyc/iter  %5.1f%%\n", names[k], clk[k], (double)clk[k] / it[0], 100.0 * clk[k] / tot);
+  printf("  extra trials: %llu (%.3f per iteration, %.0f cycles each)\n", clk[9], (double)clk[9] / it[0], clk[9] ? (double)clk[8] / clk[9] : 0.0);
   return 0;
 }
