@@ -67,3 +67,34 @@ def test_distinct_contexts_are_independent_across_host_threads(qn, ob):
             assert np.array_equal(got[key][..., sel], ref[key], equal_nan=True), (n, key)
     for e in engines:
         e.close()
+
+
+def test_two_threads_on_one_context(eng, qn, ob):
+    """Two host threads calling the host entry of ONE context at the same time (ctypes releases the
+    GIL): the context's mutex is held for the whole call, so neither can see — or free — the other's
+    staging (round-1 advisor finding).  Different sizes per thread so that a mixed-up staging buffer
+    could not go unnoticed; each result must be the oracle's."""
+    import threading
+    jobs = [(60, 700, 1), (24, 1500, 2), (60, 64, 3), (100, 90, 4)]
+    out = {}
+
+    def work(tid):
+        res = []
+        for rep in range(3):
+            for n, batch, key in jobs[tid::2]:
+                Theta = starts(n, batch, key=key)
+                res.append((n, key, Theta, eng.optimize_batched(qn.Rosenbrock(), Theta)))
+        out[tid] = res
+
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for tid in range(2):
+        assert len(out[tid]) == 6
+        for n, key, Theta, got in out[tid]:
+            sel = np.linspace(0, Theta.shape[1] - 1, 16).astype(int)
+            ref = ob.optimize_batch(ob.rosenbrock(), np.asfortranarray(Theta[:, sel]))
+            for k in ("x", "g", "ell", "iters", "fevals", "status"):
+                assert np.array_equal(got[k][..., sel], ref[k], equal_nan=True), (n, key, k)
