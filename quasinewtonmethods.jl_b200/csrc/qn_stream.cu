@@ -79,6 +79,15 @@ int persist_setup(qn_context* ctx, StreamWork& w) {
   qn::StreamParams& p = w.p;
   p.persist_sb = 0;
   w.persist_bytes = 0;
+  // A slab that fits the L2 with room to spare (every shard of the row-sharded mode at n = 8192 on 8
+  // GPUs: 64 MiB of 126 MB; one GPU up to n ≈ 2 800) needs no window at all: its sweeps just drop
+  // their eviction hints (.lu loads, .cs stores) and the matrix stays cached from sweep to sweep
+  // and from iteration to iteration.  Option "l2_resident": -1 auto, 0 never, 1 always.
+  {
+    const size_t hb = sizeof(double) * (size_t)p.ld * p.n;
+    const int v = ctx->opt.l2_resident;
+    if (v > 0 || (v < 0 && hb * 20 <= (size_t)ctx->prop.l2CacheSize * 11)) { p.persist_sb = p.nsb; return QN_OK; }
+  }
   const long long want_mb = ctx->opt.l2_persist_mb;
   if (want_mb == 0) return QN_OK;
   const size_t cap = (size_t)ctx->prop.persistingL2CacheMaxSize;
