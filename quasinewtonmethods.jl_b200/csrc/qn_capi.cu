@@ -23,6 +23,7 @@
 #endif
 #include "qn_resident.cuh"
 #include "qn_resident_tile.cuh"
+#include "qn_resident_tile128.cuh"
 #include "qn_resident_packed.cuh"
 #include "qn_internal.h"
 
@@ -196,6 +197,27 @@ int launch_tile_tmem(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
   return QN_OK;
 }
 
+// n = 128 Rosenbrock: the leader/helper tile kernel with the whole tile in tensor memory
+// (qn_resident_tile128.cuh): CTAs of 256 threads = one problem, 256 columns each, two CTAs per SM.
+int launch_tile128(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
+  const size_t smem = sizeof(double) * (size_t)qn::Tile128::kSmemDoubles;
+  auto kern = qn::qn_resident_tile128_kernel;
+  QN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  long long grid = 2LL * ctx->prop.multiProcessorCount; // 2 x 256 tensor-memory columns, 2 x 256 x 128 registers
+  if (grid > p.batch) grid = p.batch;
+  p.counter = qn_next_counter(ctx, st);
+  p.sm_count = ctx->prop.multiProcessorCount;
+  arm_exit_stamps(ctx, p, grid, st);
+  kern<<<(unsigned)grid, 256, smem, st>>>(p);
+  QN_CUDA_TRY(cudaGetLastError());
+  ctx->last_path = 0;
+  ctx->last_grid = (int)grid;
+  ctx->last_block = 256;
+  ctx->last_smem = (int)smem;
+  ctx->last_launches = 1;
+  return QN_OK;
+}
+
 // Where the tile lives: tensor memory when it is the faster home (measured per size on B200,
 // 2^15-2^16 problems: n = 44 +1 %, 48 +6 %, 50 +8 %, 56 +1 %, 60 +3 %, 64 +8 %; n = 36, 40, 52 are
 // 1-3 % faster from registers) and the batch fills 8 problems per SM; option "tile_tmem" = 0 / 1 forces
@@ -280,7 +302,11 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
   const bool onepass = (flags & QN_FLAG_ONE_PASS) != 0; // honoured by these policies (and the streaming path)
   if constexpr (Obj::kPairRegister) {
     if (!(flags & QN_FLAG_FORCE_SMEM)) {
-      const char variant = ctx->opt.pair_rows ? (char)ctx->opt.pair_rows : (Obj::kRegisterPaths ? (n == 128 && !onepass ? 't' : 'h') : '4');
+      const char variant = ctx->opt.pair_rows ? (char)ctx->opt.pair_rows : (Obj::kRegisterPaths ? (n == 128 && !onepass ? 'L' : 'h') : '4');
+      // 'L' (n = 128 Rosenbrock, the default): leader/helper warps, the whole tile in tensor memory
+      if constexpr (std::is_same<Obj, qn::Rosenbrock>::value) {
+        if (variant == 'L' && n == 128 && !onepass) return launch_tile128(ctx, p, st);
+      }
       // n = 128 (BASELINE.json configs[2], [3]) has its own instantiations with n at compile time
       // (hybrid 6.3e7 against 4.7e7 iterations/s with n at run time; dense Gaussian 1.04e6 against
       // 0.68e6 solves/s); the other sizes share the run-time-n build

@@ -1,0 +1,365 @@
+// qn_resident_tile128.cuh — n = 128 Rosenbrock (BASELINE.json configs[2], configs[3]): the leader/helper
+// tile kernel of qn_resident_tile.cuh at the size where B⁻¹ (128 KB) fills half of the SM's tensor memory.
+//
+// One CTA of 256 threads = ONE problem.  Thread (q, b) owns rows 4q..4q+3 of the rule-C2 column block b
+// (16 columns): a 4×16 fp64 tile = 128 columns of its own tensor-memory lane (warps 0-3 on the lanes'
+// first 128 columns, warps 4-7 on the next 128: 256 columns per CTA, two CTAs = two problems per SM).
+// A warp is one column block — its 32 lanes read the block's column operands as one broadcast.
+//
+// Warp 0 is the LEADER: it holds every vector as FOUR elements per lane (element l + 32k in slot k —
+// exactly the lane accumulators of rule C1) and runs the whole O(n) part alone: objective, line
+// search, dot products, butterflies.  At n = 128 a Rosenbrock pair (i, i + 64) lives in ONE lane, so
+// the objective needs no exchange at all.  The other seven warps only sweep their tile (pass 1,
+// pass 2) between CTA barriers.  The kernel it replaces (qn_resident.cuh, `Team` protocol: one thread
+// per element, every reduction staged through shared memory behind a CTA barrier) ran at 7.2e7
+// iterations/s with FP64 37 % busy and its warps waiting on shared-memory scoreboards and barriers.
+// Same canonical order: the same bits as the oracle and as that kernel.
+#pragma once
+
+#include "qn_resident_tile.cuh"
+
+namespace qn {
+
+struct Tile128 {
+  static constexpr int N = 128, RT = 4, CT = 16, NB = 8, NG = 32, THREADS = 256, EPL = 4;
+  // shared memory (doubles)
+  static constexpr int kRec = 4;                      // {c₁s, -u, s, ∇} per column
+  static constexpr int oRec = 0;                      // [128 columns][4]
+  static constexpr int oYb = oRec + N * kRec;         // y by column [128]
+  static constexpr int oS = oYb + N;                  // s by row [128]
+  static constexpr int oNu = oS + N;                  // -u by row [128]
+  static constexpr int oPart1 = oNu + N;              // block partials [8 blocks][128 rows]
+  static constexpr int oPart2 = oPart1 + NB * N;
+  static constexpr int oCmd = oPart2 + NB * N;        // command word
+  static constexpr int oEnd = oCmd + 2;               // (+ 2 doubles: the work-queue slot)
+  static constexpr int kSmemDoubles = oEnd + 2;
+};
+
+struct Vec4 { double v[4]; };
+
+// Rosenbrock at n = 128 on the leader's layout: lane l holds θ[l], θ[l+32], θ[l+64], θ[l+96]; the pairs
+// (i, i + 64) of test/runtests.jl:8-9 are (slot 0, slot 2) and (slot 1, slot 3) of one lane.
+// Returns this lane's rule-C1 accumulator of the @simd sum: term[l] + term[l + 32].
+template <bool GRAD>
+__device__ __forceinline__ double rosenbrock128_terms(const Vec4& x, Vec4& g) {
+  double acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const double t1 = x.v[k], t2 = x.v[k + 2];
+    const double a = t2 - t1 * t1;
+    const double b = 1.0 - t1;
+    const double term = 100.0 * (a * a) + b * b; // runtests.jl:9,23
+    acc = (k == 0) ? term : acc + term;
+    if (GRAD) {
+      g.v[k] = (400.0 * a) * t1 + 2.0 * b;   // ∇[i],    runtests.jl:24
+      g.v[k + 2] = 200.0 * (t1 * t1 - t2);   // ∇[i+N],  runtests.jl:25
+    }
+  }
+  return acc;
+}
+
+__device__ __forceinline__ double dot128(const Vec4& a, const Vec4& b) { // lane accumulator of rule C1
+  double p = a.v[0] * b.v[0];
+#pragma unroll
+  for (int k = 1; k < 4; ++k) p = p + a.v[k] * b.v[k];
+  return p;
+}
+
+__global__ void __launch_bounds__(256, 2)
+qn_resident_tile128_kernel(const __grid_constant__ BatchParams p) {
+  using C = Tile128;
+  constexpr int N = C::N, RT = C::RT, CT = C::CT, NB = C::NB;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ uint32_t tmem_base_s;
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n"
+                 :: "l"((unsigned long long)__cvta_generic_to_shared(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const uint32_t tmem = __reduce_max_sync(0xffffffffu, tmem_base_s + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 128u);
+  const int b = warp;        // column block of this thread's tile
+  const int q = lane;        // row group
+  const int row0 = RT * q, col0 = CT * b;
+  double* rec = smem + C::oRec;
+  double* yb_arr = smem + C::oYb;
+  double* s_arr = smem + C::oS;
+  double* nu_arr = smem + C::oNu;
+  double* part1 = smem + C::oPart1;
+  double* part2 = smem + C::oPart2;
+  volatile int* cmd = reinterpret_cast<volatile int*>(smem + C::oCmd);
+  volatile long long* next = reinterpret_cast<volatile long long*>(smem + C::kSmemDoubles - 2);
+  const bool leader = (warp == 0);
+  constexpr int EPC = 4, WPC = 8, NCH = CT; // one tile column (4 rows) per chunk, 8 32-bit columns
+
+  auto pass1 = [&]() { // t[i] = Σ_k y[col0+k] H[row0+i, col0+k], QN.jl:44-49
+    double tt[RT];
+#pragma unroll
+    for (int i = 0; i < RT; ++i) tt[i] = 0.0;
+    const double2* yb2 = reinterpret_cast<const double2*>(yb_arr + col0);
+    double2 yy[CT / 2];
+#pragma unroll
+    for (int k = 0; k < CT / 2; ++k) yy[k] = yb2[k];
+    TmChunk<EPC> ring[2];
+    tm_load(ring[0], tmem);
+#pragma unroll
+    for (int k = 0; k < CT; ++k) {
+      const double yk = (k & 1) ? yy[k >> 1].y : yy[k >> 1].x;
+      tm_wait_load();
+      if (k + 1 < NCH) tm_load(ring[(k + 1) & 1], tmem + WPC * (k + 1));
+#pragma unroll
+      for (int r = 0; r < RT; ++r) tt[r] = fma(yk, ring[k & 1].d[r], tt[r]);
+    }
+    double* pp = part1 + b * N + row0;
+    *reinterpret_cast<double2*>(pp) = make_double2(tt[0], tt[1]);
+    *reinterpret_cast<double2*>(pp + 2) = make_double2(tt[2], tt[3]);
+  };
+  auto pass2 = [&]() { // H ← H + c₁ssᵀ - usᵀ - suᵀ fused with d = H⁺∇_new, QN.jl:56-67
+    double sc_[RT], nuc[RT], acc[RT];
+    {
+      const double2 s01 = *reinterpret_cast<const double2*>(s_arr + row0), s23 = *reinterpret_cast<const double2*>(s_arr + row0 + 2);
+      const double2 n01 = *reinterpret_cast<const double2*>(nu_arr + row0), n23 = *reinterpret_cast<const double2*>(nu_arr + row0 + 2);
+      sc_[0] = s01.x; sc_[1] = s01.y; sc_[2] = s23.x; sc_[3] = s23.y;
+      nuc[0] = n01.x; nuc[1] = n01.y; nuc[2] = n23.x; nuc[3] = n23.y;
+    }
+#pragma unroll
+    for (int i = 0; i < RT; ++i) acc[i] = 0.0;
+    const double* rb_ = rec + col0 * C::kRec;
+    TmChunk<EPC> ring[2];
+    tm_load(ring[0], tmem);
+#pragma unroll
+    for (int k = 0; k < CT; ++k) {
+      const double2 wn = *reinterpret_cast<const double2*>(rb_ + k * C::kRec);
+      const double2 sg = *reinterpret_cast<const double2*>(rb_ + k * C::kRec + 2);
+      TmChunk<EPC>& cur = ring[k & 1];
+      tm_wait_load();
+      if (k + 1 < NCH) tm_load(ring[(k + 1) & 1], tmem + WPC * (k + 1));
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        double hh = cur.d[r];
+        hh = fma(wn.x, sc_[r], hh);  // + (c₁ s[r]) s[c]
+        hh = fma(wn.y, sc_[r], hh);  // - u[r] s[c]
+        hh = fma(nuc[r], sg.x, hh);  // - u[c] s[r]
+        cur.d[r] = hh;
+        acc[r] = fma(hh, sg.y, acc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < RT; ++r) tm_store1(tmem + WPC * k + 2 * r, cur.d[r]); // one element per store: no staging moves
+    }
+    tm_wait_store();
+    double* pp = part2 + b * N + row0;
+    *reinterpret_cast<double2*>(pp) = make_double2(acc[0], acc[1]);
+    *reinterpret_cast<double2*>(pp + 2) = make_double2(acc[2], acc[3]);
+  };
+  auto reset_tile = [&]() { // B⁻¹ ← I, QN.jl:144-148
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      TmChunk<EPC> hc;
+#pragma unroll
+      for (int r = 0; r < RT; ++r) hc.d[r] = (row0 + r == col0 + k) ? 1.0 : 0.0;
+      tm_store(tmem + WPC * k, hc);
+    }
+    tm_wait_store();
+  };
+  auto write_h = [&](const long long j) {
+    if (!p.h_out) return;
+    double* ho = p.h_out + j * p.h_stride;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      TmChunk<EPC> hc;
+      tm_load(hc, tmem + WPC * k);
+      tm_wait_load();
+#pragma unroll
+      for (int r = 0; r < RT; ++r) ho[(row0 + r) + (long long)p.ldh * (col0 + k)] = hc.d[r];
+    }
+  };
+  // Σ_b part[b][e] in ascending block order (rule C2) for the leader's four elements
+  auto combine = [&](const double* part) {
+    Vec4 T;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int e = lane + 32 * k;
+      double acc = part[e];
+#pragma unroll
+      for (int bb = 1; bb < NB; ++bb) acc = acc + part[bb * N + e];
+      T.v[k] = acc;
+    }
+    return T;
+  };
+
+  if (t == 0) stamp_start(p);
+  for (;;) {
+    __syncthreads(); // the previous problem's shared-memory traffic is finished
+    if (t == 0) *next = (long long)atomicAdd(p.counter, 1ULL);
+    __syncthreads();
+    const long long j = *next;
+    if (j >= p.batch) break;
+
+    if (!leader) { // ---- helpers: their part of the two sweeps, between CTA barriers
+      for (;;) {
+        __syncthreads();                 // (A) a command and the operands of pass 1 are published
+        const int c = *cmd;
+        if (c & kLhReset) reset_tile();
+        if (c & kLhExit) break;
+        pass1();
+        __syncthreads();                 // (B) pass-1 partials
+        __syncthreads();                 // (C) c₁s, -u published
+        pass2();
+        __syncthreads();                 // (D) pass-2 partials
+      }
+      write_h(j);
+      continue;
+    }
+
+    // ---- leader
+    Vec4 x, g, s, y, gp;
+    double l0, sy = 0.0;
+    {
+      const double* th = p.theta0 + j * p.theta_stride; // copyto!(x_old, x), QN.jl:248
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { x.v[k] = th[lane + 32 * k]; s.v[k] = y.v[k] = gp.v[k] = 0.0; }
+      l0 = 0.0 - warp_butterfly(rosenbrock128_terms<true>(x, g)); // QN.jl:254 of iteration 1
+    }
+    const LsParams ls = p.ls;
+    const double tol = p.tol;
+    const int max_iter = p.max_iter;
+    const int ntrace = p.trace != nullptr ? p.ntrace : 0;
+    double result = __longlong_as_double(0x7ff8000000000000LL); // NaN, QN.jl:291
+    int iters = 0, fevals = 0, status = QN_MAX_ITER;
+    bool helper_reset = false;
+    auto command = [&](const int c) {
+      if (lane == 0) *cmd = c;
+      __syncthreads(); // (A)
+    };
+    struct Spec { Vec4 g; double term_next, sy; };
+    // a line-search trial at step a together with what the next iteration needs if it is accepted
+    // (see spec_eval in qn_resident_tile.cuh): the trial point is fma(a, d, x), the accepted point x + a·d
+    auto spec_eval = [&](const double a, const Vec4& d, Spec& sp, double& term_trial) {
+      Vec4 sn, xo, yn;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { sn.v[k] = a * d.v[k]; xo.v[k] = x.v[k] + sn.v[k]; }
+      sp.term_next = rosenbrock128_terms<true>(xo, sp.g);
+      if (a == 1.0) {
+        term_trial = sp.term_next;
+      } else {
+        Vec4 xn, unused;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xn.v[k] = fma(a, d.v[k], x.v[k]);
+        term_trial = rosenbrock128_terms<false>(xn, unused);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) yn.v[k] = g.v[k] - sp.g.v[k];
+      sp.sy = dot128(sn, yn);
+    };
+
+    for (int it = 1; it <= max_iter; ++it) { // QN.jl:250,253
+      ++fevals;
+      bool small = true;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) small = small && (fabs(g.v[k]) < tol);
+      const bool all_small = __all_sync(0xffffffffu, small);
+      if (!isfinite(l0) || all_small) {
+        iters = it - 1;
+        if (!isfinite(l0)) { status = QN_NONFINITE; if (!(it & 1)) g = gp; }
+        else { status = QN_CONVERGED; result = l0; }
+        break;
+      }
+      double m;
+      Vec4 d;
+      Spec sp;
+      double lx1 = 0.0;
+      bool have_trial = false;
+      if (it == 1) {
+        m = -1.0; // QN.jl:263-264
+      } else {
+        // ---- BFGS_update!  QN.jl:34-69: the operands of every column block
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int e = lane + 32 * k;
+          s_arr[e] = s.v[k];
+          yb_arr[e] = y.v[k];
+          *reinterpret_cast<double2*>(rec + e * C::kRec + 2) = make_double2(s.v[k], g.v[k]);
+        }
+        command(kLhPass | (helper_reset ? kLhReset : 0));
+        helper_reset = false;
+        const double rho = 1.0 / sy; // QN.jl:42 (no guard)
+        pass1();
+        __syncthreads(); // (B)
+        {
+          const Vec4 T = combine(part1);
+          const double yHy = warp_butterfly(dot128(T, y)); // Σ_c t[c] y[c], QN.jl:51
+          const double c1 = fma(yHy, rho, 1.0) * rho;      // QN.jl:54
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int e = lane + 32 * k;
+            const double nu = -(T.v[k] * rho);             // -B⁻¹y[c] = -(t ρ), QN.jl:50
+            nu_arr[e] = nu;
+            *reinterpret_cast<double2*>(rec + e * C::kRec) = make_double2(c1 * s.v[k], nu); // (c₁ s[r]) once per r (rule C4)
+          }
+        }
+        __syncthreads(); // (C)
+        pass2();
+        __syncthreads(); // (D)
+        d = combine(part2); // the new direction d = H⁺∇_new; `s, y = y, s`, QN.jl:65,268
+        double tterm;
+        spec_eval(1.0, d, sp, tterm);
+        m = dot128(d, g);
+        warp_butterfly3(m, tterm, sp.sy, lane);
+        sp.term_next = tterm;
+        lx1 = 0.0 - tterm;
+        have_trial = true;
+      }
+      if (m <= 0.0) { // QN.jl:272-280: H ← I, s ← ∇_new, m ← ∇ᵀ∇
+        reset_tile();
+        helper_reset = true;
+        d = g;
+        m = warp_butterfly(dot128(g, g));
+        have_trial = false;
+      }
+      double alpha;
+      {
+        auto trial = [&](const double a) {
+          double tterm;
+          spec_eval(a, d, sp, tterm);
+          warp_butterfly3(tterm, sp.term_next, sp.sy, lane);
+          ++fevals;
+          return 0.0 - tterm;
+        };
+        if (have_trial) ++fevals;
+        alpha = backtracking_linesearch(ls, l0, m, trial, lx1, have_trial, lx1);
+      }
+      if (alpha == 0.0) { status = QN_LINESEARCH_FAILED; iters = it - 1; if (!(it & 1)) g = gp; break; } // QN.jl:284
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { s.v[k] = alpha * d.v[k]; x.v[k] = x.v[k] + s.v[k]; } // update_state!, QN.jl:21-27
+      if (it <= ntrace) {
+        double* tr = p.trace + (j * p.ntrace + (it - 1)) * (long long)N;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tr[lane + 32 * k] = x.v[k];
+      }
+      if (it == max_iter) { iters = it; if (!(it & 1)) g = gp; break; }
+      gp = g;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) y.v[k] = g.v[k] - sp.g.v[k]; // y = ∇_old - ∇_new, QN.jl:38
+      sy = sp.sy;
+      g = sp.g;
+      l0 = (alpha == 1.0) ? lx1 : 0.0 - sp.term_next;
+    }
+    command(kLhExit | (helper_reset ? kLhReset : 0));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (p.x_out) p.x_out[j * p.x_stride + lane + 32 * k] = x.v[k];
+      if (p.g_out) p.g_out[j * p.g_stride + lane + 32 * k] = g.v[k];
+    }
+    write_h(j);
+    write_problem_scalars(p, j, lane, result, iters, fevals, status);
+  }
+  if (t == 0) stamp_exit(p, (int)blockIdx.x);
+  __syncthreads(); // every warp is done with the tensor memory
+  if (threadIdx.x < 32)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" :: "r"(tmem_base_s) : "memory");
+}
+
+}  // namespace qn
