@@ -197,22 +197,25 @@ int launch_tile_tmem(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
   return QN_OK;
 }
 
-// n = 128 Rosenbrock: the leader/helper tile kernel with the whole tile in tensor memory
-// (qn_resident_tile128.cuh): CTAs of 256 threads = one problem, 256 columns each, two CTAs per SM.
-int launch_tile128(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
-  const size_t smem = sizeof(double) * (size_t)qn::Tile128::kSmemDoubles;
-  auto kern = qn::qn_resident_tile128_kernel;
+// n = 32·RT Rosenbrock (n = 128: RT = 4, n = 160: RT = 5, n = 96: RT = 3): the leader/helper tile kernel
+// with the whole tile in tensor memory (qn_resident_tile128.cuh): one CTA = one problem, a warp per
+// rule-C2 column block; two problems per SM at n <= 128, one at n = 160 (480 of the 512 columns).
+template <int RT>
+int launch_tilew(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
+  using C = qn::TileW<RT>;
+  const size_t smem = sizeof(double) * (size_t)C::kSmemDoubles;
+  auto kern = qn::qn_resident_tilew_kernel<RT>;
   QN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  long long grid = 2LL * ctx->prop.multiProcessorCount; // 2 x 256 tensor-memory columns, 2 x 256 x 128 registers
+  long long grid = (long long)C::kCtasPerSm * ctx->prop.multiProcessorCount; // tensor-memory columns bound the residency
   if (grid > p.batch) grid = p.batch;
   p.counter = qn_next_counter(ctx, st);
   p.sm_count = ctx->prop.multiProcessorCount;
   arm_exit_stamps(ctx, p, grid, st);
-  kern<<<(unsigned)grid, 256, smem, st>>>(p);
+  kern<<<(unsigned)grid, C::THREADS, smem, st>>>(p);
   QN_CUDA_TRY(cudaGetLastError());
   ctx->last_path = 0;
   ctx->last_grid = (int)grid;
-  ctx->last_block = 256;
+  ctx->last_block = C::THREADS;
   ctx->last_smem = (int)smem;
   ctx->last_launches = 1;
   return QN_OK;
@@ -302,10 +305,16 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
   const bool onepass = (flags & QN_FLAG_ONE_PASS) != 0; // honoured by these policies (and the streaming path)
   if constexpr (Obj::kPairRegister) {
     if (!(flags & QN_FLAG_FORCE_SMEM)) {
-      const char variant = ctx->opt.pair_rows ? (char)ctx->opt.pair_rows : (Obj::kRegisterPaths ? (n == 128 && !onepass ? 'L' : 'h') : '4');
-      // 'L' (n = 128 Rosenbrock, the default): leader/helper warps, the whole tile in tensor memory
+      const bool lh_size = (n == 96 || n == 128 || n == 160);
+      const char variant = ctx->opt.pair_rows ? (char)ctx->opt.pair_rows
+                                              : (Obj::kRegisterPaths ? (lh_size && !onepass ? 'L' : 'h') : '4');
+      // 'L' (Rosenbrock n = 96, 128, 160, the default): leader/helper warps, the whole tile in tensor memory
       if constexpr (std::is_same<Obj, qn::Rosenbrock>::value) {
-        if (variant == 'L' && n == 128 && !onepass) return launch_tile128(ctx, p, st);
+        if (variant == 'L' && !onepass) {
+          if (n == 128) return launch_tilew<4>(ctx, p, st);
+          if (n == 160) return launch_tilew<5>(ctx, p, st);
+          if (n == 96) return launch_tilew<3>(ctx, p, st);
+        }
       }
       // n = 128 (BASELINE.json configs[2], [3]) has its own instantiations with n at compile time
       // (hybrid 6.3e7 against 4.7e7 iterations/s with n at run time; dense Gaussian 1.04e6 against

@@ -20,8 +20,15 @@
 
 namespace qn {
 
-struct Tile128 {
-  static constexpr int N = 128, RT = 4, CT = 16, NB = 8, NG = 32, THREADS = 256, EPL = 4;
+// RT rows per thread = elements per lane of the leader: n = 32·RT (RT = 4: n = 128, two problems per SM;
+// RT = 5: n = 160, 480 of the 512 columns, one problem per SM; RT = 3: n = 96).
+template <int RT_>
+struct TileW {
+  static constexpr int RT = RT_, N = 32 * RT_, CT = 16, NB = N / 16, THREADS = 32 * NB, EPL = RT_;
+  static constexpr int kTmemCols = 32 * RT;                                // 32-bit columns of one thread's tile
+  static constexpr int kBands = (NB + 3) / 4;                              // groups of four warps share the 128 lanes
+  static constexpr int kAlloc = kBands * kTmemCols <= 128 ? 128 : (kBands * kTmemCols <= 256 ? 256 : 512);
+  static constexpr int kCtasPerSm = 512 / kAlloc;
   // shared memory (doubles)
   static constexpr int kRec = 4;                      // {c₁s, -u, s, ∇} per column
   static constexpr int oRec = 0;                      // [128 columns][4]
@@ -35,52 +42,114 @@ struct Tile128 {
   static constexpr int kSmemDoubles = oEnd + 2;
 };
 
-struct Vec4 { double v[4]; };
+using Tile128 = TileW<4>;
+template <int R>
+struct VecR { double v[R]; };
 
-// Rosenbrock at n = 128 on the leader's layout: lane l holds θ[l], θ[l+32], θ[l+64], θ[l+96]; the pairs
-// (i, i + 64) of test/runtests.jl:8-9 are (slot 0, slot 2) and (slot 1, slot 3) of one lane.
-// Returns this lane's rule-C1 accumulator of the @simd sum: term[l] + term[l + 32].
-template <bool GRAD>
-__device__ __forceinline__ double rosenbrock128_terms(const Vec4& x, Vec4& g) {
+// Rosenbrock on the leader's layout: lane l holds θ[l + 32k] in slot k.  The pairs (i, i + n/2) of
+// test/runtests.jl:8-9: for even RT both elements sit in ONE lane (slots k and k + RT/2) and the
+// objective needs no exchange; for odd RT (n/2 = 32·hk + 16) the partner sits in lane ^ 16, slot
+// k + hk (+ 1 for lanes >= 16), one 64-bit shuffle per pair slot each way.
+// Returns this lane's rule-C1 accumulator of the @simd sum: Σ_k term[l + 32k] in ascending k.
+template <int RT, bool GRAD>
+__device__ __forceinline__ double rosenbrock_w_terms(const int lane, const VecR<RT>& x, VecR<RT>& g) {
   double acc = 0.0;
+  if constexpr (RT % 2 == 0) {
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const double t1 = x.v[k], t2 = x.v[k + 2];
-    const double a = t2 - t1 * t1;
-    const double b = 1.0 - t1;
-    const double term = 100.0 * (a * a) + b * b; // runtests.jl:9,23
-    acc = (k == 0) ? term : acc + term;
-    if (GRAD) {
-      g.v[k] = (400.0 * a) * t1 + 2.0 * b;   // ∇[i],    runtests.jl:24
-      g.v[k + 2] = 200.0 * (t1 * t1 - t2);   // ∇[i+N],  runtests.jl:25
+    for (int k = 0; k < RT / 2; ++k) {
+      const double t1 = x.v[k], t2 = x.v[k + RT / 2];
+      const double a = t2 - t1 * t1;
+      const double b = 1.0 - t1;
+      const double term = 100.0 * (a * a) + b * b; // runtests.jl:9,23
+      acc = (k == 0) ? term : acc + term;
+      if (GRAD) {
+        g.v[k] = (400.0 * a) * t1 + 2.0 * b;        // ∇[i],    runtests.jl:24
+        g.v[k + RT / 2] = 200.0 * (t1 * t1 - t2);   // ∇[i+N],  runtests.jl:25
+      }
+    }
+  } else {
+    constexpr int hk = (RT - 1) / 2;
+    const bool low = lane < 16;
+#pragma unroll
+    for (int k = 0; k <= hk; ++k) {
+      // what lane ^ 16 needs from me for ITS pair slot k: my slot k + hk (+ 1 when I am a low lane)
+      const double send = low ? (k + hk + 1 < RT ? x.v[k + hk + 1 < RT ? k + hk + 1 : 0] : 0.0) : x.v[k + hk];
+      const double t2 = __shfl_xor_sync(0xffffffffu, send, 16);
+      const bool have = (k < hk) || low;          // element lane + 32k is a θ1 (index < n/2)
+      const double t1 = x.v[k];
+      const double a = t2 - t1 * t1;
+      const double b = 1.0 - t1;
+      const double term = have ? 100.0 * (a * a) + b * b : 0.0;
+      acc = (k == 0) ? term : acc + term;
+      if (GRAD) {
+        const double g2 = 200.0 * (t1 * t1 - t2); // ∇[i+N] goes back along the same route
+        const double r = __shfl_xor_sync(0xffffffffu, g2, 16);
+        if (have) g.v[k] = (400.0 * a) * t1 + 2.0 * b;
+        if (low) { if (k + hk + 1 < RT) g.v[k + hk + 1 < RT ? k + hk + 1 : 0] = r; }
+        else g.v[k + hk] = r;
+      }
     }
   }
   return acc;
 }
 
-__device__ __forceinline__ double dot128(const Vec4& a, const Vec4& b) { // lane accumulator of rule C1
+template <int RT>
+__device__ __forceinline__ double dot_w(const VecR<RT>& a, const VecR<RT>& b) { // lane accumulator of rule C1
   double p = a.v[0] * b.v[0];
 #pragma unroll
-  for (int k = 1; k < 4; ++k) p = p + a.v[k] * b.v[k];
+  for (int k = 1; k < RT; ++k) p = p + a.v[k] * b.v[k];
   return p;
 }
 
-__global__ void __launch_bounds__(256, 2)
-qn_resident_tile128_kernel(const __grid_constant__ BatchParams p) {
-  using C = Tile128;
+// One tile column (RT rows) of the calling thread's tensor-memory lane.  The first four (RT = 3: two)
+// rows of the 16 tile columns are one aligned group of columns each (.x8 / .x4 loads), the last row
+// of every tile column follows behind them (.x2): a load never starts off its natural alignment.
+template <int RT>
+struct TileCol { double d[RT]; };
+__device__ __forceinline__ void tm_load1(double& v, const uint32_t addr) {
+  asm volatile("{\n.reg .b32 ta, tb;\ntcgen05.ld.sync.aligned.32x32b.x2.b32 {ta, tb}, [%1];\nmov.b64 %0, {ta, tb};\n}\n" : "=d"(v) : "r"(addr));
+}
+// 32-bit column (relative to the thread's band) of row r of tile column k
+template <int RT>
+__device__ __forceinline__ constexpr uint32_t tile_word(const int k, const int r) {
+  constexpr int G = (RT >= 4) ? 4 : 2;                 // rows in the aligned group
+  return r < G ? (uint32_t)(2 * G * k + 2 * r) : (uint32_t)(2 * G * 16 + 2 * (RT - G) * k + 2 * (r - G));
+}
+template <int RT>
+__device__ __forceinline__ void tile_col_load(TileCol<RT>& c, const uint32_t base, const int k) {
+  static_assert(RT == 3 || RT == 4 || RT == 5, "rows per thread");
+  if constexpr (RT >= 4) {
+    TmChunk<4> q;
+    tm_load(q, base + tile_word<RT>(k, 0));
+#pragma unroll
+    for (int r = 0; r < 4; ++r) c.d[r] = q.d[r];
+    if constexpr (RT == 5) tm_load1(c.d[4], base + tile_word<RT>(k, 4));
+  } else {
+    TmChunk<2> q;
+    tm_load(q, base + tile_word<RT>(k, 0));
+    c.d[0] = q.d[0]; c.d[1] = q.d[1];
+    tm_load1(c.d[2], base + tile_word<RT>(k, 2));
+  }
+}
+
+template <int RT_>
+__global__ void __launch_bounds__(TileW<RT_>::THREADS, TileW<RT_>::kCtasPerSm)
+qn_resident_tilew_kernel(const __grid_constant__ BatchParams p) {
+  using C = TileW<RT_>;
+  using Vec = VecR<RT_>;
   constexpr int N = C::N, RT = C::RT, CT = C::CT, NB = C::NB;
   extern __shared__ __align__(16) double smem[];
   __shared__ uint32_t tmem_base_s;
   if (threadIdx.x < 32) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n"
-                 :: "l"((unsigned long long)__cvta_generic_to_shared(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
+                 :: "l"((unsigned long long)__cvta_generic_to_shared(&tmem_base_s)), "n"(C::kAlloc) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const uint32_t tmem = __reduce_max_sync(0xffffffffu, tmem_base_s + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 128u);
+  const uint32_t tmem = __reduce_max_sync(0xffffffffu, tmem_base_s + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * (uint32_t)C::kTmemCols);
   const int b = warp;        // column block of this thread's tile
   const int q = lane;        // row group
   const int row0 = RT * q, col0 = CT * b;
@@ -93,7 +162,7 @@ qn_resident_tile128_kernel(const __grid_constant__ BatchParams p) {
   volatile int* cmd = reinterpret_cast<volatile int*>(smem + C::oCmd);
   volatile long long* next = reinterpret_cast<volatile long long*>(smem + C::kSmemDoubles - 2);
   const bool leader = (warp == 0);
-  constexpr int EPC = 4, WPC = 8, NCH = CT; // one tile column (4 rows) per chunk, 8 32-bit columns
+  constexpr int NCH = CT; // one tile column (RT rows) per step
 
   auto pass1 = [&]() { // t[i] = Σ_k y[col0+k] H[row0+i, col0+k], QN.jl:44-49
     double tt[RT];
@@ -103,40 +172,36 @@ qn_resident_tile128_kernel(const __grid_constant__ BatchParams p) {
     double2 yy[CT / 2];
 #pragma unroll
     for (int k = 0; k < CT / 2; ++k) yy[k] = yb2[k];
-    TmChunk<EPC> ring[2];
-    tm_load(ring[0], tmem);
+    TileCol<RT> ring[2];
+    tile_col_load<RT>(ring[0], tmem, 0);
 #pragma unroll
     for (int k = 0; k < CT; ++k) {
       const double yk = (k & 1) ? yy[k >> 1].y : yy[k >> 1].x;
       tm_wait_load();
-      if (k + 1 < NCH) tm_load(ring[(k + 1) & 1], tmem + WPC * (k + 1));
+      if (k + 1 < NCH) tile_col_load<RT>(ring[(k + 1) & 1], tmem, k + 1);
 #pragma unroll
       for (int r = 0; r < RT; ++r) tt[r] = fma(yk, ring[k & 1].d[r], tt[r]);
     }
     double* pp = part1 + b * N + row0;
-    *reinterpret_cast<double2*>(pp) = make_double2(tt[0], tt[1]);
-    *reinterpret_cast<double2*>(pp + 2) = make_double2(tt[2], tt[3]);
+#pragma unroll
+    for (int r = 0; r < RT; ++r) pp[r] = tt[r];
   };
   auto pass2 = [&]() { // H ← H + c₁ssᵀ - usᵀ - suᵀ fused with d = H⁺∇_new, QN.jl:56-67
     double sc_[RT], nuc[RT], acc[RT];
-    {
-      const double2 s01 = *reinterpret_cast<const double2*>(s_arr + row0), s23 = *reinterpret_cast<const double2*>(s_arr + row0 + 2);
-      const double2 n01 = *reinterpret_cast<const double2*>(nu_arr + row0), n23 = *reinterpret_cast<const double2*>(nu_arr + row0 + 2);
-      sc_[0] = s01.x; sc_[1] = s01.y; sc_[2] = s23.x; sc_[3] = s23.y;
-      nuc[0] = n01.x; nuc[1] = n01.y; nuc[2] = n23.x; nuc[3] = n23.y;
-    }
+#pragma unroll
+    for (int r = 0; r < RT; ++r) { sc_[r] = s_arr[row0 + r]; nuc[r] = nu_arr[row0 + r]; }
 #pragma unroll
     for (int i = 0; i < RT; ++i) acc[i] = 0.0;
     const double* rb_ = rec + col0 * C::kRec;
-    TmChunk<EPC> ring[2];
-    tm_load(ring[0], tmem);
+    TileCol<RT> ring[2];
+    tile_col_load<RT>(ring[0], tmem, 0);
 #pragma unroll
     for (int k = 0; k < CT; ++k) {
       const double2 wn = *reinterpret_cast<const double2*>(rb_ + k * C::kRec);
       const double2 sg = *reinterpret_cast<const double2*>(rb_ + k * C::kRec + 2);
-      TmChunk<EPC>& cur = ring[k & 1];
+      TileCol<RT>& cur = ring[k & 1];
       tm_wait_load();
-      if (k + 1 < NCH) tm_load(ring[(k + 1) & 1], tmem + WPC * (k + 1));
+      if (k + 1 < NCH) tile_col_load<RT>(ring[(k + 1) & 1], tmem, k + 1);
 #pragma unroll
       for (int r = 0; r < RT; ++r) {
         double hh = cur.d[r];
@@ -147,20 +212,18 @@ qn_resident_tile128_kernel(const __grid_constant__ BatchParams p) {
         acc[r] = fma(hh, sg.y, acc[r]);
       }
 #pragma unroll
-      for (int r = 0; r < RT; ++r) tm_store1(tmem + WPC * k + 2 * r, cur.d[r]); // one element per store: no staging moves
+      for (int r = 0; r < RT; ++r) tm_store1(tmem + tile_word<RT>(k, r), cur.d[r]); // one element per store: no staging moves
     }
     tm_wait_store();
     double* pp = part2 + b * N + row0;
-    *reinterpret_cast<double2*>(pp) = make_double2(acc[0], acc[1]);
-    *reinterpret_cast<double2*>(pp + 2) = make_double2(acc[2], acc[3]);
+#pragma unroll
+    for (int r = 0; r < RT; ++r) pp[r] = acc[r];
   };
   auto reset_tile = [&]() { // B⁻¹ ← I, QN.jl:144-148
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
-      TmChunk<EPC> hc;
 #pragma unroll
-      for (int r = 0; r < RT; ++r) hc.d[r] = (row0 + r == col0 + k) ? 1.0 : 0.0;
-      tm_store(tmem + WPC * k, hc);
+      for (int r = 0; r < RT; ++r) tm_store1(tmem + tile_word<RT>(k, r), (row0 + r == col0 + k) ? 1.0 : 0.0);
     }
     tm_wait_store();
   };
@@ -169,8 +232,8 @@ qn_resident_tile128_kernel(const __grid_constant__ BatchParams p) {
     double* ho = p.h_out + j * p.h_stride;
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
-      TmChunk<EPC> hc;
-      tm_load(hc, tmem + WPC * k);
+      TileCol<RT> hc;
+      tile_col_load<RT>(hc, tmem, k);
       tm_wait_load();
 #pragma unroll
       for (int r = 0; r < RT; ++r) ho[(row0 + r) + (long long)p.ldh * (col0 + k)] = hc.d[r];
@@ -178,9 +241,9 @@ qn_resident_tile128_kernel(const __grid_constant__ BatchParams p) {
   };
   // Σ_b part[b][e] in ascending block order (rule C2) for the leader's four elements
   auto combine = [&](const double* part) {
-    Vec4 T;
+    Vec T;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < RT; ++k) {
       const int e = lane + 32 * k;
       double acc = part[e];
 #pragma unroll
@@ -215,13 +278,13 @@ qn_resident_tile128_kernel(const __grid_constant__ BatchParams p) {
     }
 
     // ---- leader
-    Vec4 x, g, s, y, gp;
+    Vec x, g, s, y, gp;
     double l0, sy = 0.0;
     {
       const double* th = p.theta0 + j * p.theta_stride; // copyto!(x_old, x), QN.jl:248
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { x.v[k] = th[lane + 32 * k]; s.v[k] = y.v[k] = gp.v[k] = 0.0; }
-      l0 = 0.0 - warp_butterfly(rosenbrock128_terms<true>(x, g)); // QN.jl:254 of iteration 1
+      for (int k = 0; k < RT; ++k) { x.v[k] = th[lane + 32 * k]; s.v[k] = y.v[k] = gp.v[k] = 0.0; }
+      l0 = 0.0 - warp_butterfly(rosenbrock_w_terms<RT, true>(lane, x, g)); // QN.jl:254 of iteration 1
     }
     const LsParams ls = p.ls;
     const double tol = p.tol;
@@ -234,32 +297,32 @@ qn_resident_tile128_kernel(const __grid_constant__ BatchParams p) {
       if (lane == 0) *cmd = c;
       __syncthreads(); // (A)
     };
-    struct Spec { Vec4 g; double term_next, sy; };
+    struct Spec { Vec g; double term_next, sy; };
     // a line-search trial at step a together with what the next iteration needs if it is accepted
     // (see spec_eval in qn_resident_tile.cuh): the trial point is fma(a, d, x), the accepted point x + a·d
-    auto spec_eval = [&](const double a, const Vec4& d, Spec& sp, double& term_trial) {
-      Vec4 sn, xo, yn;
+    auto spec_eval = [&](const double a, const Vec& d, Spec& sp, double& term_trial) {
+      Vec sn, xo, yn;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { sn.v[k] = a * d.v[k]; xo.v[k] = x.v[k] + sn.v[k]; }
-      sp.term_next = rosenbrock128_terms<true>(xo, sp.g);
+      for (int k = 0; k < RT; ++k) { sn.v[k] = a * d.v[k]; xo.v[k] = x.v[k] + sn.v[k]; }
+      sp.term_next = rosenbrock_w_terms<RT, true>(lane, xo, sp.g);
       if (a == 1.0) {
         term_trial = sp.term_next;
       } else {
-        Vec4 xn, unused;
+        Vec xn, unused;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) xn.v[k] = fma(a, d.v[k], x.v[k]);
-        term_trial = rosenbrock128_terms<false>(xn, unused);
+        for (int k = 0; k < RT; ++k) xn.v[k] = fma(a, d.v[k], x.v[k]);
+        term_trial = rosenbrock_w_terms<RT, false>(lane, xn, unused);
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) yn.v[k] = g.v[k] - sp.g.v[k];
-      sp.sy = dot128(sn, yn);
+      for (int k = 0; k < RT; ++k) yn.v[k] = g.v[k] - sp.g.v[k];
+      sp.sy = dot_w<RT>(sn, yn);
     };
 
     for (int it = 1; it <= max_iter; ++it) { // QN.jl:250,253
       ++fevals;
       bool small = true;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) small = small && (fabs(g.v[k]) < tol);
+      for (int k = 0; k < RT; ++k) small = small && (fabs(g.v[k]) < tol);
       const bool all_small = __all_sync(0xffffffffu, small);
       if (!isfinite(l0) || all_small) {
         iters = it - 1;
@@ -268,7 +331,7 @@ qn_resident_tile128_kernel(const __grid_constant__ BatchParams p) {
         break;
       }
       double m;
-      Vec4 d;
+      Vec d;
       Spec sp;
       double lx1 = 0.0;
       bool have_trial = false;
@@ -277,7 +340,7 @@ qn_resident_tile128_kernel(const __grid_constant__ BatchParams p) {
       } else {
         // ---- BFGS_update!  QN.jl:34-69: the operands of every column block
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < RT; ++k) {
           const int e = lane + 32 * k;
           s_arr[e] = s.v[k];
           yb_arr[e] = y.v[k];
@@ -289,11 +352,11 @@ qn_resident_tile128_kernel(const __grid_constant__ BatchParams p) {
         pass1();
         __syncthreads(); // (B)
         {
-          const Vec4 T = combine(part1);
-          const double yHy = warp_butterfly(dot128(T, y)); // Σ_c t[c] y[c], QN.jl:51
+          const Vec T = combine(part1);
+          const double yHy = warp_butterfly(dot_w<RT>(T, y)); // Σ_c t[c] y[c], QN.jl:51
           const double c1 = fma(yHy, rho, 1.0) * rho;      // QN.jl:54
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < RT; ++k) {
             const int e = lane + 32 * k;
             const double nu = -(T.v[k] * rho);             // -B⁻¹y[c] = -(t ρ), QN.jl:50
             nu_arr[e] = nu;
@@ -306,7 +369,7 @@ qn_resident_tile128_kernel(const __grid_constant__ BatchParams p) {
         d = combine(part2); // the new direction d = H⁺∇_new; `s, y = y, s`, QN.jl:65,268
         double tterm;
         spec_eval(1.0, d, sp, tterm);
-        m = dot128(d, g);
+        m = dot_w<RT>(d, g);
         warp_butterfly3(m, tterm, sp.sy, lane);
         sp.term_next = tterm;
         lx1 = 0.0 - tterm;
@@ -316,7 +379,7 @@ qn_resident_tile128_kernel(const __grid_constant__ BatchParams p) {
         reset_tile();
         helper_reset = true;
         d = g;
-        m = warp_butterfly(dot128(g, g));
+        m = warp_butterfly(dot_w<RT>(g, g));
         have_trial = false;
       }
       double alpha;
@@ -333,23 +396,23 @@ qn_resident_tile128_kernel(const __grid_constant__ BatchParams p) {
       }
       if (alpha == 0.0) { status = QN_LINESEARCH_FAILED; iters = it - 1; if (!(it & 1)) g = gp; break; } // QN.jl:284
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { s.v[k] = alpha * d.v[k]; x.v[k] = x.v[k] + s.v[k]; } // update_state!, QN.jl:21-27
+      for (int k = 0; k < RT; ++k) { s.v[k] = alpha * d.v[k]; x.v[k] = x.v[k] + s.v[k]; } // update_state!, QN.jl:21-27
       if (it <= ntrace) {
         double* tr = p.trace + (j * p.ntrace + (it - 1)) * (long long)N;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tr[lane + 32 * k] = x.v[k];
+        for (int k = 0; k < RT; ++k) tr[lane + 32 * k] = x.v[k];
       }
       if (it == max_iter) { iters = it; if (!(it & 1)) g = gp; break; }
       gp = g;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) y.v[k] = g.v[k] - sp.g.v[k]; // y = ∇_old - ∇_new, QN.jl:38
+      for (int k = 0; k < RT; ++k) y.v[k] = g.v[k] - sp.g.v[k]; // y = ∇_old - ∇_new, QN.jl:38
       sy = sp.sy;
       g = sp.g;
       l0 = (alpha == 1.0) ? lx1 : 0.0 - sp.term_next;
     }
     command(kLhExit | (helper_reset ? kLhReset : 0));
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < RT; ++k) {
       if (p.x_out) p.x_out[j * p.x_stride + lane + 32 * k] = x.v[k];
       if (p.g_out) p.g_out[j * p.g_stride + lane + 32 * k] = g.v[k];
     }
@@ -359,7 +422,7 @@ qn_resident_tile128_kernel(const __grid_constant__ BatchParams p) {
   if (t == 0) stamp_exit(p, (int)blockIdx.x);
   __syncthreads(); // every warp is done with the tensor memory
   if (threadIdx.x < 32)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" :: "r"(tmem_base_s) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_base_s), "n"(C::kAlloc) : "memory");
 }
 
 }  // namespace qn
