@@ -69,6 +69,23 @@ unsigned long long* qn_next_counter(qn_context* ctx, cudaStream_t st) {
 
 namespace {
 
+// Resident CTAs per SM of a kernel that allocates tensor memory.  cudaOccupancyMaxActiveBlocksPerMulti-
+// processor answers 1 for such a kernel (it cannot know the column count), so the residency is derived
+// here from the three on-chip limits: registers, shared memory and 512 tensor-memory columns.
+template <class K>
+int tmem_residency(const qn_context* ctx, K kern, int block, size_t dyn_smem, int columns) {
+  cudaFuncAttributes fa{};
+  if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) { cudaGetLastError(); return 1; }
+  const int warps = (block + 31) / 32;
+  const int regs_per_warp = ((fa.numRegs * 32 + 255) / 256) * 256;   // allocation granularity: 256 registers per warp
+  const int by_regs = regs_per_warp > 0 ? ctx->prop.regsPerMultiprocessor / (regs_per_warp * warps) : 32;
+  const size_t per_cta = dyn_smem + fa.sharedSizeBytes + 1024;        // + the 1 KB the system reserves per CTA
+  const int by_smem = (int)(ctx->prop.sharedMemPerMultiprocessor / per_cta);
+  const int by_tmem = 512 / columns;
+  const int by_threads = ctx->prop.maxThreadsPerMultiProcessor / block;
+  return std::max(1, std::min(std::min(by_regs, by_smem), std::min(by_tmem, by_threads)));
+}
+
 // option "record_exit": arm the exit stamps for a launch with `slots` problem slots
 void arm_exit_stamps(qn_context* ctx, qn::BatchParams& p, long long slots, cudaStream_t st) {
   p.exit_ns = nullptr;
@@ -130,7 +147,7 @@ int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Par
   const int block = nthreads;
   int occ = 0;
   QN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
-  if (PTM) occ = 2; // the occupancy query answers 1 for a kernel that allocates tensor memory (see launch_tile_tmem)
+  if (PTM) occ = tmem_residency(ctx, kern, block, smem, 128); // the occupancy query answers 1 for a kernel that allocates tensor memory
   if (probe_occ) { *probe_occ = occ; return QN_OK; }
   if (occ < 1) return fail(QN_ERR_UNSUPPORTED_SIZE, "resident kernel does not fit on an SM (n=%d)", n);
   long long grid = (long long)occ * ctx->prop.multiProcessorCount;
@@ -174,7 +191,7 @@ int launch_tile(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
 // The same kernel with the tile in tensor memory (qn_resident_tile.cuh, TM): CTAs of 128 threads =
 // two problems, 128 columns of tensor memory each, 4 CTAs = 8 problems per SM where the register
 // file holds 6.  cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for a kernel that calls
-// tcgen05.alloc (it cannot know the column count); the grid is sized for the 4 CTAs per SM that
+// tcgen05.alloc (it cannot know the column count); tmem_residency derives the 4 CTAs per SM that
 // registers (128 × 128 × 4 = the file), shared memory and 4 × 128 columns allow — measured: the
 // throughput grows 1.6e8 → 2.5e8 → 3.0e8 → 3.7e8 iterations/s from 1 to 4 CTAs per SM (n = 60).
 template <int N, int PF>
@@ -183,7 +200,7 @@ int launch_tile_tmem(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
   auto kern = qn::qn_resident_tile_tmem_kernel<N, PF>;
   p.sm_count = ctx->prop.multiProcessorCount;
   QN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  long long grid = 4LL * ctx->prop.multiProcessorCount;
+  long long grid = (long long)tmem_residency(ctx, kern, 128, smem, 128) * ctx->prop.multiProcessorCount; // 4 per SM on B200
   if (grid > (p.batch + 1) / 2) grid = (p.batch + 1) / 2;
   p.counter = qn_next_counter(ctx, st);
   arm_exit_stamps(ctx, p, 2 * grid, st);
@@ -206,7 +223,7 @@ int launch_tilew(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
   const size_t smem = sizeof(double) * (size_t)C::kSmemDoubles;
   auto kern = qn::qn_resident_tilew_kernel<RT>;
   QN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  long long grid = (long long)C::kCtasPerSm * ctx->prop.multiProcessorCount; // tensor-memory columns bound the residency
+  long long grid = (long long)tmem_residency(ctx, kern, C::THREADS, smem, C::kAlloc) * ctx->prop.multiProcessorCount;
   if (grid > p.batch) grid = p.batch;
   p.counter = qn_next_counter(ctx, st);
   p.sm_count = ctx->prop.multiProcessorCount;

@@ -197,12 +197,35 @@ __device__ __forceinline__ void warp_butterfly3(double& a, double& b, double& c,
 // 2's 480 instructions per thread); a .x2 store takes the DFMA's own register pair.
 #define QN_TM_STW 1
 #endif
+#ifndef QN_TM_RAW
+#define QN_TM_RAW 1 // 1: tcgen05.ld hands back raw 32-bit registers, paired into fp64 only AFTER tcgen05.wait::ld
+#endif
 template <int EPC>
 struct TmChunk { double d[EPC]; };
 // tcgen05.wait::ld emits no instruction: ptxas guards the destination registers of LDTM with a
-// scoreboard like those of any load, so a value is never read before it has arrived; the statement
-// only marks, for the PTX memory model, where the loaded values may be used.
+// scoreboard like those of any load.  The PTX contract nevertheless leaves them undefined until the
+// wait, so the load returns the raw 32-bit registers (TmRaw) and tm_unpack — called after
+// tm_wait_load() — pairs them into doubles; the pairing is register naming, not an instruction.
+template <int EPC>
+struct TmRaw { uint32_t w[2 * EPC]; };
 __device__ __forceinline__ void tm_wait_load() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+template <int EPC>
+__device__ __forceinline__ void tm_load_raw(TmRaw<EPC>& c, const uint32_t addr) {
+  static_assert(EPC == 2 || EPC == 4, "chunk of 2 or 4 elements");
+  if constexpr (EPC == 2) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(c.w[0]), "=r"(c.w[1]), "=r"(c.w[2]), "=r"(c.w[3]) : "r"(addr));
+  } else {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(c.w[0]), "=r"(c.w[1]), "=r"(c.w[2]), "=r"(c.w[3]), "=r"(c.w[4]), "=r"(c.w[5]), "=r"(c.w[6]), "=r"(c.w[7])
+                 : "r"(addr));
+  }
+}
+template <int EPC>
+__device__ __forceinline__ void tm_unpack(TmChunk<EPC>& c, const TmRaw<EPC>& r) {
+#pragma unroll
+  for (int k = 0; k < EPC; ++k) c.d[k] = __hiloint2double((int)r.w[2 * k + 1], (int)r.w[2 * k]);
+}
 template <int EPC>
 __device__ __forceinline__ void tm_load(TmChunk<EPC>& c, const uint32_t addr) {
   static_assert(EPC == 2 || EPC == 4, "chunk of 2 or 4 elements");
@@ -760,9 +783,15 @@ __device__ __forceinline__ void tile_solve_lh(const BatchParams& p, const long l
     for (int k = 0; k < (CT + 1) / 2; ++k) yy[k] = yb2[k];
     __syncwarp(); // keeps the loads above it
     if constexpr (TM) {
+#if QN_TM_RAW
+      TmRaw<EPC> ring[TD + 1];
+#pragma unroll
+      for (int c = 0; c < TD && c < NCH; ++c) tm_load_raw(ring[c], tmem + WPC * c);
+#else
       TmChunk<EPC> ring[TD + 1];
 #pragma unroll
       for (int c = 0; c < TD && c < NCH; ++c) tm_load(ring[c], tmem + WPC * c);
+#endif
 #pragma unroll
       for (int k = 0; k < CT; ++k) {
         const double yk = (k & 1) ? yy[k >> 1].y : yy[k >> 1].x;
@@ -770,10 +799,17 @@ __device__ __forceinline__ void tile_solve_lh(const BatchParams& p, const long l
         for (int sc = 0; sc < SPC; ++sc) {
           const int c = k * SPC + sc;
           tm_wait_load();
+#if QN_TM_RAW
+          TmChunk<EPC> cur;
+          tm_unpack(cur, ring[c % (TD + 1)]);
+          if (c + TD < NCH) tm_load_raw(ring[(c + TD) % (TD + 1)], tmem + WPC * (c + TD));
+#else
           if (c + TD < NCH) tm_load(ring[(c + TD) % (TD + 1)], tmem + WPC * (c + TD));
+          const TmChunk<EPC>& cur = ring[c % (TD + 1)];
+#endif
           if (C::kFull || col0 + k < N) {
 #pragma unroll
-            for (int r = 0; r < EPC; ++r) tt[sc * EPC + r] = fma(yk, ring[c % (TD + 1)].d[r], tt[sc * EPC + r]);
+            for (int r = 0; r < EPC; ++r) tt[sc * EPC + r] = fma(yk, cur.d[r], tt[sc * EPC + r]);
           }
         }
       }
@@ -805,18 +841,30 @@ __device__ __forceinline__ void tile_solve_lh(const BatchParams& p, const long l
     auto ld_wn = [&](const int k) { return *reinterpret_cast<const double2*>(rb_ + k * L::kRec); };
     auto ld_sg = [&](const int k) { return *reinterpret_cast<const double2*>(rb_ + k * L::kRec + 2); };
     if constexpr (TM) {
+#if QN_TM_RAW
+      TmRaw<EPC> ring[TD + 1];
+#pragma unroll
+      for (int c = 0; c < TD && c < NCH; ++c) tm_load_raw(ring[c], tmem + WPC * c);
+#else
       TmChunk<EPC> ring[TD + 1];
 #pragma unroll
       for (int c = 0; c < TD && c < NCH; ++c) tm_load(ring[c], tmem + WPC * c);
+#endif
 #pragma unroll
       for (int k = 0; k < CT; ++k) {
         const double2 wn = ld_wn(k), sg = ld_sg(k);
 #pragma unroll
         for (int sc = 0; sc < SPC; ++sc) {
           const int c = k * SPC + sc;
-          TmChunk<EPC>& cur = ring[c % (TD + 1)];
           tm_wait_load();
+#if QN_TM_RAW
+          TmChunk<EPC> cur;
+          tm_unpack(cur, ring[c % (TD + 1)]);
+          if (c + TD < NCH) tm_load_raw(ring[(c + TD) % (TD + 1)], tmem + WPC * (c + TD));
+#else
+          TmChunk<EPC>& cur = ring[c % (TD + 1)];
           if (c + TD < NCH) tm_load(ring[(c + TD) % (TD + 1)], tmem + WPC * (c + TD));
+#endif
           if (C::kFull || col0 + k < N) {
 #pragma unroll
             for (int r = 0; r < EPC; ++r) {
@@ -890,9 +938,11 @@ __device__ __forceinline__ void tile_solve_lh(const BatchParams& p, const long l
     if constexpr (TM) {
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        TmChunk<EPC> hc;
-        tm_load(hc, tmem + WPC * c);
+        TmRaw<EPC> hr;
+        tm_load_raw(hr, tmem + WPC * c);
         tm_wait_load();
+        TmChunk<EPC> hc;
+        tm_unpack(hc, hr);
 #pragma unroll
         for (int r = 0; r < EPC; ++r) {
           const int k = c / SPC, i = (c % SPC) * EPC + r;

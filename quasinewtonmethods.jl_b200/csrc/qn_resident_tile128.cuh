@@ -106,8 +106,10 @@ __device__ __forceinline__ double dot_w(const VecR<RT>& a, const VecR<RT>& b) { 
 // of every tile column follows behind them (.x2): a load never starts off its natural alignment.
 template <int RT>
 struct TileCol { double d[RT]; };
-__device__ __forceinline__ void tm_load1(double& v, const uint32_t addr) {
-  asm volatile("{\n.reg .b32 ta, tb;\ntcgen05.ld.sync.aligned.32x32b.x2.b32 {ta, tb}, [%1];\nmov.b64 %0, {ta, tb};\n}\n" : "=d"(v) : "r"(addr));
+template <int RT>
+struct TileColRaw { uint32_t w[2 * RT]; }; // as loaded; paired into doubles only after tcgen05.wait::ld
+__device__ __forceinline__ void tm_load1_raw(uint32_t& lo, uint32_t& hi, const uint32_t addr) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n" : "=r"(lo), "=r"(hi) : "r"(addr));
 }
 // 32-bit column (relative to the thread's band) of row r of tile column k
 template <int RT>
@@ -116,20 +118,26 @@ __device__ __forceinline__ constexpr uint32_t tile_word(const int k, const int r
   return r < G ? (uint32_t)(2 * G * k + 2 * r) : (uint32_t)(2 * G * 16 + 2 * (RT - G) * k + 2 * (r - G));
 }
 template <int RT>
-__device__ __forceinline__ void tile_col_load(TileCol<RT>& c, const uint32_t base, const int k) {
+__device__ __forceinline__ void tile_col_load(TileColRaw<RT>& c, const uint32_t base, const int k) {
   static_assert(RT == 3 || RT == 4 || RT == 5, "rows per thread");
   if constexpr (RT >= 4) {
-    TmChunk<4> q;
-    tm_load(q, base + tile_word<RT>(k, 0));
+    TmRaw<4> q;
+    tm_load_raw(q, base + tile_word<RT>(k, 0));
 #pragma unroll
-    for (int r = 0; r < 4; ++r) c.d[r] = q.d[r];
-    if constexpr (RT == 5) tm_load1(c.d[4], base + tile_word<RT>(k, 4));
+    for (int i = 0; i < 8; ++i) c.w[i] = q.w[i];
+    if constexpr (RT == 5) tm_load1_raw(c.w[8], c.w[9], base + tile_word<RT>(k, 4));
   } else {
-    TmChunk<2> q;
-    tm_load(q, base + tile_word<RT>(k, 0));
-    c.d[0] = q.d[0]; c.d[1] = q.d[1];
-    tm_load1(c.d[2], base + tile_word<RT>(k, 2));
+    TmRaw<2> q;
+    tm_load_raw(q, base + tile_word<RT>(k, 0));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c.w[i] = q.w[i];
+    tm_load1_raw(c.w[4], c.w[5], base + tile_word<RT>(k, 2));
   }
+}
+template <int RT>
+__device__ __forceinline__ void tile_col_unpack(TileCol<RT>& c, const TileColRaw<RT>& r) { // after tm_wait_load()
+#pragma unroll
+  for (int k = 0; k < RT; ++k) c.d[k] = __hiloint2double((int)r.w[2 * k + 1], (int)r.w[2 * k]);
 }
 
 template <int RT_>
@@ -172,15 +180,17 @@ qn_resident_tilew_kernel(const __grid_constant__ BatchParams p) {
     double2 yy[CT / 2];
 #pragma unroll
     for (int k = 0; k < CT / 2; ++k) yy[k] = yb2[k];
-    TileCol<RT> ring[2];
+    TileColRaw<RT> ring[2];
     tile_col_load<RT>(ring[0], tmem, 0);
 #pragma unroll
     for (int k = 0; k < CT; ++k) {
       const double yk = (k & 1) ? yy[k >> 1].y : yy[k >> 1].x;
       tm_wait_load();
+      TileCol<RT> cur;
+      tile_col_unpack<RT>(cur, ring[k & 1]);
       if (k + 1 < NCH) tile_col_load<RT>(ring[(k + 1) & 1], tmem, k + 1);
 #pragma unroll
-      for (int r = 0; r < RT; ++r) tt[r] = fma(yk, ring[k & 1].d[r], tt[r]);
+      for (int r = 0; r < RT; ++r) tt[r] = fma(yk, cur.d[r], tt[r]);
     }
     double* pp = part1 + b * N + row0;
 #pragma unroll
@@ -193,14 +203,15 @@ qn_resident_tilew_kernel(const __grid_constant__ BatchParams p) {
 #pragma unroll
     for (int i = 0; i < RT; ++i) acc[i] = 0.0;
     const double* rb_ = rec + col0 * C::kRec;
-    TileCol<RT> ring[2];
+    TileColRaw<RT> ring[2];
     tile_col_load<RT>(ring[0], tmem, 0);
 #pragma unroll
     for (int k = 0; k < CT; ++k) {
       const double2 wn = *reinterpret_cast<const double2*>(rb_ + k * C::kRec);
       const double2 sg = *reinterpret_cast<const double2*>(rb_ + k * C::kRec + 2);
-      TileCol<RT>& cur = ring[k & 1];
       tm_wait_load();
+      TileCol<RT> cur;
+      tile_col_unpack<RT>(cur, ring[k & 1]);
       if (k + 1 < NCH) tile_col_load<RT>(ring[(k + 1) & 1], tmem, k + 1);
 #pragma unroll
       for (int r = 0; r < RT; ++r) {
@@ -232,9 +243,11 @@ qn_resident_tilew_kernel(const __grid_constant__ BatchParams p) {
     double* ho = p.h_out + j * p.h_stride;
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
-      TileCol<RT> hc;
-      tile_col_load<RT>(hc, tmem, k);
+      TileColRaw<RT> hr;
+      tile_col_load<RT>(hr, tmem, k);
       tm_wait_load();
+      TileCol<RT> hc;
+      tile_col_unpack<RT>(hc, hr);
 #pragma unroll
       for (int r = 0; r < RT; ++r) ho[(row0 + r) + (long long)p.ldh * (col0 + k)] = hc.d[r];
     }
