@@ -189,9 +189,26 @@ PassKernel pass_one_kernel(bool deep = false) {
 #ifndef QN_STREAM_TMA_DEFAULT
 #define QN_STREAM_TMA_DEFAULT 0
 #endif
-bool sweep_tma(const qn_context* ctx, const qn::StreamParams& p) {
+// auto (-1) = QN_STREAM_TMA_DEFAULT = off.  Measured (profiles/r2_stream_tma_vs_ldg.txt, r2_tma_small.txt):
+// equal to the LDG.128 sweeps for 512-row tiles (4 KB per bulk copy, n >= 4096) and SLOWER for the
+// shorter tiles of small n and of the row-sharded slabs (n = 1024: 77 against 47 µs per iteration) —
+// one elected thread issues one bulk copy per 0.5-1 KB column run, and that issue rate, not the
+// bytes in flight, bounds the sweep; a 2-D tensor map (one copy per stage) would lift it.
+bool sweep_tma(const qn_context* ctx, const qn::StreamParams& p, int pass_threads) {
   const int v = ctx->opt.stream_tma;
-  return !p.onepass && (v < 0 ? QN_STREAM_TMA_DEFAULT != 0 : v != 0);
+  if (p.onepass) return false;
+  return v < 0 ? (QN_STREAM_TMA_DEFAULT != 0 && pass_threads <= 128) : v != 0;
+}
+// the ring shape for a tile of 2·threads rows: <= 96 KB, two CTAs per SM
+void tma_shape(int pass_threads, int& cols, int& stages) {
+  stages = 3;
+  cols = pass_threads >= 256 ? 8 : pass_threads >= 128 ? 16 : 32;
+}
+PassKernel pass1_tma_kernel(int pass_threads) {
+  return pass_threads >= 256 ? qn::stream_pass1_tma<8, 3> : pass_threads >= 128 ? qn::stream_pass1_tma<16, 3> : qn::stream_pass1_tma<32, 3>;
+}
+PassKernel pass2_tma_kernel(int pass_threads) {
+  return pass_threads >= 256 ? qn::stream_pass2_tma<8, 3> : pass_threads >= 128 ? qn::stream_pass2_tma<16, 3> : qn::stream_pass2_tma<32, 3>;
 }
 // extra dynamic shared memory for pass1, a residency knob (bytes): QN_P1_PAD_KB
 size_t pass1_pad() { return (size_t)hint_opt(opts().p1_pad_kb, 0, 200) * 1024; }
@@ -221,9 +238,11 @@ int enqueue_iteration(qn_context* ctx, const StreamWork& w, cudaStream_t st) {
     return QN_OK;
   }
   if (p.fused2) { // three kernels per iteration; the head of iteration 1 ran before the graph
-    if (sweep_tma(ctx, p)) {
-      qn::stream_pass1_tma<<<grid, w.pass_threads, qn::tma_smem_bytes(p.sbcols, 1, 2 * w.pass_threads), st>>>(p);
-      qn::stream_pass2_tma<<<grid, w.pass_threads, qn::tma_smem_bytes(p.sbcols, 4, 2 * w.pass_threads), st>>>(p);
+    if (sweep_tma(ctx, p, w.pass_threads)) {
+      int tc, ts;
+      tma_shape(w.pass_threads, tc, ts);
+      pass1_tma_kernel(w.pass_threads)<<<grid, w.pass_threads, qn::tma_smem_bytes(p.sbcols, 1, 2 * w.pass_threads, tc, ts), st>>>(p);
+      pass2_tma_kernel(w.pass_threads)<<<grid, w.pass_threads, qn::tma_smem_bytes(p.sbcols, 4, 2 * w.pass_threads, tc, ts), st>>>(p);
     } else {
       pass1_kernel(deep)<<<grid, w.pass_threads, sizeof(double) * p.sbcols + pass1_pad(), st>>>(p);
       pass2_kernel(deep)<<<grid, w.pass_threads, sizeof(double) * 4 * p.sbcols, st>>>(p);
@@ -354,11 +373,13 @@ int stream_capture(qn_context* ctx, StreamWork& w, cudaStream_t st) {
   if (pass1_pad())
     QN_TRY_REL(cudaFuncSetAttribute(pass1_kernel(deep), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(sizeof(double) * p.sbcols + pass1_pad())));
-  if (sweep_tma(ctx, p)) {
-    QN_TRY_REL(cudaFuncSetAttribute(qn::stream_pass1_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)qn::tma_smem_bytes(p.sbcols, 1, 2 * w.pass_threads)));
-    QN_TRY_REL(cudaFuncSetAttribute(qn::stream_pass2_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)qn::tma_smem_bytes(p.sbcols, 4, 2 * w.pass_threads)));
+  if (sweep_tma(ctx, p, w.pass_threads)) {
+    int tc, ts;
+    tma_shape(w.pass_threads, tc, ts);
+    QN_TRY_REL(cudaFuncSetAttribute(pass1_tma_kernel(w.pass_threads), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)qn::tma_smem_bytes(p.sbcols, 1, 2 * w.pass_threads, tc, ts)));
+    QN_TRY_REL(cudaFuncSetAttribute(pass2_tma_kernel(w.pass_threads), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)qn::tma_smem_bytes(p.sbcols, 4, 2 * w.pass_threads, tc, ts)));
   }
   if (w.vec_smem) {
     QN_TRY_REL(cudaFuncSetAttribute(vec_begin_kernel(p.obj_kind), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.vec_smem));

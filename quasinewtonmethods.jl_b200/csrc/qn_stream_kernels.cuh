@@ -714,8 +714,11 @@ __device__ __forceinline__ void pass2_finish(const StreamParams& p, const Stream
 // stage and the same engine stores them (cp.async.bulk.global.shared::cta + bulk groups); a stage is
 // refilled once its stores have READ the shared memory (cp.async.bulk.wait_group.read).
 // Same arithmetic, same order (rule C2) as stream_pass1 / stream_pass2: the same bits.
-constexpr int kTmaCols = 8;    // columns per stage
-constexpr int kTmaStages = 3;  // 3 × 8 × 4 KB = 96 KB of ring per CTA, two CTAs per SM
+// columns per stage × stages, chosen by the host for the tile height so that the ring stays <= 96 KB
+// (two CTAs per SM): 512-row tiles (4 KB per column) 8 × 3; 256 rows 16 × 3; 128 rows 32 × 3 — the
+// shorter the run per column, the more columns have to be on their way to cover the HBM latency
+// (a thread of the LDG sweeps walks its 256 columns in 16 dependent round trips of 16 loads).
+constexpr int kTmaChunk = 8;   // columns a thread takes out of a landed stage at a time
 
 __device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, const unsigned count) {
@@ -750,14 +753,17 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // shared memory of a TMA sweep: [operands of the super-block | mbarriers | ring]
 __host__ __device__ constexpr size_t tma_ring_offset(const int sbcols, const int ops_per_col) {
-  return (((size_t)sbcols * ops_per_col * sizeof(double) + kTmaStages * sizeof(uint64_t)) + 127) & ~(size_t)127;
+  return (((size_t)sbcols * ops_per_col * sizeof(double) + 8 * sizeof(uint64_t)) + 127) & ~(size_t)127;
 }
-__host__ __device__ constexpr size_t tma_smem_bytes(const int sbcols, const int ops_per_col, const int tile_rows) {
-  return tma_ring_offset(sbcols, ops_per_col) + (size_t)kTmaStages * kTmaCols * tile_rows * sizeof(double);
+__host__ __device__ constexpr size_t tma_smem_bytes(const int sbcols, const int ops_per_col, const int tile_rows,
+                                                    const int cols, const int stages) {
+  return tma_ring_offset(sbcols, ops_per_col) + (size_t)stages * cols * tile_rows * sizeof(double);
 }
 
 // ---- pass 1, TMA-staged
+template <int kTmaCols, int kTmaStages>
 __global__ void __launch_bounds__(kPassThreads, 2) stream_pass1_tma(const StreamParams p) {
+  static_assert(kTmaCols % kTmaChunk == 0 && kTmaStages <= 8, "ring shape");
   const StreamScalars* sc = p.sc;
   if (sc->done || sc->skip_update) return;
   extern __shared__ __align__(128) unsigned char smraw[];
@@ -802,23 +808,26 @@ __global__ void __launch_bounds__(kPassThreads, 2) stream_pass1_tma(const Stream
     const int slot = stg % kTmaStages;
     if (!reset) mbar_wait(full + slot, (unsigned)(stg / kTmaStages) & 1u);
     const double2* src = reinterpret_cast<const double2*>(ring + (size_t)slot * kTmaCols * tile_rows * sizeof(double)) + threadIdx.x;
-    double2 h[kTmaCols];
+#pragma unroll 1
+    for (int ch = 0; ch < kTmaCols / kTmaChunk; ++ch) {
+      double2 h[kTmaChunk];
 #pragma unroll
-    for (int k = 0; k < kTmaCols; ++k) {
-      const int r = r_begin + stg * kTmaCols + k;
-      h[k] = reset ? make_double2(c0 == r ? 1.0 : 0.0, c0 + 1 == r ? 1.0 : 0.0) : src[(size_t)k * blockDim.x];
-    }
+      for (int k = 0; k < kTmaChunk; ++k) {
+        const int r = r_begin + stg * kTmaCols + ch * kTmaChunk + k;
+        h[k] = reset ? make_double2(c0 == r ? 1.0 : 0.0, c0 + 1 == r ? 1.0 : 0.0) : src[(size_t)(ch * kTmaChunk + k) * blockDim.x];
+      }
 #pragma unroll
-    for (int k = 0; k < kTmaCols; ++k) {
-      const int cc = stg * kTmaCols + k;
-      if (cc < ncols && rowok) {
-        const double yr = ys[cc];
-        t0 = fma(yr, h[k].x, t0);
-        t1 = fma(yr, h[k].y, t1);
-        if (++inblk == rb || cc == ncols - 1) { // the block's chain is complete: add its partial in order
-          S0 = first ? t0 : S0 + t0;
-          S1 = first ? t1 : S1 + t1;
-          first = false; t0 = 0.0; t1 = 0.0; inblk = 0;
+      for (int k = 0; k < kTmaChunk; ++k) {
+        const int cc = stg * kTmaCols + ch * kTmaChunk + k;
+        if (cc < ncols && rowok) {
+          const double yr = ys[cc];
+          t0 = fma(yr, h[k].x, t0);
+          t1 = fma(yr, h[k].y, t1);
+          if (++inblk == rb || cc == ncols - 1) { // the block's chain is complete: add its partial in order
+            S0 = first ? t0 : S0 + t0;
+            S1 = first ? t1 : S1 + t1;
+            first = false; t0 = 0.0; t1 = 0.0; inblk = 0;
+          }
         }
       }
     }
@@ -829,7 +838,9 @@ __global__ void __launch_bounds__(kPassThreads, 2) stream_pass1_tma(const Stream
 }
 
 // ---- pass 2, TMA-staged: columns land in the ring, are updated in place and stored by the engine
+template <int kTmaCols, int kTmaStages>
 __global__ void __launch_bounds__(kPassThreads, 2) stream_pass2_tma(const StreamParams p) {
+  static_assert(kTmaCols % kTmaChunk == 0 && kTmaStages <= 8, "ring shape");
   const StreamScalars* sc = p.sc;
   if (sc->done || sc->skip_update) return;
   extern __shared__ __align__(128) unsigned char smraw[];
@@ -880,28 +891,31 @@ __global__ void __launch_bounds__(kPassThreads, 2) stream_pass2_tma(const Stream
     const int slot = stg % kTmaStages;
     if (!reset) mbar_wait(full + slot, (unsigned)(stg / kTmaStages) & 1u);
     double2* buf = reinterpret_cast<double2*>(stage_ptr(slot, 0)) + threadIdx.x;
-    double2 h[kTmaCols];
+#pragma unroll 1
+    for (int ch = 0; ch < kTmaCols / kTmaChunk; ++ch) {
+      double2 h[kTmaChunk];
 #pragma unroll
-    for (int k = 0; k < kTmaCols; ++k) {
-      const int r = r_begin + stg * kTmaCols + k;
-      h[k] = reset ? make_double2(c0 == r ? 1.0 : 0.0, c0 + 1 == r ? 1.0 : 0.0) : buf[(size_t)k * blockDim.x];
-    }
+      for (int k = 0; k < kTmaChunk; ++k) {
+        const int r = r_begin + stg * kTmaCols + ch * kTmaChunk + k;
+        h[k] = reset ? make_double2(c0 == r ? 1.0 : 0.0, c0 + 1 == r ? 1.0 : 0.0) : buf[(size_t)(ch * kTmaChunk + k) * blockDim.x];
+      }
 #pragma unroll
-    for (int k = 0; k < kTmaCols; ++k) {
-      const int cc = stg * kTmaCols + k;
-      if (cc < ncols && rowok) {
-        const double4 o = ops[cc];
-        double h0 = h[k].x, h1 = h[k].y;
-        h0 = fma(o.x, s0, h0); h1 = fma(o.x, s1, h1);     // + (c₁ s[r]) s[c]
-        h0 = fma(o.y, s0, h0); h1 = fma(o.y, s1, h1);     // - u[r] s[c]
-        h0 = fma(nu0, o.z, h0); h1 = fma(nu1, o.z, h1);   // - u[c] s[r]
-        buf[(size_t)k * blockDim.x] = make_double2(h0, h1);
-        a0 = fma(h0, o.w, a0);
-        a1 = fma(h1, o.w, a1);
-        if (++inblk == rb || cc == ncols - 1) {
-          S0 = first ? a0 : S0 + a0;
-          S1 = first ? a1 : S1 + a1;
-          first = false; a0 = 0.0; a1 = 0.0; inblk = 0;
+      for (int k = 0; k < kTmaChunk; ++k) {
+        const int cc = stg * kTmaCols + ch * kTmaChunk + k;
+        if (cc < ncols && rowok) {
+          const double4 o = ops[cc];
+          double h0 = h[k].x, h1 = h[k].y;
+          h0 = fma(o.x, s0, h0); h1 = fma(o.x, s1, h1);     // + (c₁ s[r]) s[c]
+          h0 = fma(o.y, s0, h0); h1 = fma(o.y, s1, h1);     // - u[r] s[c]
+          h0 = fma(nu0, o.z, h0); h1 = fma(nu1, o.z, h1);   // - u[c] s[r]
+          buf[(size_t)(ch * kTmaChunk + k) * blockDim.x] = make_double2(h0, h1);
+          a0 = fma(h0, o.w, a0);
+          a1 = fma(h1, o.w, a1);
+          if (++inblk == rb || cc == ncols - 1) {
+            S0 = first ? a0 : S0 + a0;
+            S1 = first ? a1 : S1 + a1;
+            first = false; a0 = 0.0; a1 = 0.0; inblk = 0;
+          }
         }
       }
     }
