@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 SO = os.path.join(HERE, "libqn_cuda.so")
 
-SOURCES = ["qn_capi.cu", "qn_eval.cu", "qn_multi.cu", "qn_microbench.cu", "qn_stream.cu"]
+SOURCES = ["qn_capi.cu", "qn_launch_tiles.cu", "qn_launch_small.cu", "qn_eval.cu", "qn_multi.cu", "qn_microbench.cu", "qn_stream.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -22,10 +22,8 @@
 #include QN_USER_OBJECTIVE_HEADER  // the build's plug-in objective (include/qn_objective.cuh)
 #endif
 #include "qn_resident.cuh"
-#include "qn_resident_tile.cuh"
-#include "qn_resident_tile128.cuh"
-#include "qn_resident_packed.cuh"
 #include "qn_internal.h"
+#include "qn_launch.h"
 
 namespace {
 thread_local char g_err[512] = "";
@@ -68,37 +66,6 @@ unsigned long long* qn_next_counter(qn_context* ctx, cudaStream_t st) {
 }
 
 namespace {
-
-// Resident CTAs per SM of a kernel that allocates tensor memory.  cudaOccupancyMaxActiveBlocksPerMulti-
-// processor answers 1 for such a kernel (it cannot know the column count), so the residency is derived
-// here from the three on-chip limits: registers, shared memory and 512 tensor-memory columns.
-template <class K>
-int tmem_residency(const qn_context* ctx, K kern, int block, size_t dyn_smem, int columns) {
-  cudaFuncAttributes fa{};
-  if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) { cudaGetLastError(); return 1; }
-  const int warps = (block + 31) / 32;
-  const int regs_per_warp = ((fa.numRegs * 32 + 255) / 256) * 256;   // allocation granularity: 256 registers per warp
-  const int by_regs = regs_per_warp > 0 ? ctx->prop.regsPerMultiprocessor / (regs_per_warp * warps) : 32;
-  const size_t per_cta = dyn_smem + fa.sharedSizeBytes + 1024;        // + the 1 KB the system reserves per CTA
-  const int by_smem = (int)(ctx->prop.sharedMemPerMultiprocessor / per_cta);
-  const int by_tmem = 512 / columns;
-  const int by_threads = ctx->prop.maxThreadsPerMultiProcessor / block;
-  return std::max(1, std::min(std::min(by_regs, by_smem), std::min(by_tmem, by_threads)));
-}
-
-// option "record_exit": arm the exit stamps for a launch with `slots` problem slots
-void arm_exit_stamps(qn_context* ctx, qn::BatchParams& p, long long slots, cudaStream_t st) {
-  p.exit_ns = nullptr;
-  p.exit_cap = 0;
-  ctx->exit_slots_used = 0;
-  if (!ctx->opt.record_exit) return;
-  const int used = (int)std::min<long long>(slots, qn_context::kExitSlots);
-  cudaMemsetAsync(ctx->exit_ns, 0xff, sizeof(unsigned long long), st);                 // earliest start
-  cudaMemsetAsync(ctx->exit_ns + 1, 0, sizeof(unsigned long long) * (used + 1), st);   // latest end, slots
-  p.exit_ns = ctx->exit_ns;
-  p.exit_cap = used;
-  ctx->exit_slots_used = used;
-}
 
 // ---- kernel launchers ------------------------------------------------------
 // ONEPASS: the deferred-update order (QN_FLAG_ONE_PASS) — shared-memory and register-pair policies
@@ -164,116 +131,6 @@ int launch_resident(qn_context* ctx, qn::BatchParams& p, const typename Obj::Par
   return QN_OK;
 }
 
-// The register-tile kernel evaluates the objective warp-locally; only Rosenbrock has
-// that form (qn_resident_tile.cuh).
-template <int N, int MINB, int PF>
-int launch_tile(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
-  const size_t smem = sizeof(double) * (size_t)qn::tile_problem_smem_doubles<N>();
-  auto kern = qn::qn_resident_tile_kernel<N, MINB, PF>;
-  p.sm_count = ctx->prop.multiProcessorCount;
-  int occ = 0;
-  QN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 64, smem));
-  if (occ < 1) return fail(QN_ERR_UNSUPPORTED_SIZE, "tile kernel does not fit on an SM (n=%d)", N);
-  long long grid = (long long)occ * ctx->prop.multiProcessorCount;
-  if (grid > p.batch) grid = p.batch;
-  p.counter = qn_next_counter(ctx, st);
-  arm_exit_stamps(ctx, p, grid, st);
-  kern<<<(unsigned)grid, 64, smem, st>>>(p);
-  QN_CUDA_TRY(cudaGetLastError());
-  ctx->last_path = 0;
-  ctx->last_grid = (int)grid;
-  ctx->last_block = 64;
-  ctx->last_smem = (int)smem;
-  ctx->last_launches = 1;
-  return QN_OK;
-}
-
-// The same kernel with the tile in tensor memory (qn_resident_tile.cuh, TM): CTAs of 128 threads =
-// two problems, 128 columns of tensor memory each, 4 CTAs = 8 problems per SM where the register
-// file holds 6.  cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for a kernel that calls
-// tcgen05.alloc (it cannot know the column count); tmem_residency derives the 4 CTAs per SM that
-// registers (128 × 128 × 4 = the file), shared memory and 4 × 128 columns allow — measured: the
-// throughput grows 1.6e8 → 2.5e8 → 3.0e8 → 3.7e8 iterations/s from 1 to 4 CTAs per SM (n = 60).
-template <int N, int PF>
-int launch_tile_tmem(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
-  const size_t smem = 2 * sizeof(double) * (size_t)qn::tile_problem_smem_doubles<N>();
-  auto kern = qn::qn_resident_tile_tmem_kernel<N, PF>;
-  p.sm_count = ctx->prop.multiProcessorCount;
-  QN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  long long grid = (long long)tmem_residency(ctx, kern, 128, smem, 128) * ctx->prop.multiProcessorCount; // 4 per SM on B200
-  if (grid > (p.batch + 1) / 2) grid = (p.batch + 1) / 2;
-  p.counter = qn_next_counter(ctx, st);
-  arm_exit_stamps(ctx, p, 2 * grid, st);
-  kern<<<(unsigned)grid, 128, smem, st>>>(p);
-  QN_CUDA_TRY(cudaGetLastError());
-  ctx->last_path = 0;
-  ctx->last_grid = (int)grid;
-  ctx->last_block = 128;
-  ctx->last_smem = (int)smem;
-  ctx->last_launches = 1;
-  return QN_OK;
-}
-
-// n = 32·RT Rosenbrock (n = 128: RT = 4, n = 160: RT = 5, n = 96: RT = 3): the leader/helper tile kernel
-// with the whole tile in tensor memory (qn_resident_tile128.cuh): one CTA = one problem, a warp per
-// rule-C2 column block; two problems per SM at n <= 128, one at n = 160 (480 of the 512 columns).
-template <int RT>
-int launch_tilew(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
-  using C = qn::TileW<RT>;
-  const size_t smem = sizeof(double) * (size_t)C::kSmemDoubles;
-  auto kern = qn::qn_resident_tilew_kernel<RT>;
-  QN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  long long grid = (long long)tmem_residency(ctx, kern, C::THREADS, smem, C::kAlloc) * ctx->prop.multiProcessorCount;
-  if (grid > p.batch) grid = p.batch;
-  p.counter = qn_next_counter(ctx, st);
-  p.sm_count = ctx->prop.multiProcessorCount;
-  arm_exit_stamps(ctx, p, grid, st);
-  kern<<<(unsigned)grid, C::THREADS, smem, st>>>(p);
-  QN_CUDA_TRY(cudaGetLastError());
-  ctx->last_path = 0;
-  ctx->last_grid = (int)grid;
-  ctx->last_block = C::THREADS;
-  ctx->last_smem = (int)smem;
-  ctx->last_launches = 1;
-  return QN_OK;
-}
-
-// Where the tile lives: tensor memory when it is the faster home (measured per size on B200,
-// 2^15-2^16 problems: n = 44 +1 %, 48 +6 %, 50 +8 %, 56 +1 %, 60 +3 %, 64 +8 %; n = 36, 40, 52 are
-// 1-3 % faster from registers) and the batch fills 8 problems per SM; option "tile_tmem" = 0 / 1 forces
-// the register file / tensor memory.
-inline bool tile_in_tensor_memory(const qn_context* ctx, const int n, const long long batch) {
-  if (ctx->opt.tile_tmem == 0) return false;
-  if (ctx->opt.tile_tmem == 1) return true;
-  const bool faster = n == 44 || n == 48 || n == 50 || n == 56 || n == 60 || n == 64;
-  return faster && batch >= 8LL * ctx->prop.multiProcessorCount;
-}
-
-// n = 8, 16, 32 (Rosenbrock): several problems per warp (qn_resident_packed.cuh)
-template <int N, int RPT, int MINB>
-int launch_packed(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
-  using C = qn::PackedCfg<N, RPT>;
-  const size_t smem = sizeof(double) * (size_t)C::kSmemDoubles;
-  auto kern = qn::qn_resident_packed_kernel<N, RPT, MINB>;
-  const int block = C::kWarps * 32;
-  int occ = 0;
-  QN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
-  if (occ < 1) return fail(QN_ERR_UNSUPPORTED_SIZE, "packed kernel does not fit on an SM (n=%d)", N);
-  long long grid = (long long)occ * ctx->prop.multiProcessorCount;
-  const long long need = (p.batch + C::kWarps * C::kSub - 1) / (C::kWarps * C::kSub);
-  if (grid > need) grid = need;
-  if (grid < 1) grid = 1;
-  p.counter = qn_next_counter(ctx, st);
-  kern<<<(unsigned)grid, block, smem, st>>>(p);
-  QN_CUDA_TRY(cudaGetLastError());
-  ctx->last_path = 0;
-  ctx->last_grid = (int)grid;
-  ctx->last_block = block;
-  ctx->last_smem = (int)smem;
-  ctx->last_launches = 1;
-  return QN_OK;
-}
-
 template <class Obj>
 int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Params& op,
                   uint32_t flags, cudaStream_t st) {
@@ -281,26 +138,16 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
   if constexpr (Obj::kRegisterPaths) {
     if (!(flags & QN_FLAG_FORCE_SMEM)) {
       if constexpr (std::is_same<Obj, qn::Rosenbrock>::value) {
-        if (ctx->opt.pack) { // A/B knob: the thread-per-row kernels stay available
-          const int rpt = ctx->opt.pack_variant; // tuning knob: rows per lane
-          // defaults measured on B200 (2^18 problems): n = 8: 2 rows per lane 8.2e9 it/s (1: 6.7e9);
-          // n = 16: 2 rows 3.7e9 (1: 2.8e9, 4: 3.3e9); n = 32: 2 rows 1.14e9 (thread per row: 0.90e9)
-          if (n == 8) return rpt == 1 ? launch_packed<8, 1, 8>(ctx, p, st) : rpt == 4 ? launch_packed<8, 4, 4>(ctx, p, st) : launch_packed<8, 2, 6>(ctx, p, st);
-          if (n == 16) return rpt == 1 ? launch_packed<16, 1, 6>(ctx, p, st) : rpt == 4 ? launch_packed<16, 4, 2>(ctx, p, st) : launch_packed<16, 2, 4>(ctx, p, st);
-          if (n == 32) return launch_packed<32, 2, 2>(ctx, p, st);
-        }
+        // the Rosenbrock-only kernels (packed small n, 4×CT tiles, leader/helper tensor-memory tiles)
+        int rc = qn_launch_rosenbrock_small(ctx, p, st, (flags & QN_FLAG_ONE_PASS) != 0);
+        if (rc >= 0) return rc;
+        rc = qn_launch_rosenbrock_tiles(ctx, p, st);
+        if (rc >= 0) return rc;
       }
       switch (n) {
 #define QN_REG_CASE(N, BLOCK, MINB) \
   case N: return launch_resident<Obj, N, BLOCK, MINB>(ctx, p, op, st);
-#define QN_TILE_CASE(N, MINB) \
-  case N:                      \
-    if constexpr (std::is_same<Obj, qn::Rosenbrock>::value) {                                        \
-      if (tile_in_tensor_memory(ctx, N, p.batch)) return launch_tile_tmem<N, 1>(ctx, p, st);          \
-      /* 6 CTAs per SM (168 registers); 4, 5 and 7 were measured slower */            \
-      return launch_tile<N, MINB, 1>(ctx, p, st);                                                    \
-    }                                                                                                \
-    break;
+#define QN_TILE_CASE(N, MINB)
 #include "qn_reg_sizes.inc"
 #undef QN_REG_CASE
 #undef QN_TILE_CASE
@@ -325,14 +172,6 @@ int dispatch_size(qn_context* ctx, qn::BatchParams& p, const typename Obj::Param
       const bool lh_size = (n == 96 || n == 128 || n == 160);
       const char variant = ctx->opt.pair_rows ? (char)ctx->opt.pair_rows
                                               : (Obj::kRegisterPaths ? (lh_size && !onepass ? 'L' : 'h') : '4');
-      // 'L' (Rosenbrock n = 96, 128, 160, the default): leader/helper warps, the whole tile in tensor memory
-      if constexpr (std::is_same<Obj, qn::Rosenbrock>::value) {
-        if (variant == 'L' && !onepass) {
-          if (n == 128) return launch_tilew<4>(ctx, p, st);
-          if (n == 160) return launch_tilew<5>(ctx, p, st);
-          if (n == 96) return launch_tilew<3>(ctx, p, st);
-        }
-      }
       // n = 128 (BASELINE.json configs[2], [3]) has its own instantiations with n at compile time
       // (hybrid 6.3e7 against 4.7e7 iterations/s with n at run time; dense Gaussian 1.04e6 against
       // 0.68e6 solves/s); the other sizes share the run-time-n build

@@ -1,0 +1,89 @@
+// qn_launch_tiles.cu — launchers of the 4×CT tile kernels (33 <= n <= 64, Rosenbrock): B⁻¹ tiles in the
+// register file or in tensor memory (qn_resident_tile.cuh).  Its own translation unit: these 18
+// instantiations are most of the library's build time.
+#include <cuda_runtime.h>
+
+#include "qn_resident_tile.cuh"
+#include "qn_launch.h"
+
+#define fail qn_fail
+
+namespace {
+
+// The register-tile kernel evaluates the objective warp-locally; only Rosenbrock has
+// that form (qn_resident_tile.cuh).
+template <int N, int MINB, int PF>
+int launch_tile(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
+  const size_t smem = sizeof(double) * (size_t)qn::tile_problem_smem_doubles<N>();
+  auto kern = qn::qn_resident_tile_kernel<N, MINB, PF>;
+  p.sm_count = ctx->prop.multiProcessorCount;
+  int occ = 0;
+  QN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 64, smem));
+  if (occ < 1) return fail(QN_ERR_UNSUPPORTED_SIZE, "tile kernel does not fit on an SM (n=%d)", N);
+  long long grid = (long long)occ * ctx->prop.multiProcessorCount;
+  if (grid > p.batch) grid = p.batch;
+  p.counter = qn_next_counter(ctx, st);
+  arm_exit_stamps(ctx, p, grid, st);
+  kern<<<(unsigned)grid, 64, smem, st>>>(p);
+  QN_CUDA_TRY(cudaGetLastError());
+  ctx->last_path = 0;
+  ctx->last_grid = (int)grid;
+  ctx->last_block = 64;
+  ctx->last_smem = (int)smem;
+  ctx->last_launches = 1;
+  return QN_OK;
+}
+
+// The same kernel with the tile in tensor memory (qn_resident_tile.cuh, TM): CTAs of 128 threads =
+// two problems, 128 columns of tensor memory each, 4 CTAs = 8 problems per SM where the register
+// file holds 6.  cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for a kernel that calls
+// tcgen05.alloc (it cannot know the column count); tmem_residency derives the 4 CTAs per SM that
+// registers (128 × 128 × 4 = the file), shared memory and 4 × 128 columns allow — measured: the
+// throughput grows 1.6e8 → 2.5e8 → 3.0e8 → 3.7e8 iterations/s from 1 to 4 CTAs per SM (n = 60).
+template <int N, int PF>
+int launch_tile_tmem(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
+  const size_t smem = 2 * sizeof(double) * (size_t)qn::tile_problem_smem_doubles<N>();
+  auto kern = qn::qn_resident_tile_tmem_kernel<N, PF>;
+  p.sm_count = ctx->prop.multiProcessorCount;
+  QN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  long long grid = (long long)tmem_residency(ctx, kern, 128, smem, 128) * ctx->prop.multiProcessorCount; // 4 per SM on B200
+  if (grid > (p.batch + 1) / 2) grid = (p.batch + 1) / 2;
+  p.counter = qn_next_counter(ctx, st);
+  arm_exit_stamps(ctx, p, 2 * grid, st);
+  kern<<<(unsigned)grid, 128, smem, st>>>(p);
+  QN_CUDA_TRY(cudaGetLastError());
+  ctx->last_path = 0;
+  ctx->last_grid = (int)grid;
+  ctx->last_block = 128;
+  ctx->last_smem = (int)smem;
+  ctx->last_launches = 1;
+  return QN_OK;
+}
+
+// Where the tile lives: tensor memory when it is the faster home (measured per size on B200,
+// 2^15-2^16 problems: n = 44 +1 %, 48 +6 %, 50 +8 %, 56 +1 %, 60 +3 %, 64 +8 %; n = 36, 40, 52 are
+// 1-3 % faster from registers) and the batch fills 8 problems per SM; option "tile_tmem" = 0 / 1 forces
+// the register file / tensor memory.
+inline bool tile_in_tensor_memory(const qn_context* ctx, const int n, const long long batch) {
+  if (ctx->opt.tile_tmem == 0) return false;
+  if (ctx->opt.tile_tmem == 1) return true;
+  const bool faster = n == 44 || n == 48 || n == 50 || n == 56 || n == 60 || n == 64;
+  return faster && batch >= 8LL * ctx->prop.multiProcessorCount;
+}
+
+}  // namespace
+
+int qn_launch_rosenbrock_tiles(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
+  switch (p.n) {
+#define QN_REG_CASE(N, BLOCK, MINB)
+#define QN_TILE_CASE(N, MINB)                                                                       \
+  case N:                                                                                            \
+    if (tile_in_tensor_memory(ctx, N, p.batch)) return launch_tile_tmem<N, 1>(ctx, p, st);           \
+    /* 6 CTAs per SM (168 registers); 4, 5 and 7 were measured slower */             \
+    return launch_tile<N, MINB, 1>(ctx, p, st);
+#include "qn_reg_sizes.inc"
+#undef QN_REG_CASE
+#undef QN_TILE_CASE
+    default: return -1;
+  }
+}
