@@ -282,6 +282,10 @@ int dispatch_model(qn_context* ctx, const qn_model* model, qn::BatchParams& p,
       if (model->n != p.n)
         return fail(QN_ERR_INVALID_ARGUMENT, "dense Gaussian model has n=%d, call has n=%d",
                     model->n, p.n);
+      if (!(flags & (QN_FLAG_FORCE_SMEM | QN_FLAG_ONE_PASS))) { // n = 96, 128, 160: leader/helper tensor-memory tiles
+        const int rc = qn_launch_gaussian_tilew(ctx, p, model->d_a, model->d_b, st);
+        if (rc >= 0) return rc;
+      }
       qn::DenseGaussian::Params op{model->d_a, model->d_b, 0};
       // register-pair policy (n = 128): shared memory is free, keep Λ there (128 KB of the 227 KB)
       if (p.n == 128 && !(flags & QN_FLAG_FORCE_SMEM) && ctx->opt.lambda_smem) op.lam_in_smem = 1;

@@ -47,3 +47,4 @@ void arm_exit_stamps(qn_context* ctx, qn::BatchParams& p, long long slots, cudaS
 // tensor-memory tiles of n = 96, 128, 160.  Each returns -1 when it has no kernel for the request.
 int qn_launch_rosenbrock_tiles(qn_context* ctx, qn::BatchParams& p, cudaStream_t st);
 int qn_launch_rosenbrock_small(qn_context* ctx, qn::BatchParams& p, cudaStream_t st, bool onepass);
+int qn_launch_gaussian_tilew(qn_context* ctx, qn::BatchParams& p, const double* d_mu, const double* d_lambda, cudaStream_t st);

@@ -14,18 +14,23 @@ namespace {
 // n = 32·RT Rosenbrock (n = 128: RT = 4, n = 160: RT = 5, n = 96: RT = 3): the leader/helper tile kernel
 // with the whole tile in tensor memory (qn_resident_tile128.cuh): one CTA = one problem, a warp per
 // rule-C2 column block; two problems per SM at n <= 128, one at n = 160 (480 of the 512 columns).
-template <int RT>
-int launch_tilew(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
+template <int RT, class WObj = qn::WRosenbrock>
+int launch_tilew(qn_context* ctx, qn::BatchParams& p, cudaStream_t st, const typename WObj::Params op = {}) {
   using C = qn::TileW<RT>;
   const size_t smem = sizeof(double) * (size_t)C::kSmemDoubles;
-  auto kern = qn::qn_resident_tilew_kernel<RT>;
-  QN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  long long grid = (long long)tmem_residency(ctx, kern, C::THREADS, smem, C::kAlloc) * ctx->prop.multiProcessorCount;
+  auto kern = qn::qn_resident_tilew_kernel<RT, WObj>;
+  // A cooperative objective reads its parameters (Λ: 8 n² bytes, 128 KB at n = 128) through L1 in every
+  // evaluation: leave the SM's 256 KB to the cache except for what the resident CTAs need.
+  const int ctas = tmem_residency(ctx, kern, C::THREADS, smem, C::kAlloc);
+  const int carve = WObj::kCoop ? (int)std::min<size_t>(100, ((smem + 2048) * ctas * 100 + ctx->prop.sharedMemPerMultiprocessor - 1) / ctx->prop.sharedMemPerMultiprocessor + 5)
+                                : (int)cudaSharedmemCarveoutMaxShared;
+  QN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+  long long grid = (long long)ctas * ctx->prop.multiProcessorCount;
   if (grid > p.batch) grid = p.batch;
   p.counter = qn_next_counter(ctx, st);
   p.sm_count = ctx->prop.multiProcessorCount;
   arm_exit_stamps(ctx, p, grid, st);
-  kern<<<(unsigned)grid, C::THREADS, smem, st>>>(p);
+  kern<<<(unsigned)grid, C::THREADS, smem, st>>>(p, op);
   QN_CUDA_TRY(cudaGetLastError());
   ctx->last_path = 0;
   ctx->last_grid = (int)grid;
@@ -79,5 +84,16 @@ int qn_launch_rosenbrock_small(qn_context* ctx, qn::BatchParams& p, cudaStream_t
     if (n == 160) return launch_tilew<5>(ctx, p, st);
     if (n == 96) return launch_tilew<3>(ctx, p, st);
   }
+  return -1;
+}
+
+// dense Gaussian at n = 96, 128, 160 (BASELINE.json configs[2]: n = 128): the same leader/helper kernel
+// with the CTA-cooperative objective (WGaussian)
+int qn_launch_gaussian_tilew(qn_context* ctx, qn::BatchParams& p, const double* d_mu, const double* d_lambda, cudaStream_t st) {
+  const qn::WGaussian::Params op{d_mu, d_lambda};
+  if (ctx->opt.pair_rows != 0 && ctx->opt.pair_rows != 'L') return -1;
+  if (p.n == 128) return launch_tilew<4, qn::WGaussian>(ctx, p, st, op);
+  if (p.n == 160) return launch_tilew<5, qn::WGaussian>(ctx, p, st, op);
+  if (p.n == 96) return launch_tilew<3, qn::WGaussian>(ctx, p, st, op);
   return -1;
 }

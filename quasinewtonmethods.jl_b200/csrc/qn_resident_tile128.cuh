@@ -37,7 +37,9 @@ struct TileW {
   static constexpr int oNu = oS + N;                  // -u by row [128]
   static constexpr int oPart1 = oNu + N;              // block partials [8 blocks][128 rows]
   static constexpr int oPart2 = oPart1 + NB * N;
-  static constexpr int oCmd = oPart2 + NB * N;        // command word
+  static constexpr int oD0 = oPart2 + NB * N;         // cooperative objectives: the point(s) being evaluated, θ-μ [N] each
+  static constexpr int oD1 = oD0 + N;
+  static constexpr int oCmd = oD1 + N;                // command word
   static constexpr int oEnd = oCmd + 2;               // (+ 2 doubles: the work-queue slot)
   static constexpr int kSmemDoubles = oEnd + 2;
 };
@@ -140,9 +142,29 @@ __device__ __forceinline__ void tile_col_unpack(TileCol<RT>& c, const TileColRaw
   for (int k = 0; k < RT; ++k) c.d[k] = __hiloint2double((int)r.w[2 * k + 1], (int)r.w[2 * k]);
 }
 
-template <int RT_>
+// The objective of this kernel (logdensity / ∂logdensity!, QN.jl:8-9).
+//  - WRosenbrock: evaluated by the leader alone, in its own lanes.
+//  - WGaussian (build-defined): ℓ = -½ dᵀΛd, ∇ = -Λd, d = θ-μ.  z = Λd is a sweep of the
+//    SAME shape as pass 1 — thread (q, b) the rows RT·q… of column block b, Λ read through L1 (128 KB at
+//    n = 128, shared by the SM's CTAs and by every problem) — so all warps take part: the leader
+//    publishes d (for the accepted point, and for the trial point when they differ: one sweep serves
+//    both), commands an EVAL, and adds the block partials in ascending order (rule C2), the oracle's
+//    gauss_eval order.  One GEMV gives the value AND the gradient.
+struct WRosenbrock {
+  static constexpr bool kCoop = false;
+  struct Params {};
+  __device__ __forceinline__ static double finish(const double sum) { return 0.0 - sum; } // runtests.jl:6-10: s -= term
+};
+struct WGaussian {
+  static constexpr bool kCoop = true;
+  struct Params { const double* mu; const double* lam; };
+  __device__ __forceinline__ static double finish(const double q) { return -0.5 * q; }
+};
+constexpr int kLhEval = 8, kLhEval2 = 16; // cooperative objective: evaluate at one / two published points
+
+template <int RT_, class WObj>
 __global__ void __launch_bounds__(TileW<RT_>::THREADS, TileW<RT_>::kCtasPerSm)
-qn_resident_tilew_kernel(const __grid_constant__ BatchParams p) {
+qn_resident_tilew_kernel(const __grid_constant__ BatchParams p, const __grid_constant__ typename WObj::Params op) {
   using C = TileW<RT_>;
   using Vec = VecR<RT_>;
   constexpr int N = C::N, RT = C::RT, CT = C::CT, NB = C::NB;
@@ -266,6 +288,43 @@ qn_resident_tilew_kernel(const __grid_constant__ BatchParams p) {
     return T;
   };
 
+  double* dvec0 = smem + C::oD0;
+  double* dvec1 = smem + C::oD1;
+  // cooperative objective: this thread's block partials of z = Λd for the published point(s) -> part1 (part2)
+  auto eval_sweep = [&](const bool second) {
+    if constexpr (WObj::kCoop) {
+      double zo[RT], zn[RT];
+#pragma unroll
+      for (int r = 0; r < RT; ++r) { zo[r] = 0.0; zn[r] = 0.0; }
+      const double* lamp = op.lam + row0 + (size_t)N * col0;
+#pragma unroll 8
+      for (int k = 0; k < CT; ++k) {
+        double lam[RT];
+        if constexpr (RT == 4) { // the thread's four rows of column k: 32 contiguous, 32-byte aligned bytes = two full-sector LDG.128
+          const double2 l01 = __ldg(reinterpret_cast<const double2*>(lamp + (size_t)N * k));
+          const double2 l23 = __ldg(reinterpret_cast<const double2*>(lamp + (size_t)N * k + 2));
+          lam[0] = l01.x; lam[1] = l01.y; lam[2] = l23.x; lam[3] = l23.y;
+        } else {
+#pragma unroll
+          for (int r = 0; r < RT; ++r) lam[r] = __ldg(lamp + (size_t)N * k + r);
+        }
+        const double d0 = dvec0[col0 + k];
+#pragma unroll
+        for (int r = 0; r < RT; ++r) zo[r] = fma(lam[r], d0, zo[r]);
+        if (second) {
+          const double d1 = dvec1[col0 + k];
+#pragma unroll
+          for (int r = 0; r < RT; ++r) zn[r] = fma(lam[r], d1, zn[r]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        part1[b * N + row0 + r] = zo[r];
+        if (second) part2[b * N + row0 + r] = zn[r];
+      }
+    }
+  };
+
   if (t == 0) stamp_start(p);
   for (;;) {
     __syncthreads(); // the previous problem's shared-memory traffic is finished
@@ -274,12 +333,17 @@ qn_resident_tilew_kernel(const __grid_constant__ BatchParams p) {
     const long long j = *next;
     if (j >= p.batch) break;
 
-    if (!leader) { // ---- helpers: their part of the two sweeps, between CTA barriers
+    if (!leader) { // ---- helpers: their part of the sweeps, between CTA barriers
       for (;;) {
-        __syncthreads();                 // (A) a command and the operands of pass 1 are published
+        __syncthreads();                 // (A) a command and its operands are published
         const int c = *cmd;
         if (c & kLhReset) reset_tile();
         if (c & kLhExit) break;
+        if (c & kLhEval) {               // cooperative objective
+          eval_sweep((c & kLhEval2) != 0);
+          __syncthreads();               // (E) the partials of z
+          continue;
+        }
         pass1();
         __syncthreads();                 // (B) pass-1 partials
         __syncthreads();                 // (C) c₁s, -u published
@@ -297,7 +361,44 @@ qn_resident_tilew_kernel(const __grid_constant__ BatchParams p) {
       const double* th = p.theta0 + j * p.theta_stride; // copyto!(x_old, x), QN.jl:248
 #pragma unroll
       for (int k = 0; k < RT; ++k) { x.v[k] = th[lane + 32 * k]; s.v[k] = y.v[k] = gp.v[k] = 0.0; }
-      l0 = 0.0 - warp_butterfly(rosenbrock_w_terms<RT, true>(lane, x, g)); // QN.jl:254 of iteration 1
+    }
+    Vec muv;
+#pragma unroll
+    for (int k = 0; k < RT; ++k) muv.v[k] = 0.0;
+    if constexpr (WObj::kCoop) {
+#pragma unroll
+      for (int k = 0; k < RT; ++k) muv.v[k] = __ldg(op.mu + lane + 32 * k);
+    }
+    // ∂logdensity! at xo (gradient to gout, lane accumulator of the ℓ-sum returned in acc_o) and, when
+    // `second`, logdensity at xn (acc_n): ℓ = WObj::finish(rule-C1 sum of the accumulators)
+    auto eval_pair = [&](const Vec& xo, const bool second, const Vec& xn, Vec& gout, double& acc_o, double& acc_n) {
+      if constexpr (!WObj::kCoop) {
+        acc_o = rosenbrock_w_terms<RT, true>(lane, xo, gout);
+        if (second) { Vec unused; acc_n = rosenbrock_w_terms<RT, false>(lane, xn, unused); }
+      } else {
+        Vec d_o, d_n;
+#pragma unroll
+        for (int k = 0; k < RT; ++k) {
+          d_o.v[k] = xo.v[k] - muv.v[k];
+          dvec0[lane + 32 * k] = d_o.v[k];
+          d_n.v[k] = 0.0;
+          if (second) { d_n.v[k] = xn.v[k] - muv.v[k]; dvec1[lane + 32 * k] = d_n.v[k]; }
+        }
+        if (lane == 0) *cmd = kLhEval | (second ? kLhEval2 : 0);
+        __syncthreads(); // (A)
+        eval_sweep(second);
+        __syncthreads(); // (E)
+        const Vec z = combine(part1);
+#pragma unroll
+        for (int k = 0; k < RT; ++k) gout.v[k] = -z.v[k];
+        acc_o = dot_w<RT>(d_o, z);
+        if (second) { const Vec zn = combine(part2); acc_n = dot_w<RT>(d_n, zn); }
+      }
+    };
+    {
+      Vec unused_x; double acc, unused_acc;
+      eval_pair(x, false, unused_x, g, acc, unused_acc);      // QN.jl:254 of iteration 1
+      l0 = WObj::finish(warp_butterfly(acc));
     }
     const LsParams ls = p.ls;
     const double tol = p.tol;
@@ -317,14 +418,14 @@ qn_resident_tilew_kernel(const __grid_constant__ BatchParams p) {
       Vec sn, xo, yn;
 #pragma unroll
       for (int k = 0; k < RT; ++k) { sn.v[k] = a * d.v[k]; xo.v[k] = x.v[k] + sn.v[k]; }
-      sp.term_next = rosenbrock_w_terms<RT, true>(lane, xo, sp.g);
       if (a == 1.0) {
+        eval_pair(xo, false, xo, sp.g, sp.term_next, term_trial);
         term_trial = sp.term_next;
       } else {
-        Vec xn, unused;
+        Vec xn;
 #pragma unroll
         for (int k = 0; k < RT; ++k) xn.v[k] = fma(a, d.v[k], x.v[k]);
-        term_trial = rosenbrock_w_terms<RT, false>(lane, xn, unused);
+        eval_pair(xo, true, xn, sp.g, sp.term_next, term_trial);
       }
 #pragma unroll
       for (int k = 0; k < RT; ++k) yn.v[k] = g.v[k] - sp.g.v[k];
@@ -385,7 +486,7 @@ qn_resident_tilew_kernel(const __grid_constant__ BatchParams p) {
         m = dot_w<RT>(d, g);
         warp_butterfly3(m, tterm, sp.sy, lane);
         sp.term_next = tterm;
-        lx1 = 0.0 - tterm;
+        lx1 = WObj::finish(tterm);
         have_trial = true;
       }
       if (m <= 0.0) { // QN.jl:272-280: H ← I, s ← ∇_new, m ← ∇ᵀ∇
@@ -402,7 +503,7 @@ qn_resident_tilew_kernel(const __grid_constant__ BatchParams p) {
           spec_eval(a, d, sp, tterm);
           warp_butterfly3(tterm, sp.term_next, sp.sy, lane);
           ++fevals;
-          return 0.0 - tterm;
+          return WObj::finish(tterm);
         };
         if (have_trial) ++fevals;
         alpha = backtracking_linesearch(ls, l0, m, trial, lx1, have_trial, lx1);
@@ -421,7 +522,7 @@ qn_resident_tilew_kernel(const __grid_constant__ BatchParams p) {
       for (int k = 0; k < RT; ++k) y.v[k] = g.v[k] - sp.g.v[k]; // y = ∇_old - ∇_new, QN.jl:38
       sy = sp.sy;
       g = sp.g;
-      l0 = (alpha == 1.0) ? lx1 : 0.0 - sp.term_next;
+      l0 = (alpha == 1.0) ? lx1 : WObj::finish(sp.term_next);
     }
     command(kLhExit | (helper_reset ? kLhReset : 0));
 #pragma unroll
