@@ -323,6 +323,7 @@ const OptKey kOptKeys[] = {
   {"stream_tma", &qn_options::stream_tma, "QN_STREAM_TMA", 0},
   {"l2_persist_mb", &qn_options::l2_persist_mb, "QN_L2_PERSIST_MB", 0},
   {"l2_resident", &qn_options::l2_resident, "QN_L2_RESIDENT", 0},
+  {"sweep_fine", &qn_options::sweep_fine, "QN_SWEEP_FINE", 0},
   {"sweep_order", &qn_options::sweep_order, "QN_SWEEP_ORDER", 0},
   {"sweep_depth", &qn_options::sweep_depth, "QN_SWEEP_DEPTH", 0},
   {"hint_p1_ld", &qn_options::hint_p1_ld, "QN_HINT_P1_LD", 0},

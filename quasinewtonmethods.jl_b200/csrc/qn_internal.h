@@ -31,6 +31,7 @@ struct qn_options {
   int stream_tma = -1;    // "stream_tma":  -1 auto, 0 LDG sweeps, 1 cp.async.bulk-staged sweeps    (QN_STREAM_TMA)
   int l2_persist_mb = 0;  // "l2_persist_mb": leading part of B⁻¹ kept resident in L2 by the streaming path; -1 device maximum, 0 off = default: measured SLOWER beyond 16 MB (QN_L2_PERSIST_MB)
   int l2_resident = -1;   // "l2_resident": sweeps without eviction hints when B⁻¹ (or this GPU's slab) fits the L2; -1 auto, 0, 1 (QN_L2_RESIDENT)
+  int sweep_fine = -1;    // "sweep_fine": one rule-C2 block per sweep CTA instead of a super-block; -1 auto (small grids), 0, 1 (QN_SWEEP_FINE)
   int sweep_order = -1;   // "sweep_order": -1 default, 0 ascending, 1 pass1 descending, 2 pass2 descending (QN_SWEEP_ORDER)
   int sweep_depth = 0;    // "sweep_depth": 0 auto, 8 or 16 loads in flight                         (QN_SWEEP_DEPTH)
   int hint_p1_ld = 0, hint_p2_ld = 2, hint_p2_st = 1, hint_one_ld = 4; // cache hints, QN_HINT_*

@@ -156,6 +156,7 @@ int hint_opt(int k, int dflt, int hi) { return (k < 0 || k > hi) ? dflt : k; }
 bool sweep_deep(const qn_context* ctx, const qn::StreamParams& p) {
   const int v = hint_opt(ctx->opt.sweep_depth, 0, 16);
   if (v) return v == 16;
+  if (p.grp_cols < p.sbcols) return true; // one block per CTA: its <= 16 columns are one batch of loads
   return p.ntiles * p.nsb <= ctx->prop.multiProcessorCount;
 }
 // option "sweep_order": 0 both sweeps walk their column blocks in ascending order (round 1), 1 pass1
@@ -228,7 +229,7 @@ VecKernel cluster_kernel(int ppt, bool onepass) {
 int enqueue_iteration(qn_context* ctx, const StreamWork& w, cudaStream_t st) {
   t_opt = &ctx->opt;
   const qn::StreamParams& p = w.p;
-  const dim3 grid(p.ntiles, p.nsb);
+  const dim3 grid(p.ntiles, p.ngrp);
   const bool deep = sweep_deep(ctx, p);
   if (p.onepass) { // two kernels per iteration; the head of iteration 1 ran before the graph
     pass_one_kernel(deep)<<<grid, w.pass_threads, sizeof(double) * 6 * p.sbcols, st>>>(p);
@@ -315,17 +316,32 @@ int stream_setup(qn_context* ctx, StreamWork& w, int n, const double* theta0, bo
   }
   // sweep CTAs: 2 rows per thread; halve the CTA (down to 64 threads) while the grid would leave
   // SMs idle — a single SM cannot keep enough loads in flight to use its share of the bandwidth
+  p.grp_cols = p.sbcols;
+  p.ngrp = p.nsb;
+  auto tiles_of = [&](int threads) { return (p.rows + 2 * threads - 1) / (2 * threads); };
+  // A grid of super-block CTAs that leaves SMs idle (small n; the slabs of the row-sharded mode): one
+  // rule-C2 BLOCK per CTA instead — 16× the CTAs, every load of a thread in flight at once (option
+  // "sweep_fine": -1 auto, 0, 1; two-pass mode only)
+  // Measured (profiles/r2_stream_sweep_fine.txt): n = 512 43.5 -> 30.7 µs per iteration, n = 1024 46.9 -> 35.9;
+  // from n = 2048 on the super-block grid already has >= 128 CTAs and one block per CTA LOSES (66 against
+  // 47 µs; n = 6144 332 against 184: 16x the CTAs, each paying its prologue, its arrival atomic and a
+  // two-level tail over n/16 partials) — so auto means: only while even 128-row tiles leave half the SMs idle.
+  const bool fine = !onepass && (ctx->opt.sweep_fine > 0 ||
+                                 (ctx->opt.sweep_fine < 0 && tiles_of(64) * p.nsb <= ctx->prop.multiProcessorCount / 2));
+  if (fine) {
+    p.grp_cols = p.rb;
+    p.ngrp = (n + p.rb - 1) / p.rb;
+  }
   w.pass_threads = kPassThreads;
-  while (w.pass_threads > 64 &&
-         ((p.rows + 2 * w.pass_threads - 1) / (2 * w.pass_threads)) * p.nsb < 2 * ctx->prop.multiProcessorCount)
+  while (w.pass_threads > 64 && tiles_of(w.pass_threads) * p.ngrp < 2 * ctx->prop.multiProcessorCount)
     w.pass_threads /= 2;
-  p.ntiles = (p.rows + 2 * w.pass_threads - 1) / (2 * w.pass_threads);
+  p.ntiles = tiles_of(w.pass_threads);
   p.ld = (p.rows + 15) & ~15;
   QN_TRY_REL(cudaMalloc(&p.H, sizeof(double) * (size_t)p.ld * n));
   { const int prc = persist_setup(ctx, w); if (prc) return prc; }
   const size_t nv = ((size_t)n + 31) & ~(size_t)31;
   p.nvstride = (int)nv;
-  const size_t words = nv * 22 + 2 * (size_t)p.nsb * n + 128 + 4 * (size_t)row_tiles; // + one counter per 128-row CTA tile
+  const size_t words = nv * 22 + 2 * (size_t)p.ngrp * n + 128 + 4 * (size_t)row_tiles; // + one counter per 128-row CTA tile
   cudaError_t e = cudaMalloc(&w.block, sizeof(double) * words);
   if (e != cudaSuccess)
     return qn_fail(QN_ERR_CUDA, "cudaMalloc failed for the streaming work space: %s", cudaGetErrorString(e));
@@ -339,8 +355,8 @@ int stream_setup(qn_context* ctx, StreamWork& w, int n, const double* theta0, bo
   p.tvec = base + 15 * nv; p.wvec = base + 16 * nv; // and their odd-iteration copies at 17, 18 (row-sharded mode)
   p.tmp2 = base + 19 * nv;
   p.partial = base + 22 * nv;
-  p.partial2 = p.partial + (size_t)p.nsb * n;
-  double* tail = p.partial2 + (size_t)p.nsb * n;
+  p.partial2 = p.partial + (size_t)p.ngrp * n;
+  double* tail = p.partial2 + (size_t)p.ngrp * n;
   p.sc = reinterpret_cast<StreamScalars*>(tail);          // 32 doubles reserved
   p.flags = reinterpret_cast<unsigned int*>(tail + 32);   // 2·kMaxShards words
   p.tiles_done = reinterpret_cast<unsigned int*>(tail + 48);
@@ -498,7 +514,7 @@ int qn_stream_solve(qn_context* ctx, int n, const double* d_theta0, const qn_bac
   if (rc != QN_OK) { stream_release(w); return rc; }
   const StreamParams& p = w.p;
   ctx->last_path = 2;
-  ctx->last_grid = p.ntiles * p.nsb;
+  ctx->last_grid = p.ntiles * p.ngrp;
   ctx->last_block = w.pass_threads;
   ctx->last_smem = (int)(sizeof(double) * 4 * p.sbcols);
   {
@@ -626,7 +642,7 @@ extern "C" int32_t qn_bfgs_optimize_rowsharded_f64(
   rc = finish();
   for (int g = 0; g < G; ++g) {
     ctxs[g]->last_path = 2;
-    ctxs[g]->last_grid = ws[g].p.ntiles * ws[g].p.nsb;
+    ctxs[g]->last_grid = ws[g].p.ntiles * ws[g].p.ngrp;
     ctxs[g]->last_block = ws[g].pass_threads;
     const int its = host.it + (host.done ? 1 : 0);
     ctxs[g]->last_launches = onepass ? 1 + 2 * its : ws[g].p.fused2 ? 1 + 3 * its : 6 * its;

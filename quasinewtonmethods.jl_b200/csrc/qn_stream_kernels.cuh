@@ -61,6 +61,12 @@ struct StreamScalars {
 
 struct StreamParams {
   int n, ld, rb, sbcols, nsb, max_iter;
+  // columns of B⁻¹ one sweep CTA covers, and how many such groups a row has: a SUPER-block (16 rule-C2
+  // blocks, ngrp = nsb) when that fills the GPU, ONE block (ngrp = blocks of a row) when the matrix —
+  // or this GPU's slab of it — is small: 16× the CTAs, each with all its loads in flight at once
+  // instead of a walk of 16 dependent batches.  The partial sums are per group either way, and
+  // pass_tail adds them in the canonical two-level order, so the bits do not depend on the choice.
+  int grp_cols, ngrp;
   double tol;
   LsParams ls;
   double* H;
@@ -363,7 +369,7 @@ __device__ __forceinline__ bool pass_tail(const StreamParams& p, int which, unsi
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned prev = atomicAdd(p.tile_count + blockIdx.x, 1u);
-    is_last = (prev == (unsigned)p.nsb - 1);
+    is_last = (prev == (unsigned)p.ngrp - 1);
     if (is_last) p.tile_count[blockIdx.x] = 0; // ready for the next pass
   }
   __syncthreads();
@@ -373,10 +379,31 @@ __device__ __forceinline__ bool pass_tail(const StreamParams& p, int which, unsi
   if (c0 < p.n) {
     const bool two = (c0 + 1 < p.n);
     const volatile double* part = p.partial + c0; // written by other CTAs of this launch
-    double T0 = part[0], T1 = two ? part[1] : 0.0;
-    for (int j = 1; j < p.nsb; ++j) {
-      T0 = T0 + part[(size_t)j * p.n];
-      if (two) T1 = T1 + part[(size_t)j * p.n + 1];
+    double T0, T1;
+    if (p.ngrp == p.nsb) { // one partial per super-block: added in ascending order (rule C2, second level)
+      T0 = part[0]; T1 = two ? part[1] : 0.0;
+      for (int j = 1; j < p.nsb; ++j) {
+        T0 = T0 + part[(size_t)j * p.n];
+        if (two) T1 = T1 + part[(size_t)j * p.n + 1];
+      }
+    } else { // one partial per block: blocks in ascending order inside a super-block of 16, then the super-blocks
+      T0 = 0.0; T1 = 0.0;
+      for (int g0 = 0, sbi = 0; g0 < p.ngrp; g0 += 16, ++sbi) {
+        const int g1 = min(g0 + 16, p.ngrp);
+        double v0[16], v1[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { // the loads of a super-block are in flight together
+          const bool ok = g0 + k < g1;
+          v0[k] = ok ? part[(size_t)(g0 + k) * p.n] : 0.0;
+          v1[k] = (ok && two) ? part[(size_t)(g0 + k) * p.n + 1] : 0.0;
+        }
+        double S0 = v0[0], S1 = v1[0];
+#pragma unroll
+        for (int k = 1; k < 16; ++k)
+          if (g0 + k < g1) { S0 = S0 + v0[k]; S1 = S1 + v1[k]; }
+        T0 = (sbi == 0) ? S0 : T0 + S0;
+        T1 = (sbi == 0) ? S1 : T1 + S1;
+      }
     }
     finish(c0, T0);
     if (two) finish(c0 + 1, T1);
@@ -498,19 +525,19 @@ __device__ __forceinline__ void pass2_finish(const StreamParams& p, const Stream
 // order — they wait in registers), so that the sweep starts where the previous sweep over B⁻¹ ended:
 // what that sweep left in the 126 MB L2 is read before it is evicted.
 template <int LDH, int STH, int DEPTH = 8, bool DESC = false>
-__global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : (DESC ? 2 : QN_PASS1_MINB)) stream_pass1(const StreamParams p) {
+__global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 2 : (DESC ? 2 : QN_PASS1_MINB)) stream_pass1(const StreamParams p) {
   const StreamScalars* sc = p.sc;
   if (sc->done || sc->skip_update) return;
   extern __shared__ __align__(16) double sm[];
   double* ys = sm; // y of this super-block's columns
   const int n = p.n, ld = p.ld, rb = p.rb;
   const int sb = blockIdx.y;
-  const int r_begin = sb * p.sbcols;
-  const int r_end = min(r_begin + p.sbcols, n);
+  const int r_begin = sb * p.grp_cols;
+  const int r_end = min(r_begin + p.grp_cols, n);
   for (int r = r_begin + threadIdx.x; r < r_end; r += blockDim.x) ys[r - r_begin] = p.y[r];
   __syncthreads();
   const bool reset = p.fused2 && sc->need_reset != 0; // B⁻¹ ← I (QN.jl:144-148) folded into the sweeps
-  const bool keep = sb < p.persist_sb;                 // this super-block stays in L2
+  const bool keep = r_begin / p.sbcols < p.persist_sb; // this super-block stays in L2
   const int c0 = p.row0 + (int)(blockIdx.x * 2 * blockDim.x) + 2 * (int)threadIdx.x;
   const bool two = (c0 + 1 < n);
   const double* hp = p.H + (c0 - p.row0);
@@ -607,17 +634,17 @@ __device__ __forceinline__ void pass1_finish(const StreamParams& p, const Stream
 // in flight) beat 3 or 4 (measured at n = 8192, profiles/r1_stream_residency.txt: pass2 172 µs at 2 CTAs/SM
 // against 207 µs at 3-4; the one-pass sweep 201 / 245 / 253 µs per iteration at 2 / 3 / 4).
 template <int LDH, int STH, int DEPTH = 8, bool DESC = false>
-__global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASS2_MINB) stream_pass2(const StreamParams p) {
+__global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 2 : QN_PASS2_MINB) stream_pass2(const StreamParams p) {
   const StreamScalars* sc = p.sc;
   if (sc->done || sc->skip_update) return;
   extern __shared__ __align__(16) double sm[];
   double4* ops = reinterpret_cast<double4*>(sm); // {c₁s[r], -u[r], s[r], ∇[r]} per column
   const int n = p.n, ld = p.ld, rb = p.rb;
   const int sb = blockIdx.y;
-  const int r_begin = sb * p.sbcols;
-  const int r_end = min(r_begin + p.sbcols, n);
+  const int r_begin = sb * p.grp_cols;
+  const int r_end = min(r_begin + p.grp_cols, n);
   const bool reset = p.fused2 && sc->need_reset != 0;
-  const bool keep = sb < p.persist_sb; // this super-block stays in L2
+  const bool keep = r_begin / p.sbcols < p.persist_sb; // this super-block stays in L2
   const double c1 = sc->c1;
   for (int r = r_begin + threadIdx.x; r < r_end; r += blockDim.x) {
     const double sr = p.s[r];
@@ -773,8 +800,8 @@ __global__ void __launch_bounds__(kPassThreads, 2) stream_pass1_tma(const Stream
   const int tile_rows = 2 * (int)blockDim.x;
   unsigned char* ring = smraw + tma_ring_offset(p.sbcols, 1);
   const int sb = blockIdx.y;
-  const int r_begin = sb * p.sbcols;
-  const int r_end = min(r_begin + p.sbcols, n);
+  const int r_begin = sb * p.grp_cols;
+  const int r_end = min(r_begin + p.grp_cols, n);
   const int ncols = r_end - r_begin;
   const int nstg = (ncols + kTmaCols - 1) / kTmaCols;
   const bool reset = p.fused2 && sc->need_reset != 0; // B⁻¹ ← I: nothing to fetch
@@ -850,8 +877,8 @@ __global__ void __launch_bounds__(kPassThreads, 2) stream_pass2_tma(const Stream
   const int tile_rows = 2 * (int)blockDim.x;
   unsigned char* ring = smraw + tma_ring_offset(p.sbcols, 4);
   const int sb = blockIdx.y;
-  const int r_begin = sb * p.sbcols;
-  const int r_end = min(r_begin + p.sbcols, n);
+  const int r_begin = sb * p.grp_cols;
+  const int r_end = min(r_begin + p.grp_cols, n);
   const int ncols = r_end - r_begin;
   const int nstg = (ncols + kTmaCols - 1) / kTmaCols;
   const bool reset = p.fused2 && sc->need_reset != 0;
