@@ -525,7 +525,7 @@ __device__ __forceinline__ void pass2_finish(const StreamParams& p, const Stream
 // order — they wait in registers), so that the sweep starts where the previous sweep over B⁻¹ ended:
 // what that sweep left in the 126 MB L2 is read before it is evicted.
 template <int LDH, int STH, int DEPTH = 8, bool DESC = false>
-__global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 2 : (DESC ? 2 : QN_PASS1_MINB)) stream_pass1(const StreamParams p) {
+__global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : (DESC ? 2 : QN_PASS1_MINB)) stream_pass1(const StreamParams p) {
   const StreamScalars* sc = p.sc;
   if (sc->done || sc->skip_update) return;
   extern __shared__ __align__(16) double sm[];
@@ -634,7 +634,7 @@ __device__ __forceinline__ void pass1_finish(const StreamParams& p, const Stream
 // in flight) beat 3 or 4 (measured at n = 8192, profiles/r1_stream_residency.txt: pass2 172 µs at 2 CTAs/SM
 // against 207 µs at 3-4; the one-pass sweep 201 / 245 / 253 µs per iteration at 2 / 3 / 4).
 template <int LDH, int STH, int DEPTH = 8, bool DESC = false>
-__global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 2 : QN_PASS2_MINB) stream_pass2(const StreamParams p) {
+__global__ void __launch_bounds__(kPassThreads, DEPTH > 8 ? 1 : QN_PASS2_MINB) stream_pass2(const StreamParams p) {
   const StreamScalars* sc = p.sc;
   if (sc->done || sc->skip_update) return;
   extern __shared__ __align__(16) double sm[];
