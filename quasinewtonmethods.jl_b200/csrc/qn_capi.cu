@@ -314,6 +314,7 @@ int dispatch_model(qn_context* ctx, const qn_model* model, qn::BatchParams& p,
 struct OptKey { const char* key; int qn_options::*field; const char* env; int env_mode; }; // env_mode 0: atoi, 1: presence clears, 2: first char
 const OptKey kOptKeys[] = {
   {"tile_tmem", &qn_options::tile_tmem, "QN_TILE_TMEM", 0},
+  {"tile_3w", &qn_options::tile_3w, "QN_TILE_3W", 0},
   {"pack", &qn_options::pack, "QN_NO_PACK", 1},
   {"pack_variant", &qn_options::pack_variant, "QN_PACK_VARIANT", 0},
   {"pair_rows", &qn_options::pair_rows, "QN_PAIR_ROWS", 2},

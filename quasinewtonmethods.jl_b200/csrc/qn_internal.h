@@ -22,6 +22,7 @@ int qn_fail(int code, const char* fmt, ...);
 // same names are read ONCE, in qn_create, as defaults — dispatch never calls getenv).
 struct qn_options {
   int tile_tmem = -1;     // "tile_tmem":  -1 auto, 0 tile in registers, 1 tile in tensor memory   (QN_TILE_TMEM)
+  int tile_3w = 0;        // "tile_3w":    tensor-memory tiles with three warps per problem and a speculative pass 1; measured 3 % SLOWER than leader/helper pairs, off by default (QN_TILE_3W)
   int pack = 1;           // "pack":        several small problems per warp (n = 8, 16, 32)        (QN_NO_PACK clears)
   int pack_variant = 0;   // "pack_variant": rows per lane 1 | 2 | 4, 0 = measured default         (QN_PACK_VARIANT)
   int pair_rows = 0;      // "pair_rows":   0 auto, else 'h' | 't' | '4' | '2' | 's'                 (QN_PAIR_ROWS)

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include "qn_resident_tile.cuh"
+#include "qn_resident_tile3w.cuh"
 #include "qn_launch.h"
 
 #define fail qn_fail
@@ -60,6 +61,29 @@ int launch_tile_tmem(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
   return QN_OK;
 }
 
+// Three warps per problem, speculative pass 1 (qn_resident_tile3w.cuh): CTAs of 384 threads = four problems,
+// 256 tensor-memory columns each, two CTAs = 8 problems per SM.
+template <int N>
+int launch_tile3w(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
+  const size_t smem = qn::k3wProblems * sizeof(double) * (size_t)qn::Tile3wCfg<N>::kDoubles;
+  auto kern = qn::qn_resident_tile3w_kernel<N>;
+  QN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  long long grid = (long long)tmem_residency(ctx, kern, qn::k3wThreads, smem, 256) * ctx->prop.multiProcessorCount;
+  const long long need = (p.batch + qn::k3wProblems - 1) / qn::k3wProblems;
+  if (grid > need) grid = need;
+  p.counter = qn_next_counter(ctx, st);
+  p.sm_count = ctx->prop.multiProcessorCount;
+  arm_exit_stamps(ctx, p, qn::k3wProblems * grid, st);
+  kern<<<(unsigned)grid, qn::k3wThreads, smem, st>>>(p);
+  QN_CUDA_TRY(cudaGetLastError());
+  ctx->last_path = 0;
+  ctx->last_grid = (int)grid;
+  ctx->last_block = qn::k3wThreads;
+  ctx->last_smem = (int)smem;
+  ctx->last_launches = 1;
+  return QN_OK;
+}
+
 // Where the tile lives: tensor memory when it is the faster home (measured per size on B200,
 // 2^15-2^16 problems: n = 44 +1 %, 48 +6 %, 50 +8 %, 56 +1 %, 60 +3 %, 64 +8 %; n = 36, 40, 52 are
 // 1-3 % faster from registers) and the batch fills 8 problems per SM; option "tile_tmem" = 0 / 1 forces
@@ -78,7 +102,8 @@ int qn_launch_rosenbrock_tiles(qn_context* ctx, qn::BatchParams& p, cudaStream_t
 #define QN_REG_CASE(N, BLOCK, MINB)
 #define QN_TILE_CASE(N, MINB)                                                                       \
   case N:                                                                                            \
-    if (tile_in_tensor_memory(ctx, N, p.batch)) return launch_tile_tmem<N, 1>(ctx, p, st);           \
+    if (tile_in_tensor_memory(ctx, N, p.batch))                                                      \
+      return ctx->opt.tile_3w != 0 ? launch_tile3w<N>(ctx, p, st) : launch_tile_tmem<N, 1>(ctx, p, st); \
     /* 6 CTAs per SM (168 registers); 4, 5 and 7 were measured slower */             \
     return launch_tile<N, MINB, 1>(ctx, p, st);
 #include "qn_reg_sizes.inc"

@@ -704,6 +704,9 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
 #ifndef QN_LH_HOIST
 #define QN_LH_HOIST 1
 #endif
+#ifndef QN_TM_DEPTH1
+#define QN_TM_DEPTH1 QN_TM_DEPTH // chunks in flight in pass 1 (leader/helper kernels)
+#endif
 template <int N>
 struct TileLhCfg {
   static constexpr int kRec = 6;                 // doubles per column record {c₁s, -u, s, ∇, pad, pad}
@@ -783,14 +786,17 @@ __device__ __forceinline__ void tile_solve_lh(const BatchParams& p, const long l
     for (int k = 0; k < (CT + 1) / 2; ++k) yy[k] = yb2[k];
     __syncwarp(); // keeps the loads above it
     if constexpr (TM) {
+      // pass 1 does 4 DFMA per chunk and keeps few registers: its ring is deeper than pass 2's (TD1 chunks
+      // in flight) — with one chunk ahead the sweep is a chain of 15 exposed tensor-memory load latencies
+      constexpr int TD1 = QN_TM_DEPTH1;
 #if QN_TM_RAW
-      TmRaw<EPC> ring[TD + 1];
+      TmRaw<EPC> ring[TD1 + 1];
 #pragma unroll
-      for (int c = 0; c < TD && c < NCH; ++c) tm_load_raw(ring[c], tmem + WPC * c);
+      for (int c = 0; c < TD1 && c < NCH; ++c) tm_load_raw(ring[c], tmem + WPC * c);
 #else
-      TmChunk<EPC> ring[TD + 1];
+      TmChunk<EPC> ring[TD1 + 1];
 #pragma unroll
-      for (int c = 0; c < TD && c < NCH; ++c) tm_load(ring[c], tmem + WPC * c);
+      for (int c = 0; c < TD1 && c < NCH; ++c) tm_load(ring[c], tmem + WPC * c);
 #endif
 #pragma unroll
       for (int k = 0; k < CT; ++k) {
@@ -801,11 +807,11 @@ __device__ __forceinline__ void tile_solve_lh(const BatchParams& p, const long l
           tm_wait_load();
 #if QN_TM_RAW
           TmChunk<EPC> cur;
-          tm_unpack(cur, ring[c % (TD + 1)]);
-          if (c + TD < NCH) tm_load_raw(ring[(c + TD) % (TD + 1)], tmem + WPC * (c + TD));
+          tm_unpack(cur, ring[c % (TD1 + 1)]);
+          if (c + TD1 < NCH) tm_load_raw(ring[(c + TD1) % (TD1 + 1)], tmem + WPC * (c + TD1));
 #else
-          if (c + TD < NCH) tm_load(ring[(c + TD) % (TD + 1)], tmem + WPC * (c + TD));
-          const TmChunk<EPC>& cur = ring[c % (TD + 1)];
+          if (c + TD1 < NCH) tm_load(ring[(c + TD1) % (TD1 + 1)], tmem + WPC * (c + TD1));
+          const TmChunk<EPC>& cur = ring[c % (TD1 + 1)];
 #endif
           if (C::kFull || col0 + k < N) {
 #pragma unroll

@@ -160,7 +160,7 @@ def test_config2_full_batch_host_and_multi_entry(eng, qn, ob):
     n, batch = 60, 1 << 16
     Theta = starts(n, batch)
     got = eng.optimize_batched(qn.Rosenbrock(), Theta)
-    assert eng.last_launch()["block"] == 128  # B⁻¹ tiles in tensor memory
+    assert eng.last_launch()["block"] in (128, 384)  # B⁻¹ tiles in tensor memory
     # the reference's own assertions (runtests.jl:42-45, README.md:59-75) for every problem
     assert (got["status"] == qn.CONVERGED).all()
     assert np.abs(got["g"]).max() < 1e-8

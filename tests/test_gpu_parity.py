@@ -122,7 +122,7 @@ def test_tile_kernel_in_tensor_memory(eng, qn, ob, n, option):
         Theta = starts(n, batch, key=8000 + n)
         for order in (2, 3):
             got = eng.optimize_batched(R, Theta, ls=qn.BackTracking[order](), ntrace=5)
-            assert eng.last_launch()["path"] == qn._lib.PATH_REGISTER and eng.last_launch()["block"] == 128
+            assert eng.last_launch()["path"] == qn._lib.PATH_REGISTER and eng.last_launch()["block"] in (128, 384)
             ref = ob.optimize_batch(ob.rosenbrock(), Theta, ls=ob.backtracking(order), ntrace=5)
             _check(got, ref)
     # final B⁻¹ (read back from tensor memory) and the BFGSState layout
@@ -131,7 +131,7 @@ def test_tile_kernel_in_tensor_memory(eng, qn, ob, n, option):
     sb = qn.BFGSStateBatch(n, batch)
     sb.data[:] = np.nan
     r = eng.optimize_batched(R, Theta, states=sb, flags=qn._lib.FLAG_WRITE_H)
-    assert eng.last_launch()["block"] == 128
+    assert eng.last_launch()["block"] in (128, 384)
     L = sb.L
     for j in range(batch):
         o = ob.optimize(ob.rosenbrock(), Theta[:, j], L=L)
@@ -381,3 +381,40 @@ def test_device_objectives_match_oracle(eng, qn, ob):
     gbuf = np.empty(9)
     assert qn.dlogdensity_(gbuf, qn.Rosenbrock(), x) == qn.logdensity(qn.Rosenbrock(), x)
     assert np.array_equal(gbuf, ob.dlogdensity(ob.rosenbrock(), x)[1])
+
+
+@pytest.mark.parametrize("n", [36, 50, 60, 64])
+def test_three_warp_speculative_kernel(eng, qn, ob, n, option):
+    """Option tile_3w = 1 (qn_resident_tile3w.cuh): two helper warps own the tile, a third warp the
+    vectors, and pass 1 of the next update is swept speculatively while the first trial is still being
+    judged (discarded when another step is taken, B⁻¹ is reset or the solve ends).  Same bits as the
+    oracle: traces, counts, both line-search orders, the final B⁻¹, iteration caps, ragged batches."""
+    option("tile_tmem", 1)
+    option("tile_3w", 1)
+    R = qn.Rosenbrock()
+    for batch in (1, 3, 23):
+        Theta = starts(n, batch, key=8300 + n + batch)
+        for order in (2, 3):
+            got = eng.optimize_batched(R, Theta, ls=qn.BackTracking[order](), ntrace=5)
+            assert eng.last_launch()["block"] == 384
+            ref = ob.optimize_batch(ob.rosenbrock(), Theta, ls=ob.backtracking(order), ntrace=5)
+            _check(got, ref)
+    batch = 5
+    Theta = starts(n, batch, key=8400 + n)
+    sb = qn.BFGSStateBatch(n, batch)
+    eng.optimize_batched(R, Theta, states=sb, flags=qn._lib.FLAG_WRITE_H)
+    L = sb.L
+    for j in range(batch):
+        o = ob.optimize(ob.rosenbrock(), Theta[:, j], L=L)
+        assert np.array_equal(sb.data[j, 7 * L:].reshape(n, L)[:, :n], o["state"][7 * L:].reshape(n, L)[:, :n])
+        assert np.array_equal(sb.data[j, :n], o["x"]) and np.array_equal(sb.data[j, L:L + n], o["g"])
+    for cap in (1, 2, 5, 6):
+        Th = starts(n, 4, key=cap)
+        if cap == 5:
+            Th[3, 2] = np.nan
+        got = eng.optimize_batched(R, Th, max_iter=cap, ntrace=cap)
+        ref = ob.optimize_batch(ob.rosenbrock(), Th, max_iter=cap, ntrace=cap)
+        for k in ("x", "g", "trace", "ell"):
+            assert np.array_equal(got[k], ref[k], equal_nan=True), (n, cap, k)
+        for k in ("iters", "fevals", "status"):
+            assert np.array_equal(got[k], ref[k]), (n, cap, k)
