@@ -739,12 +739,20 @@ __device__ __forceinline__ void lh_bar_init(uint64_t* bar, const unsigned count)
 __device__ __forceinline__ void lh_arrive(uint64_t* bar) { // every lane of the warp: count 32, release
   asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];\n" :: "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
-__device__ __forceinline__ void lh_wait(uint64_t* bar, const unsigned parity) { // acquire
+// acquire.  The suspend-time hint lets the hardware park the waiting warp until the phase completes (or
+// the hint, in ns, runs out) instead of returning after its short default limit: without it a waiting
+// helper re-issued try_wait + branch ~60 times per wait — 38 % of the kernel's warp-stall samples sat on
+// these branches and 1.7e9 of its instructions were spin iterations (profiles/r2_tile60_hot_sass.txt),
+// issue slots taken from the leaders that share the scheduler.
+#ifndef QN_LH_SUSPEND_NS
+#define QN_LH_SUSPEND_NS 1000000
+#endif
+__device__ __forceinline__ void lh_wait(uint64_t* bar, const unsigned parity) {
   asm volatile(
       "{\n.reg .pred P1;\nLH_WAIT:\n"
-      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 P1, [%0], %1;\n"
+      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 P1, [%0], %1, %2;\n"
       "@P1 bra.uni LH_DONE;\nbra.uni LH_WAIT;\nLH_DONE:\n}\n"
-      :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+      :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity), "r"((uint32_t)QN_LH_SUSPEND_NS) : "memory");
 }
 
 // `ph`: this warp's parity bits of the four hand-shakes (bit k = barrier k), carried across problems.
