@@ -341,7 +341,7 @@ int stream_setup(qn_context* ctx, StreamWork& w, int n, const double* theta0, bo
   { const int prc = persist_setup(ctx, w); if (prc) return prc; }
   const size_t nv = ((size_t)n + 31) & ~(size_t)31;
   p.nvstride = (int)nv;
-  const size_t words = nv * 22 + 2 * (size_t)p.ngrp * n + 128 + 4 * (size_t)row_tiles; // + one counter per 128-row CTA tile
+  const size_t words = nv * 22 + 2 * (size_t)p.ngrp * n + 192 + 4 * (size_t)row_tiles; // + one counter per 128-row CTA tile
   cudaError_t e = cudaMalloc(&w.block, sizeof(double) * words);
   if (e != cudaSuccess)
     return qn_fail(QN_ERR_CUDA, "cudaMalloc failed for the streaming work space: %s", cudaGetErrorString(e));
@@ -354,13 +354,16 @@ int stream_setup(qn_context* ctx, StreamWork& w, int n, const double* theta0, bo
   p.ps = base + 13 * nv; p.pu = base + 14 * nv;
   p.tvec = base + 15 * nv; p.wvec = base + 16 * nv; // and their odd-iteration copies at 17, 18 (row-sharded mode)
   p.tmp2 = base + 19 * nv;
-  p.partial = base + 22 * nv;
-  p.partial2 = p.partial + (size_t)p.ngrp * n;
-  double* tail = p.partial2 + (size_t)p.ngrp * n;
+  // Everything a PEER addresses (the vectors, the flags) sits in front of the partial-sum arrays, whose
+  // size depends on this shard's own choice of sweep granularity (ngrp): the row-sharded mode computes
+  // peer addresses as peer_base + (address - base), so those offsets must be the same on every shard.
+  double* tail = base + 22 * nv;
   p.sc = reinterpret_cast<StreamScalars*>(tail);          // 32 doubles reserved
   p.flags = reinterpret_cast<unsigned int*>(tail + 32);   // 2·kMaxShards words
   p.tiles_done = reinterpret_cast<unsigned int*>(tail + 48);
-  p.tile_count = reinterpret_cast<unsigned int*>(tail + 64);
+  p.tile_count = reinterpret_cast<unsigned int*>(tail + 64); // 4 counters per 512-row tile (one per 128-row CTA tile)
+  p.partial = tail + 64 + (((size_t)4 * row_tiles + 63) & ~(size_t)63);
+  p.partial2 = p.partial + (size_t)p.ngrp * n;
   static_assert(sizeof(StreamScalars) <= 32 * sizeof(double), "scalars overflow their slot");
   // vec kernels stage their reductions in shared memory (n doubles; three arrays in one-pass mode)
   const size_t vec_smem = sizeof(double) * (onepass ? 3 : 1) * (((size_t)n + 1) & ~(size_t)1);
