@@ -65,6 +65,16 @@ unsigned long long* qn_next_counter(qn_context* ctx, cudaStream_t st) {
   return c;
 }
 
+// Number of column ranges a host-pointer entry pipelines a batch of `batch` problems in.
+int qn_host_ranges(const qn_context* ctx, int64_t batch, int ntrace) {
+  int r = ctx->opt.host_chunks;
+  if (r < 0) r = batch >= 16384 ? 8 : batch >= 4096 ? 4 : 1;
+  if (r < 1 || ntrace > 0 || ctx->opt.record_exit) r = 1;
+  if (r > qn_context::kRangeStreams) r = qn_context::kRangeStreams;
+  if ((int64_t)r > batch) r = (int)batch;
+  return r < 1 ? 1 : r;
+}
+
 namespace {
 
 // ---- kernel launchers ------------------------------------------------------
@@ -334,6 +344,8 @@ const OptKey kOptKeys[] = {
   {"p1_pad_kb", &qn_options::p1_pad_kb, "QN_P1_PAD_KB", 0},
   {"latency", &qn_options::latency, "QN_LATENCY", 0},
   {"record_exit", &qn_options::record_exit, "QN_RECORD_EXIT", 0},
+  {"lead_parity", &qn_options::lead_parity, "QN_LEAD_PARITY", 0},
+  {"host_chunks", &qn_options::host_chunks, "QN_HOST_CHUNKS", 0},
 };
 void options_from_env(qn_options& o) {
   for (const OptKey& k : kOptKeys) {
@@ -406,7 +418,9 @@ int32_t qn_create(qn_context** out, int32_t device) {
   ctx->device = device;
   options_from_env(ctx->opt); // the only place the environment is read
   cudaError_t err = cudaGetDeviceProperties(&ctx->prop, device);
-  if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < qn_context::kRangeStreams && err == cudaSuccess; ++i)
+    err = cudaStreamCreateWithFlags(&ctx->range_stream[i], cudaStreamNonBlocking);
+  ctx->stream = ctx->range_stream[0];
   if (err == cudaSuccess)
     err = cudaMalloc(&ctx->counter, sizeof(unsigned long long) * qn_context::kCounterSlots);
   if (err == cudaSuccess)
@@ -420,7 +434,7 @@ int32_t qn_create(qn_context** out, int32_t device) {
     int major = ctx->prop.major, minor = ctx->prop.minor;
     cudaFree(ctx->counter);
     cudaFree(ctx->exit_ns);
-    cudaStreamDestroy(ctx->stream);
+    for (cudaStream_t t : ctx->range_stream) cudaStreamDestroy(t);
     delete ctx;
     return fail(QN_ERR_NO_DEVICE, "device is sm_%d%d; libqn_cuda is built for sm_100a only", major,
                 minor);
@@ -432,12 +446,12 @@ int32_t qn_create(qn_context** out, int32_t device) {
 int32_t qn_destroy(qn_context* ctx) {
   if (!ctx) return QN_OK;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  for (cudaStream_t t : ctx->range_stream) cudaStreamSynchronize(t);
   if (ctx->stage) cudaFree(ctx->stage);
   if (ctx->hstage) cudaFreeHost(ctx->hstage);
   cudaFree(ctx->counter);
   cudaFree(ctx->exit_ns);
-  cudaStreamDestroy(ctx->stream);
+  for (cudaStream_t t : ctx->range_stream) cudaStreamDestroy(t);
   delete ctx;
   return QN_OK;
 }
@@ -712,71 +726,102 @@ int32_t qn_bfgs_optimize_batched_f64(qn_context* ctx, const qn_model* model, int
   // B⁻¹ is staged in the layout of the state blocks (column stride ld), so ONE strided copy returns it
   const size_t hblk = (size_t)n * ld;
   const size_t o_h = carve(want_h ? sizeof(double) * hblk * batch : 0);
-  // One lock from staging to the final synchronise: the staging buffer and the stream belong to the
+  // One lock from staging to the final synchronise: the staging buffer and the streams belong to the
   // context, so two host calls on one context run one after the other.
   std::lock_guard<std::mutex> lock(ctx->mu);
   rc = qn_ensure_stage(ctx, off);
   if (rc) return rc;
   char* base = (char*)ctx->stage;
-  cudaStream_t st = ctx->stream;
-  QN_CUDA_TRY(cudaMemcpyAsync(base + o_theta, theta0, sizeof(double) * nb, cudaMemcpyHostToDevice, st));
-  if (ntrace > 0) {
-    // rows past a problem's last iteration stay as the caller initialised them
-    QN_CUDA_TRY(cudaMemcpyAsync(base + o_tr, trace_out, sizeof(double) * nb * ntrace,
+
+  // A large batch is cut into column ranges, each on a stream of its own: the host->device copy of
+  // range k+1 and the device->host copy of range k-1 run under the kernel of range k, and the CTAs
+  // of kernel k+1 take the SM slots kernel k frees while its last problems finish.  Every problem
+  // is solved by the same kernel as in one launch (same bits).  All launches are enqueued before
+  // the first copy back, so a pageable destination (whose copy blocks the host) costs no overlap.
+  const int chunks = qn_host_ranges(ctx, batch, ntrace);
+  std::vector<qn::BatchParams> ps((size_t)chunks);
+  int launches = 0;
+  auto sync_all = [&] {
+    cudaError_t e = cudaSuccess;
+    for (int c = 0; c < chunks; ++c) {
+      cudaError_t ec = cudaStreamSynchronize(ctx->range_stream[c]);
+      if (e == cudaSuccess) e = ec;
+    }
+    return e;
+  };
+  for (int c = 0; c < chunks; ++c) {
+    const int64_t c0 = batch * c / chunks, cnt = batch * (c + 1) / chunks - c0;
+    const size_t e0 = (size_t)n * c0, ne = (size_t)n * cnt;
+    cudaStream_t st = ctx->range_stream[c];
+    QN_CUDA_TRY(cudaMemcpyAsync(base + o_theta + sizeof(double) * e0, theta0 + e0, sizeof(double) * ne,
                                 cudaMemcpyHostToDevice, st));
+    if (ntrace > 0) {
+      // rows past a problem's last iteration stay as the caller initialised them
+      QN_CUDA_TRY(cudaMemcpyAsync(base + o_tr, trace_out, sizeof(double) * nb * ntrace,
+                                  cudaMemcpyHostToDevice, st));
+    }
+    qn::BatchParams& p = ps[c];
+    p.n = n;
+    p.max_iter = max_iter;
+    p.batch = cnt;
+    p.theta0 = (const double*)(base + o_theta) + e0;
+    p.theta_stride = n;
+    p.tol = tol;
+    p.ls = qn::LsParams{ls->c1, ls->rho_hi, ls->rho_lo, (long long)ls->iterations, ls->order};
+    p.x_out = (double*)(base + o_x) + e0;
+    p.x_stride = n;
+    p.g_out = (double*)(base + o_g) + e0;
+    p.g_stride = n;
+    if (want_h) {
+      p.h_out = (double*)(base + o_h) + hblk * (size_t)c0;
+      p.h_stride = (long long)hblk;
+      p.ldh = ld;
+      if (ld > n) // the padding rows are never written by the kernels: give the copy defined bytes
+        QN_CUDA_TRY(cudaMemsetAsync(p.h_out, 0, sizeof(double) * hblk * cnt, st));
+    }
+    p.ell_out = (double*)(base + o_ell) + c0;
+    p.iters_out = (int*)(base + o_it) + c0;
+    p.fevals_out = (int*)(base + o_fe) + c0;
+    p.status_out = (int*)(base + o_st) + c0;
+    p.ntrace = ntrace;
+    p.trace = ntrace ? (double*)(base + o_tr) : nullptr;
+    rc = dispatch_model(ctx, model, p, ls, flags, st);
+    if (rc) {
+      sync_all();
+      return rc;
+    }
+    launches += ctx->last_launches;
   }
-
-  qn::BatchParams p{};
-  p.n = n;
-  p.max_iter = max_iter;
-  p.batch = batch;
-  p.theta0 = (const double*)(base + o_theta);
-  p.theta_stride = n;
-  p.tol = tol;
-  p.ls = qn::LsParams{ls->c1, ls->rho_hi, ls->rho_lo, (long long)ls->iterations, ls->order};
-  p.x_out = (double*)(base + o_x);
-  p.x_stride = n;
-  p.g_out = (double*)(base + o_g);
-  p.g_stride = n;
-  if (want_h) {
-    p.h_out = (double*)(base + o_h);
-    p.h_stride = (long long)hblk;
-    p.ldh = ld;
-    if (ld > n) // the padding rows are never written by the kernels: give the copy defined bytes
-      QN_CUDA_TRY(cudaMemsetAsync(base + o_h, 0, sizeof(double) * hblk * batch, st));
-  }
-  p.ell_out = (double*)(base + o_ell);
-  p.iters_out = (int*)(base + o_it);
-  p.fevals_out = (int*)(base + o_fe);
-  p.status_out = (int*)(base + o_st);
-  p.ntrace = ntrace;
-  p.trace = ntrace ? (double*)(base + o_tr) : nullptr;
-  rc = dispatch_model(ctx, model, p, ls, flags, st);
-  if (rc) return rc;
-
-  // results back to the caller's buffers
-  if (states) {
-    // θ* -> offset 0, ∇ -> offset ld of each block (QN.jl:135,138): strided 2-D copies
-    QN_CUDA_TRY(cudaMemcpy2DAsync(states, sizeof(double) * state_stride, base + o_x,
-                                  sizeof(double) * n, sizeof(double) * n, batch,
-                                  cudaMemcpyDeviceToHost, st));
-    QN_CUDA_TRY(cudaMemcpy2DAsync(states + ld, sizeof(double) * state_stride, base + o_g,
-                                  sizeof(double) * n, sizeof(double) * n, batch,
-                                  cudaMemcpyDeviceToHost, st));
-    if (want_h) // field 8 of every block (QN.jl:142), n·ld contiguous doubles per problem: one strided copy
-      QN_CUDA_TRY(cudaMemcpy2DAsync(states + 7 * (int64_t)ld, sizeof(double) * state_stride, base + o_h,
-                                    sizeof(double) * hblk, sizeof(double) * hblk, batch,
+  ctx->last_launches = launches;
+  // results back to the caller's buffers, range by range
+  for (int c = 0; c < chunks; ++c) {
+    const qn::BatchParams& p = ps[c];
+    const int64_t c0 = batch * c / chunks, cnt = p.batch;
+    const size_t e0 = (size_t)n * c0, ne = (size_t)n * cnt;
+    cudaStream_t st = ctx->range_stream[c];
+    if (states) {
+      double* sblk = states + state_stride * c0;
+      // θ* -> offset 0, ∇ -> offset ld of each block (QN.jl:135,138): strided 2-D copies
+      QN_CUDA_TRY(cudaMemcpy2DAsync(sblk, sizeof(double) * state_stride, p.x_out, sizeof(double) * n,
+                                    sizeof(double) * n, cnt, cudaMemcpyDeviceToHost, st));
+      QN_CUDA_TRY(cudaMemcpy2DAsync(sblk + ld, sizeof(double) * state_stride, p.g_out,
+                                    sizeof(double) * n, sizeof(double) * n, cnt,
                                     cudaMemcpyDeviceToHost, st));
+      if (want_h) // field 8 of every block (QN.jl:142), n·ld contiguous doubles per problem: one strided copy
+        QN_CUDA_TRY(cudaMemcpy2DAsync(sblk + 7 * (int64_t)ld, sizeof(double) * state_stride, p.h_out,
+                                      sizeof(double) * hblk, sizeof(double) * hblk, cnt,
+                                      cudaMemcpyDeviceToHost, st));
+    }
+    if (x_out) QN_CUDA_TRY(cudaMemcpyAsync(x_out + e0, p.x_out, sizeof(double) * ne, cudaMemcpyDeviceToHost, st));
+    if (g_out) QN_CUDA_TRY(cudaMemcpyAsync(g_out + e0, p.g_out, sizeof(double) * ne, cudaMemcpyDeviceToHost, st));
+    if (ell_out) QN_CUDA_TRY(cudaMemcpyAsync(ell_out + c0, p.ell_out, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+    if (iters_out) QN_CUDA_TRY(cudaMemcpyAsync(iters_out + c0, p.iters_out, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, st));
+    if (fevals_out) QN_CUDA_TRY(cudaMemcpyAsync(fevals_out + c0, p.fevals_out, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, st));
+    if (status_out) QN_CUDA_TRY(cudaMemcpyAsync(status_out + c0, p.status_out, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, st));
+    if (ntrace > 0)
+      QN_CUDA_TRY(cudaMemcpyAsync(trace_out, base + o_tr, sizeof(double) * nb * ntrace, cudaMemcpyDeviceToHost, st));
   }
-  if (x_out) QN_CUDA_TRY(cudaMemcpyAsync(x_out, base + o_x, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
-  if (g_out) QN_CUDA_TRY(cudaMemcpyAsync(g_out, base + o_g, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
-  if (ell_out) QN_CUDA_TRY(cudaMemcpyAsync(ell_out, base + o_ell, sizeof(double) * batch, cudaMemcpyDeviceToHost, st));
-  if (iters_out) QN_CUDA_TRY(cudaMemcpyAsync(iters_out, base + o_it, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, st));
-  if (fevals_out) QN_CUDA_TRY(cudaMemcpyAsync(fevals_out, base + o_fe, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, st));
-  if (status_out) QN_CUDA_TRY(cudaMemcpyAsync(status_out, base + o_st, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, st));
-  if (ntrace > 0)
-    QN_CUDA_TRY(cudaMemcpyAsync(trace_out, base + o_tr, sizeof(double) * nb * ntrace, cudaMemcpyDeviceToHost, st));
-  QN_CUDA_TRY(cudaStreamSynchronize(st));
+  QN_CUDA_TRY(sync_all());
   return QN_OK;
 }
 

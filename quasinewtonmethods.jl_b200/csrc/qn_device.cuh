@@ -49,7 +49,7 @@ struct BatchParams {
   // stamp at which problem slot `slot` found the work queue empty — the tail of a launch made visible
   unsigned long long* exit_ns;
   int exit_cap;
-  int sm_count; // SMs of the device (tile kernels: which warp of a pair leads alternates per residency slot)
+  int lead_div;  // tile kernels: warp (blockIdx / lead_div) & 1 of a pair leads; 0 = the same warp in every CTA
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {

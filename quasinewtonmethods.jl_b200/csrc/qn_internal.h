@@ -38,13 +38,17 @@ struct qn_options {
   int hint_p1_ld = 0, hint_p2_ld = 2, hint_p2_st = 1, hint_one_ld = 4; // cache hints, QN_HINT_*
   int p1_pad_kb = 0;      // "p1_pad_kb"                                                            (QN_P1_PAD_KB)
   int latency = -1;       // "latency":     -1 auto, 0/1 the single-problem latency kernel          (QN_LATENCY)
+  int host_chunks = -1;   // "host_chunks": host-pointer entry: column ranges pipelined over two streams, -1 auto (QN_HOST_CHUNKS)
+  int lead_parity = 0;    // "lead_parity": tile kernels, which warp of a pair leads: 0 the same in every CTA, d > 0 warp (blockIdx / d) & 1, -1 d = #SM (QN_LEAD_PARITY)
   int record_exit = 0;    // "record_exit": tile kernels stamp %globaltimer when a problem slot runs dry
 };
 
 struct qn_context {
   int device = 0;
   qn_options opt;
-  cudaStream_t stream = nullptr;
+  static constexpr int kRangeStreams = 8;
+  cudaStream_t range_stream[kRangeStreams] = {}; // one per pipelined column range of a host-pointer entry
+  cudaStream_t stream = nullptr;                 // = range_stream[0]: the context's stream
   cudaDeviceProp prop{};
   unsigned long long* counter = nullptr; // ring of work-queue counters
   int counter_slot = 0;
@@ -83,6 +87,8 @@ int qn_optimize_device_locked(qn_context* ctx, const qn_model* model, int32_t n,
                               int32_t ld, double* x_out, double* g_out, double* ell_out,
                               int32_t* iters_out, int32_t* fevals_out, int32_t* status_out,
                               int32_t ntrace, double* trace_out, uint32_t flags, cudaStream_t st);
+// how many column ranges a host-pointer entry pipelines `batch` problems in (option "host_chunks")
+int qn_host_ranges(const qn_context* ctx, int64_t batch, int ntrace);
 // next zeroed work-queue counter, zeroing enqueued on `st`
 unsigned long long* qn_next_counter(qn_context* ctx, cudaStream_t st);
 

@@ -25,6 +25,12 @@ int tmem_residency(const qn_context* ctx, K kern, int block, size_t dyn_smem, in
   return std::max(1, std::min(std::min(by_regs, by_smem), std::min(by_tmem, by_threads)));
 }
 
+// option "lead_parity" -> BatchParams::lead_div (which warp of a leader/helper pair leads)
+inline int lead_divisor(const qn_context* ctx) {
+  const int v = ctx->opt.lead_parity;
+  return v > 0 ? v : (v < 0 ? ctx->prop.multiProcessorCount : 0);
+}
+
 // option "record_exit": arm the exit stamps for a launch with `slots` problem slots
 void arm_exit_stamps(qn_context* ctx, qn::BatchParams& p, long long slots, cudaStream_t st) {
   p.exit_ns = nullptr;

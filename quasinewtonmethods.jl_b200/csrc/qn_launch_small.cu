@@ -28,7 +28,7 @@ int launch_tilew(qn_context* ctx, qn::BatchParams& p, cudaStream_t st, const typ
   long long grid = (long long)ctas * ctx->prop.multiProcessorCount;
   if (grid > p.batch) grid = p.batch;
   p.counter = qn_next_counter(ctx, st);
-  p.sm_count = ctx->prop.multiProcessorCount;
+  p.lead_div = lead_divisor(ctx);
   arm_exit_stamps(ctx, p, grid, st);
   kern<<<(unsigned)grid, C::THREADS, smem, st>>>(p, op);
   QN_CUDA_TRY(cudaGetLastError());

@@ -15,9 +15,9 @@ namespace {
 // that form (qn_resident_tile.cuh).
 template <int N, int MINB, int PF>
 int launch_tile(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
-  const size_t smem = sizeof(double) * (size_t)qn::tile_problem_smem_doubles<N>();
+  const size_t smem = sizeof(double) * (size_t)qn::tile_problem_smem_doubles<N, false>();
   auto kern = qn::qn_resident_tile_kernel<N, MINB, PF>;
-  p.sm_count = ctx->prop.multiProcessorCount;
+  p.lead_div = lead_divisor(ctx);
   int occ = 0;
   QN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 64, smem));
   if (occ < 1) return fail(QN_ERR_UNSUPPORTED_SIZE, "tile kernel does not fit on an SM (n=%d)", N);
@@ -43,9 +43,9 @@ int launch_tile(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
 // throughput grows 1.6e8 → 2.5e8 → 3.0e8 → 3.7e8 iterations/s from 1 to 4 CTAs per SM (n = 60).
 template <int N, int PF>
 int launch_tile_tmem(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
-  const size_t smem = 2 * sizeof(double) * (size_t)qn::tile_problem_smem_doubles<N>();
+  const size_t smem = 2 * sizeof(double) * (size_t)qn::tile_problem_smem_doubles<N, true>();
   auto kern = qn::qn_resident_tile_tmem_kernel<N, PF>;
-  p.sm_count = ctx->prop.multiProcessorCount;
+  p.lead_div = lead_divisor(ctx);
   QN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   long long grid = (long long)tmem_residency(ctx, kern, 128, smem, 128) * ctx->prop.multiProcessorCount; // 4 per SM on B200
   if (grid > (p.batch + 1) / 2) grid = (p.batch + 1) / 2;
@@ -72,7 +72,7 @@ int launch_tile3w(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
   const long long need = (p.batch + qn::k3wProblems - 1) / qn::k3wProblems;
   if (grid > need) grid = need;
   p.counter = qn_next_counter(ctx, st);
-  p.sm_count = ctx->prop.multiProcessorCount;
+  p.lead_div = lead_divisor(ctx);
   arm_exit_stamps(ctx, p, qn::k3wProblems * grid, st);
   kern<<<(unsigned)grid, qn::k3wThreads, smem, st>>>(p);
   QN_CUDA_TRY(cudaGetLastError());
@@ -84,15 +84,15 @@ int launch_tile3w(qn_context* ctx, qn::BatchParams& p, cudaStream_t st) {
   return QN_OK;
 }
 
-// Where the tile lives: tensor memory when it is the faster home (measured per size on B200,
-// 2^15-2^16 problems: n = 44 +1 %, 48 +6 %, 50 +8 %, 56 +1 %, 60 +3 %, 64 +8 %; n = 36, 40, 52 are
-// 1-3 % faster from registers) and the batch fills 8 problems per SM; option "tile_tmem" = 0 / 1 forces
-// the register file / tensor memory.
+// Where the tile lives: tensor memory (leader/helper pairs, 8 problems per SM) once the batch gives
+// every SM its 8 problems — measured on B200 at 2^15 problems it is 19-27 % faster than the
+// all-register kernel at every n of the tile range (profiles/r2_lead_parity_sizes.txt); smaller
+// batches stay in the register file.  Option "tile_tmem" = 0 / 1 forces either.
 inline bool tile_in_tensor_memory(const qn_context* ctx, const int n, const long long batch) {
+  (void)n;
   if (ctx->opt.tile_tmem == 0) return false;
   if (ctx->opt.tile_tmem == 1) return true;
-  const bool faster = n == 44 || n == 48 || n == 50 || n == 56 || n == 60 || n == 64;
-  return faster && batch >= 8LL * ctx->prop.multiProcessorCount;
+  return batch >= 8LL * ctx->prop.multiProcessorCount;
 }
 
 }  // namespace

@@ -4,7 +4,8 @@
 // work queue, and the host gathers the results: θ* and ∇ with one strided copy per device (rows
 // of n doubles), the per-problem scalars with ONE contiguous copy per device into pinned host
 // staging followed by a host de-interleave (a strided copy of 4- or 8-byte rows would be one DMA
-// descriptor per problem).  Every context's mutex is held from staging to the last synchronise.
+// descriptor per problem).  A device's share is pipelined in ranges over the context's streams
+// (option "host_chunks").  Every context's mutex is held from staging to the last synchronise.
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -31,80 +32,116 @@ extern "C" int32_t qn_bfgs_optimize_batched_multi_f64(
   std::vector<std::unique_lock<std::mutex>> locks;
   locks.reserve(G);
   for (int g = 0; g < G; ++g) locks.emplace_back(ctxs[g]->mu);
+  // Every device's share is cut into ranges (option "host_chunks"), each on a stream of its own, so
+  // the copies of one range run under the kernels of the others and the kernel of range k+1 fills
+  // the SM slots range k frees while its last problems finish.
+  struct Range {
+    int64_t i0 = 0, count = 0; // local problems [i0, i0+count) of the device
+    size_t o_theta, o_x, o_g, o_ell, o_it, o_fe, o_st, o_h, scalar_bytes;
+  };
   struct Shard {
     int64_t count = 0;
+    int ranges = 0;
     char* base = nullptr;
-    char* hbase = nullptr; // pinned host staging: ell | iters | fevals | status, contiguous
-    size_t o_theta, o_x, o_g, o_ell, o_it, o_fe, o_st, scalar_bytes;
+    char* hbase = nullptr; // pinned host staging: per range ell | iters | fevals | status, contiguous
+    Range r[qn_context::kRangeStreams];
   };
   std::vector<Shard> sh(G);
-  // phase 1: scatter (interleaved columns) and launch on every device, no waiting
+  int max_ranges = 0;
   for (int g = 0; g < G; ++g) {
     qn_context* ctx = ctxs[g];
     Shard& s = sh[g];
     s.count = (batch - g + G - 1) / G;
     if (s.count <= 0) continue;
+    s.ranges = qn_host_ranges(ctx, s.count, 0);
+    if (s.ranges > max_ranges) max_ranges = s.ranges;
     QN_CUDA_TRY(cudaSetDevice(ctx->device));
-    size_t off = 0;
+    size_t off = 0, hoff = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    const size_t nb = sizeof(double) * (size_t)n * s.count;
-    s.o_theta = carve(nb); s.o_x = carve(nb); s.o_g = carve(nb);
-    // the four scalar arrays sit back to back (8-byte aligned), so one copy brings them all home
-    s.o_ell = carve(0);
-    s.o_it = s.o_ell + sizeof(double) * s.count;
-    s.o_fe = s.o_it + sizeof(int32_t) * ((s.count + 1) & ~(int64_t)1);
-    s.o_st = s.o_fe + sizeof(int32_t) * ((s.count + 1) & ~(int64_t)1);
-    s.scalar_bytes = s.o_st + sizeof(int32_t) * s.count - s.o_ell;
-    off = s.o_ell + s.scalar_bytes;
+    for (int c = 0; c < s.ranges; ++c) {
+      Range& r = s.r[c];
+      r.i0 = s.count * c / s.ranges;
+      r.count = s.count * (c + 1) / s.ranges - r.i0;
+      const size_t nb = sizeof(double) * (size_t)n * r.count;
+      r.o_theta = carve(nb); r.o_x = carve(nb); r.o_g = carve(nb);
+      // the four scalar arrays sit back to back (8-byte aligned), so one copy brings them all home
+      r.o_ell = carve(0);
+      r.o_it = r.o_ell + sizeof(double) * r.count;
+      r.o_fe = r.o_it + sizeof(int32_t) * ((r.count + 1) & ~(int64_t)1);
+      r.o_st = r.o_fe + sizeof(int32_t) * ((r.count + 1) & ~(int64_t)1);
+      r.scalar_bytes = r.o_st + sizeof(int32_t) * ((r.count + 1) & ~(int64_t)1) - r.o_ell;
+      off = r.o_ell + r.scalar_bytes;
+      carve(0);
+      r.o_h = hoff;
+      hoff += r.scalar_bytes;
+    }
     int rc = qn_ensure_stage(ctx, off);
     if (rc) return rc;
-    rc = qn_ensure_hstage(ctx, s.scalar_bytes);
+    rc = qn_ensure_hstage(ctx, hoff);
     if (rc) return rc;
     s.base = (char*)ctx->stage;
     s.hbase = (char*)ctx->hstage;
-    // columns g, g+G, g+2G, ... of theta0: pitch G*n doubles, width n doubles
-    QN_CUDA_TRY(cudaMemcpy2DAsync(s.base + s.o_theta, sizeof(double) * n, theta0 + (size_t)g * n,
-                                  sizeof(double) * n * G, sizeof(double) * n, s.count,
-                                  cudaMemcpyHostToDevice, ctx->stream));
-    rc = qn_optimize_device_locked(
-        ctx, models[g], n, s.count, (const double*)(s.base + s.o_theta), n, ls, tol, max_iter,
-        nullptr, 0, 0, (double*)(s.base + s.o_x), (double*)(s.base + s.o_g),
-        (double*)(s.base + s.o_ell), (int32_t*)(s.base + s.o_it), (int32_t*)(s.base + s.o_fe),
-        (int32_t*)(s.base + s.o_st), 0, nullptr, flags, ctx->stream);
-    if (rc) return rc;
   }
+  // phase 1: scatter (interleaved columns) and launch, range by range on every device, no waiting
+  for (int c = 0; c < max_ranges; ++c)
+    for (int g = 0; g < G; ++g) {
+      qn_context* ctx = ctxs[g];
+      Shard& s = sh[g];
+      if (c >= s.ranges) continue;
+      const Range& r = s.r[c];
+      QN_CUDA_TRY(cudaSetDevice(ctx->device));
+      cudaStream_t st = ctx->range_stream[c];
+      // columns g + (i0+i)·G of theta0: pitch G*n doubles, width n doubles
+      QN_CUDA_TRY(cudaMemcpy2DAsync(s.base + r.o_theta, sizeof(double) * n,
+                                    theta0 + ((size_t)g + (size_t)r.i0 * G) * n, sizeof(double) * n * G,
+                                    sizeof(double) * n, r.count, cudaMemcpyHostToDevice, st));
+      int rc = qn_optimize_device_locked(
+          ctx, models[g], n, r.count, (const double*)(s.base + r.o_theta), n, ls, tol, max_iter,
+          nullptr, 0, 0, (double*)(s.base + r.o_x), (double*)(s.base + r.o_g),
+          (double*)(s.base + r.o_ell), (int32_t*)(s.base + r.o_it), (int32_t*)(s.base + r.o_fe),
+          (int32_t*)(s.base + r.o_st), 0, nullptr, flags, st);
+      if (rc) return rc;
+    }
   // phase 2: gather
-  for (int g = 0; g < G; ++g) {
-    qn_context* ctx = ctxs[g];
-    Shard& s = sh[g];
-    if (s.count <= 0) continue;
-    QN_CUDA_TRY(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    if (x_out)
-      QN_CUDA_TRY(cudaMemcpy2DAsync(x_out + (size_t)g * n, sizeof(double) * n * G, s.base + s.o_x,
-                                    sizeof(double) * n, sizeof(double) * n, s.count,
+  for (int c = 0; c < max_ranges; ++c)
+    for (int g = 0; g < G; ++g) {
+      qn_context* ctx = ctxs[g];
+      Shard& s = sh[g];
+      if (c >= s.ranges) continue;
+      const Range& r = s.r[c];
+      QN_CUDA_TRY(cudaSetDevice(ctx->device));
+      cudaStream_t st = ctx->range_stream[c];
+      const size_t col = ((size_t)g + (size_t)r.i0 * G) * n;
+      if (x_out)
+        QN_CUDA_TRY(cudaMemcpy2DAsync(x_out + col, sizeof(double) * n * G, s.base + r.o_x,
+                                      sizeof(double) * n, sizeof(double) * n, r.count,
+                                      cudaMemcpyDeviceToHost, st));
+      if (g_out)
+        QN_CUDA_TRY(cudaMemcpy2DAsync(g_out + col, sizeof(double) * n * G, s.base + r.o_g,
+                                      sizeof(double) * n, sizeof(double) * n, r.count,
+                                      cudaMemcpyDeviceToHost, st));
+      if (ell_out || iters_out || fevals_out || status_out)
+        QN_CUDA_TRY(cudaMemcpyAsync(s.hbase + r.o_h, s.base + r.o_ell, r.scalar_bytes,
                                     cudaMemcpyDeviceToHost, st));
-    if (g_out)
-      QN_CUDA_TRY(cudaMemcpy2DAsync(g_out + (size_t)g * n, sizeof(double) * n * G, s.base + s.o_g,
-                                    sizeof(double) * n, sizeof(double) * n, s.count,
-                                    cudaMemcpyDeviceToHost, st));
-    if (ell_out || iters_out || fevals_out || status_out)
-      QN_CUDA_TRY(cudaMemcpyAsync(s.hbase, s.base + s.o_ell, s.scalar_bytes, cudaMemcpyDeviceToHost, st));
-  }
-  for (int g = 0; g < G; ++g) {
-    Shard& s = sh[g];
-    if (s.count <= 0) continue;
-    QN_CUDA_TRY(cudaSetDevice(ctxs[g]->device));
-    QN_CUDA_TRY(cudaStreamSynchronize(ctxs[g]->stream));
-    // de-interleave this device's scalars: its problem i is problem g + i·G of the batch
-    const double* h_ell = (const double*)s.hbase;
-    const int32_t* h_it = (const int32_t*)(s.hbase + (s.o_it - s.o_ell));
-    const int32_t* h_fe = (const int32_t*)(s.hbase + (s.o_fe - s.o_ell));
-    const int32_t* h_st = (const int32_t*)(s.hbase + (s.o_st - s.o_ell));
-    if (ell_out) for (int64_t i = 0; i < s.count; ++i) ell_out[g + i * G] = h_ell[i];
-    if (iters_out) for (int64_t i = 0; i < s.count; ++i) iters_out[g + i * G] = h_it[i];
-    if (fevals_out) for (int64_t i = 0; i < s.count; ++i) fevals_out[g + i * G] = h_fe[i];
-    if (status_out) for (int64_t i = 0; i < s.count; ++i) status_out[g + i * G] = h_st[i];
-  }
+    }
+  for (int c = 0; c < max_ranges; ++c)
+    for (int g = 0; g < G; ++g) {
+      Shard& s = sh[g];
+      if (c >= s.ranges) continue;
+      const Range& r = s.r[c];
+      QN_CUDA_TRY(cudaSetDevice(ctxs[g]->device));
+      QN_CUDA_TRY(cudaStreamSynchronize(ctxs[g]->range_stream[c]));
+      // de-interleave this range's scalars: local problem i0+i is problem g + (i0+i)·G of the batch
+      const char* hb = s.hbase + r.o_h;
+      const double* h_ell = (const double*)hb;
+      const int32_t* h_it = (const int32_t*)(hb + (r.o_it - r.o_ell));
+      const int32_t* h_fe = (const int32_t*)(hb + (r.o_fe - r.o_ell));
+      const int32_t* h_st = (const int32_t*)(hb + (r.o_st - r.o_ell));
+      const int64_t j0 = g + r.i0 * G;
+      if (ell_out) for (int64_t i = 0; i < r.count; ++i) ell_out[j0 + i * G] = h_ell[i];
+      if (iters_out) for (int64_t i = 0; i < r.count; ++i) iters_out[j0 + i * G] = h_it[i];
+      if (fevals_out) for (int64_t i = 0; i < r.count; ++i) fevals_out[j0 + i * G] = h_fe[i];
+      if (status_out) for (int64_t i = 0; i < r.count; ++i) status_out[j0 + i * G] = h_st[i];
+    }
   return QN_OK;
 }

@@ -696,10 +696,17 @@ __device__ __forceinline__ void tile_solve_one(const BatchParams& p, const long 
 //   OPS2  leader -> helper   c₁s, -u (column records) and -u by row are published
 //   P2    helper -> leader   the helper's pass-2 partials are in shared memory
 // Exactly one command per iteration and the leader waits for P2 before the next one, so a hand-shake
-// never overtakes the previous one.  Which warp of a pair leads alternates with the CTA's residency
-// slot, so that every scheduler of the SM hosts two leaders and two helpers.
+// never overtakes the previous one.  The SAME warp of every pair leads (BatchParams::lead_div):
+// leaders and helpers then sit on different schedulers of the SM, and a helper's idle polling
+// never takes an issue slot from a leader's dependent chain.
+// QN_TILE_LH: the tensor-memory kernel (65.9 ms per 2^16 n = 60 problems with, 71.3 without).
+// QN_TILE_LH_REG: the all-register kernel, which is faster WITHOUT the split (80.3 ms against 87.9;
+// profiles/r2_lead_variants.txt): its six resident problems already fill the schedulers.
 #ifndef QN_TILE_LH
 #define QN_TILE_LH 1
+#endif
+#ifndef QN_TILE_LH_REG
+#define QN_TILE_LH_REG 0
 #endif
 #ifndef QN_LH_HOIST
 #define QN_LH_HOIST 1
@@ -727,9 +734,9 @@ struct TileLhCfg {
 template <int N>
 __host__ __device__ constexpr int tile_lh_smem_doubles() { return TileLhCfg<N>::oEnd + 2; }
 // shared memory (doubles) of one problem in the tile kernels as they are built
-template <int N>
+template <int N, bool TM>
 __host__ __device__ constexpr int tile_problem_smem_doubles() {
-  return QN_TILE_LH ? tile_lh_smem_doubles<N>() : tile_smem_doubles<N>();
+  return (TM ? QN_TILE_LH : QN_TILE_LH_REG) ? tile_lh_smem_doubles<N>() : tile_smem_doubles<N>();
 }
 
 constexpr int kLhPass = 1, kLhExit = 2, kLhReset = 4;
@@ -1215,13 +1222,13 @@ template <int N, int MINB, int PF>
 __global__ void __launch_bounds__(64) __maxnreg__(MINB >= 7 ? 144 : (MINB == 6 ? 168 : (MINB == 5 ? 200 : 255)))
 qn_resident_tile_kernel(const __grid_constant__ BatchParams p) {
   extern __shared__ __align__(16) double smem[];
-#if QN_TILE_LH
+#if QN_TILE_LH_REG
   volatile long long* next = reinterpret_cast<volatile long long*>(smem + tile_lh_smem_doubles<N>() - 2);
   if (threadIdx.x == 0) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TileLhCfg<N>::oBar);
     for (int k = 0; k < 4; ++k) lh_bar_init(bars + k, 32);
   }
-  const bool leader = (int)(threadIdx.x >> 5) == (int)((blockIdx.x / (p.sm_count > 0 ? p.sm_count : 148)) & 1);
+  const bool leader = (threadIdx.x >> 5) == (p.lead_div > 0 ? (blockIdx.x / (unsigned)p.lead_div) & 1u : 0u);
   unsigned ph = 0;
 #else
   volatile long long* next = reinterpret_cast<volatile long long*>(smem + tile_smem_doubles<N>() - 2);
@@ -1233,7 +1240,7 @@ qn_resident_tile_kernel(const __grid_constant__ BatchParams p) {
     __syncthreads();
     const long long j = *next;
     if (j >= p.batch) break;
-#if QN_TILE_LH
+#if QN_TILE_LH_REG
     tile_solve_lh<N, PF, false>(p, j, smem, 0u, leader, ph);
 #else
     tile_solve_one<N, PF>(p, j, smem);
@@ -1261,8 +1268,11 @@ qn_resident_tile_tmem_kernel(const __grid_constant__ BatchParams p) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + TileLhCfg<N>::oBar);
     for (int k = 0; k < 4; ++k) lh_bar_init(bars + k, 32);
   }
-  // which warp of a pair leads alternates with the CTA's residency slot (CTA b, b + #SM, ... share an SM)
-  const bool leader = (int)((threadIdx.x >> 5) & 1) == (int)((blockIdx.x / (p.sm_count > 0 ? p.sm_count : 148)) & 1);
+  // Which warp of a pair leads.  The same one in every CTA (lead_div = 0) is the fastest: the
+  // helpers' idle polling then shares its two scheduler partitions with other helpers only, not
+  // with a leader's dependent chain (n = 60: 69.0 ms alternating per residency slot, 66.2 ms
+  // alternating per CTA, 65.3 ms the same everywhere; profiles/r2_lead_parity.txt).
+  const bool leader = ((threadIdx.x >> 5) & 1u) == (p.lead_div > 0 ? (blockIdx.x / (unsigned)p.lead_div) & 1u : 0u);
   unsigned ph = 0;
 #endif
   if (threadIdx.x < 32) {

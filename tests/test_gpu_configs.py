@@ -180,3 +180,58 @@ def test_config2_full_batch_host_and_multi_entry(eng, qn, ob):
         assert np.array_equal(multi[k], got[k], equal_nan=True), k
     for e in engines[1:]:
         e.close()
+
+
+# ------------------------------------------------------------------ host entries: pipelined column ranges
+@pytest.mark.parametrize("n,batch", [(8, 5000), (60, 4099), (24, 16411)])
+def test_host_entry_ranges_same_bits(eng, qn, option, n, batch):
+    """Option "host_chunks": the host-pointer entry cuts a batch into column ranges pipelined over
+    the context's streams (copies under kernels, the next kernel filling the tail of the previous).
+    One range, the automatic choice and odd range counts return the same bytes, BFGSState blocks and
+    B⁻¹ (QN.jl:135-142) included."""
+    Theta = starts(n, batch)
+    ref_states = qn.BFGSStateBatch(n, batch)
+    ref_states.data[...] = 0.0  # the fields the solve does not return keep the caller's bytes
+    option("host_chunks", 1)
+    ref = eng.optimize_batched(qn.Rosenbrock(), Theta, states=ref_states, flags=qn._lib.FLAG_WRITE_H)
+    assert eng.last_launch()["kernel_launches"] == 1
+    for chunks in (-1, 3, 8):
+        option("host_chunks", chunks)
+        st = qn.BFGSStateBatch(n, batch)
+        st.data[...] = 0.0
+        got = eng.optimize_batched(qn.Rosenbrock(), Theta, states=st, flags=qn._lib.FLAG_WRITE_H)
+        want = {(-1): 8 if batch >= 16384 else 4}.get(chunks, chunks)
+        assert eng.last_launch()["kernel_launches"] == want
+        for k in ("x", "g", "ell", "iters", "fevals", "status"):
+            assert np.array_equal(got[k], ref[k], equal_nan=True), (chunks, k)
+        assert np.array_equal(st.data, ref_states.data, equal_nan=True), chunks
+    # a recorded trace keeps the batch in one launch
+    option("host_chunks", 8)
+    tr = eng.optimize_batched(qn.Rosenbrock(), Theta[:, :4200], ntrace=3)
+    assert eng.last_launch()["kernel_launches"] == 1
+    one = eng.optimize_batched(qn.Rosenbrock(), Theta[:, :4200])
+    assert np.array_equal(tr["x"], one["x"])
+
+
+def test_multi_entry_ranges_same_bits(eng, qn, option):
+    """The multi-GPU entry pipelines every device's share the same way; ragged shares and range
+    counts that do not divide them give the bytes of the one-range call."""
+    n, batch = 60, 9001
+    Theta = starts(n, batch)
+    G = qn._lib.load().qn_device_count()
+    engines = [eng] + [qn.Engine(d) for d in range(1, G)]
+    try:
+        for e in engines:
+            e.set_option("host_chunks", 1)
+        ref = qn.optimize_batched_multi(engines, qn.Rosenbrock(), Theta)
+        for chunks in (-1, 3, 8):
+            for e in engines:
+                e.set_option("host_chunks", chunks)
+            got = qn.optimize_batched_multi(engines, qn.Rosenbrock(), Theta)
+            for k in ("x", "g", "ell", "iters", "fevals", "status"):
+                assert np.array_equal(got[k], ref[k], equal_nan=True), (chunks, k)
+        assert (ref["status"] == qn.CONVERGED).all()
+    finally:
+        eng.set_option("host_chunks", -1)
+        for e in engines[1:]:
+            e.close()

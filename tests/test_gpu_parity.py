@@ -418,3 +418,23 @@ def test_three_warp_speculative_kernel(eng, qn, ob, n, option):
             assert np.array_equal(got[k], ref[k], equal_nan=True), (n, cap, k)
         for k in ("iters", "fevals", "status"):
             assert np.array_equal(got[k], ref[k]), (n, cap, k)
+
+
+@pytest.mark.parametrize("n", [36, 52, 60])
+def test_leader_placement_is_not_numerics(eng, qn, ob, n, option):
+    """Option lead_parity picks WHICH warp of a leader/helper pair leads (0: the same in every CTA,
+    the default; -1 / d: alternating with blockIdx) — scheduling only: the bits equal the oracle's for
+    every placement, in tensor memory and in the all-register kernel (which runs without the split)."""
+    Theta = starts(n, 1500, key=8600 + n)
+    idx = np.arange(0, 1500, 47)
+    ref = ob.optimize_batch(ob.rosenbrock(), Theta[:, idx])
+    for tm in (1, 0):
+        option("tile_tmem", tm)
+        for parity in (0, -1, 1, 3):
+            option("lead_parity", parity)
+            got = eng.optimize_batched(qn.Rosenbrock(), Theta)
+            assert eng.last_launch()["block"] == (128 if tm else 64)
+            for k in ("x", "g", "ell"):
+                assert np.array_equal(got[k][..., idx], ref[k]), (tm, parity, k)
+            for k in ("iters", "fevals", "status"):
+                assert np.array_equal(got[k][idx], ref[k]), (tm, parity, k)

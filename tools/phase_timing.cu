@@ -22,13 +22,13 @@ int main(int argc, char** argv) {
   qn::BatchParams p{};
   p.n = n; p.max_iter = 10000; p.batch = nprob; p.theta0 = d_th; p.theta_stride = n; p.tol = 1e-8;
   p.ls = qn::LsParams{1e-4, 0.5, 0.1, 1000, 2};
-  p.x_out = d_x; p.x_stride = n; p.iters_out = d_it; p.counter = d_cnt; p.sm_count = 148;
+  p.x_out = d_x; p.x_stride = n; p.iters_out = d_it; p.counter = d_cnt; p.lead_div = 0;
 #ifdef PT_TMEM // the tensor-memory kernel: CTAs of 128 threads = two problems (build with -DPT_TMEM)
-  const size_t smem = 2 * sizeof(double) * qn::tile_problem_smem_doubles<60>();
+  const size_t smem = 2 * sizeof(double) * qn::tile_problem_smem_doubles<60, true>();
   cudaFuncSetAttribute(qn::qn_resident_tile_tmem_kernel<60, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   qn::qn_resident_tile_tmem_kernel<60, 1><<<(nprob + 1) / 2, 128, smem>>>(p);
 #else
-  const size_t smem = sizeof(double) * qn::tile_problem_smem_doubles<60>();
+  const size_t smem = sizeof(double) * qn::tile_problem_smem_doubles<60, false>();
   qn::qn_resident_tile_kernel<60, 6, 1><<<nprob, 64, smem>>>(p);
 #endif
   cudaError_t e = cudaDeviceSynchronize();

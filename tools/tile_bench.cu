@@ -57,11 +57,11 @@ int main(int argc, char** argv) {
   p.x_out = d_x; p.x_stride = n; p.g_out = d_g; p.g_stride = n; p.ell_out = d_ell;
   p.iters_out = d_it; p.fevals_out = d_fe; p.status_out = d_st; p.counter = d_cnt;
 #ifdef TB_TMEM // the tensor-memory variant: two problems per CTA of 128 threads
-  const size_t smem = 2 * sizeof(double) * qn::tile_problem_smem_doubles<n>();
+  const size_t smem = 2 * sizeof(double) * qn::tile_problem_smem_doubles<n, true>();
   auto kern = qn::qn_resident_tile_tmem_kernel<n, TB_PF>;
   const int block = 128;
 #else
-  const size_t smem = sizeof(double) * qn::tile_problem_smem_doubles<n>();
+  const size_t smem = sizeof(double) * qn::tile_problem_smem_doubles<n, false>();
   auto kern = qn::qn_resident_tile_kernel<n, TB_MINB, TB_PF>;
   const int block = 64;
 #endif
@@ -69,7 +69,8 @@ int main(int argc, char** argv) {
   int perSM = 0, sms = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, block, smem);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  p.sm_count = sms;
+  p.lead_div = getenv("TB_LEAD_DIV") ? atoi(getenv("TB_LEAD_DIV")) : 0; // -1 -> #SM below
+  if (p.lead_div < 0) p.lead_div = sms;
   const int occ_api = perSM;
 #ifdef TB_TMEM
   perSM = 4; // the occupancy API answers 1 for a kernel that allocates tensor memory; 4 x 128 columns fit
