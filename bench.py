@@ -180,7 +180,7 @@ def run_reference_arm(args, rank):
         "e2e": {"value": r["solves_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -442,10 +442,32 @@ def run_ours(args, rank, world, local_rank):
             line["weak"] = weak
         if cpu is not None:
             line["cpu_baseline"] = cpu_baseline_block(cpu)
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries ONE JSON line and nothing else: file descriptor 1 is pointed at stderr for the
+    rest of the process (NCCL prints its version banner to stdout, libraries may chat), the line
+    itself goes to a private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -466,12 +488,14 @@ def main():
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
     if args.impl == "reference":
+        claim_stdout()
         return run_reference_arm(args, rank)
     if world == 1 and args.gpus > 1:
         # the driver launches N>1 through torchrun; a bare `--gpus N` re-launches itself that way
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000)] + sys.argv
         return subprocess.call(cmd)
+    claim_stdout()
     return run_ours(args, rank, world, local_rank)
 
 

@@ -68,7 +68,9 @@ unsigned long long* qn_next_counter(qn_context* ctx, cudaStream_t st) {
 // Number of column ranges a host-pointer entry pipelines a batch of `batch` problems in.
 int qn_host_ranges(const qn_context* ctx, int64_t batch, int ntrace) {
   int r = ctx->opt.host_chunks;
-  if (r < 0) r = batch >= 16384 ? 8 : batch >= 4096 ? 4 : 1;
+  // auto: ranges of at least 2048 problems — a range must still fill the SMs' resident problem
+  // slots (1184 on B200 for the tensor-memory tiles), or the dispatch would pick a smaller kernel
+  if (r < 0) r = (int)std::min<int64_t>(batch / 2048, qn_context::kRangeStreams);
   if (r < 1 || ntrace > 0 || ctx->opt.record_exit) r = 1;
   if (r > qn_context::kRangeStreams) r = qn_context::kRangeStreams;
   if ((int64_t)r > batch) r = (int)batch;

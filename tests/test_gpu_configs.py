@@ -200,7 +200,7 @@ def test_host_entry_ranges_same_bits(eng, qn, option, n, batch):
         st = qn.BFGSStateBatch(n, batch)
         st.data[...] = 0.0
         got = eng.optimize_batched(qn.Rosenbrock(), Theta, states=st, flags=qn._lib.FLAG_WRITE_H)
-        want = {(-1): 8 if batch >= 16384 else 4}.get(chunks, chunks)
+        want = {(-1): min(8, batch // 2048)}.get(chunks, chunks)
         assert eng.last_launch()["kernel_launches"] == want
         for k in ("x", "g", "ell", "iters", "fevals", "status"):
             assert np.array_equal(got[k], ref[k], equal_nan=True), (chunks, k)
