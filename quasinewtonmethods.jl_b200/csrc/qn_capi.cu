@@ -347,6 +347,7 @@ const OptKey kOptKeys[] = {
   {"latency", &qn_options::latency, "QN_LATENCY", 0},
   {"record_exit", &qn_options::record_exit, "QN_RECORD_EXIT", 0},
   {"lead_parity", &qn_options::lead_parity, "QN_LEAD_PARITY", 0},
+  {"lead_warp", &qn_options::lead_warp, "QN_LEAD_WARP", 0},
   {"host_chunks", &qn_options::host_chunks, "QN_HOST_CHUNKS", 0},
 };
 void options_from_env(qn_options& o) {

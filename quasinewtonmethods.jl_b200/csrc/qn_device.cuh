@@ -50,6 +50,7 @@ struct BatchParams {
   unsigned long long* exit_ns;
   int exit_cap;
   int lead_div;  // tile kernels: warp (blockIdx / lead_div) & 1 of a pair leads; 0 = the same warp in every CTA
+  int lead_warp; // one-CTA-per-problem tile kernels (n = 96, 128, 160): the warp that leads
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {

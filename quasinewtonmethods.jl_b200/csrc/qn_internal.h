@@ -40,6 +40,7 @@ struct qn_options {
   int latency = -1;       // "latency":     -1 auto, 0/1 the single-problem latency kernel          (QN_LATENCY)
   int host_chunks = -1;   // "host_chunks": host-pointer entry: column ranges pipelined over two streams, -1 auto (QN_HOST_CHUNKS)
   int lead_parity = 0;    // "lead_parity": tile kernels, which warp of a pair leads: 0 the same in every CTA, d > 0 warp (blockIdx / d) & 1, -1 d = #SM (QN_LEAD_PARITY)
+  int lead_warp = -1;     // "lead_warp": n = 96, 128, 160 tiles (one CTA per problem): the leading warp, -1 auto (QN_LEAD_WARP)
   int record_exit = 0;    // "record_exit": tile kernels stamp %globaltimer when a problem slot runs dry
 };
 

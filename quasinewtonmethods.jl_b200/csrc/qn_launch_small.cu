@@ -29,6 +29,7 @@ int launch_tilew(qn_context* ctx, qn::BatchParams& p, cudaStream_t st, const typ
   if (grid > p.batch) grid = p.batch;
   p.counter = qn_next_counter(ctx, st);
   p.lead_div = lead_divisor(ctx);
+  p.lead_warp = (ctx->opt.lead_warp >= 0 && ctx->opt.lead_warp < C::THREADS / 32) ? ctx->opt.lead_warp : 0;
   arm_exit_stamps(ctx, p, grid, st);
   kern<<<(unsigned)grid, C::THREADS, smem, st>>>(p, op);
   QN_CUDA_TRY(cudaGetLastError());

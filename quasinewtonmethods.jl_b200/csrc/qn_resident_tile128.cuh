@@ -191,7 +191,7 @@ qn_resident_tilew_kernel(const __grid_constant__ BatchParams p, const __grid_con
   double* part2 = smem + C::oPart2;
   volatile int* cmd = reinterpret_cast<volatile int*>(smem + C::oCmd);
   volatile long long* next = reinterpret_cast<volatile long long*>(smem + C::kSmemDoubles - 2);
-  const bool leader = (warp == 0);
+  const bool leader = (warp == p.lead_warp);
   constexpr int NCH = CT; // one tile column (RT rows) per step
 
   auto pass1 = [&]() { // t[i] = Σ_k y[col0+k] H[row0+i, col0+k], QN.jl:44-49
