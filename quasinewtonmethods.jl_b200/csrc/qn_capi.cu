@@ -752,79 +752,86 @@ int32_t qn_bfgs_optimize_batched_f64(qn_context* ctx, const qn_model* model, int
     }
     return e;
   };
-  for (int c = 0; c < chunks; ++c) {
-    const int64_t c0 = batch * c / chunks, cnt = batch * (c + 1) / chunks - c0;
-    const size_t e0 = (size_t)n * c0, ne = (size_t)n * cnt;
-    cudaStream_t st = ctx->range_stream[c];
-    QN_CUDA_TRY(cudaMemcpyAsync(base + o_theta + sizeof(double) * e0, theta0 + e0, sizeof(double) * ne,
-                                cudaMemcpyHostToDevice, st));
-    if (ntrace > 0) {
-      // rows past a problem's last iteration stay as the caller initialised them
-      QN_CUDA_TRY(cudaMemcpyAsync(base + o_tr, trace_out, sizeof(double) * nb * ntrace,
+  // everything is enqueued inside one lambda so that an error on any range still waits for the
+  // ranges already in flight (they write into the caller's buffers) before the call returns
+  auto enqueue = [&]() -> int {
+    for (int c = 0; c < chunks; ++c) {
+      const int64_t c0 = batch * c / chunks, cnt = batch * (c + 1) / chunks - c0;
+      const size_t e0 = (size_t)n * c0, ne = (size_t)n * cnt;
+      cudaStream_t st = ctx->range_stream[c];
+      QN_CUDA_TRY(cudaMemcpyAsync(base + o_theta + sizeof(double) * e0, theta0 + e0, sizeof(double) * ne,
                                   cudaMemcpyHostToDevice, st));
+      if (ntrace > 0) {
+        // rows past a problem's last iteration stay as the caller initialised them
+        QN_CUDA_TRY(cudaMemcpyAsync(base + o_tr, trace_out, sizeof(double) * nb * ntrace,
+                                    cudaMemcpyHostToDevice, st));
+      }
+      qn::BatchParams& p = ps[c];
+      p.n = n;
+      p.max_iter = max_iter;
+      p.batch = cnt;
+      p.theta0 = (const double*)(base + o_theta) + e0;
+      p.theta_stride = n;
+      p.tol = tol;
+      p.ls = qn::LsParams{ls->c1, ls->rho_hi, ls->rho_lo, (long long)ls->iterations, ls->order};
+      p.x_out = (double*)(base + o_x) + e0;
+      p.x_stride = n;
+      p.g_out = (double*)(base + o_g) + e0;
+      p.g_stride = n;
+      if (want_h) {
+        p.h_out = (double*)(base + o_h) + hblk * (size_t)c0;
+        p.h_stride = (long long)hblk;
+        p.ldh = ld;
+        if (ld > n) // the padding rows are never written by the kernels: give the copy defined bytes
+          QN_CUDA_TRY(cudaMemsetAsync(p.h_out, 0, sizeof(double) * hblk * cnt, st));
+      }
+      p.ell_out = (double*)(base + o_ell) + c0;
+      p.iters_out = (int*)(base + o_it) + c0;
+      p.fevals_out = (int*)(base + o_fe) + c0;
+      p.status_out = (int*)(base + o_st) + c0;
+      p.ntrace = ntrace;
+      p.trace = ntrace ? (double*)(base + o_tr) : nullptr;
+      const int drc = dispatch_model(ctx, model, p, ls, flags, st);
+      if (drc) return drc;
+      launches += ctx->last_launches;
     }
-    qn::BatchParams& p = ps[c];
-    p.n = n;
-    p.max_iter = max_iter;
-    p.batch = cnt;
-    p.theta0 = (const double*)(base + o_theta) + e0;
-    p.theta_stride = n;
-    p.tol = tol;
-    p.ls = qn::LsParams{ls->c1, ls->rho_hi, ls->rho_lo, (long long)ls->iterations, ls->order};
-    p.x_out = (double*)(base + o_x) + e0;
-    p.x_stride = n;
-    p.g_out = (double*)(base + o_g) + e0;
-    p.g_stride = n;
-    if (want_h) {
-      p.h_out = (double*)(base + o_h) + hblk * (size_t)c0;
-      p.h_stride = (long long)hblk;
-      p.ldh = ld;
-      if (ld > n) // the padding rows are never written by the kernels: give the copy defined bytes
-        QN_CUDA_TRY(cudaMemsetAsync(p.h_out, 0, sizeof(double) * hblk * cnt, st));
-    }
-    p.ell_out = (double*)(base + o_ell) + c0;
-    p.iters_out = (int*)(base + o_it) + c0;
-    p.fevals_out = (int*)(base + o_fe) + c0;
-    p.status_out = (int*)(base + o_st) + c0;
-    p.ntrace = ntrace;
-    p.trace = ntrace ? (double*)(base + o_tr) : nullptr;
-    rc = dispatch_model(ctx, model, p, ls, flags, st);
-    if (rc) {
-      sync_all();
-      return rc;
-    }
-    launches += ctx->last_launches;
-  }
-  ctx->last_launches = launches;
-  // results back to the caller's buffers, range by range
-  for (int c = 0; c < chunks; ++c) {
-    const qn::BatchParams& p = ps[c];
-    const int64_t c0 = batch * c / chunks, cnt = p.batch;
-    const size_t e0 = (size_t)n * c0, ne = (size_t)n * cnt;
-    cudaStream_t st = ctx->range_stream[c];
-    if (states) {
-      double* sblk = states + state_stride * c0;
-      // θ* -> offset 0, ∇ -> offset ld of each block (QN.jl:135,138): strided 2-D copies
-      QN_CUDA_TRY(cudaMemcpy2DAsync(sblk, sizeof(double) * state_stride, p.x_out, sizeof(double) * n,
-                                    sizeof(double) * n, cnt, cudaMemcpyDeviceToHost, st));
-      QN_CUDA_TRY(cudaMemcpy2DAsync(sblk + ld, sizeof(double) * state_stride, p.g_out,
-                                    sizeof(double) * n, sizeof(double) * n, cnt,
-                                    cudaMemcpyDeviceToHost, st));
-      if (want_h) // field 8 of every block (QN.jl:142), n·ld contiguous doubles per problem: one strided copy
-        QN_CUDA_TRY(cudaMemcpy2DAsync(sblk + 7 * (int64_t)ld, sizeof(double) * state_stride, p.h_out,
-                                      sizeof(double) * hblk, sizeof(double) * hblk, cnt,
+    ctx->last_launches = launches;
+    // results back to the caller's buffers, range by range
+    for (int c = 0; c < chunks; ++c) {
+      const qn::BatchParams& p = ps[c];
+      const int64_t c0 = batch * c / chunks, cnt = p.batch;
+      const size_t e0 = (size_t)n * c0, ne = (size_t)n * cnt;
+      cudaStream_t st = ctx->range_stream[c];
+      if (states) {
+        double* sblk = states + state_stride * c0;
+        // θ* -> offset 0, ∇ -> offset ld of each block (QN.jl:135,138): strided 2-D copies
+        QN_CUDA_TRY(cudaMemcpy2DAsync(sblk, sizeof(double) * state_stride, p.x_out, sizeof(double) * n,
+                                      sizeof(double) * n, cnt, cudaMemcpyDeviceToHost, st));
+        QN_CUDA_TRY(cudaMemcpy2DAsync(sblk + ld, sizeof(double) * state_stride, p.g_out,
+                                      sizeof(double) * n, sizeof(double) * n, cnt,
                                       cudaMemcpyDeviceToHost, st));
+        if (want_h) // field 8 of every block (QN.jl:142), n·ld contiguous doubles per problem: one strided copy
+          QN_CUDA_TRY(cudaMemcpy2DAsync(sblk + 7 * (int64_t)ld, sizeof(double) * state_stride, p.h_out,
+                                        sizeof(double) * hblk, sizeof(double) * hblk, cnt,
+                                        cudaMemcpyDeviceToHost, st));
+      }
+      if (x_out) QN_CUDA_TRY(cudaMemcpyAsync(x_out + e0, p.x_out, sizeof(double) * ne, cudaMemcpyDeviceToHost, st));
+      if (g_out) QN_CUDA_TRY(cudaMemcpyAsync(g_out + e0, p.g_out, sizeof(double) * ne, cudaMemcpyDeviceToHost, st));
+      if (ell_out) QN_CUDA_TRY(cudaMemcpyAsync(ell_out + c0, p.ell_out, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+      if (iters_out) QN_CUDA_TRY(cudaMemcpyAsync(iters_out + c0, p.iters_out, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, st));
+      if (fevals_out) QN_CUDA_TRY(cudaMemcpyAsync(fevals_out + c0, p.fevals_out, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, st));
+      if (status_out) QN_CUDA_TRY(cudaMemcpyAsync(status_out + c0, p.status_out, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, st));
+      if (ntrace > 0)
+        QN_CUDA_TRY(cudaMemcpyAsync(trace_out, base + o_tr, sizeof(double) * nb * ntrace, cudaMemcpyDeviceToHost, st));
     }
-    if (x_out) QN_CUDA_TRY(cudaMemcpyAsync(x_out + e0, p.x_out, sizeof(double) * ne, cudaMemcpyDeviceToHost, st));
-    if (g_out) QN_CUDA_TRY(cudaMemcpyAsync(g_out + e0, p.g_out, sizeof(double) * ne, cudaMemcpyDeviceToHost, st));
-    if (ell_out) QN_CUDA_TRY(cudaMemcpyAsync(ell_out + c0, p.ell_out, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
-    if (iters_out) QN_CUDA_TRY(cudaMemcpyAsync(iters_out + c0, p.iters_out, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, st));
-    if (fevals_out) QN_CUDA_TRY(cudaMemcpyAsync(fevals_out + c0, p.fevals_out, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, st));
-    if (status_out) QN_CUDA_TRY(cudaMemcpyAsync(status_out + c0, p.status_out, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, st));
-    if (ntrace > 0)
-      QN_CUDA_TRY(cudaMemcpyAsync(trace_out, base + o_tr, sizeof(double) * nb * ntrace, cudaMemcpyDeviceToHost, st));
+    return QN_OK;
+  };
+  rc = enqueue();
+  {
+    const cudaError_t e = sync_all();
+    if (rc) return rc;
+    QN_CUDA_TRY(e);
   }
-  QN_CUDA_TRY(sync_all());
   return QN_OK;
 }
 
