@@ -106,7 +106,7 @@ int32_t qn_device_info(qn_context* ctx, char* name, size_t name_len, int32_t* sm
  * "pack_variant" (0 | 1 | 2 | 4), "pair_rows" (0 auto | 'h' | 't' | '4' | '2' | 's'), "smem_rows" (0 | 2 | 4),
  * "lambda_smem", "stream_cluster", "stream_tma" (-1 auto | 0 | 1), "sweep_depth" (0 | 8 | 16),
  * "sweep_fine" (-1 auto | 0 | 1), "sweep_order" (0 | 1 | 2), "l2_persist_mb", "l2_resident",
- * "hint_p1_ld", "hint_p2_ld", "hint_p2_st", "hint_one_ld", "p1_pad_kb", "latency" (-1 auto | 0 | 1),
+ * "hint_p1_ld", "hint_p2_ld", "hint_p2_st", "hint_one_ld", "p1_pad_kb",
  * "tile_3w" (0 | 1), "lead_parity" (0 the same warp of every leader/helper pair leads | d > 0 warp
  * (blockIdx / d) & 1 | -1 d = #SM), "host_chunks" (host-pointer entries: column ranges pipelined over
  * the context's streams; -1 auto | 1 off | up to 8), "record_exit" (0 | 1).  None of them changes a

@@ -344,7 +344,6 @@ const OptKey kOptKeys[] = {
   {"hint_p2_st", &qn_options::hint_p2_st, "QN_HINT_P2_ST", 0},
   {"hint_one_ld", &qn_options::hint_one_ld, "QN_HINT_ONE_LD", 0},
   {"p1_pad_kb", &qn_options::p1_pad_kb, "QN_P1_PAD_KB", 0},
-  {"latency", &qn_options::latency, "QN_LATENCY", 0},
   {"record_exit", &qn_options::record_exit, "QN_RECORD_EXIT", 0},
   {"lead_parity", &qn_options::lead_parity, "QN_LEAD_PARITY", 0},
   {"lead_warp", &qn_options::lead_warp, "QN_LEAD_WARP", 0},

@@ -37,7 +37,6 @@ struct qn_options {
   int sweep_depth = 0;    // "sweep_depth": 0 auto, 8 or 16 loads in flight                         (QN_SWEEP_DEPTH)
   int hint_p1_ld = 0, hint_p2_ld = 2, hint_p2_st = 1, hint_one_ld = 4; // cache hints, QN_HINT_*
   int p1_pad_kb = 0;      // "p1_pad_kb"                                                            (QN_P1_PAD_KB)
-  int latency = -1;       // "latency":     -1 auto, 0/1 the single-problem latency kernel          (QN_LATENCY)
   int host_chunks = -1;   // "host_chunks": host-pointer entry: column ranges pipelined over two streams, -1 auto (QN_HOST_CHUNKS)
   int lead_parity = 0;    // "lead_parity": tile kernels, which warp of a pair leads: 0 the same in every CTA, d > 0 warp (blockIdx / d) & 1, -1 d = #SM (QN_LEAD_PARITY)
   int lead_warp = -1;     // "lead_warp": n = 96, 128, 160 tiles (one CTA per problem): the leading warp, -1 auto (QN_LEAD_WARP)
