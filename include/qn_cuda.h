@@ -108,7 +108,7 @@ int32_t qn_device_info(qn_context* ctx, char* name, size_t name_len, int32_t* sm
  * "sweep_fine" (-1 auto | 0 | 1), "sweep_order" (0 | 1 | 2), "l2_persist_mb", "l2_resident",
  * "hint_p1_ld", "hint_p2_ld", "hint_p2_st", "hint_one_ld", "p1_pad_kb",
  * "tile_3w" (0 | 1), "lead_parity" (0 the same warp of every leader/helper pair leads | d > 0 warp
- * (blockIdx / d) & 1 | -1 d = #SM), "host_chunks" (host-pointer entries: column ranges pipelined over
+ * (blockIdx / d) & 1 | -1 d = #SM), "lead_warp" (n = 96, 128, 160 tiles: the leading warp), "host_chunks" (host-pointer entries: column ranges pipelined over
  * the context's streams; -1 auto | 1 off | up to 8), "record_exit" (0 | 1).  None of them changes a
  * result bit.  Unknown key -> QN_ERR_INVALID_ARGUMENT. */
 int32_t qn_set_option(qn_context* ctx, const char* key, int64_t value);
