@@ -48,7 +48,7 @@ WORKLOAD = ("batched Rosenbrock n=60, one global batch of 2^16 N(0,1) starts (Ph
 # dram__bytes_write.sum, ncu --set full on this command): profiles/r2_tile60_lh_bench_ncu.txt for the
 # kernel with the tiles in tensor memory (CTAs of 128 threads), profiles/r1_tile60_bench_ncu.txt for
 # the all-register kernel (CTAs of 64 threads)
-TILE_KERNEL_DRAM_BYTES_PER_LAUNCH = {128: 31934976 + 13278976, 64: 33576192 + 32338944}
+TILE_KERNEL_DRAM_BYTES_PER_LAUNCH = {128: 31864320 + 11734016, 64: 33576192 + 32338944}
 
 
 def global_starts(batch=BATCH, n=N_DIM, key=SEED):
