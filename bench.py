@@ -45,7 +45,7 @@ UNIT = "solves/s"
 WORKLOAD = ("batched Rosenbrock n=60, one global batch of 2^16 N(0,1) starts (Philox key 20261018), "
             "BackTracking order 2, tol 1e-8 (BASELINE.json configs[1])")
 # DRAM bytes of ONE launch of the headline kernel on the full 2^16 batch (dram__bytes_read.sum +
-# dram__bytes_write.sum, ncu --set full on this command): profiles/r2_tile60_lh_bench_ncu.txt for the
+# dram__bytes_write.sum, ncu --set full on this command): profiles/r2_tile60_final_bench_ncu.txt for the
 # kernel with the tiles in tensor memory (CTAs of 128 threads), profiles/r1_tile60_bench_ncu.txt for
 # the all-register kernel (CTAs of 64 threads)
 TILE_KERNEL_DRAM_BYTES_PER_LAUNCH = {128: 31864320 + 11734016, 64: 33576192 + 32338944}
