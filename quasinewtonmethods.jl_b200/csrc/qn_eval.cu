@@ -28,6 +28,7 @@ qn_eval_kernel(int n, long long batch, const double* __restrict__ theta, double*
   tm.tpr = 1;
   tm.part = nullptr;
   tm.scratch = smem + 3 * B;
+  Obj::prologue(tm, op); // once per CTA (include/qn_objective.cuh)
   for (long long j = blockIdx.x; j < batch; j += gridDim.x) {
     __syncthreads();
     tm.xs[tm.c] = (tm.c < n) ? theta[j * n + tm.c] : 0.0;
