@@ -113,78 +113,6 @@ __device__ __forceinline__ double chain_rowsum(int K, F&& term) {
   return T;
 }
 
-// Two rows at once: the same rule-C2 row sums as two chain_rowsum calls (each row's additions in the
-// same order, so the same bits), with the shared operand b[r] fetched once and two independent fma
-// chains in flight.  term2(r, a0, a1, b): row 0's and row 1's left operands and the common right one.
-template <class F>
-__device__ __forceinline__ void chain_rowsum2(int K, F&& term2, double& out0, double& out1) {
-  const int rb = chain_block(K);
-  double T0 = 0.0, S0 = 0.0, T1 = 0.0, S1 = 0.0;
-  int blk = 0;
-  for (int r0 = 0; r0 < K; r0 += rb, ++blk) {
-    const int r1 = min(r0 + rb, K);
-    double t0 = 0.0, t1 = 0.0;
-    int r = r0;
-    for (; r + 8 <= r1; r += 8) {
-      double a0[8], a1[8], b[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) term2(r + k, a0[k], a1[k], b[k]);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { t0 = fma(a0[k], b[k], t0); t1 = fma(a1[k], b[k], t1); }
-    }
-    for (; r < r1; ++r) {
-      double a0, a1, b;
-      term2(r, a0, a1, b);
-      t0 = fma(a0, b, t0);
-      t1 = fma(a1, b, t1);
-    }
-    const bool first = (blk & 15) == 0, last = (blk & 15) == 15 || r1 == K;
-    S0 = first ? t0 : S0 + t0;
-    S1 = first ? t1 : S1 + t1;
-    if (last) { T0 = (blk < 16) ? S0 : T0 + S0; T1 = (blk < 16) ? S1 : T1 + S1; }
-  }
-  out0 = T0;
-  out1 = T1;
-}
-
-// superblock_sum with two block chains in flight: blocks b and b + 1 are independent fma chains from
-// +0.0 (rule C2); their partials are still added to S in ascending block order — the same bits.
-template <class F>
-__device__ __forceinline__ double superblock_sum_ilp2(int K, int sb, F&& term) {
-  const int rb = chain_block(K);
-  double S = 0.0;
-  const int rend = min(K, (sb + 1) * 16 * rb);
-  bool first = true;
-  int r0 = sb * 16 * rb;
-  for (; r0 + 2 * rb <= rend; r0 += 2 * rb) {
-    double ta = 0.0, tb = 0.0;
-    int r = 0;
-    for (; r + 8 <= rb; r += 8) {
-      double a[8], b[8], c[8], d[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { term(r0 + r + k, a[k], b[k]); term(r0 + rb + r + k, c[k], d[k]); }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { ta = fma(a[k], b[k], ta); tb = fma(c[k], d[k], tb); }
-    }
-    for (; r < rb; ++r) {
-      double a, b, c, d;
-      term(r0 + r, a, b);
-      term(r0 + rb + r, c, d);
-      ta = fma(a, b, ta);
-      tb = fma(c, d, tb);
-    }
-    S = first ? ta : S + ta;
-    first = false;
-    S = S + tb;
-  }
-  for (; r0 < rend; r0 += rb) {
-    const double t = block_chain(r0, min(r0 + rb, rend), term);
-    S = first ? t : S + t;
-    first = false;
-  }
-  return S;
-}
-
 // One rule-C2 SUPER-block (16 blocks) of a row sum over K terms: block partials added in order.
 template <class F>
 __device__ __forceinline__ double superblock_sum(int K, int sb, F&& term) {

@@ -158,6 +158,88 @@ struct Logistic {
     sg = (z >= 0.0 ? 1.0 : e) / (1.0 + e);
   }
 
+  // The two GEMVs walk X (and Xᵀ) with RUNNING POINTERS: with the element index multiplied out
+  // ((size_t)m * j) every load cost five integer instructions — IMAD, LEA and VIADD were 46 % of the
+  // kernel's instructions, DFMA 12 % (profiles/r2_logistic_hot_sass.txt).
+  // rows2: z0 = Σ_j a[j·ld] b[j], z1 = Σ_j a[second + j·ld] b[j] as rule-C2 row sums (the bits of
+  // chain_rowsum for each row), b[j] read once for both rows, two fma chains in flight.
+  __device__ __forceinline__ static void rows2(const double* a, const int second, const int ld, const int K,
+                                               const double* b, double& out0, double& out1) {
+    const int rb = chain_block(K);
+    double T0 = 0.0, S0 = 0.0, T1 = 0.0, S1 = 0.0;
+    int blk = 0;
+    for (int r0 = 0; r0 < K; r0 += rb, ++blk) {
+      const int r1 = min(r0 + rb, K);
+      double t0 = 0.0, t1 = 0.0;
+      const double* bb = b + r0;
+      int r = r0;
+      for (; r + 8 <= r1; r += 8, bb += 8) {
+        double a0[8], a1[8], bv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a0[k] = __ldg(a); a1[k] = __ldg(a + second); a += ld; bv[k] = bb[k]; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { t0 = fma(a0[k], bv[k], t0); t1 = fma(a1[k], bv[k], t1); }
+      }
+      for (; r < r1; ++r, ++bb) {
+        const double a0 = __ldg(a), a1 = __ldg(a + second), bv = *bb;
+        a += ld;
+        t0 = fma(a0, bv, t0);
+        t1 = fma(a1, bv, t1);
+      }
+      const bool first = (blk & 15) == 0, last = (blk & 15) == 15 || r1 == K;
+      S0 = first ? t0 : S0 + t0;
+      S1 = first ? t1 : S1 + t1;
+      if (last) { T0 = (blk < 16) ? S0 : T0 + S0; T1 = (blk < 16) ? S1 : T1 + S1; }
+    }
+    out0 = T0;
+    out1 = T1;
+  }
+  // superblock2: rule-C2 super-block sb of Σ_i a[i·ld] b[i] over K terms (the bits of superblock_sum),
+  // two consecutive blocks' fma chains in flight, their partials added in ascending block order.
+  __device__ __forceinline__ static double superblock2(const double* a, const int ld, const int K, const int sb,
+                                                       const double* b) {
+    const int rb = chain_block(K);
+    const int rend = min(K, (sb + 1) * 16 * rb);
+    int r0 = sb * 16 * rb;
+    const double* pa = a + (size_t)ld * r0;
+    const size_t skip = (size_t)ld * rb;
+    double S = 0.0;
+    bool first = true;
+    for (; r0 + 2 * rb <= rend; r0 += 2 * rb) {
+      const double* pb = pa + skip;
+      const double* ba = b + r0;
+      const double* bb = ba + rb;
+      double ta = 0.0, tb = 0.0;
+      int r = 0;
+      for (; r + 8 <= rb; r += 8, ba += 8, bb += 8) {
+        double x0[8], y0[8], x1[8], y1[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { x0[k] = __ldg(pa); x1[k] = __ldg(pb); pa += ld; pb += ld; y0[k] = ba[k]; y1[k] = bb[k]; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { ta = fma(x0[k], y0[k], ta); tb = fma(x1[k], y1[k], tb); }
+      }
+      for (; r < rb; ++r, ++ba, ++bb) {
+        const double x0 = __ldg(pa), x1 = __ldg(pb);
+        pa += ld; pb += ld;
+        ta = fma(x0, *ba, ta);
+        tb = fma(x1, *bb, tb);
+      }
+      pa = pb; // block b + 1 has been consumed as well
+      S = first ? ta : S + ta;
+      first = false;
+      S = S + tb;
+    }
+    for (; r0 < rend; r0 += rb) {
+      const int r1 = min(r0 + rb, rend);
+      double tt = 0.0;
+      const double* ba = b + r0;
+      for (int r = r0; r < r1; ++r, ++ba) { tt = fma(__ldg(pa), *ba, tt); pa += ld; }
+      S = first ? tt : S + tt;
+      first = false;
+    }
+    return S;
+  }
+
   template <bool GRAD>
   __device__ __forceinline__ static double eval(Team& t, const Params& p, double& g) {
     const int n = t.n, c = t.c, m = p.m;
@@ -177,7 +259,7 @@ struct Logistic {
       if (mine) xc[c] = t.xs[c];
       if (threadIdx.x == 0) *valid = 1;
       // z = Xθ, two rows per thread at a time (i and i + nthr): θ[j] is read once for both and two
-      // rule-C2 chains are in flight (chain_rowsum2: each row's bits are those of chain_rowsum)
+      // rule-C2 chains are in flight (rows2: each row's bits are those of chain_rowsum)
       auto finish_row = [&](const int i, const double z) {
         const double yi = __ldg(p.y + i);
         double sp, sg;
@@ -186,23 +268,11 @@ struct Logistic {
         rs[i] = yi - sg;
       };
       for (int i = c; i < m; i += 2 * nthr) {
-        const double* col = p.X + i;
-        if (i + nthr < m) {
-          double z0, z1;
-          chain_rowsum2(n, [&](int j, double& a0, double& a1, double& b) {
-            const double* e = col + (size_t)m * j;
-            a0 = __ldg(e);
-            a1 = __ldg(e + nthr);
-            b = t.xs[j];
-          }, z0, z1);
-          finish_row(i, z0);
-          finish_row(i + nthr, z1);
-        } else {
-          finish_row(i, chain_rowsum(n, [&](int j, double& a, double& b) {
-            a = __ldg(col + (size_t)m * j);
-            b = t.xs[j];
-          }));
-        }
+        const bool two = i + nthr < m;
+        double z0, z1;
+        rows2(p.X + i, two ? nthr : 0, m, n, t.xs, z0, z1);
+        finish_row(i, z0);
+        if (two) finish_row(i + nthr, z1);
       }
     }
     const double th = (c < n) ? t.xs[c] : 0.0;
@@ -211,6 +281,7 @@ struct Logistic {
     const double pen = t.finish(n);
     // csum over the m staged values (rule C1), every warp redundantly
     double pp = (t.lane < m) ? vs[t.lane] : 0.0;
+#pragma unroll 8
     for (int i = t.lane + 32; i < m; i += 32) pp = pp + vs[i];
     const double S = warp_butterfly(pp);
     const double ell = fma(-(0.5 * p.lam), pen, S);
@@ -229,7 +300,7 @@ struct Logistic {
         double* sp = t.scratch + 2 * ((m + 31) & ~31); // [nsb][nvec]
         const int row = c % t.nvec, hgrp = c / t.nvec, ns = nsb(m);
         if (row < n && hgrp < t.tpr)
-          for (int sb = hgrp; sb < ns; sb += t.tpr) sp[sb * t.nvec + row] = superblock_sum_ilp2(m, sb, term(row));
+          for (int sb = hgrp; sb < ns; sb += t.tpr) sp[sb * t.nvec + row] = superblock2(Xt + row, n, m, sb, rs);
         __syncthreads();
         if (c < n) {
           double T = sp[c];
