@@ -24,6 +24,7 @@ ap.add_argument("--gpus", type=int, default=1)
 ap.add_argument("--quick", action="store_true")
 ap.add_argument("--no-cpu", action="store_true")
 ap.add_argument("--row-seconds", type=float, default=4.0)
+ap.add_argument("--objectives-only", action="store_true", help="only the n = 128 dense-Gaussian / logistic rows; merged into the existing JSON")
 args = ap.parse_args()
 G = args.gpus
 assert qn._lib.load().qn_device_count() >= G, "not enough GPUs"
@@ -76,7 +77,7 @@ rows = {"config": "BASELINE.json configs[2], configs[3]", "gpus": G, "dfma_tflop
 # measured round-1 single-GPU rates (iterations/s) to predict a row's time and skip the hopeless ones
 rate1 = {8: 8.9e9, 16: 4.0e9, 32: 1.1e9, 60: 3.9e8, 128: 7.0e7, 160: 2.2e7}
 iters1 = {8: 103, 16: 172, 32: 280, 60: 435, 128: 723, 160: 835}
-ns = [8, 16, 32, 60, 128, 160]
+ns = [] if args.objectives_only else [8, 16, 32, 60, 128, 160]
 cpu_done = set()
 batches = [1 << 10, 1 << 14] if args.quick else [1 << k for k in range(10, 19)]
 for n in ns:
@@ -119,5 +120,11 @@ for name, obj in (("dense_gaussian", qn.DenseGaussian(mu, lam)), ("logistic", qn
             name, b, G, r["ms"], r["solves_per_s"], r["converged"], b, r["mean_iters"],
             ("cpu %.0f solves/s on %d cores" % (r["cpu_solves_per_s"], r["cpu_cores"])) if "cpu_solves_per_s" in r else ""), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
+if args.objectives_only:  # keep the Rosenbrock rows of the committed sweep, replace the objectives
+    prev = os.path.join(ROOT, "profiles", "r2_sweep_%dgpu.json" % G)
+    if os.path.exists(prev):
+        old = json.load(open(prev))
+        rows["rosenbrock"], rows["skipped"] = old.get("rosenbrock", []), old.get("skipped", [])
+        rows["note"] = "objectives re-measured after the logistic GEMV rewrite; Rosenbrock rows from the earlier run of this round"
 json.dump(rows, open("gpurun_out/r2_sweep_%dgpu.json" % G, "w"), indent=1)
 print("wrote gpurun_out/r2_sweep_%dgpu.json" % G)
